@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Headline benchmark: IQL gradient steps/sec, summed over ensemble members.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One bench *step* = one fused engine call that runs ``inner`` IQL updates
+(replay sample + V/Q/actor update + Polyak + LR schedule) for every one of the
+S ensemble members resident on the GPU, i.e. ``S * inner`` gradient steps.
+Default workload = BASELINE.json configs[2]: halfcheetah-medium-replay shape
+(obs 17, act 6, 2x256 MLPs, Gaussian actor, batch 256), 64-member ensemble on a
+1M-transition synthetic buffer, one B200.  Multi-GPU (torchrun) keeps S members
+per GPU (weak scaling); members never exchange data -- the only collective is
+the NCCL all-gather of the per-step loss scalars.
+
+`--impl reference` times the reference's CPU implementation of the same path
+(the numpy port under oracle/, since /root/reference does not travel to the GPU
+box) on the host cores, one member, a bounded number of steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: dict(S, A, H, L, B, det, dropout, members, beta, iql_tau, tau, antmaze)
+    "halfcheetah_ens64": dict(S=17, A=6, H=256, L=2, B=256, det=False, dropout=0.0, members=64, beta=3.0, iql_tau=0.7,
+                              tau=0.005, antmaze=False, desc="BASELINE configs[2]: halfcheetah-medium-replay shape, 64-seed ensemble"),
+    "hopper_ens64": dict(S=11, A=3, H=256, L=2, B=256, det=True, dropout=0.0, members=64, beta=3.0, iql_tau=0.7,
+                         tau=0.001, antmaze=False, desc="north_star target: hopper-medium shape, 64-seed ensemble"),
+    "hopper_single": dict(S=11, A=3, H=256, L=2, B=256, det=True, dropout=0.0, members=1, beta=3.0, iql_tau=0.7,
+                          tau=0.001, antmaze=False, desc="BASELINE configs[0]: hopper-medium shape, single seed"),
+    "antmaze_jsrl": dict(S=29, A=8, H=256, L=3, B=256, det=False, dropout=0.0, members=1, beta=10.0, iql_tau=0.9,
+                         tau=0.005, antmaze=True, desc="BASELINE configs[1]: antmaze-umaze shape, 3x256, single learner"),
+    "pen_sweep256": dict(S=45, A=24, H=256, L=2, B=256, det=False, dropout=0.1, members=256, beta=3.0, iql_tau=0.8,
+                         tau=0.005, antmaze=False, desc="BASELINE configs[3]: pen-human shape, dropout actor, 256-member sweep"),
+    "stress_4x1024": dict(S=11, A=3, H=1024, L=4, B=4096, det=True, dropout=0.0, members=1, beta=3.0, iql_tau=0.7,
+                          tau=0.005, antmaze=False, desc="BASELINE configs[4]: batch 4096, 4x1024 MLPs, hopper shape"),
+}
+N_ROWS = 1_000_000
+
+
+def flops_per_step(w):
+    """GEMM FLOPs of one member-step."""
+    S, A, H, L, B = w["S"], w["A"], w["H"], w["L"], w["B"]
+
+    def fwd(i, o):
+        return 2 * (i * H + (L - 1) * H * H + H * o)
+
+    def bwd(i, o):
+        return 2 * fwd(i, o) - 2 * i * H
+
+    v, q, pi = (S, 1), (S + A, 1), (S, A)
+    return B * (2 * fwd(*v) + 4 * fwd(*q) + fwd(*pi) + bwd(*v) + 2 * bwd(*q) + bwd(*pi))
+
+
+def gather_bytes_per_step(w):
+    return w["B"] * (2 * w["S"] + w["A"] + 2) * 4
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def measure_tf32_peak(torch, device):
+    """cuBLAS TF32 8192^3 GEMM, sustained for ~1.5 s, same method as MEASURED_PEAKS.json uses for bf16
+    (the file has no TF32 entry).  Library call used as a yardstick only."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=device)
+        b = torch.randn(n, n, device=device)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 40
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize(device)
+        return 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference algorithm on the host cores (numpy port of the oracle)
+# ---------------------------------------------------------------------------
+def cpu_reference_steps_per_sec(w, steps, warmup, n_rows=200_000):
+    import numpy as np
+
+    from jsrl_corl_b200.ensemble import reference_init
+    from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
+
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    data = synthetic_dataset(n_rows, w["S"], w["A"], 0, antmaze_rewards=w["antmaze"])
+    q, v, actor = reference_init(0, w["S"], w["A"], w["H"], w["L"], w["det"], w["dropout"])
+    init = {g: {k: t.detach().numpy().copy() for k, t in mod.state_dict().items()} for g, mod in (("qf", q), ("vf", v), ("actor", actor))}
+    orc = NumpyIQL(OracleConfig(w["S"], w["A"], w["H"], w["L"], w["det"], w["dropout"], w["iql_tau"], w["beta"], 0.99,
+                                w["tau"]), init, np.float32)
+    rng = np.random.RandomState(0)
+    keep = 1.0 - w["dropout"]
+
+    def one():
+        idx = np.random.randint(0, n_rows, size=w["B"])  # the reference's sampler (iql.py:172)
+        batch = [data["observations"][idx], data["actions"][idx], data["rewards"][idx][:, None],
+                 data["next_observations"][idx], data["terminals"][idx].astype(np.float32)[:, None]]
+        masks = (rng.uniform(size=(w["L"], w["B"], w["H"])) < keep) if w["dropout"] > 0 else None
+        orc.train(batch, dropout_masks=masks)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt, cores
+
+
+def run_reference_arm(args, w, rank):
+    if rank != 0:
+        return
+    inner = args.inner if args.inner else 25
+    steps_total = max(1, args.steps) * inner
+    sps, dt, cores = cpu_reference_steps_per_sec(w, steps_total, max(3, args.warmup))
+    line = {
+        "impl": "reference", "metric": "iql_gradient_steps_per_sec_summed_over_seeds", "value": sps, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "members": 1, "inner_steps_per_bench_step": inner,
+                   "batch": w["B"], "hidden": f'{w["L"]}x{w["H"]}', "obs": w["S"], "act": w["A"]},
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps_total} sample+train steps of ONE member (numpy port of the reference update, "
+                                   f"200k-row buffer), {dt:.1f} s"},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_ours(args, w, rank, world, local_rank):
+    import numpy as np
+    import torch
+
+    from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
+    from jsrl_corl_b200.synthetic import synthetic_dataset
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    S_local = w["members"]
+    inner = args.inner if args.inner else (50 if w["H"] <= 256 and w["B"] <= 256 else 4)
+    first_member = rank * S_local  # weak scaling: every GPU trains its own block of members
+    seeds = list(range(first_member, first_member + S_local))
+    hp = [dict(beta=w["beta"], iql_tau=w["iql_tau"], tau=w["tau"], cosine_t_max=1_000_000) for _ in seeds]
+    ens = IQLEnsemble(S_local, w["S"], w["A"], w["H"], w["L"], w["B"], deterministic=w["det"], actor_dropout=w["dropout"],
+                      math_mode=args.math, device=device, max_steps_per_call=inner, seeds=seeds, hparams=hp,
+                      init=not args.fast_init)
+    if args.fast_init:  # same distribution family, one draw for all members (bench-only shortcut)
+        ens.init_member(0, seeds[0])
+        ens.engine.params[1:] = ens.engine.params[0]
+        ens.engine.target[1:] = ens.engine.target[0]
+    data = synthetic_dataset(N_ROWS, w["S"], w["A"], 0, antmaze_rewards=w["antmaze"])
+    rb = ReplayBuffer(w["S"], w["A"], N_ROWS, device)
+    rb.load_d4rl_dataset(data)
+    ens.bind_replay(rb)
+    eng = ens.engine
+    losses = torch.empty(S_local, inner, 3, dtype=torch.float32, device=device)
+    gathered = torch.empty(world, S_local, inner, 3, dtype=torch.float32, device=device) if world > 1 else None
+
+    def step():
+        eng.train_steps(inner, out=losses)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, losses)  # the only collective: log scalars
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with ClockSampler(local_rank) as clk:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+            launches += eng.last_launch_count()
+        e1.record()
+        sync_all()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    final = losses.cpu().numpy()
+    assert np.isfinite(final).all(), "non-finite losses in the timed region"
+    total_steps = world * S_local * inner * args.steps
+    value = total_steps / (ms * 1e-3)
+
+    # ---- e2e: the same work through the public API with HOST inputs -------------
+    # every bench step copies that step's sample indices (the reference draws them on the host,
+    # iql.py:172) from pinned host memory and reads the loss scalars back.
+    idx_host = torch.from_numpy(np.random.RandomState(rank).randint(0, N_ROWS, size=(S_local, inner, w["B"]))).pin_memory()
+    loss_host = torch.empty(S_local, inner, 3, dtype=torch.float32).pin_memory()
+    idx_dev = torch.empty_like(idx_host, device=device)
+
+    def e2e_step():
+        idx_dev.copy_(idx_host, non_blocking=True)
+        out = eng.train_steps(inner, mode="indices", indices=idx_dev, out=losses)
+        loss_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()  # the caller consumes the log dict every step
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e2e_steps = max(2, args.steps // 2)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = world * S_local * inner * e2e_steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        tf32_peak = measure_tf32_peak(torch, device) if args.math == "tf32" else None
+        fl = flops_per_step(w)
+        achieved_tflops = (S_local * inner * args.steps * fl) / (ms * 1e-3) / 1e12  # per GPU
+        if args.math == "tf32":
+            roof = {"bound": "tensor", "achieved": achieved_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tflops / tf32_peak, "traffic": None,
+                    "kernel": "whole fused K-step update (all kernels of the step)",
+                    "peak_source": "cuBLAS TF32 8192^3 measured live (MEASURED_PEAKS.json has no TF32 entry); "
+                                   f"bf16 {peak_src}: {peaks.get('bf16_tflops')}"}
+        else:
+            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            roof = {"bound": "tensor", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tflops / fp32_peak, "traffic": None,
+                    "kernel": "whole fused K-step update, FP32 CUDA-core validation path",
+                    "peak_source": "nominal FP32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz"}
+        cpu = None
+        if not args.no_cpu_baseline:
+            sps, dt, cores = cpu_reference_steps_per_sec(w, args.cpu_steps, 5)
+            cpu = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_steps} sample+train steps of ONE member, numpy port of the reference update, {dt:.1f} s"}
+        line = {
+            "metric": "iql_gradient_steps_per_sec_summed_over_seeds", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": w["desc"], "members_per_gpu": S_local, "members_total": world * S_local,
+                       "inner_steps_per_bench_step": inner, "batch": w["B"], "hidden": f'{w["L"]}x{w["H"]}', "obs": w["S"],
+                       "act": w["A"], "buffer_rows": N_ROWS, "sampler": "philox in-kernel",
+                       "l2_policy": "inputs larger than L2: per-step working set (params+Adam+activations of all members) "
+                                    f"= {(eng.params.numel() * 4 * 4 + eng.workspace.numel()) / 1e6:.0f} MB plus random rows of a "
+                                    f"{rb.rows.numel() * 4 / 1e6:.0f} MB buffer",
+                       "math_mode": args.math, "parallelism": f"members sharded x{world}, no update-path collective"},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": idx_host.numel() * 8,
+                    "d2h_bytes_per_step": loss_host.numel() * 4,
+                    "note": "host-drawn int64 sample indices in, loss scalars out, one sync per bench step"},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "hbm": {"gather_bytes_per_member_step": gather_bytes_per_step(w), "hbm_peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "clocks": clk.summary(),
+            "flop_per_member_step": fl,
+            "last_losses_member0": [float(x) for x in final[0, -1]],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="halfcheetah_ens64", choices=sorted(WORKLOADS))
+    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--inner", type=int, default=0, help="updates per engine call (0 = workload default)")
+    ap.add_argument("--members", type=int, default=0, help="override members per GPU")
+    ap.add_argument("--cpu-steps", type=int, default=1500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast-init", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.members:
+        w["members"] = args.members
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, w, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        print(json.dumps({"error": f"--gpus {args.gpus} must be launched with torch.distributed.run (one rank per GPU)"}))
+        sys.exit(2)
+    run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

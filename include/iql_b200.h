@@ -1,0 +1,194 @@
+/*
+ * iql_b200.h -- C-ABI of the B200-native IQL(+JSRL) update engine.
+ *
+ * Plain C, no torch types: pointers are CUDA device pointers unless a
+ * parameter says "host"; `stream` is a cudaStream_t passed as void*.
+ * Every entry point returns IQL_OK (0) or an IQL_ERR_* code; the message for
+ * the last failure is available through iql_last_error().
+ *
+ * The reference (LaurenYTaylor/jsrl-CORL) is pure Python and has no FFI layer;
+ * its "boundary" is the class API of algorithms/finetune/iql.py.  Each entry
+ * point below names the reference interface (file:line, relative to
+ * /root/reference/algorithms/finetune/) it replaces.  The Python facade in
+ * jsrl_corl_b200/ binds exactly these symbols with ctypes (INTEGRATION.md shows
+ * the stub a reference maintainer would add).
+ *
+ * Ownership: the caller (torch) allocates every device buffer -- parameter /
+ * Adam / target arenas, replay rows, workspace -- and the engine borrows the
+ * pointers for the lifetime of the handle.  The library never cudaMalloc's.
+ * Calls on one handle are not re-entrant.
+ */
+#ifndef IQL_B200_H
+#define IQL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IQL_OK 0
+#define IQL_ERR_INVALID 1 /* bad argument            -> ValueError            */
+#define IQL_ERR_CUDA 2    /* CUDA runtime failure    -> RuntimeError          */
+#define IQL_ERR_STATE 3   /* call order / not bound  -> RuntimeError          */
+#define IQL_ERR_SHAPE 4   /* iql.py:530 "Actions shape missmatch" -> RuntimeError */
+
+#define IQL_MATH_FP32_SIMT 0    /* CUDA-core FP32 validation path            */
+#define IQL_MATH_TF32_TCGEN05 1 /* tcgen05.mma kind::tf32, FP32 accumulate   */
+
+#define IQL_SAMPLE_PHILOX 0    /* indices drawn in-kernel (Philox4x32-10)     */
+#define IQL_SAMPLE_INDICES 1   /* caller-supplied int64 indices [S][K][B]     */
+#define IQL_SAMPLE_PRELOADED 2 /* batch already staged by iql_load_batch (K=1) */
+
+#define IQL_NET_Q1 0
+#define IQL_NET_Q2 1
+#define IQL_NET_V 2
+#define IQL_NET_ACTOR 3
+
+#define IQL_KIND_WEIGHT 0
+#define IQL_KIND_BIAS 1
+#define IQL_KIND_LOG_STD 2
+
+typedef struct iql_engine iql_engine;
+
+/* Shapes shared by all members of an ensemble (TwinQ / ValueFunction / policy
+ * constructor arguments, iql.py:347-442; batch_size from TrainConfig iql.py:48). */
+typedef struct iql_config {
+  int32_t n_members;     /* S: independent seeds / hyper-parameter configs   */
+  int32_t state_dim;
+  int32_t action_dim;
+  int32_t hidden_dim;    /* multiple of 4                                     */
+  int32_t n_hidden;      /* >= 1                                              */
+  int32_t batch_size;
+  int32_t deterministic; /* 0 GaussianPolicy (iql.py:347), 1 DeterministicPolicy (iql.py:382) */
+  int32_t math_mode;     /* IQL_MATH_*                                        */
+  int32_t max_steps_per_call; /* K upper bound (loss ring size)               */
+  int32_t reserved[7];
+} iql_config;
+
+/* Per-member hyper-parameters (ImplicitQLearning ctor iql.py:445-480, Adam
+ * defaults jsrl_utils.py:263-265, CosineAnnealingLR iql.py:471).  Doubles, as
+ * Python holds them; the engine derives the fp32 scalars the way torch does. */
+typedef struct iql_hparams {
+  double beta;
+  double iql_tau;
+  double discount;
+  double tau; /* Polyak */
+  double vf_lr, qf_lr, actor_lr; /* actor_lr = schedule base lr */
+  double actor_dropout;
+  double adam_beta1, adam_beta2, adam_eps;
+  double lr_eta_min;
+  int64_t cosine_t_max; /* 0: no schedule (max_steps=None, iql.py:472-473)  */
+  uint64_t seed;        /* Philox key: index sampling and dropout masks     */
+} iql_hparams;
+
+/* Step counters of one member (checkpoint fields, iql.py:565-579). */
+typedef struct iql_counters {
+  int64_t v_step, q_step, actor_step; /* Adam state["step"]                  */
+  int64_t sched_epoch;                /* CosineAnnealingLR.last_epoch        */
+  int64_t total_it;                   /* ImplicitQLearning.total_it          */
+  int64_t sample_step;                /* Philox sampling counter             */
+} iql_counters;
+
+/* Packed replay row: [ s(S) a(A) pad | s'(S) r d pad ], 16-byte aligned
+ * segments, so one transition is ONE contiguous, float4-loadable row
+ * (replaces the five SoA tensors of ReplayBuffer.__init__, iql.py:123-147). */
+typedef struct iql_row_layout {
+  int32_t state_dim, action_dim;
+  int32_t row_floats; /* multiple of 4 */
+  int32_t off_state, off_action, off_next_state, off_reward, off_done;
+} iql_row_layout;
+
+typedef struct iql_layout {
+  int64_t param_floats;  /* per-member block size of params/exp_avg/exp_avg_sq arenas */
+  int64_t q_floats;      /* leading part owned by the Q optimizer == per-member target block */
+  int64_t v_begin, v_end;         /* V optimizer range inside the block        */
+  int64_t actor_begin, actor_end; /* actor optimizer range                     */
+  int64_t workspace_bytes;        /* for all members                           */
+  int32_t n_tensors;              /* tensors per member block                  */
+  int32_t reserved;
+  iql_row_layout row;
+} iql_layout;
+
+typedef struct iql_tensor_info {
+  int32_t net;   /* IQL_NET_*  */
+  int32_t layer; /* Linear index 0..n_hidden */
+  int32_t kind;  /* IQL_KIND_* */
+  int32_t rows, cols; /* weight [rows, cols]; bias/log_std [rows], cols = 1 */
+  int32_t reserved;
+  int64_t offset; /* float offset inside the member block */
+} iql_tensor_info;
+
+const char* iql_version(void);
+/* Message of the last failure on this handle (NULL handle: last failed create). */
+const char* iql_last_error(const iql_engine* e);
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* replaces: ImplicitQLearning.__init__ iql.py:445-480 (for S members at once) */
+int iql_create(const iql_config* cfg, iql_engine** out);
+void iql_destroy(iql_engine* e);
+int iql_get_layout(const iql_engine* e, iql_layout* out);
+int iql_tensor_at(const iql_engine* e, int32_t index, iql_tensor_info* out);
+
+/* params / exp_avg / exp_avg_sq / grads: [S][param_floats]; target: [S][q_floats];
+ * workspace: workspace_bytes.  All 128-byte aligned device memory. */
+int iql_bind_state(iql_engine* e, float* params, float* exp_avg, float* exp_avg_sq,
+                   float* target, float* grads, void* workspace, size_t workspace_bytes);
+int iql_set_hparams(iql_engine* e, int32_t member, const iql_hparams* hp);
+int iql_set_counters(iql_engine* e, int32_t member, const iql_counters* c);
+int iql_get_counters(iql_engine* e, int32_t member, iql_counters* out, void* stream);
+/* replaces: copy.deepcopy(self.qf) iql.py:464,584,598 (q_target <- qf) */
+int iql_sync_target(iql_engine* e, int32_t member, void* stream);
+
+/* ---- replay data plane (no handle needed) -------------------------------- */
+int iql_replay_row_layout(int32_t state_dim, int32_t action_dim, iql_row_layout* out);
+/* replaces: ReplayBuffer.load_d4rl_dataset iql.py:153-169 (bulk pack of n rows
+ * starting at row `first_row`; inputs are dense [n,S],[n,A],[n],[n,S],[n]) */
+int iql_replay_pack(float* rows, const iql_row_layout* lay, int64_t first_row, int64_t n,
+                    const float* states, const float* actions, const float* rewards,
+                    const float* next_states, const float* dones, void* stream);
+/* replaces: ReplayBuffer.add_transition iql.py:180-196 (one fused row insert;
+ * `staged_row` is a device row in packed layout) */
+int iql_replay_insert(float* rows, const iql_row_layout* lay, int64_t pointer,
+                      const float* staged_row, void* stream);
+/* replaces: ReplayBuffer.sample iql.py:171-178.  indices == NULL: draw them
+ * in-kernel from Philox4x32-10 keyed by (seed, step); else gather the given
+ * int64 indices (reference-compatible mode: numpy's MT19937 stream on host).
+ * Outputs are dense [B,S],[B,A],[B,1],[B,S],[B,1]; idx_out (optional) gets the
+ * indices used. */
+int iql_replay_sample(const float* rows, const iql_row_layout* lay, int64_t size, int64_t batch,
+                      const int64_t* indices, uint64_t seed, uint64_t step,
+                      float* states, float* actions, float* rewards, float* next_states,
+                      float* dones, int64_t* idx_out, void* stream);
+
+/* ---- the update ----------------------------------------------------------- */
+/* Attach member's replay rows (several members may share one buffer). */
+int iql_bind_replay(iql_engine* e, int32_t member, const float* rows, int64_t capacity, int64_t size);
+int iql_set_replay_size(iql_engine* e, int32_t member, int64_t size);
+/* Stage an externally sampled batch for member (drop-in `train(batch)` path):
+ * dense [B,S],[B,A],[B] or [B,1],[B,S],[B] or [B,1]. */
+int iql_load_batch(iql_engine* e, int32_t member, const float* states, const float* actions,
+                   const float* rewards, const float* next_states, const float* dones,
+                   void* stream);
+/* replaces: K x [ReplayBuffer.sample iql.py:171 + ImplicitQLearning.train iql.py:542-563]
+ * for all S members.  out_losses: [S][K][3] = value_loss, q_loss, actor_loss
+ * (the log_dict of iql.py:563).  indices: [S][K][B] int64 (IQL_SAMPLE_INDICES).
+ * dropout_masks: optional [S][K][n_hidden][B][H] uint8 keep-masks (test hook,
+ * SURVEY.md section 7 hard-part 5); NULL = Philox masks in-kernel.
+ * idx_out: optional [S][K][B] int64, the indices actually used. */
+int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mode, const int64_t* indices,
+                    const uint8_t* dropout_masks, float* out_losses, int64_t* idx_out,
+                    void* stream);
+/* replaces: actor(obs).mean / DeterministicPolicy.forward as used by
+ * GaussianPolicy.act / DeterministicPolicy.act iql.py:371-379,403-413 in eval
+ * mode: out[n,A] = clamp(max_action * tanh(MLP(states[n,S]))). */
+int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float max_action,
+            float* out_actions, void* stream);
+/* number of kernel launches issued by the last iql_train_steps call */
+int64_t iql_last_launch_count(const iql_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IQL_B200_H */

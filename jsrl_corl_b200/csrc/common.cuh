@@ -1,0 +1,83 @@
+// Shared device/host helpers for the IQL engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace iql {
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), the counter-based generator behind index
+// sampling and dropout masks.  Restated on the CPU in oracle/philox.py and
+// oracle/philox_ref.c; the two are compared bit for bit in tests.
+// ---------------------------------------------------------------------------
+#define IQL_PHILOX_M0 0xD2511F53u
+#define IQL_PHILOX_M1 0xCD9E8D57u
+#define IQL_PHILOX_W0 0x9E3779B9u
+#define IQL_PHILOX_W1 0xBB67AE85u
+
+#define IQL_STREAM_SAMPLE 0u        // counter word 3 for replay index sampling
+#define IQL_STREAM_DROPOUT_BASE 1u  // + hidden layer index, for dropout masks
+
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ void philox_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  hi = (uint32_t)(p >> 32);
+  lo = (uint32_t)p;
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    philox_mulhilo(IQL_PHILOX_M0, c0, hi0, lo0);
+    philox_mulhilo(IQL_PHILOX_M1, c2, hi1, lo1);
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n1 = lo1;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    uint32_t n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += IQL_PHILOX_W0;
+    k1 += IQL_PHILOX_W1;
+  }
+  Philox4 o{c0, c1, c2, c3};
+  return o;
+}
+
+// Uniform index in [0, size): the b-th draw of (seed, step).  Two indices per
+// Philox block: counter = (b >> 1, step_lo, step_hi, STREAM_SAMPLE); the 64-bit
+// word (hi<<32 | lo) of lanes (x,y) for even b, (z,w) for odd b, mapped with
+// a 64x64->128 multiply-high (bias < size / 2^64).
+__host__ __device__ __forceinline__ int64_t philox_index(uint64_t seed, uint64_t step, uint32_t b, uint64_t size) {
+  Philox4 r = philox4x32_10(b >> 1, (uint32_t)step, (uint32_t)(step >> 32), IQL_STREAM_SAMPLE,
+                            (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint64_t u = (b & 1u) ? (((uint64_t)r.w << 32) | r.z) : (((uint64_t)r.y << 32) | r.x);
+#ifdef __CUDA_ARCH__
+  return (int64_t)__umul64hi(u, size);
+#else
+  return (int64_t)(((unsigned __int128)u * (unsigned __int128)size) >> 64);
+#endif
+}
+
+// Dropout keep decisions for 4 consecutive elements (quad = element_index / 4)
+// of hidden layer `layer` at update `step`: keep iff word >= threshold where
+// threshold = floor(p * 2^32).
+__host__ __device__ __forceinline__ Philox4 philox_dropout_quad(uint64_t seed, uint64_t step, uint32_t layer,
+                                                                uint32_t quad) {
+  return philox4x32_10(quad, (uint32_t)step, (uint32_t)(step >> 32), IQL_STREAM_DROPOUT_BASE + layer,
+                       (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(double p) {
+  double t = p * 4294967296.0;
+  if (t <= 0.0) return 0u;
+  if (t >= 4294967295.0) return 4294967295u;
+  return (uint32_t)t;
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace iql

@@ -1,0 +1,583 @@
+// C-ABI + host orchestration of the IQL update engine (see include/iql_b200.h).
+//
+// The handle owns only host metadata; every device byte it touches was
+// allocated by the caller (torch) and bound through iql_bind_state /
+// iql_bind_replay.  The first part of the caller's workspace holds the small
+// device tables (per-member scalars, counters, replay bindings, grouped-GEMM
+// problem descriptors, loss ring); the rest is the per-member activation area.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "engine.h"
+#include "umma_gemm.h"
+
+using namespace iql;
+
+static thread_local std::string g_create_error;
+
+struct Phase {
+  int mode;      // 0 NT, 1 NN, 2 TN
+  int first;     // index into problem table
+  int count;
+  int maxM, maxN;
+  int K;         // common K of the phase (0 if mixed)
+  bool umma_ok;  // eligible for the tcgen05 kernel
+};
+
+struct iql_engine {
+  iql_config cfg;
+  iql_layout layout;
+  WorkspaceLayout wl;
+  std::vector<iql_tensor_info> tensors;
+  int64_t w_off[4][16], b_off[4][16];
+  int64_t log_std_off = 0;
+  // bound device memory
+  float *params = nullptr, *exp_avg = nullptr, *exp_avg_sq = nullptr, *target = nullptr, *grads = nullptr;
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  // device tables inside the workspace
+  MemberScalars* d_scalars = nullptr;
+  iql_counters* d_counters = nullptr;
+  ReplayBinding* d_replay = nullptr;
+  GemmProb* d_probs = nullptr;
+  int64_t* d_act_off = nullptr;  // [2][L+1]
+  float* d_loss_ring = nullptr;
+  float* d_ws_f = nullptr;       // activation area
+  int64_t tables_bytes = 0;
+  // host shadows
+  std::vector<MemberScalars> h_scalars;
+  std::vector<iql_hparams> h_hparams;
+  std::vector<iql_counters> h_counters;
+  std::vector<ReplayBinding> h_replay;
+  std::vector<GemmProb> h_probs;
+  std::vector<Phase> fwd_phases, bwd_phases;
+  bool bound = false, tables_dirty = true, scalars_dirty = true, counters_dirty = true, replay_dirty = true;
+  std::vector<char> preloaded;
+  int64_t last_launches = 0;
+  std::string err;
+  // CUDA graphs of the K-step sequence, keyed by K (Philox sampling mode only)
+  std::map<int, std::pair<cudaGraphExec_t, int64_t>> graphs;
+  bool use_graphs = true;
+};
+
+static int fail(iql_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(e, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t _err = (call);                                                             \
+    if (_err != cudaSuccess)                                                               \
+      return fail(e, IQL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err)); \
+  } while (0)
+
+extern "C" const char* iql_version(void) { return "iql_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* iql_last_error(const iql_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+static int net_in_dim(const iql_config& c, int net) {
+  return (net == IQL_NET_Q1 || net == IQL_NET_Q2) ? c.state_dim + c.action_dim : c.state_dim;
+}
+static int net_out_dim(const iql_config& c, int net) { return net == IQL_NET_ACTOR ? c.action_dim : 1; }
+
+static void build_layout(iql_engine* e) {
+  const iql_config& c = e->cfg;
+  const int L = c.n_hidden, H = c.hidden_dim;
+  int64_t off = 0;
+  auto add = [&](int net, int layer, int kind, int rows, int cols) {
+    iql_tensor_info t;
+    memset(&t, 0, sizeof(t));
+    t.net = net; t.layer = layer; t.kind = kind; t.rows = rows; t.cols = cols; t.offset = off;
+    e->tensors.push_back(t);
+    off = round_up(off + (int64_t)rows * cols, 32);  // every tensor starts 128-byte aligned
+    return t.offset;
+  };
+  // order == reference optimizer parameter order: qf.parameters() = q1 then q2 (iql.py:422-423),
+  // vf, actor (log_std registered after net but listed first by nn.Module? no: see below)
+  for (int net = 0; net < 4; ++net) {
+    if (net == IQL_NET_V) { e->layout.q_floats = off; e->layout.v_begin = off; }
+    if (net == IQL_NET_ACTOR) {
+      e->layout.v_end = off;
+      e->layout.actor_begin = off;
+      if (!c.deterministic) e->log_std_off = add(net, 0, IQL_KIND_LOG_STD, c.action_dim, 1);
+    }
+    for (int l = 0; l <= L; ++l) {
+      const int in = (l == 0) ? net_in_dim(c, net) : H;
+      const int out = (l == L) ? net_out_dim(c, net) : H;
+      e->w_off[net][l] = add(net, l, IQL_KIND_WEIGHT, out, in);
+      e->b_off[net][l] = add(net, l, IQL_KIND_BIAS, out, 1);
+    }
+  }
+  e->layout.actor_end = off;
+  e->layout.param_floats = off;
+  e->layout.n_tensors = (int)e->tensors.size();
+  make_row_layout(c.state_dim, c.action_dim, &e->layout.row);
+
+  // workspace (per member, floats; every region 128-byte aligned)
+  WorkspaceLayout& wl = e->wl;
+  const int64_t B = c.batch_size;
+  wl.Ald = (int)round_up(c.action_dim, 4);
+  int64_t w = 0;
+  auto region = [&](int64_t n) { int64_t o = w; w = round_up(w + n, 32); return o; };
+  wl.xrow = region(B * e->layout.row.row_floats);
+  wl.act = region((int64_t)N_PASS * L * B * H);
+  wl.yq = region(6 * B);
+  wl.zpi = region(B * wl.Ald);
+  wl.gy = region(3 * B);
+  wl.gpi = region(B * wl.Ald);
+  wl.gh = region((int64_t)4 * 2 * B * H);
+  wl.member_floats = w;
+
+  const int S = c.n_members;
+  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L);
+  int64_t tb = 0;
+  auto tab = [&](int64_t bytes) { int64_t o = tb; tb = round_up(tb + bytes, 256); return o; };
+  tab(sizeof(MemberScalars) * S);
+  tab(sizeof(iql_counters) * S);
+  tab(sizeof(ReplayBinding) * S);
+  tab(sizeof(GemmProb) * nprob);
+  tab(sizeof(int64_t) * 2 * (L + 1));
+  tab(sizeof(float) * 3 * (int64_t)S * c.max_steps_per_call);
+  e->tables_bytes = tb;
+  e->layout.workspace_bytes = tb + (int64_t)S * wl.member_floats * (int64_t)sizeof(float);
+}
+
+extern "C" int iql_create(const iql_config* cfg, iql_engine** out) {
+  if (!cfg || !out) return fail(nullptr, IQL_ERR_INVALID, "iql_create: null argument");
+  if (cfg->n_members <= 0 || cfg->state_dim <= 0 || cfg->action_dim <= 0 || cfg->batch_size <= 0)
+    return fail(nullptr, IQL_ERR_INVALID, "iql_create: n_members, state_dim, action_dim, batch_size must be positive");
+  if (cfg->n_hidden < 1 || cfg->n_hidden > 15) return fail(nullptr, IQL_ERR_INVALID, "iql_create: n_hidden must be in [1, 15]");
+  if (cfg->hidden_dim <= 0 || (cfg->hidden_dim & 3)) return fail(nullptr, IQL_ERR_INVALID, "iql_create: hidden_dim must be a positive multiple of 4");
+  if (cfg->math_mode != IQL_MATH_FP32_SIMT && cfg->math_mode != IQL_MATH_TF32_TCGEN05)
+    return fail(nullptr, IQL_ERR_INVALID, "iql_create: unknown math_mode");
+  if (cfg->max_steps_per_call <= 0) return fail(nullptr, IQL_ERR_INVALID, "iql_create: max_steps_per_call must be positive");
+  iql_engine* e = new iql_engine();
+  e->cfg = *cfg;
+  memset(&e->layout, 0, sizeof(e->layout));
+  memset(e->w_off, 0, sizeof(e->w_off));
+  memset(e->b_off, 0, sizeof(e->b_off));
+  build_layout(e);
+  const int S = cfg->n_members;
+  e->h_scalars.resize(S);
+  e->h_hparams.resize(S);
+  e->h_counters.assign(S, iql_counters{0, 0, 0, 0, 0, 0});
+  e->h_replay.assign(S, ReplayBinding{nullptr, 0, 0});
+  e->preloaded.assign(S, 0);
+  iql_hparams def;
+  memset(&def, 0, sizeof(def));
+  def.beta = 3.0; def.iql_tau = 0.7; def.discount = 0.99; def.tau = 0.005;
+  def.vf_lr = def.qf_lr = def.actor_lr = 3e-4;
+  def.adam_beta1 = 0.9; def.adam_beta2 = 0.999; def.adam_eps = 1e-8;
+  def.cosine_t_max = 1000000;
+  for (int m = 0; m < S; ++m) { def.seed = (uint64_t)m; iql_set_hparams(e, m, &def); }
+  const char* g = getenv("IQL_B200_GRAPHS");
+  if (g && g[0] == '0') e->use_graphs = false;
+  *out = e;
+  return IQL_OK;
+}
+
+extern "C" void iql_destroy(iql_engine* e) {
+  if (!e) return;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);
+  delete e;
+}
+
+extern "C" int iql_get_layout(const iql_engine* e, iql_layout* out) {
+  if (!e || !out) return IQL_ERR_INVALID;
+  *out = e->layout;
+  return IQL_OK;
+}
+
+extern "C" int iql_tensor_at(const iql_engine* e, int32_t index, iql_tensor_info* out) {
+  if (!e || !out || index < 0 || index >= (int)e->tensors.size()) return IQL_ERR_INVALID;
+  *out = e->tensors[index];
+  return IQL_OK;
+}
+
+extern "C" int iql_set_hparams(iql_engine* e, int32_t member, const iql_hparams* hp) {
+  if (!e || !hp || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_set_hparams: bad member or null");
+  if (hp->actor_dropout < 0.0 || hp->actor_dropout >= 1.0) return fail(e, IQL_ERR_INVALID, "iql_set_hparams: actor_dropout must be in [0, 1)");
+  if (hp->cosine_t_max < 0) return fail(e, IQL_ERR_INVALID, "iql_set_hparams: cosine_t_max must be >= 0");
+  e->h_hparams[member] = *hp;
+  MemberScalars& s = e->h_scalars[member];
+  memset(&s, 0, sizeof(s));
+  s.beta = (float)hp->beta;
+  s.iql_tau = (float)hp->iql_tau;
+  s.discount = (float)hp->discount;
+  s.tau = (float)hp->tau;
+  s.one_minus_tau = (float)(1.0 - hp->tau);
+  s.adam_w1 = (float)(1.0 - hp->adam_beta1);
+  s.adam_beta2 = (float)hp->adam_beta2;
+  s.adam_one_minus_b2 = (float)(1.0 - hp->adam_beta2);
+  s.adam_eps = (float)hp->adam_eps;
+  s.drop_scale = (float)(1.0 / (1.0 - hp->actor_dropout));
+  s.drop_threshold = dropout_threshold(hp->actor_dropout);
+  s.adam_beta1_d = hp->adam_beta1;
+  s.adam_beta2_d = hp->adam_beta2;
+  s.vf_lr = hp->vf_lr; s.qf_lr = hp->qf_lr; s.actor_lr = hp->actor_lr; s.lr_eta_min = hp->lr_eta_min;
+  s.cosine_t_max = hp->cosine_t_max;
+  s.seed = hp->seed;
+  e->scalars_dirty = true;
+  return IQL_OK;
+}
+
+extern "C" int iql_set_counters(iql_engine* e, int32_t member, const iql_counters* c) {
+  if (!e || !c || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_set_counters: bad member or null");
+  e->h_counters[member] = *c;
+  e->counters_dirty = true;
+  return IQL_OK;
+}
+
+extern "C" int iql_get_counters(iql_engine* e, int32_t member, iql_counters* out, void* stream) {
+  (void)stream;  // the host shadow advances in lock-step with the device copy
+  if (!e || !out || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_get_counters: bad member or null");
+  *out = e->h_counters[member];
+  return IQL_OK;
+}
+
+static void build_problems(iql_engine* e) {
+  const iql_config& c = e->cfg;
+  const int S = c.n_members, L = c.n_hidden, H = c.hidden_dim, B = c.batch_size;
+  const int ROW = e->layout.row.row_floats;
+  const WorkspaceLayout& wl = e->wl;
+  const int64_t P = e->layout.param_floats, PQ = e->layout.q_floats;
+  e->h_probs.clear();
+  e->fwd_phases.clear();
+  e->bwd_phases.clear();
+  struct PassDef { int net; bool tgt; int in_off; int k0; };
+  const PassDef passes[N_PASS] = {
+      {IQL_NET_V, false, e->layout.row.off_next_state, c.state_dim},
+      {IQL_NET_V, false, 0, c.state_dim},
+      {IQL_NET_Q1, true, 0, c.state_dim + c.action_dim},
+      {IQL_NET_Q2, true, 0, c.state_dim + c.action_dim},
+      {IQL_NET_Q1, false, 0, c.state_dim + c.action_dim},
+      {IQL_NET_Q2, false, 0, c.state_dim + c.action_dim},
+      {IQL_NET_ACTOR, false, 0, c.state_dim},
+  };
+  auto wsm = [&](int m) { return e->d_ws_f + (int64_t)m * wl.member_floats; };
+  auto actp = [&](int m, int f, int l) { return wsm(m) + wl.act + ((int64_t)(f * L + l)) * B * H; };
+  auto blank = [&]() { GemmProb p; memset(&p, 0, sizeof(p)); p.drop_layer = -1; return p; };
+  // ---- forward phases, layer 0..L ----
+  for (int l = 0; l <= L; ++l) {
+    Phase ph; ph.mode = 0; ph.first = (int)e->h_probs.size(); ph.maxM = B; ph.maxN = 0; ph.K = 0; ph.umma_ok = false;
+    for (int m = 0; m < S; ++m)
+      for (int f = 0; f < N_PASS; ++f) {
+        const PassDef& pd = passes[f];
+        const float* blk = pd.tgt ? e->target + (int64_t)m * PQ : e->params + (int64_t)m * P;
+        GemmProb p = blank();
+        p.member = m;
+        p.M = B;
+        if (l == 0) { p.A = wsm(m) + wl.xrow + pd.in_off; p.lda = ROW; p.K = pd.k0; }
+        else { p.A = actp(m, f, l - 1); p.lda = H; p.K = H; }
+        p.B = blk + e->w_off[pd.net][l];
+        p.ldb = p.K;
+        p.bias = blk + e->b_off[pd.net][l];
+        if (l < L) {
+          p.N = H; p.C = actp(m, f, l); p.ldc = H; p.epi = EPI_RELU;
+          p.drop_layer = (f == PASS_PI) ? l : -1;
+        } else if (f == PASS_PI) {
+          p.N = c.action_dim; p.C = wsm(m) + wl.zpi; p.ldc = wl.Ald; p.epi = EPI_LINEAR;
+        } else {
+          p.N = 1; p.C = wsm(m) + wl.yq + (int64_t)f * B; p.ldc = 1; p.epi = EPI_LINEAR;
+        }
+        if (p.N > ph.maxN) ph.maxN = p.N;
+        e->h_probs.push_back(p);
+      }
+    ph.count = (int)e->h_probs.size() - ph.first;
+    ph.K = (l >= 1) ? H : 0;
+    ph.umma_ok = (l >= 1 && l < L);
+    e->fwd_phases.push_back(ph);
+  }
+  // ---- backward phases ----
+  struct TrainDef { int net; int pass; };
+  const TrainDef tr[4] = {{IQL_NET_V, PASS_V}, {IQL_NET_Q1, PASS_Q1}, {IQL_NET_Q2, PASS_Q2}, {IQL_NET_ACTOR, PASS_PI}};
+  auto ghp = [&](int m, int t, int which) { return wsm(m) + wl.gh + ((int64_t)(t * 2 + which)) * B * H; };
+  for (int l = L; l >= 0; --l) {
+    // weight gradient  dW_l = G_l^T H_l   (TN)
+    Phase pw; pw.mode = 2; pw.first = (int)e->h_probs.size(); pw.maxM = 0; pw.maxN = 0; pw.K = B; pw.umma_ok = (l >= 1 && l < L);
+    for (int m = 0; m < S; ++m)
+      for (int t = 0; t < 4; ++t) {
+        const int net = tr[t].net, f = tr[t].pass;
+        const PassDef& pd = passes[f];
+        GemmProb p = blank();
+        p.member = m;
+        p.K = B;
+        if (l == L) {
+          if (t == 3) { p.A = wsm(m) + wl.gpi; p.lda = wl.Ald; p.M = c.action_dim; }
+          else { p.A = wsm(m) + wl.gy + (int64_t)t * B; p.lda = 1; p.M = 1; }
+        } else { p.A = ghp(m, t, (L - 1 - l) & 1); p.lda = H; p.M = H; }
+        if (l == 0) { p.B = wsm(m) + wl.xrow + pd.in_off; p.ldb = ROW; p.N = pd.k0; }
+        else { p.B = actp(m, f, l - 1); p.ldb = H; p.N = H; }
+        p.C = e->grads + (int64_t)m * P + e->w_off[net][l];
+        p.ldc = p.N;
+        p.dbias = e->grads + (int64_t)m * P + e->b_off[net][l];
+        p.epi = EPI_NONE;
+        if (p.M > pw.maxM) pw.maxM = p.M;
+        if (p.N > pw.maxN) pw.maxN = p.N;
+        e->h_probs.push_back(p);
+      }
+    pw.count = (int)e->h_probs.size() - pw.first;
+    e->bwd_phases.push_back(pw);
+    if (l == 0) break;
+    // activation gradient  G_{l-1} = (G_l W_l) * [H_l > 0]   (NN)
+    Phase px; px.mode = 1; px.first = (int)e->h_probs.size(); px.maxM = B; px.maxN = H; px.K = (l < L) ? H : 0; px.umma_ok = (l < L);
+    for (int m = 0; m < S; ++m)
+      for (int t = 0; t < 4; ++t) {
+        const int net = tr[t].net, f = tr[t].pass;
+        GemmProb p = blank();
+        p.member = m;
+        p.M = B; p.N = H;
+        if (l == L) {
+          if (t == 3) { p.A = wsm(m) + wl.gpi; p.lda = wl.Ald; p.K = c.action_dim; }
+          else { p.A = wsm(m) + wl.gy + (int64_t)t * B; p.lda = 1; p.K = 1; }
+        } else { p.A = ghp(m, t, (L - 1 - l) & 1); p.lda = H; p.K = H; }
+        p.B = e->params + (int64_t)m * P + e->w_off[net][l];
+        p.ldb = H;
+        p.C = ghp(m, t, (L - l) & 1);
+        p.ldc = H;
+        p.mask = actp(m, f, l - 1);
+        p.ldmask = H;
+        p.epi = EPI_DRELU;
+        p.drop_layer = (t == 3) ? (l - 1) : -1;
+        e->h_probs.push_back(p);
+      }
+    px.count = (int)e->h_probs.size() - px.first;
+    e->bwd_phases.push_back(px);
+  }
+}
+
+extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, float* exp_avg_sq, float* target,
+                              float* grads, void* workspace, size_t workspace_bytes) {
+  if (!e) return IQL_ERR_INVALID;
+  if (!params || !exp_avg || !exp_avg_sq || !target || !grads || !workspace)
+    return fail(e, IQL_ERR_INVALID, "iql_bind_state: null device pointer");
+  if ((int64_t)workspace_bytes < e->layout.workspace_bytes) return fail(e, IQL_ERR_INVALID, "iql_bind_state: workspace too small");
+  const uintptr_t all = (uintptr_t)params | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)target |
+                        (uintptr_t)grads | (uintptr_t)workspace;
+  if (all & 127) return fail(e, IQL_ERR_INVALID, "iql_bind_state: pointers must be 128-byte aligned");
+  e->params = params; e->exp_avg = exp_avg; e->exp_avg_sq = exp_avg_sq; e->target = target; e->grads = grads;
+  e->ws = (char*)workspace; e->ws_bytes = workspace_bytes;
+  const int S = e->cfg.n_members, L = e->cfg.n_hidden;
+  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L);
+  int64_t tb = 0;
+  auto tab = [&](int64_t bytes) { char* o = e->ws + tb; tb = round_up(tb + bytes, 256); return o; };
+  e->d_scalars = (MemberScalars*)tab(sizeof(MemberScalars) * S);
+  e->d_counters = (iql_counters*)tab(sizeof(iql_counters) * S);
+  e->d_replay = (ReplayBinding*)tab(sizeof(ReplayBinding) * S);
+  e->d_probs = (GemmProb*)tab(sizeof(GemmProb) * nprob);
+  e->d_act_off = (int64_t*)tab(sizeof(int64_t) * 2 * (L + 1));
+  e->d_loss_ring = (float*)tab(sizeof(float) * 3 * (int64_t)S * e->cfg.max_steps_per_call);
+  e->d_ws_f = (float*)(e->ws + e->tables_bytes);
+  build_problems(e);
+  if ((int64_t)e->h_probs.size() != nprob) return fail(e, IQL_ERR_STATE, "internal: problem count mismatch");
+  e->bound = true;
+  e->tables_dirty = e->scalars_dirty = e->counters_dirty = e->replay_dirty = true;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);
+  e->graphs.clear();
+  return IQL_OK;
+}
+
+static int flush_tables(iql_engine* e, cudaStream_t st) {
+  const int S = e->cfg.n_members, L = e->cfg.n_hidden;
+  if (e->tables_dirty) {
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_probs, e->h_probs.data(), sizeof(GemmProb) * e->h_probs.size(), cudaMemcpyHostToDevice, st));
+    std::vector<int64_t> off(2 * (L + 1));
+    for (int l = 0; l <= L; ++l) {
+      off[l] = e->w_off[IQL_NET_ACTOR][l];
+      off[L + 1 + l] = e->b_off[IQL_NET_ACTOR][l];
+    }
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_act_off, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(e, cudaStreamSynchronize(st));  // `off` is a stack temporary
+    e->tables_dirty = false;
+  }
+  if (e->scalars_dirty) {
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_scalars, e->h_scalars.data(), sizeof(MemberScalars) * S, cudaMemcpyHostToDevice, st));
+    e->scalars_dirty = false;
+  }
+  if (e->counters_dirty) {
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_counters, e->h_counters.data(), sizeof(iql_counters) * S, cudaMemcpyHostToDevice, st));
+    e->counters_dirty = false;
+  }
+  if (e->replay_dirty) {
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_replay, e->h_replay.data(), sizeof(ReplayBinding) * S, cudaMemcpyHostToDevice, st));
+    e->replay_dirty = false;
+  }
+  return IQL_OK;
+}
+
+static StepCtx make_ctx(const iql_engine* e) {
+  StepCtx c;
+  memset(&c, 0, sizeof(c));
+  c.B = e->cfg.batch_size;
+  c.S_dim = e->cfg.state_dim; c.A_dim = e->cfg.action_dim; c.H = e->cfg.hidden_dim; c.L = e->cfg.n_hidden;
+  c.deterministic = e->cfg.deterministic;
+  c.n_members = e->cfg.n_members;
+  c.P = e->layout.param_floats; c.PQ = e->layout.q_floats;
+  c.v_begin = e->layout.v_begin; c.v_end = e->layout.v_end;
+  c.a_begin = e->layout.actor_begin; c.a_end = e->layout.actor_end;
+  c.log_std_off = e->log_std_off;
+  c.row = e->layout.row;
+  c.scalars = e->d_scalars; c.counters = e->d_counters; c.replay = e->d_replay;
+  c.loss_ring = e->d_loss_ring;
+  c.k_max = e->cfg.max_steps_per_call;
+  return c;
+}
+
+extern "C" int iql_sync_target(iql_engine* e, int32_t member, void* stream) {
+  if (!e || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_sync_target: bad member");
+  if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_sync_target: state not bound");
+  const int64_t PQ = e->layout.q_floats, P = e->layout.param_floats;
+  CUDA_TRY(e, cudaMemcpyAsync(e->target + member * PQ, e->params + member * P, PQ * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return IQL_OK;
+}
+
+extern "C" int iql_bind_replay(iql_engine* e, int32_t member, const float* rows, int64_t capacity, int64_t size) {
+  if (!e || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_bind_replay: bad member");
+  if (!rows || capacity <= 0 || size < 0 || size > capacity) return fail(e, IQL_ERR_INVALID, "iql_bind_replay: bad rows/capacity/size");
+  if ((uintptr_t)rows & 15) return fail(e, IQL_ERR_INVALID, "iql_bind_replay: rows must be 16-byte aligned");
+  e->h_replay[member] = ReplayBinding{rows, capacity, size};
+  e->replay_dirty = true;
+  return IQL_OK;
+}
+
+extern "C" int iql_set_replay_size(iql_engine* e, int32_t member, int64_t size) {
+  if (!e || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_set_replay_size: bad member");
+  if (size < 0 || size > e->h_replay[member].capacity) return fail(e, IQL_ERR_INVALID, "iql_set_replay_size: size out of range");
+  e->h_replay[member].size = size;
+  e->replay_dirty = true;
+  return IQL_OK;
+}
+
+extern "C" int iql_load_batch(iql_engine* e, int32_t member, const float* states, const float* actions,
+                              const float* rewards, const float* next_states, const float* dones, void* stream) {
+  if (!e || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_load_batch: bad member");
+  if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_load_batch: state not bound");
+  if (!states || !actions || !rewards || !next_states || !dones) return fail(e, IQL_ERR_INVALID, "iql_load_batch: null batch tensor");
+  StepCtx ctx = make_ctx(e);
+  float* xrow = e->d_ws_f + (int64_t)member * e->wl.member_floats + e->wl.xrow;
+  launch_load_batch(ctx, member, xrow, states, actions, rewards, next_states, dones, (cudaStream_t)stream);
+  CUDA_TRY(e, cudaGetLastError());
+  e->preloaded[member] = 1;
+  return IQL_OK;
+}
+
+// one update step for all members; returns number of launches
+static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t st) {
+  int launches = 0;
+  const bool tf32 = e->cfg.math_mode == IQL_MATH_TF32_TCGEN05;
+  if (gather) { launch_gather(ctx, e->d_ws_f, e->wl.member_floats, e->wl.xrow, st); ++launches; }
+  auto run_phase = [&](const Phase& ph) {
+    if (tf32 && ph.umma_ok && umma_phase_supported(ph.mode, e->cfg.batch_size, e->cfg.hidden_dim)) {
+      launch_umma_gemm(ph.mode, e->d_probs + ph.first, ph.count, ph.maxM, ph.maxN, ph.K, ctx, st);
+    } else {
+      launch_simt_gemm(ph.mode, e->d_probs + ph.first, ph.count, ph.maxM, ph.maxN, ctx, st);
+    }
+    ++launches;
+  };
+  for (const Phase& ph : e->fwd_phases) run_phase(ph);
+  launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, st);
+  ++launches;
+  for (const Phase& ph : e->bwd_phases) run_phase(ph);
+  launch_adam(ctx, e->params, e->exp_avg, e->exp_avg_sq, e->target, e->grads, st);
+  ++launches;
+  return launches;
+}
+
+extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mode, const int64_t* indices,
+                               const uint8_t* dropout_masks, float* out_losses, int64_t* idx_out, void* stream) {
+  if (!e) return IQL_ERR_INVALID;
+  if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_train_steps: state not bound");
+  if (k_steps <= 0 || k_steps > e->cfg.max_steps_per_call) return fail(e, IQL_ERR_INVALID, "iql_train_steps: k_steps out of range");
+  const int S = e->cfg.n_members;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sample_mode == IQL_SAMPLE_INDICES) {
+    if (!indices) return fail(e, IQL_ERR_INVALID, "iql_train_steps: IQL_SAMPLE_INDICES needs indices");
+  } else if (sample_mode == IQL_SAMPLE_PRELOADED) {
+    if (k_steps != 1) return fail(e, IQL_ERR_INVALID, "iql_train_steps: IQL_SAMPLE_PRELOADED runs exactly one step");
+    for (int m = 0; m < S; ++m)
+      if (!e->preloaded[m]) return fail(e, IQL_ERR_STATE, "iql_train_steps: no batch staged (call iql_load_batch)");
+  } else if (sample_mode != IQL_SAMPLE_PHILOX) {
+    return fail(e, IQL_ERR_INVALID, "iql_train_steps: unknown sample_mode");
+  }
+  if (sample_mode != IQL_SAMPLE_PRELOADED)
+    for (int m = 0; m < S; ++m) {
+      if (!e->h_replay[m].rows) return fail(e, IQL_ERR_STATE, "iql_train_steps: replay buffer not bound");
+      if (e->h_replay[m].size <= 0 && sample_mode == IQL_SAMPLE_PHILOX)
+        return fail(e, IQL_ERR_INVALID, "iql_train_steps: cannot sample from an empty replay buffer");
+    }
+  int rc = flush_tables(e, st);
+  if (rc != IQL_OK) return rc;
+
+  StepCtx ctx = make_ctx(e);
+  ctx.K = k_steps;
+  ctx.indices = (sample_mode == IQL_SAMPLE_INDICES) ? indices : nullptr;
+  ctx.dropout_masks = dropout_masks;
+  ctx.idx_out = idx_out;
+  const bool gather = sample_mode != IQL_SAMPLE_PRELOADED;
+  // the legacy default stream cannot be captured; the facade runs the engine on its own stream
+  const bool graphable = e->use_graphs && st != nullptr && sample_mode == IQL_SAMPLE_PHILOX && !dropout_masks &&
+                         !idx_out && k_steps > 1;
+  int64_t launches = 0;
+  if (graphable) {
+    auto it = e->graphs.find(k_steps);
+    if (it == e->graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      for (int k = 0; k < k_steps; ++k) { ctx.k = k; launches += enqueue_step(e, ctx, gather, st); }
+      launch_advance(ctx, k_steps, st);
+      ++launches;
+      cudaError_t cerr = cudaStreamEndCapture(st, &graph);
+      if (cerr != cudaSuccess) return fail(e, IQL_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(cerr));
+      cudaGraphExec_t exec = nullptr;
+      CUDA_TRY(e, cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      it = e->graphs.emplace(k_steps, std::make_pair(exec, launches)).first;
+    }
+    CUDA_TRY(e, cudaGraphLaunch(it->second.first, st));
+    launches = it->second.second;
+  } else {
+    for (int k = 0; k < k_steps; ++k) { ctx.k = k; launches += enqueue_step(e, ctx, gather, st); }
+    launch_advance(ctx, k_steps, st);
+    ++launches;
+  }
+  CUDA_TRY(e, cudaGetLastError());
+  for (int m = 0; m < S; ++m) {
+    iql_counters& c = e->h_counters[m];
+    c.v_step += k_steps; c.q_step += k_steps; c.actor_step += k_steps; c.total_it += k_steps; c.sample_step += k_steps;
+    if (e->h_hparams[m].cosine_t_max > 0) c.sched_epoch += k_steps;
+    e->preloaded[m] = 0;
+  }
+  if (out_losses) {
+    const size_t row = sizeof(float) * 3 * (size_t)k_steps;
+    CUDA_TRY(e, cudaMemcpy2DAsync(out_losses, row, e->d_loss_ring, sizeof(float) * 3 * (size_t)e->cfg.max_steps_per_call, row, S,
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  e->last_launches = launches;
+  return IQL_OK;
+}
+
+extern "C" int64_t iql_last_launch_count(const iql_engine* e) { return e ? e->last_launches : 0; }
+
+extern "C" int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float max_action,
+                       float* out_actions, void* stream) {
+  if (!e || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_act: bad member");
+  if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_act: state not bound");
+  if (!states || !out_actions || n < 0) return fail(e, IQL_ERR_INVALID, "iql_act: null or negative n");
+  if (n == 0) return IQL_OK;
+  int rc = flush_tables(e, (cudaStream_t)stream);
+  if (rc != IQL_OK) return rc;
+  StepCtx ctx = make_ctx(e);
+  const int L = e->cfg.n_hidden;
+  launch_act(ctx, e->params + (int64_t)member * e->layout.param_floats, e->d_act_off, e->d_act_off + (L + 1), states, n,
+             max_action, out_actions, (cudaStream_t)stream);
+  CUDA_TRY(e, cudaGetLastError());
+  return IQL_OK;
+}

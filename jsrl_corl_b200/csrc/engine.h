@@ -1,0 +1,119 @@
+// Internal declarations shared by the engine translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/iql_b200.h"
+
+namespace iql {
+
+int make_row_layout(int S, int A, iql_row_layout* out);
+
+// ---- grouped GEMM problem descriptor (one entry per member x network) -----
+enum Epilogue : int {
+  EPI_NONE = 0,    // C = acc                       (weight gradients)
+  EPI_LINEAR = 1,  // C = acc + bias[j]             (output layer)
+  EPI_RELU = 2,    // C = drop(relu(acc + bias[j])) (hidden layer, optional dropout)
+  EPI_DRELU = 3,   // C = acc * [mask > 0] * scale  (activation gradient)
+};
+
+struct GemmProb {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;   // EPI_LINEAR / EPI_RELU
+  float* dbias;        // TN mode: column sums of A (bias gradient), may be null
+  const float* mask;   // EPI_DRELU: forward activation
+  int M, N, K;
+  int lda, ldb, ldc, ldmask;
+  int epi;
+  int member;
+  int drop_layer;      // >= 0: hidden-layer index whose dropout applies (actor only)
+  int pad0;
+};
+
+// Per-member scalars derived on the host the way torch derives them
+// (Python float64 -> fp32 scalar operands).
+struct MemberScalars {
+  float beta, iql_tau, discount;
+  float tau, one_minus_tau;
+  float adam_w1;           // (float)(1 - beta1)
+  float adam_beta2;        // (float)beta2
+  float adam_one_minus_b2; // (float)(1 - beta2)
+  float adam_eps;
+  float drop_scale;        // (float)(1/(1-p))
+  uint32_t drop_threshold; // floor(p * 2^32); 0 = no dropout
+  uint32_t pad0;
+  double adam_beta1_d, adam_beta2_d;
+  double vf_lr, qf_lr, actor_lr, lr_eta_min;
+  int64_t cosine_t_max;
+  uint64_t seed;
+};
+
+struct ReplayBinding {
+  const float* rows;
+  int64_t capacity;
+  int64_t size;
+};
+
+// Context passed by value to every kernel of a step.
+struct StepCtx {
+  int k;                         // step offset inside this call (0..K-1)
+  int K;                         // steps in this call
+  int B;
+  int S_dim, A_dim, H, L;
+  int deterministic;
+  int n_members;
+  int64_t P;                     // member block floats
+  int64_t PQ;                    // q range [0, PQ)
+  int64_t v_begin, v_end, a_begin, a_end;
+  int64_t log_std_off;           // inside member block (Gaussian only)
+  iql_row_layout row;
+  const MemberScalars* scalars;  // [S]
+  iql_counters* counters;        // [S] device
+  const ReplayBinding* replay;   // [S] device
+  const int64_t* indices;        // [S][K][B] or null
+  const uint8_t* dropout_masks;  // [S][K][L][B][H] or null
+  int64_t* idx_out;              // [S][K][B] or null
+  float* loss_ring;              // [S][Kmax][3]
+  int k_max;
+};
+
+struct TensorDesc {
+  iql_tensor_info info;
+};
+
+// Offsets (floats) into one member's workspace block.
+struct WorkspaceLayout {
+  int64_t xrow;      // [B][ROW]
+  int64_t act;       // [7][L][B][H]  hidden activations H_1..H_L of the 7 forward passes
+  int64_t yq;        // [6][B]        scalar heads: V(s'), V(s), tq1, tq2, q1, q2
+  int64_t zpi;       // [B][Ald]      actor pre-tanh output
+  int64_t gy;        // [3][B]        dL/dy of V, q1, q2
+  int64_t gpi;       // [B][Ald]      dL/dz of actor
+  int64_t gh;        // [4][2][B][H]  ping-pong activation gradients of the 4 trainable nets
+  int64_t member_floats;
+  int Ald;
+};
+
+// forward pass ids
+enum Pass : int { PASS_V_NEXT = 0, PASS_V = 1, PASS_TQ1 = 2, PASS_TQ2 = 3, PASS_Q1 = 4, PASS_Q2 = 5, PASS_PI = 6, N_PASS = 7 };
+
+// launchers implemented in kernels_simt.cu
+void launch_simt_gemm(int mode /*0 NT,1 NN,2 TN*/, const GemmProb* probs, int nprob, int maxM, int maxN,
+                      const StepCtx& ctx, cudaStream_t st);
+void launch_gather(const StepCtx& ctx, float* ws, int64_t ws_member_floats, int64_t xrow_off, cudaStream_t st);
+void launch_loss(const StepCtx& ctx, float* ws, int64_t ws_member_floats, const WorkspaceLayout& wl,
+                 const float* params, float* grads, cudaStream_t st);
+void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_avg_sq, float* target,
+                 const float* grads, cudaStream_t st);
+void launch_advance(const StepCtx& ctx, int K, cudaStream_t st);
+void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float* s, const float* a, const float* r,
+                       const float* s2, const float* d, cudaStream_t st);
+void launch_act(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
+                const float* states, int64_t n, float max_action, float* out, cudaStream_t st);
+
+}  // namespace iql

@@ -1,0 +1,491 @@
+// FP32 CUDA-core ("SIMT") kernels of the IQL update: grouped GEMM with fused
+// epilogues, the replay gather into the step workspace, the loss / output-
+// gradient kernel, and the fused Adam + Polyak + cosine-LR kernel.
+//
+// This is the validation path of the engine (IQL_MATH_FP32_SIMT): plain fp32
+// FMAs in a fixed summation order, no tensor cores.  The math follows the
+// reference step algorithms/finetune/iql.py:482-563.
+#include <math.h>
+
+#include "common.cuh"
+#include "engine.h"
+
+namespace iql {
+
+// ===========================================================================
+// grouped SGEMM, 64x64x16 tiles, 256 threads, 4x4 register tile per thread.
+//   A_KC: A(i,k) stored with k contiguous (row-major [M][K]); else [K][M].
+//   B_KC: B(k,j) stored with k contiguous (row-major [N][K]); else [K][N].
+//   NT (fwd  Y = X W^T)      : A_KC=1, B_KC=1
+//   NN (dgrad dX = dZ W)     : A_KC=1, B_KC=0
+//   TN (wgrad dW = dZ^T X)   : A_KC=0, B_KC=0
+// ===========================================================================
+constexpr int BM = 64, BN = 64, BK = 16, LDS_PAD = 4;
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProb* __restrict__ probs, StepCtx ctx) {
+  const GemmProb p = probs[blockIdx.z];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= p.M || n0 >= p.N) return;
+
+  __shared__ __align__(16) float As[BK][BM + LDS_PAD];
+  __shared__ __align__(16) float Bs[BK][BN + LDS_PAD];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool do_bsum = (!A_KC) && p.dbias != nullptr && blockIdx.x == 0 && tx == 0;
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    // ---- stage A tile ----
+    if (A_KC) {
+      const int k = tid & 15;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = (tid >> 4) + r * 16;
+        float v = 0.f;
+        if (m0 + i < p.M && k0 + k < p.K) v = p.A[(int64_t)(m0 + i) * p.lda + k0 + k];
+        As[k][i] = v;
+      }
+    } else {
+      const int i = tid & 63;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = (tid >> 6) + r * 4;
+        float v = 0.f;
+        if (m0 + i < p.M && k0 + k < p.K) v = p.A[(int64_t)(k0 + k) * p.lda + m0 + i];
+        As[k][i] = v;
+      }
+    }
+    // ---- stage B tile ----
+    if (B_KC) {
+      const int k = tid & 15;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = (tid >> 4) + r * 16;
+        float v = 0.f;
+        if (n0 + j < p.N && k0 + k < p.K) v = p.B[(int64_t)(n0 + j) * p.ldb + k0 + k];
+        Bs[k][j] = v;
+      }
+    } else {
+      const int j = tid & 63;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = (tid >> 6) + r * 4;
+        float v = 0.f;
+        if (n0 + j < p.N && k0 + k < p.K) v = p.B[(int64_t)(k0 + k) * p.ldb + n0 + j];
+        Bs[k][j] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (do_bsum) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bsum[i] += a[i];
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  const MemberScalars* sc = ctx.scalars + p.member;
+  const bool philox_drop = (p.epi == EPI_RELU) && p.drop_layer >= 0 && sc->drop_threshold != 0u;
+  uint64_t step = 0;
+  if (philox_drop) step = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= p.M) continue;
+    const int col0 = n0 + tx * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j];
+    if (p.epi == EPI_LINEAR || p.epi == EPI_RELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col0 + j < p.N) v[j] += p.bias[col0 + j];
+    }
+    if (p.epi == EPI_RELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      if (philox_drop) {
+        if (ctx.dropout_masks) {
+          // injected keep-masks [S][K][L][B][H] (test hook)
+          const uint8_t* mk = ctx.dropout_masks +
+                              ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + j < p.N) v[j] = mk[col0 + j] ? v[j] * sc->drop_scale : 0.f;
+        } else {
+          const uint32_t quad = (uint32_t)(((int64_t)row * p.N + col0) >> 2);
+          const Philox4 r = philox_dropout_quad(sc->seed, step, (uint32_t)p.drop_layer, quad);
+          const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = (w[j] >= sc->drop_threshold) ? v[j] * sc->drop_scale : 0.f;
+        }
+      }
+    } else if (p.epi == EPI_DRELU) {
+      // d relu (and the dropout scale: H = relu(Z) * keep / (1-p), so [H > 0] == [Z > 0 and kept])
+      const float dscale = (p.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col0 + j < p.N) v[j] = (p.mask[(int64_t)row * p.ldmask + col0 + j] > 0.f) ? v[j] * dscale : 0.f;
+    }
+    float* crow = p.C + (int64_t)row * p.ldc;
+    if (col0 + 3 < p.N && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+      *reinterpret_cast<float4*>(crow + col0) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col0 + j < p.N) crow[col0 + j] = v[j];
+    }
+  }
+  if (do_bsum) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = m0 + ty * 4 + i;
+      if (row < p.M) p.dbias[row] = bsum[i];
+    }
+  }
+}
+
+void launch_simt_gemm(int mode, const GemmProb* probs, int nprob, int maxM, int maxN, const StepCtx& ctx,
+                      cudaStream_t st) {
+  dim3 grid((maxN + BN - 1) / BN, (maxM + BM - 1) / BM, nprob);
+  if (mode == 0) simt_gemm_kernel<true, true><<<grid, 256, 0, st>>>(probs, ctx);
+  else if (mode == 1) simt_gemm_kernel<true, false><<<grid, 256, 0, st>>>(probs, ctx);
+  else simt_gemm_kernel<false, false><<<grid, 256, 0, st>>>(probs, ctx);
+}
+
+// ===========================================================================
+// replay gather into the step workspace: xrow[m][b][:] = rows_m[idx][:]
+// ===========================================================================
+__global__ void __launch_bounds__(256) gather_kernel(StepCtx ctx, float* __restrict__ ws, int64_t ws_member_floats,
+                                                     int64_t xrow_off) {
+  const int m = blockIdx.y;
+  const int RF = ctx.row.row_floats, Q = RF >> 2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ctx.B * Q) return;
+  const int b = t / Q, q = t - b * Q;
+  const ReplayBinding rb = ctx.replay[m];
+  int64_t idx;
+  if (ctx.indices) {
+    idx = ctx.indices[((int64_t)m * ctx.K + ctx.k) * ctx.B + b];
+  } else {
+    const uint64_t step = (uint64_t)(ctx.counters[m].sample_step + ctx.k);
+    idx = philox_index(ctx.scalars[m].seed, step, (uint32_t)b, (uint64_t)rb.size);
+  }
+  if (q == 0 && ctx.idx_out) ctx.idx_out[((int64_t)m * ctx.K + ctx.k) * ctx.B + b] = idx;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(rb.rows + idx * RF) + q);
+  reinterpret_cast<float4*>(ws + m * ws_member_floats + xrow_off + (int64_t)b * RF)[q] = v;
+}
+
+void launch_gather(const StepCtx& ctx, float* ws, int64_t ws_member_floats, int64_t xrow_off, cudaStream_t st) {
+  const int threads = ctx.B * (ctx.row.row_floats >> 2);
+  dim3 grid((threads + 255) / 256, ctx.n_members);
+  gather_kernel<<<grid, 256, 0, st>>>(ctx, ws, ws_member_floats, xrow_off);
+}
+
+__global__ void load_batch_kernel(iql_row_layout lay, int B, float* __restrict__ xrow, const float* __restrict__ s,
+                                  const float* __restrict__ a, const float* __restrict__ r,
+                                  const float* __restrict__ s2, const float* __restrict__ d) {
+  const int RF = lay.row_floats, S = lay.state_dim, A = lay.action_dim;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * RF) return;
+  const int row = i / RF, c = i - row * RF;
+  float v = 0.f;
+  if (c < S) v = s[(int64_t)row * S + c];
+  else if (c < S + A) v = a[(int64_t)row * A + (c - S)];
+  else if (c >= lay.off_next_state && c < lay.off_next_state + S) v = s2[(int64_t)row * S + (c - lay.off_next_state)];
+  else if (c == lay.off_reward) v = r[row];
+  else if (c == lay.off_done) v = d[row];
+  xrow[i] = v;
+}
+
+void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float* s, const float* a, const float* r,
+                       const float* s2, const float* d, cudaStream_t st) {
+  (void)member;
+  const int n = ctx.B * ctx.row.row_floats;
+  load_batch_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx.row, ctx.B, xrow, s, a, r, s2, d);
+}
+
+// ===========================================================================
+// losses and output gradients (one CTA per member)
+//   value_loss  iql.py:489-490,301-302     q_loss  iql.py:506-508
+//   actor_loss  iql.py:524-534 (+ torch Normal.log_prob)
+// ===========================================================================
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restrict__ ws, int64_t ws_member_floats,
+                                                   WorkspaceLayout wl, const float* __restrict__ params,
+                                                   float* __restrict__ grads) {
+  extern __shared__ float e_s[];  // [B] exp_adv / B
+  __shared__ float red[8];
+  const int m = blockIdx.x;
+  const int B = ctx.B, A = ctx.A_dim, RF = ctx.row.row_floats, Ald = wl.Ald;
+  float* w = ws + m * ws_member_floats;
+  const float* xrow = w + wl.xrow;
+  const float* yq = w + wl.yq;
+  const float* zpi = w + wl.zpi;
+  float* gy = w + wl.gy;
+  float* gpi = w + wl.gpi;
+  const MemberScalars sc = ctx.scalars[m];
+  const float inv_b = 1.0f / (float)B;
+  const float w_neg = fabsf(sc.iql_tau - 1.0f), w_pos = fabsf(sc.iql_tau);
+  const float* log_std = params + m * ctx.P + ctx.log_std_off;
+  constexpr float HALF_LOG_2PI = 0.9189385332046727f;
+
+  float v_acc = 0.f, q1_acc = 0.f, q2_acc = 0.f, a_acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float next_v = yq[PASS_V_NEXT * B + b];
+    const float v = yq[PASS_V * B + b];
+    const float tq = fminf(yq[PASS_TQ1 * B + b], yq[PASS_TQ2 * B + b]);
+    const float q1 = yq[PASS_Q1 * B + b], q2 = yq[PASS_Q2 * B + b];
+    const float* xr = xrow + (int64_t)b * RF;
+    const float r = xr[ctx.row.off_reward], d = xr[ctx.row.off_done];
+    // --- V (expectile) ---
+    const float adv = tq - v;
+    const float wt = adv < 0.f ? w_neg : w_pos;
+    v_acc += wt * (adv * adv);
+    gy[0 * B + b] = -((wt * inv_b) * (2.0f * adv));
+    // --- Q (TD) ---
+    const float target = r + ((1.0f - d) * sc.discount) * next_v;
+    const float d1 = q1 - target, d2 = q2 - target;
+    q1_acc += d1 * d1;
+    q2_acc += d2 * d2;
+    gy[1 * B + b] = d1 * (2.0f * inv_b) * 0.5f;
+    gy[2 * B + b] = d2 * (2.0f * inv_b) * 0.5f;
+    // --- policy (AWR) ---
+    const float e = fminf(expf(sc.beta * adv), 100.0f);
+    const float eb = e * inv_b;
+    e_s[b] = eb;
+    float bc = 0.f;
+    for (int a = 0; a < A; ++a) {
+      const float mu = tanhf(zpi[(int64_t)b * Ald + a]);
+      const float act = xr[ctx.row.off_action + a];
+      float gmu;
+      if (ctx.deterministic) {
+        const float diff = mu - act;
+        bc += diff * diff;
+        gmu = eb * (2.0f * diff);
+      } else {
+        const float ls = fminf(fmaxf(log_std[a], -20.0f), 2.0f);
+        const float sd = expf(ls);
+        const float var = sd * sd;
+        const float diff = act - mu;
+        const float logp = -(diff * diff) / (2.0f * var) - logf(sd) - HALF_LOG_2PI;
+        bc -= logp;
+        gmu = -eb * diff / var;
+      }
+      gpi[(int64_t)b * Ald + a] = gmu * (1.0f - mu * mu);
+    }
+    a_acc += e * bc;
+  }
+  const float v_sum = block_sum_256(v_acc, red);
+  const float q1_sum = block_sum_256(q1_acc, red);
+  const float q2_sum = block_sum_256(q2_acc, red);
+  const float a_sum = block_sum_256(a_acc, red);
+  if (threadIdx.x == 0) {
+    float* out = ctx.loss_ring + ((int64_t)m * ctx.k_max + ctx.k) * 3;
+    out[0] = v_sum * inv_b;
+    out[1] = (q1_sum * inv_b + q2_sum * inv_b) * 0.5f;
+    out[2] = a_sum * inv_b;
+  }
+  if (!ctx.deterministic) {
+    __syncthreads();
+    for (int a = 0; a < A; ++a) {
+      const float lsr = log_std[a];
+      const float ls = fminf(fmaxf(lsr, -20.0f), 2.0f);
+      const float sd = expf(ls);
+      const float var = sd * sd;
+      float part = 0.f;
+      for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float mu = tanhf(zpi[(int64_t)b * Ald + a]);
+        const float diff = xrow[(int64_t)b * RF + ctx.row.off_action + a] - mu;
+        part += e_s[b] * (1.0f - diff * diff / var);
+      }
+      const float tot = block_sum_256(part, red);
+      if (threadIdx.x == 0) grads[m * ctx.P + ctx.log_std_off + a] = (lsr >= -20.0f && lsr <= 2.0f) ? tot : 0.f;
+    }
+  }
+}
+
+void launch_loss(const StepCtx& ctx, float* ws, int64_t ws_member_floats, const WorkspaceLayout& wl,
+                 const float* params, float* grads, cudaStream_t st) {
+  loss_kernel<<<ctx.n_members, 256, ctx.B * sizeof(float), st>>>(ctx, ws, ws_member_floats, wl, params, grads);
+}
+
+// ===========================================================================
+// fused Adam (3 optimisers) + Polyak target update + cosine LR
+//   torch.optim.Adam defaults (jsrl_utils.py:263-265), soft_update iql.py:72-74,
+//   CosineAnnealingLR iql.py:471 (closed form of the same schedule).
+// ===========================================================================
+struct AdamScalars {
+  float neg_step_size;
+  float bc2_sqrt;
+};
+
+__device__ __forceinline__ AdamScalars adam_scalars(double lr, double b1, double b2, int64_t t) {
+  const double bc1 = 1.0 - pow(b1, (double)t);
+  const double bc2 = 1.0 - pow(b2, (double)t);
+  AdamScalars s;
+  s.neg_step_size = (float)(-(lr / bc1));
+  s.bc2_sqrt = (float)sqrt(bc2);
+  return s;
+}
+
+__global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __restrict__ params,
+                                                          float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                          float* __restrict__ target,
+                                                          const float* __restrict__ grads) {
+  __shared__ AdamScalars s_sc[3];
+  const int m = blockIdx.y;
+  const MemberScalars sc = ctx.scalars[m];
+  if (threadIdx.x < 3) {
+    const iql_counters c = ctx.counters[m];
+    double lr;
+    int64_t t;
+    if (threadIdx.x == 0) { lr = sc.qf_lr; t = c.q_step + ctx.k + 1; }
+    else if (threadIdx.x == 1) { lr = sc.vf_lr; t = c.v_step + ctx.k + 1; }
+    else {
+      t = c.actor_step + ctx.k + 1;
+      if (sc.cosine_t_max > 0) {
+        const double e = (double)(c.sched_epoch + ctx.k);
+        lr = sc.lr_eta_min + (sc.actor_lr - sc.lr_eta_min) * (1.0 + cos(M_PI * e / (double)sc.cosine_t_max)) * 0.5;
+      } else {
+        lr = sc.actor_lr;
+      }
+    }
+    s_sc[threadIdx.x] = adam_scalars(lr, sc.adam_beta1_d, sc.adam_beta2_d, t);
+  }
+  __syncthreads();
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= ctx.P) return;
+  const int opt = i < ctx.PQ ? 0 : (i < ctx.v_end ? 1 : 2);
+  const AdamScalars as = s_sc[opt];
+  const int64_t off = m * ctx.P + i;
+  const float4 g4 = *reinterpret_cast<const float4*>(grads + off);
+  float4 p4 = *reinterpret_cast<float4*>(params + off);
+  float4 m4 = *reinterpret_cast<float4*>(exp_avg + off);
+  float4 v4 = *reinterpret_cast<float4*>(exp_avg_sq + off);
+  const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+  float p[4] = {p4.x, p4.y, p4.z, p4.w};
+  float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+  float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mm[j] = fmaf(sc.adam_w1, g[j] - mm[j], mm[j]);                       // exp_avg.lerp_(grad, 1-beta1)
+    vv[j] = __fmul_rn(vv[j], sc.adam_beta2);                              // exp_avg_sq.mul_(beta2)
+    vv[j] = fmaf(__fmul_rn(sc.adam_one_minus_b2, g[j]), g[j], vv[j]);     // .addcmul_(g, g, 1-beta2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv[j]), as.bc2_sqrt), sc.adam_eps);
+    p[j] = fmaf(as.neg_step_size, __fdiv_rn(mm[j], denom), p[j]);         // addcdiv_
+  }
+  *reinterpret_cast<float4*>(params + off) = make_float4(p[0], p[1], p[2], p[3]);
+  *reinterpret_cast<float4*>(exp_avg + off) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+  *reinterpret_cast<float4*>(exp_avg_sq + off) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  if (opt == 0) {
+    // soft_update with the post-Adam Q: (1-tau)*target + tau*source, two products and a sum
+    const int64_t toff = m * ctx.PQ + i;
+    float4 t4 = *reinterpret_cast<float4*>(target + toff);
+    float t[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(sc.one_minus_tau, t[j]), __fmul_rn(sc.tau, p[j]));
+    *reinterpret_cast<float4*>(target + toff) = make_float4(t[0], t[1], t[2], t[3]);
+  }
+}
+
+void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_avg_sq, float* target,
+                 const float* grads, cudaStream_t st) {
+  dim3 grid((unsigned)((ctx.P / 4 + 255) / 256), ctx.n_members);
+  adam_polyak_kernel<<<grid, 256, 0, st>>>(ctx, params, exp_avg, exp_avg_sq, target, grads);
+}
+
+__global__ void advance_kernel(StepCtx ctx, int K) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= ctx.n_members) return;
+  iql_counters c = ctx.counters[m];
+  c.v_step += K;
+  c.q_step += K;
+  c.actor_step += K;
+  c.total_it += K;
+  c.sample_step += K;
+  if (ctx.scalars[m].cosine_t_max > 0) c.sched_epoch += K;
+  ctx.counters[m] = c;
+}
+
+void launch_advance(const StepCtx& ctx, int K, cudaStream_t st) {
+  advance_kernel<<<(ctx.n_members + 127) / 128, 128, 0, st>>>(ctx, K);
+}
+
+// ===========================================================================
+// actor inference (eval mode): out = clamp(max_action * tanh(MLP(s)))
+// one CTA per state row, one warp per output neuron, activations in smem
+// ===========================================================================
+__global__ void __launch_bounds__(256) act_kernel(int S, int A, int H, int L, const float* __restrict__ block,
+                                                  const int64_t* __restrict__ w_off,
+                                                  const int64_t* __restrict__ b_off,
+                                                  const float* __restrict__ states, float max_action,
+                                                  float* __restrict__ out) {
+  extern __shared__ float sm[];  // 2 * max(H, S)
+  const int width = H > S ? H : S;
+  float* cur = sm;
+  float* nxt = sm + width;
+  const int64_t row = blockIdx.x;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) cur[i] = states[row * S + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  int in_dim = S;
+  for (int l = 0; l <= L; ++l) {
+    const int out_dim = (l == L) ? A : H;
+    const float* W = block + w_off[l];
+    const float* bias = block + b_off[l];
+    for (int j = warp; j < out_dim; j += nwarp) {
+      float acc = 0.f;
+      for (int k = lane; k < in_dim; k += 32) acc = fmaf(W[(int64_t)j * in_dim + k], cur[k], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        acc += bias[j];
+        if (l < L) nxt[j] = fmaxf(acc, 0.f);
+        else out[row * A + j] = fminf(fmaxf(max_action * tanhf(acc), -max_action), max_action);
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+    in_dim = out_dim;
+  }
+}
+
+void launch_act(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
+                const float* states, int64_t n, float max_action, float* out, cudaStream_t st) {
+  const int width = ctx.H > ctx.S_dim ? ctx.H : ctx.S_dim;
+  act_kernel<<<(unsigned)n, 256, 2 * width * sizeof(float), st>>>(ctx.S_dim, ctx.A_dim, ctx.H, ctx.L, actor_block,
+                                                                  w_off, b_off, states, max_action, out);
+}
+
+}  // namespace iql

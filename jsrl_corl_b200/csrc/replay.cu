@@ -1,0 +1,137 @@
+// Replay data plane: packed transition rows, bulk pack, ring insert, and the
+// Philox-indexed gather.  Replaces ReplayBuffer.{load_d4rl_dataset,sample,
+// add_transition} (reference algorithms/finetune/iql.py:122-196).
+//
+// HBM layout: one transition == one contiguous row of `row_floats` fp32
+// (multiple of 4, so every row is 16-byte aligned):
+//     [ s(S) | a(A) | pad to 4 | s'(S) | r | d | pad to 4 ]
+// A sample is therefore ONE contiguous 128..480-byte read issued as float4
+// loads by adjacent lanes, instead of five sub-sector reads from five arrays.
+#include "common.cuh"
+#include "engine.h"
+
+namespace iql {
+
+int make_row_layout(int S, int A, iql_row_layout* out) {
+  if (S <= 0 || A <= 0 || !out) return IQL_ERR_INVALID;
+  int sa = (int)round_up(S + A, 4);
+  out->state_dim = S;
+  out->action_dim = A;
+  out->off_state = 0;
+  out->off_action = S;
+  out->off_next_state = sa;
+  out->off_reward = sa + S;
+  out->off_done = sa + S + 1;
+  out->row_floats = (int)round_up(sa + S + 2, 4);
+  return IQL_OK;
+}
+
+static bool layout_ok(const iql_row_layout* lay) {
+  if (!lay) return false;
+  iql_row_layout t;
+  if (make_row_layout(lay->state_dim, lay->action_dim, &t) != IQL_OK) return false;
+  return t.row_floats == lay->row_floats && t.off_action == lay->off_action &&
+         t.off_next_state == lay->off_next_state && t.off_reward == lay->off_reward &&
+         t.off_done == lay->off_done && lay->off_state == 0;
+}
+
+// ---- bulk pack: dense SoA -> packed rows ---------------------------------
+__global__ void replay_pack_kernel(float* __restrict__ rows, iql_row_layout lay, int64_t first_row, int64_t n,
+                                   const float* __restrict__ s, const float* __restrict__ a,
+                                   const float* __restrict__ r, const float* __restrict__ s2,
+                                   const float* __restrict__ d) {
+  const int RF = lay.row_floats, S = lay.state_dim, A = lay.action_dim;
+  int64_t total = n * RF;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = i / RF;
+    int c = (int)(i - row * RF);
+    float v = 0.f;
+    if (c < S) v = s[row * S + c];
+    else if (c < S + A) v = a[row * A + (c - S)];
+    else if (c >= lay.off_next_state && c < lay.off_next_state + S) v = s2[row * S + (c - lay.off_next_state)];
+    else if (c == lay.off_reward) v = r[row];
+    else if (c == lay.off_done) v = d[row];
+    rows[(first_row + row) * RF + c] = v;
+  }
+}
+
+__global__ void replay_insert_kernel(float* __restrict__ rows, int RF, int64_t pointer,
+                                     const float* __restrict__ staged) {
+  int c = threadIdx.x;
+  if (c < RF) rows[pointer * RF + c] = staged[c];
+}
+
+// ---- sample: Philox (or given) indices + vectorised row gather ------------
+// One thread per float4 of a row; the RF/4 lanes of a row are adjacent, so the
+// row read is a single coalesced burst.  The row is then scattered to the five
+// dense outputs the reference API returns.
+__global__ void replay_sample_kernel(const float* __restrict__ rows, iql_row_layout lay, int64_t size, int64_t batch,
+                                     const int64_t* __restrict__ indices, uint64_t seed, uint64_t step,
+                                     float* __restrict__ so, float* __restrict__ ao, float* __restrict__ ro,
+                                     float* __restrict__ s2o, float* __restrict__ dout,
+                                     int64_t* __restrict__ idx_out) {
+  const int RF = lay.row_floats, S = lay.state_dim, A = lay.action_dim;
+  const int Q = RF >> 2;
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= batch * Q) return;
+  int64_t b = t / Q;
+  int q = (int)(t - b * Q);
+  int64_t idx = indices ? indices[b] : philox_index(seed, step, (uint32_t)b, (uint64_t)size);
+  if (q == 0 && idx_out) idx_out[b] = idx;
+  float4 v = __ldg(reinterpret_cast<const float4*>(rows + idx * RF) + q);
+  float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = q * 4 + j;
+    float x = vals[j];
+    if (c < S) so[b * S + c] = x;
+    else if (c < S + A) ao[b * A + (c - S)] = x;
+    else if (c >= lay.off_next_state && c < lay.off_next_state + S) s2o[b * S + (c - lay.off_next_state)] = x;
+    else if (c == lay.off_reward) ro[b] = x;
+    else if (c == lay.off_done) dout[b] = x;
+  }
+}
+
+}  // namespace iql
+
+using namespace iql;
+
+extern "C" int iql_replay_row_layout(int32_t state_dim, int32_t action_dim, iql_row_layout* out) {
+  return make_row_layout(state_dim, action_dim, out);
+}
+
+extern "C" int iql_replay_pack(float* rows, const iql_row_layout* lay, int64_t first_row, int64_t n,
+                               const float* states, const float* actions, const float* rewards,
+                               const float* next_states, const float* dones, void* stream) {
+  if (!layout_ok(lay) || !rows || n < 0 || first_row < 0) return IQL_ERR_INVALID;
+  if (n == 0) return IQL_OK;
+  if (!states || !actions || !rewards || !next_states || !dones) return IQL_ERR_INVALID;
+  int64_t total = n * lay->row_floats;
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  replay_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, *lay, first_row, n, states, actions, rewards,
+                                                               next_states, dones);
+  return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
+}
+
+extern "C" int iql_replay_insert(float* rows, const iql_row_layout* lay, int64_t pointer, const float* staged_row,
+                                 void* stream) {
+  if (!layout_ok(lay) || !rows || !staged_row || pointer < 0) return IQL_ERR_INVALID;
+  int threads = (lay->row_floats + 31) / 32 * 32;
+  replay_insert_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(rows, lay->row_floats, pointer, staged_row);
+  return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
+}
+
+extern "C" int iql_replay_sample(const float* rows, const iql_row_layout* lay, int64_t size, int64_t batch,
+                                 const int64_t* indices, uint64_t seed, uint64_t step, float* states,
+                                 float* actions, float* rewards, float* next_states, float* dones,
+                                 int64_t* idx_out, void* stream) {
+  if (!layout_ok(lay) || !rows || batch < 0) return IQL_ERR_INVALID;
+  if (batch == 0) return IQL_OK;
+  if (size <= 0 && !indices) return IQL_ERR_INVALID;  // np.random.randint(0, 0) raises ValueError
+  if (!states || !actions || !rewards || !next_states || !dones) return IQL_ERR_INVALID;
+  int64_t threads = batch * (lay->row_floats >> 2);
+  int blocks = (int)((threads + 255) / 256);
+  replay_sample_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, *lay, size, batch, indices, seed, step, states,
+                                                                 actions, rewards, next_states, dones, idx_out);
+  return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
+}

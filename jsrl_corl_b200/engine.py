@@ -1,0 +1,283 @@
+"""Python handle over the C-ABI engine: S independent IQL learners on one GPU.
+
+torch is plumbing here: it allocates the flat device arenas (parameters, Adam
+moments, target network, gradients, workspace), hands their pointers to the
+engine and exposes zero-copy views with the reference's ``state_dict`` key
+layout (algorithms/finetune/iql.py:565-579).  All arithmetic of the update runs
+inside ``libiql_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Config, Counters, HParams, Layout, TensorInfo
+
+NET_NAMES = {_lib.NET_Q1: "q1", _lib.NET_Q2: "q2", _lib.NET_V: "v", _lib.NET_ACTOR: "actor"}
+MATH_MODES = {"fp32": _lib.MATH_FP32_SIMT, "tf32": _lib.MATH_TF32_TCGEN05}
+
+
+def linear_indices(n_hidden: int, dropout: bool) -> List[int]:
+    """nn.Sequential indices of the Linear modules of the reference MLP
+    (iql.py:328-341): a Dropout after every ReLU shifts them to 0,3,6,..."""
+    stride = 3 if dropout else 2
+    return [stride * i for i in range(n_hidden + 1)]
+
+
+def query_layout(n_members, state_dim, action_dim, hidden_dim, n_hidden, batch_size, deterministic,
+                 math_mode="fp32", max_steps_per_call=1):
+    """Host-only: create a handle, read its layout and tensor table, destroy it.
+    Works without a GPU (used by CPU tests and by shape planning)."""
+    L = _lib.lib()
+    cfg = Config(n_members, state_dim, action_dim, hidden_dim, n_hidden, batch_size, int(bool(deterministic)),
+                 MATH_MODES[math_mode], max_steps_per_call)
+    h = C.c_void_p()
+    _lib.check(L.iql_create(C.byref(cfg), C.byref(h)), None, "iql_create")
+    try:
+        lay = Layout()
+        _lib.check(L.iql_get_layout(h, C.byref(lay)), h)
+        tensors = []
+        for i in range(lay.n_tensors):
+            t = TensorInfo()
+            _lib.check(L.iql_tensor_at(h, i, C.byref(t)), h)
+            tensors.append((t.net, t.layer, t.kind, t.rows, t.cols, t.offset))
+    finally:
+        L.iql_destroy(h)
+    return lay, tensors
+
+
+class EnsembleEngine:
+    """S-member IQL update engine bound to one CUDA device."""
+
+    def __init__(self, n_members: int, state_dim: int, action_dim: int, hidden_dim: int = 256, n_hidden: int = 2,
+                 batch_size: int = 256, deterministic: bool = False, math_mode: str = "tf32",
+                 device="cuda", max_steps_per_call: int = 256):
+        self.device = _lib.require_cuda(device)
+        self._L = _lib.lib()
+        if math_mode not in MATH_MODES:
+            raise ValueError(f"math_mode must be one of {sorted(MATH_MODES)}")
+        self.n_members, self.state_dim, self.action_dim = n_members, state_dim, action_dim
+        self.hidden_dim, self.n_hidden, self.batch_size = hidden_dim, n_hidden, batch_size
+        self.deterministic, self.math_mode = bool(deterministic), math_mode
+        self.max_steps_per_call = max_steps_per_call
+        cfg = Config(n_members, state_dim, action_dim, hidden_dim, n_hidden, batch_size, int(self.deterministic),
+                     MATH_MODES[math_mode], max_steps_per_call)
+        self._h = C.c_void_p()
+        _lib.check(self._L.iql_create(C.byref(cfg), C.byref(self._h)), None, "iql_create")
+        self.layout = Layout()
+        _lib.check(self._L.iql_get_layout(self._h, C.byref(self.layout)), self._h)
+        self.tensors = []
+        for i in range(self.layout.n_tensors):
+            t = TensorInfo()
+            _lib.check(self._L.iql_tensor_at(self._h, i, C.byref(t)), self._h)
+            self.tensors.append(t)
+        P, PQ = self.layout.param_floats, self.layout.q_floats
+        with torch.cuda.device(self.device):
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self.params = torch.zeros(n_members, P, **f32)
+            self.exp_avg = torch.zeros(n_members, P, **f32)
+            self.exp_avg_sq = torch.zeros(n_members, P, **f32)
+            self.grads = torch.zeros(n_members, P, **f32)
+            self.target = torch.zeros(n_members, PQ, **f32)
+            self.workspace = torch.zeros(self.layout.workspace_bytes, dtype=torch.uint8, device=self.device)
+            # dedicated stream: CUDA-graph capture is not allowed on the legacy default stream
+            self.stream = torch.cuda.Stream(device=self.device)
+        _lib.check(self._L.iql_bind_state(self._h, self.params.data_ptr(), self.exp_avg.data_ptr(),
+                                          self.exp_avg_sq.data_ptr(), self.target.data_ptr(), self.grads.data_ptr(),
+                                          self.workspace.data_ptr(), self.workspace.numel()), self._h, "iql_bind_state")
+        self._hparams = [self._default_hparams(m) for m in range(n_members)]
+        self._replay_refs: Dict[int, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._L.iql_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _default_hparams(self, m: int) -> HParams:
+        return HParams(beta=3.0, iql_tau=0.7, discount=0.99, tau=0.005, vf_lr=3e-4, qf_lr=3e-4, actor_lr=3e-4,
+                       actor_dropout=0.0, adam_beta1=0.9, adam_beta2=0.999, adam_eps=1e-8, lr_eta_min=0.0,
+                       cosine_t_max=1000000, seed=m)
+
+    def set_hparams(self, member: int, **kw):
+        hp = self._hparams[member]
+        for k, v in kw.items():
+            if not hasattr(hp, k):
+                raise ValueError(f"unknown hyper-parameter {k}")
+            setattr(hp, k, v)
+        _lib.check(self._L.iql_set_hparams(self._h, member, C.byref(hp)), self._h, "iql_set_hparams")
+
+    def get_hparams(self, member: int) -> HParams:
+        return self._hparams[member]
+
+    def get_counters(self, member: int) -> Counters:
+        c = Counters()
+        _lib.check(self._L.iql_get_counters(self._h, member, C.byref(c), None), self._h)
+        return c
+
+    def set_counters(self, member: int, **kw):
+        c = self.get_counters(member)
+        for k, v in kw.items():
+            if not hasattr(c, k):
+                raise ValueError(f"unknown counter {k}")
+            setattr(c, k, int(v))
+        _lib.check(self._L.iql_set_counters(self._h, member, C.byref(c)), self._h)
+
+    # ------------------------------------------------------------------
+    # zero-copy views in the reference's checkpoint layout
+    # ------------------------------------------------------------------
+    def _views(self, arena: torch.Tensor, member: int, nets, dropout_keys: bool, limit: Optional[int] = None):
+        out: Dict[str, Dict[str, torch.Tensor]] = {}
+        a_idx = linear_indices(self.n_hidden, dropout_keys)
+        q_idx = linear_indices(self.n_hidden, False)
+        block = arena[member]
+        for t in self.tensors:
+            if t.net not in nets:
+                continue
+            if limit is not None and t.offset >= limit:
+                continue
+            n = t.rows * t.cols
+            v = block[t.offset:t.offset + n]
+            if t.kind == _lib.KIND_WEIGHT:
+                v = v.view(t.rows, t.cols)
+            if t.net in (_lib.NET_Q1, _lib.NET_Q2):
+                grp, key = "qf", f"q{1 if t.net == _lib.NET_Q1 else 2}.net.{q_idx[t.layer]}."
+            elif t.net == _lib.NET_V:
+                grp, key = "vf", f"v.net.{q_idx[t.layer]}."
+            else:
+                grp, key = "actor", f"net.net.{a_idx[t.layer]}."
+            if t.kind == _lib.KIND_LOG_STD:
+                name = "log_std"
+            else:
+                name = key + ("weight" if t.kind == _lib.KIND_WEIGHT else "bias")
+            out.setdefault(grp, {})[name] = v
+        return out
+
+    def param_views(self, member: int = 0, dropout_keys: bool = False):
+        """{"qf": {...}, "vf": {...}, "actor": {...}} views aliasing the parameter arena."""
+        return self._views(self.params, member, (0, 1, 2, 3), dropout_keys)
+
+    def moment_views(self, member: int = 0, dropout_keys: bool = False):
+        return (self._views(self.exp_avg, member, (0, 1, 2, 3), dropout_keys),
+                self._views(self.exp_avg_sq, member, (0, 1, 2, 3), dropout_keys))
+
+    def grad_views(self, member: int = 0, dropout_keys: bool = False):
+        return self._views(self.grads, member, (0, 1, 2, 3), dropout_keys)
+
+    def target_views(self, member: int = 0):
+        return self._views(self.target, member, (0, 1), False)["qf"]
+
+    def load_params(self, member: int, state: Dict[str, Dict[str, "np.ndarray | torch.Tensor"]], dropout_keys=False,
+                    sync_target: bool = True):
+        """Copy a {"qf","vf","actor"[, "q_target"]} dict of arrays into the arena."""
+        views = self.param_views(member, dropout_keys)
+        for grp in ("qf", "vf", "actor"):
+            for k, v in views[grp].items():
+                v.copy_(torch.as_tensor(np.asarray(state[grp][k]) if not torch.is_tensor(state[grp][k]) else state[grp][k]).to(v))
+        if "q_target" in state:
+            for k, v in self.target_views(member).items():
+                src = state["q_target"][k]
+                v.copy_(torch.as_tensor(np.asarray(src) if not torch.is_tensor(src) else src).to(v))
+        elif sync_target:
+            self.sync_target(member)
+
+    def sync_target(self, member: int):
+        """q_target <- qf (copy.deepcopy(self.qf), iql.py:464,584,598)."""
+        cur = torch.cuda.current_stream(self.device)
+        _lib.check(self._L.iql_sync_target(self._h, member, cur.cuda_stream), self._h)
+
+    # ------------------------------------------------------------------
+    def bind_replay(self, member: int, rows: torch.Tensor, size: int):
+        if rows.device != self.device or rows.dtype != torch.float32 or not rows.is_contiguous():
+            raise ValueError("replay rows must be a contiguous float32 tensor on the engine's device")
+        if rows.shape[1] != self.layout.row.row_floats:
+            raise ValueError("replay rows have the wrong packed width for this engine")
+        self._replay_refs[member] = rows
+        _lib.check(self._L.iql_bind_replay(self._h, member, rows.data_ptr(), rows.shape[0], int(size)), self._h)
+
+    def set_replay_size(self, member: int, size: int):
+        _lib.check(self._L.iql_set_replay_size(self._h, member, int(size)), self._h)
+
+    def load_batch(self, member: int, batch):
+        s, a, r, s2, d = [self._dense(b) for b in batch]
+        B = self.batch_size
+        if s.shape != (B, self.state_dim) or s2.shape != (B, self.state_dim):
+            raise ValueError(f"states must be [{B}, {self.state_dim}]")
+        if a.shape != (B, self.action_dim):
+            raise RuntimeError("Actions shape missmatch")  # iql.py:530
+        if r.numel() != B or d.numel() != B:
+            raise ValueError("rewards / dones must have batch_size elements")
+        st = self._enter()
+        try:
+            _lib.check(self._L.iql_load_batch(self._h, member, s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr(),
+                                              d.data_ptr(), st.cuda_stream), self._h)
+        finally:
+            self._exit()
+        self._keep = (s, a, r, s2, d)
+
+    def _dense(self, t: torch.Tensor) -> torch.Tensor:
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _enter(self) -> torch.cuda.Stream:
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        return self.stream
+
+    def _exit(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def train_steps(self, k_steps: int, mode: str = "philox", indices: Optional[torch.Tensor] = None,
+                    dropout_masks: Optional[torch.Tensor] = None, return_indices: bool = False,
+                    out: Optional[torch.Tensor] = None):
+        """Run K update steps for all members; returns losses [S, K, 3]
+        (value_loss, q_loss, actor_loss) on the device, asynchronously."""
+        S, B = self.n_members, self.batch_size
+        smode = {"philox": _lib.SAMPLE_PHILOX, "indices": _lib.SAMPLE_INDICES, "preloaded": _lib.SAMPLE_PRELOADED}[mode]
+        idx_ptr = None
+        if smode == _lib.SAMPLE_INDICES:
+            if indices is None:
+                raise ValueError("mode='indices' needs an int64 tensor [S, K, B]")
+            indices = indices.to(device=self.device, dtype=torch.int64).contiguous()
+            if indices.numel() != S * k_steps * B:
+                raise ValueError("indices must have S*K*B elements")
+            idx_ptr = indices.data_ptr()
+        mask_ptr = None
+        if dropout_masks is not None:
+            dropout_masks = dropout_masks.to(device=self.device, dtype=torch.uint8).contiguous()
+            if dropout_masks.numel() != S * k_steps * self.n_hidden * B * self.hidden_dim:
+                raise ValueError("dropout_masks must be [S, K, n_hidden, B, H]")
+            mask_ptr = dropout_masks.data_ptr()
+        if out is None:
+            out = torch.empty(S, k_steps, 3, dtype=torch.float32, device=self.device)
+        idx_out = torch.empty(S, k_steps, B, dtype=torch.int64, device=self.device) if return_indices else None
+        st = self._enter()
+        try:
+            _lib.check(self._L.iql_train_steps(self._h, k_steps, smode, idx_ptr, mask_ptr, out.data_ptr(),
+                                               idx_out.data_ptr() if idx_out is not None else None, st.cuda_stream),
+                       self._h, "iql_train_steps")
+        finally:
+            self._exit()
+        # keep argument tensors alive until the stream has consumed them
+        self._keep2 = (indices, dropout_masks)
+        return (out, idx_out) if return_indices else out
+
+    def last_launch_count(self) -> int:
+        return int(self._L.iql_last_launch_count(self._h))
+
+    def act(self, member: int, states: torch.Tensor, max_action: float = 1.0) -> torch.Tensor:
+        states = self._dense(states).view(-1, self.state_dim)
+        out = torch.empty(states.shape[0], self.action_dim, dtype=torch.float32, device=self.device)
+        st = self._enter()
+        try:
+            _lib.check(self._L.iql_act(self._h, member, states.data_ptr(), states.shape[0], float(max_action),
+                                       out.data_ptr(), st.cuda_stream), self._h, "iql_act")
+        finally:
+            self._exit()
+        return out

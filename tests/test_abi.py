@@ -1,0 +1,136 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every
+symbol include/iql_b200.h declares, rejects bad arguments with the documented
+codes, and lays parameters out in the reference's checkpoint order/shapes.
+No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from jsrl_corl_b200 import _lib
+from jsrl_corl_b200.engine import linear_indices, query_layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "iql_b200.h")).read()
+    declared = set(re.findall(r"\b(iql_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name)
+    assert b"sm_100a" in L.iql_version()
+
+
+def test_struct_sizes_match_header_expectations():
+    assert C.sizeof(_lib.Config) == 16 * 4
+    assert C.sizeof(_lib.HParams) == 12 * 8 + 16
+    assert C.sizeof(_lib.Counters) == 6 * 8
+    assert C.sizeof(_lib.RowLayout) == 8 * 4
+    assert C.sizeof(_lib.TensorInfo) == 6 * 4 + 8
+
+
+def test_create_rejects_bad_config_with_value_error():
+    L = _lib.lib()
+    h = C.c_void_p()
+    for bad in (dict(n_members=0), dict(hidden_dim=30), dict(n_hidden=0), dict(math_mode=7), dict(batch_size=0)):
+        kw = dict(n_members=1, state_dim=3, action_dim=2, hidden_dim=32, n_hidden=2, batch_size=8, deterministic=0,
+                  math_mode=0, max_steps_per_call=4)
+        kw.update(bad)
+        cfg = _lib.Config(**kw)
+        rc = L.iql_create(C.byref(cfg), C.byref(h))
+        assert rc == _lib.IQL_ERR_INVALID
+        with pytest.raises(ValueError):
+            _lib.check(rc, None, "iql_create")
+    assert L.iql_create(None, C.byref(h)) == _lib.IQL_ERR_INVALID
+
+
+def test_calls_before_bind_fail_loudly():
+    L = _lib.lib()
+    h = C.c_void_p()
+    cfg = _lib.Config(1, 3, 2, 32, 2, 8, 0, 0, 4)
+    assert L.iql_create(C.byref(cfg), C.byref(h)) == 0
+    try:
+        rc = L.iql_train_steps(h, 1, 0, None, None, None, None, None)
+        assert rc == _lib.IQL_ERR_STATE
+        assert b"not bound" in L.iql_last_error(h)
+        hp = _lib.HParams(actor_dropout=1.5)
+        assert L.iql_set_hparams(h, 0, C.byref(hp)) == _lib.IQL_ERR_INVALID
+        assert L.iql_set_hparams(h, 3, C.byref(hp)) == _lib.IQL_ERR_INVALID
+        assert L.iql_bind_replay(h, 0, None, 10, 0) == _lib.IQL_ERR_INVALID
+    finally:
+        L.iql_destroy(h)
+
+
+@pytest.mark.parametrize("S,A,H,L,det,dropout", [(11, 3, 256, 2, True, 0.0), (29, 8, 256, 3, False, 0.0),
+                                                 (45, 24, 256, 2, False, 0.1), (11, 3, 1024, 4, True, 0.0)])
+def test_layout_follows_reference_checkpoint_order(S, A, H, L, det, dropout):
+    import jsrl_corl_b200 as J
+
+    lay, tensors = query_layout(1, S, A, H, L, 256, det)
+    q = J.TwinQ(S, A, H, L)
+    v = J.ValueFunction(S, H, L)
+    actor = (J.DeterministicPolicy if det else J.GaussianPolicy)(S, A, 1.0, H, L, dropout=dropout)
+    expected = []  # optimizer parameter order == module.parameters() order (log_std first for the Gaussian actor)
+    for mod in (q, v, actor):
+        expected += [tuple(p.shape) for p in mod.parameters()]
+    got = [(r, c) if kind == _lib.KIND_WEIGHT else (r,) for (_, _, kind, r, c, _) in tensors]
+    assert got == expected
+    offs = [t[5] for t in tensors]
+    assert offs == sorted(offs) and all(o % 32 == 0 for o in offs)  # 128-byte aligned tensors
+    assert lay.q_floats == lay.v_begin and lay.v_end == lay.actor_begin and lay.actor_end == lay.param_floats
+    n_q = sum(p.numel() for p in q.parameters())
+    assert lay.q_floats >= n_q and lay.q_floats - n_q < 32 * len(list(q.parameters()))
+    # dropout shifts the Sequential indices to 0,3,6 (reference iql.py:329-333)
+    idx = linear_indices(L, dropout > 0)
+    assert [k for k in actor.state_dict() if k.endswith("weight")] == [f"net.net.{i}.weight" for i in idx]
+
+
+def test_row_layout_is_16_byte_segmented():
+    L = _lib.lib()
+    for S, A, rf in ((11, 3, 32), (17, 6, 44), (29, 8, 72), (45, 24, 120)):
+        lay = _lib.RowLayout()
+        assert L.iql_replay_row_layout(S, A, C.byref(lay)) == 0
+        assert lay.row_floats == rf and lay.row_floats % 4 == 0 and lay.off_next_state % 4 == 0
+        assert lay.off_action == S and lay.off_reward == lay.off_next_state + S and lay.off_done == lay.off_reward + 1
+    assert L.iql_replay_row_layout(0, 3, C.byref(lay)) == _lib.IQL_ERR_INVALID
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import jsrl_corl_b200 as J
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        J.ReplayBuffer(3, 2, 10, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        J.EnsembleEngine(1, 3, 2, 32, 2, 8)
+    q, v, a = J.TwinQ(3, 2, 32), J.ValueFunction(3, 32), J.GaussianPolicy(3, 2, 1.0, 32)
+    opts = [torch.optim.Adam(m.parameters()) for m in (a, q, v)]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        J.ImplicitQLearning(1.0, a, opts[0], q, opts[1], v, opts[2], device="cpu")
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "jsrl_corl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"oracle[./]_build", r"libphilox_ref", r"iql_numpy"):
+                    assert not re.search(pat, text, flags=re.M), (f, pat)
+
+
+def test_synthetic_dataset_matches_oracle_copy():
+    from jsrl_corl_b200.synthetic import synthetic_dataset as a
+    from oracle.iql_numpy import synthetic_dataset as b
+
+    for kw in (dict(n=100, state_dim=5, action_dim=2, seed=3), dict(n=50, state_dim=29, action_dim=8, seed=0, antmaze_rewards=True)):
+        x, y = a(**kw), b(**kw)
+        for k in x:
+            assert np.array_equal(x[k], y[k])

@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the ctypes facade)
+against the golden fixtures generated from the live reference and against the
+numpy / C oracle.  Run with ``-m gpu`` on a B200.
+
+Tolerances (see DESIGN.md "Parity protocol"): index sampling and gathers are
+bit-exact; losses and weights over a SHORT free-running horizon (<= 40 steps)
+agree to 1e-5 relative on the FP32-SIMT path and 1e-3 on the TF32 path; after
+1,000 steps the trajectory is chaotic (the reference in fp64 differs from the
+reference in fp32 by 4-9e-2), so the bar there is 2x the reference's own
+fp32-vs-fp64 divergence stored in the fixture.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, Golden, batch_from, network_errors_vs_floor, rel_err, tree_max_rel
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+TF32_TOL = 1e-3
+
+
+def _cpu_tree(views):
+    return {g: {k: v.detach().cpu().numpy() for k, v in d.items()} for g, d in views.items()}
+
+
+def _make_engine(g, math_mode, n_members=1, max_k=64):
+    from jsrl_corl_b200 import EnsembleEngine, ReplayBuffer
+
+    m = g.meta
+    eng = EnsembleEngine(n_members, m["S"], m["A"], m["H"], m["L"], m["B"], bool(m["det"]), math_mode, "cuda", max_k)
+    rb = ReplayBuffer(m["S"], m["A"], m["n_rows"], "cuda")
+    rb.load_d4rl_dataset(g.dataset())
+    init = g.init_tree()
+    for i in range(n_members):
+        eng.load_params(i, init, dropout_keys=m["dropout"] > 0)
+        eng.set_hparams(i, beta=m["beta"], iql_tau=m["iql_tau"], discount=m["discount"], tau=m["tau"], vf_lr=m["lr"],
+                        qf_lr=m["lr"], actor_lr=m["lr"], actor_dropout=m["dropout"], cosine_t_max=m["max_steps"], seed=i)
+        eng.bind_replay(i, rb.rows, m["n_rows"])
+    return eng, rb
+
+
+def _run_indices(eng, g, steps, masks=None, chunk=20):
+    idx = torch.from_numpy(g.indices()[:steps])
+    S = eng.n_members
+    losses = []
+    for s0 in range(0, steps, chunk):
+        k = min(chunk, steps - s0)
+        ii = idx[s0:s0 + k].unsqueeze(0).expand(S, k, -1).contiguous()
+        mk = None
+        if masks is not None:
+            mk = torch.from_numpy(masks[s0:s0 + k]).unsqueeze(0).expand(S, *masks[s0:s0 + k].shape).contiguous()
+        losses.append(eng.train_steps(k, mode="indices", indices=ii, dropout_masks=mk).cpu().numpy())
+    return np.concatenate(losses, axis=1)
+
+
+# ---------------------------------------------------------------------------
+# R2: ReplayBuffer.sample -- index stream and gathers are bit-exact
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["hopper", "pen", "one_row"])
+def test_replay_sample_reference_stream_bit_exact(tag):
+    from jsrl_corl_b200 import ReplayBuffer
+    from oracle.iql_numpy import synthetic_dataset
+
+    z = np.load(GOLDEN + "/sampler.npz")
+    S, A, n, B = [int(x) for x in z[f"{tag}/dims"]]
+    rb = ReplayBuffer(S, A, n + 5, "cuda")
+    rb.load_d4rl_dataset(synthetic_dataset(n, S, A, 3))
+    np.random.seed(42)
+    for j in range(2):
+        batch = rb.sample(B)
+        assert np.array_equal(rb._last_indices.cpu().numpy(), z[f"{tag}/indices"][j])
+        for nm, t in zip(("s", "a", "r", "s2", "d"), batch):
+            ref = z[f"{tag}/batch{j}/{nm}"]
+            assert tuple(t.shape) == ref.shape
+            assert np.array_equal(t.cpu().numpy(), ref), (tag, j, nm)
+    # the strided views expose the reference's attribute layout
+    assert rb._states.shape == (n + 5, S) and rb._rewards.shape == (n + 5, 1)
+
+
+def test_replay_philox_sampler_matches_cpu_restatement():
+    from jsrl_corl_b200 import ReplayBuffer
+    from oracle.iql_numpy import synthetic_dataset
+    from oracle.philox import philox_indices
+
+    S, A, n, B = 17, 6, 100003, 256
+    data = synthetic_dataset(n, S, A, 5)
+    rb = ReplayBuffer(S, A, n, "cuda", sampler="philox", seed=0xDEADBEEF12345)
+    rb.load_d4rl_dataset(data)
+    for step in range(3):
+        s, a, r, s2, d = [t.cpu().numpy() for t in rb.sample(B)]
+        idx = philox_indices(0xDEADBEEF12345, step, n, B)
+        assert np.array_equal(s, data["observations"][idx])
+        assert np.array_equal(a, data["actions"][idx])
+        assert np.array_equal(r[:, 0], data["rewards"][idx])
+        assert np.array_equal(s2, data["next_observations"][idx])
+        assert np.array_equal(d[:, 0], data["terminals"][idx].astype(np.float32))
+
+
+def test_replay_errors_and_ring_insert():
+    from jsrl_corl_b200 import ReplayBuffer
+
+    rb = ReplayBuffer(3, 2, 4, "cuda")
+    with pytest.raises(ValueError):
+        rb.sample(2)  # empty buffer: np.random.randint(0, 0) raises in the reference too
+    with pytest.raises(ValueError):
+        rb.load_d4rl_dataset({"observations": np.zeros((5, 3), np.float32), "actions": np.zeros((5, 2), np.float32),
+                              "rewards": np.zeros(5, np.float32), "next_observations": np.zeros((5, 3), np.float32),
+                              "terminals": np.zeros(5, bool)})
+    for i in range(6):  # wraps the 4-row ring
+        rb.add_transition(np.full(3, i, np.float32), np.full(2, -i, np.float32), float(i), np.full(3, i + 0.5, np.float32), i % 2 == 0)
+    assert rb._size == 4 and rb._pointer == 2
+    got = rb._states.cpu().numpy()[:, 0]
+    assert np.array_equal(got, np.array([4, 5, 2, 3], np.float32))
+    assert np.array_equal(rb._dones.cpu().numpy()[:, 0], np.array([1, 0, 1, 0], np.float32))
+    rb2 = ReplayBuffer(3, 2, 4, "cuda")
+    rb2.add_transition(np.zeros(3), np.zeros(2), 0.0, np.zeros(3), False)
+    with pytest.raises(ValueError):
+        rb2.load_d4rl_dataset({"observations": np.zeros((1, 3), np.float32), "actions": np.zeros((1, 2), np.float32),
+                               "rewards": np.zeros(1, np.float32), "next_observations": np.zeros((1, 3), np.float32),
+                               "terminals": np.zeros(1, bool)})
+
+
+def test_engine_philox_indices_bit_exact():
+    from oracle.philox import philox_indices
+
+    g = Golden("small_gauss")
+    eng, rb = _make_engine(g, "fp32", n_members=3)
+    eng.set_counters(1, sample_step=(1 << 33) + 5)
+    _, idx = eng.train_steps(4, mode="philox", return_indices=True)
+    idx = idx.cpu().numpy()
+    for m, base in ((0, 0), (1, (1 << 33) + 5), (2, 0)):
+        for k in range(4):
+            assert np.array_equal(idx[m, k], philox_indices(m, base + k, g.meta["n_rows"], g.meta["B"]))
+
+
+# ---------------------------------------------------------------------------
+# R10-R16: the update, short free-running horizon
+# ---------------------------------------------------------------------------
+CASES = [("small_gauss", 40), ("small_det", 20), ("halfcheetah_2x256", 30), ("antmaze_3x256", 30)]
+
+
+@pytest.mark.parametrize("name,steps", CASES)
+@pytest.mark.parametrize("math_mode,tol", [("fp32", FP32_TOL), ("tf32", TF32_TOL)])
+def test_update_matches_reference_short_horizon(name, steps, math_mode, tol):
+    g = Golden(name)
+    eng, _ = _make_engine(g, math_mode)
+    losses = _run_indices(eng, g, steps)[0]
+    ref = g.losses[:steps].astype(np.float64)
+    # value_loss is a mean of squared *differences* of O(0.1) quantities; its error is judged on
+    # the absolute scale of q_loss as well (a 1e-3 relative error on Q moves adv^2 by more than 1e-3)
+    scale = np.maximum(np.abs(ref), tol * np.abs(ref).max(axis=1, keepdims=True))
+    assert np.max(np.abs(losses - ref) / scale) < (2 * tol if math_mode == "fp32" else 5 * tol), \
+        np.max(np.abs(losses - ref) / scale)
+    worst, where = tree_max_rel(_cpu_tree(eng.param_views(0)), g.tree(f"step{steps}"))
+    assert worst < tol, (worst, where)
+
+
+@pytest.mark.parametrize("math_mode,tol", [("fp32", FP32_TOL), ("tf32", TF32_TOL)])
+def test_dropout_actor_with_injected_masks(math_mode, tol):
+    g = Golden("small_dropout")
+    eng, _ = _make_engine(g, math_mode)
+    losses = _run_indices(eng, g, 12, masks=g.dropout_masks())[0]
+    np.testing.assert_allclose(losses, g.losses[:12], rtol=5 * tol, atol=1e-7)
+    worst, where = tree_max_rel(_cpu_tree(eng.param_views(0, dropout_keys=True)), g.tree("step12"))
+    assert worst < tol, (worst, where)
+
+
+def test_adam_moments_target_and_schedule_fp32():
+    g = Golden("small_gauss")
+    eng, _ = _make_engine(g, "fp32")
+    _run_indices(eng, g, 20)
+    m1, m2 = eng.moment_views(0)
+    opt = g.opt("step20")
+    for grp in ("qf", "vf", "actor"):
+        for name, (m, v) in opt[grp].items():
+            assert rel_err(m1[grp][name].cpu().numpy(), m) < 1e-4, (grp, name)
+            assert rel_err(m2[grp][name].cpu().numpy(), v) < 1e-4, (grp, name)
+    tgt = g.tree("step20")["q_target"]
+    for k, v in eng.target_views(0).items():
+        assert rel_err(v.cpu().numpy(), tgt[k]) < 1e-6, k
+    c = eng.get_counters(0)
+    assert (c.v_step, c.q_step, c.actor_step, c.sched_epoch, c.total_it) == (20, 20, 20, 20, 20)
+
+
+def test_gradients_single_step_against_oracle():
+    """One step from the reference's initial state: the gradient arena vs the numpy oracle."""
+    from oracle.iql_numpy import NumpyIQL
+
+    g = Golden("halfcheetah_2x256")
+    eng, _ = _make_engine(g, "fp32")
+    _run_indices(eng, g, 1)
+    orc = NumpyIQL(g.oracle_config(), g.init_tree(), np.float64)
+    data, idx = g.dataset(), g.indices()
+    grads = {}
+    import oracle.iql_numpy as onp
+
+    class Spy(onp._Adam):
+        def step(self, gr):
+            grads.update(gr)
+            super().step(gr)
+
+    for o in (orc.q_opt, orc.v_opt, orc.a_opt):
+        o.__class__ = Spy
+    orc.train(batch_from(data, idx[0]))
+    gv = _cpu_tree(eng.grad_views(0))
+    flat = {**gv["qf"], **gv["vf"], **gv["actor"]}
+    for k, ref in grads.items():
+        assert rel_err(flat[k], ref) < 2e-5, (k, rel_err(flat[k], ref))
+
+
+# ---------------------------------------------------------------------------
+# long horizon: chaotic regime, judged against the reference's own noise floor
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("math_mode", ["fp32", "tf32"])
+def test_hopper_1000_steps_within_noise_floor(math_mode):
+    g = Golden("hopper_1000")
+    eng, _ = _make_engine(g, math_mode)
+    losses = _run_indices(eng, g, 1000, chunk=50)[0]
+    tol = FP32_TOL if math_mode == "fp32" else TF32_TOL
+    ref30 = g.losses[:30].astype(np.float64)
+    scale = np.maximum(np.abs(ref30), tol * np.abs(ref30).max(axis=1, keepdims=True))
+    assert np.max(np.abs(losses[:30] - ref30) / scale) < 5 * tol
+    for grp, (err, floor) in network_errors_vs_floor(g, _cpu_tree(eng.param_views(0)), "step1000").items():
+        assert err <= 2.0 * floor, (grp, err, floor)
+    a, b = losses[-100:].mean(0), g.losses[-100:].astype(np.float64).mean(0)
+    np.testing.assert_allclose(a, b, rtol=0.05)
+
+
+# ---------------------------------------------------------------------------
+# ensemble semantics: members are independent; K steps per call == K calls
+# ---------------------------------------------------------------------------
+def test_members_independent_and_k_fusion_bit_identical():
+    g = Golden("small_gauss")
+    eng4, _ = _make_engine(g, "fp32", n_members=4)
+    eng1, _ = _make_engine(g, "fp32", n_members=1)
+    eng1.set_hparams(0, seed=2)
+    l4 = eng4.train_steps(6, mode="philox").cpu().numpy()         # one graph launch of 6 steps
+    l1 = np.concatenate([eng1.train_steps(1, mode="philox").cpu().numpy() for _ in range(6)], axis=1)
+    assert np.array_equal(l4[2], l1[0])
+    a, b = _cpu_tree(eng4.param_views(2)), _cpu_tree(eng1.param_views(0))
+    for grp in a:
+        for k in a[grp]:
+            assert np.array_equal(a[grp][k], b[grp][k]), (grp, k)
+    assert eng4.last_launch_count() > 0
+
+
+# ---------------------------------------------------------------------------
+# drop-in facade: ReplayBuffer.sample + ImplicitQLearning.train, call for call
+# ---------------------------------------------------------------------------
+def _facade_trainer(g, math_mode):
+    import jsrl_corl_b200 as J
+
+    m = g.meta
+    torch.manual_seed(m["seed"])
+    q = J.TwinQ(m["S"], m["A"], m["H"], m["L"])
+    v = J.ValueFunction(m["S"], m["H"], m["L"])
+    actor = (J.DeterministicPolicy if m["det"] else J.GaussianPolicy)(m["S"], m["A"], 1.0, m["H"], m["L"], dropout=m["dropout"])
+    q, v, actor = q.to("cuda"), v.to("cuda"), actor.to("cuda")
+    vo = torch.optim.Adam(v.parameters(), lr=m["lr"])
+    qo = torch.optim.Adam(q.parameters(), lr=m["lr"])
+    ao = torch.optim.Adam(actor.parameters(), lr=m["lr"])
+    tr = J.ImplicitQLearning(1.0, actor, ao, q, qo, v, vo, iql_tau=m["iql_tau"], beta=m["beta"], max_steps=m["max_steps"],
+                             discount=m["discount"], tau=m["tau"], device="cuda", math_mode=math_mode)
+    rb = J.ReplayBuffer(m["S"], m["A"], m["n_rows"], "cuda")
+    rb.load_d4rl_dataset(g.dataset())
+    return tr, rb
+
+
+def test_facade_drop_in_trajectory_and_checkpoint_roundtrip(tmp_path):
+    g = Golden("small_gauss")
+    m = g.meta
+    tr, rb = _facade_trainer(g, "fp32")
+    # identical init as the reference under the same torch.manual_seed
+    assert tree_max_rel(_cpu_tree({"qf": dict(tr.qf.state_dict()), "vf": dict(tr.vf.state_dict()),
+                                   "actor": dict(tr.actor.state_dict())}), g.tree("init"))[0] == 0.0
+    np.random.seed(m["idx_seed"])
+    losses = []
+    for t in range(20):
+        log = tr.train(rb.sample(m["B"]))
+        losses.append([log["value_loss"], log["q_loss"], log["actor_loss"]])
+    np.testing.assert_allclose(np.array(losses), g.losses[:20], rtol=2e-5, atol=1e-8)
+    assert tr.total_it == 20
+    sd = tr.state_dict()
+    assert list(sd.keys()) == ["qf", "q_optimizer", "vf", "v_optimizer", "actor", "actor_optimizer", "actor_lr_schedule", "total_it"]
+    ref20 = g.tree("step20")
+    for grp in ("qf", "vf", "actor"):
+        assert list(sd[grp].keys()) == list(ref20[grp].keys())
+        for k in sd[grp]:
+            assert rel_err(sd[grp][k].cpu().numpy(), ref20[grp][k]) < FP32_TOL
+    assert abs(sd["actor_optimizer"]["param_groups"][0]["lr"] - float(g.z["step20/actor_lr"])) < 1e-15
+    assert sd["actor_lr_schedule"]["last_epoch"] == 20
+    st0 = sd["q_optimizer"]["state"][0]
+    assert float(st0["step"]) == 20.0 and st0["exp_avg"].shape == sd["qf"]["q1.net.0.weight"].shape
+    # save / load into a fresh trainer, continue both: identical next losses
+    path = tmp_path / "checkpoint_19.pt"
+    torch.save(sd, path)
+    tr2, _ = _facade_trainer(g, "fp32")
+    tr2.load_state_dict(torch.load(path, map_location="cuda"))
+    assert tr2.total_it == 20
+    batch = rb.sample(m["B"])
+    # the reference re-clones q_target from qf on load (iql.py:584); do the same on the live trainer
+    tr.load_state_dict(torch.load(path, map_location="cuda"))
+    a, b = tr.train(batch), tr2.train(batch)
+    assert a == b
+    # actor.act still works in stock torch on the aliased parameters and agrees with the engine kernel
+    tr.actor.eval()
+    s = np.linspace(-1, 1, m["S"]).astype(np.float32)
+    act_torch = tr.actor.act(s, "cuda")
+    act_kernel = tr._engine.act(0, torch.from_numpy(s).cuda(), 1.0).cpu().numpy().reshape(-1)
+    np.testing.assert_allclose(act_kernel, act_torch, rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError, match="Actions shape missmatch"):
+        bad = list(batch)
+        bad[1] = torch.zeros(m["B"], m["A"] + 1, device="cuda")
+        tr.train(bad)
+
+
+def test_ensemble_checkpoint_layout():
+    from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
+
+    g = Golden("small_det")
+    m = g.meta
+    ens = IQLEnsemble(3, m["S"], m["A"], m["H"], m["L"], m["B"], deterministic=True, math_mode="fp32", seeds=[0, 1, 2])
+    rb = ReplayBuffer(m["S"], m["A"], m["n_rows"], "cuda")
+    rb.load_d4rl_dataset(g.dataset())
+    ens.bind_replay(rb)
+    ens.train_steps(5)
+    sd = ens.member_state_dict(1)
+    assert sd["total_it"] == 5 and float(sd["v_optimizer"]["state"][0]["step"]) == 5.0
+    assert "log_std" not in sd["actor"] and list(sd["actor"].keys())[0] == "net.net.0.weight"
+    ens2 = IQLEnsemble(3, m["S"], m["A"], m["H"], m["L"], m["B"], deterministic=True, math_mode="fp32", seeds=[5, 6, 7])
+    ens2.load_member_state_dict(0, sd)
+    sd2 = ens2.member_state_dict(0)
+    for k in sd["qf"]:
+        assert torch.equal(sd["qf"][k], sd2["qf"][k])
+    assert sd2["actor_lr_schedule"]["last_epoch"] == 5
