@@ -11,7 +11,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 class Golden:
     def __init__(self, name):
         self.z = np.load(os.path.join(GOLDEN, name + ".npz"))
-        self.meta = dict(zip([str(k) for k in self.z["meta_keys"]], self.z["meta_vals"]))
+        self.meta = dict(zip([str(k) for k in self.z["meta_keys"]], [float(v) for v in self.z["meta_vals"]]))
         for k in ("S", "A", "H", "L", "det", "B", "steps", "n_rows", "seed", "idx_seed", "antmaze", "max_steps"):
             self.meta[k] = int(self.meta[k])
         self.losses = self.z["losses"]
