@@ -185,6 +185,13 @@ int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mode, const i
  * mode: out[n,A] = clamp(max_action * tanh(MLP(states[n,S]))). */
 int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float max_action,
             float* out_actions, void* stream);
+/* Self-test hook for the tcgen05 TF32 GEMM building block (no reference
+ * counterpart): C[M,N] = op(A) op(B), mode 0 NT (A[M,K], B[N,K]), 1 NN (A[M,K],
+ * B[K,N]), 2 TN (A[K,M], B[K,N]); M, N multiples of 256, K multiple of 32;
+ * scratch: >= 1024 B of 128-byte aligned device memory. */
+int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
+                           const float* B, int32_t ldb, float* C, int32_t ldc, void* scratch,
+                           size_t scratch_bytes, void* stream);
 /* number of kernel launches issued by the last iql_train_steps call */
 int64_t iql_last_launch_count(const iql_engine* e);
 

@@ -28,6 +28,7 @@ struct Phase {
   int maxM, maxN;
   int K;         // common K of the phase (0 if mixed)
   bool umma_ok;  // eligible for the tcgen05 kernel
+  int epi;       // common epilogue of the phase
 };
 
 struct iql_engine {
@@ -46,6 +47,8 @@ struct iql_engine {
   iql_counters* d_counters = nullptr;
   ReplayBinding* d_replay = nullptr;
   GemmProb* d_probs = nullptr;
+  char* d_maps = nullptr;        // [2 * nprob] CUtensorMap (128 B each), tcgen05 phases only
+  std::vector<char> h_maps;
   int64_t* d_act_off = nullptr;  // [2][L+1]
   float* d_loss_ring = nullptr;
   float* d_ws_f = nullptr;       // activation area
@@ -144,6 +147,7 @@ static void build_layout(iql_engine* e) {
   tab(sizeof(iql_counters) * S);
   tab(sizeof(ReplayBinding) * S);
   tab(sizeof(GemmProb) * nprob);
+  tab(128 * 2 * nprob);
   tab(sizeof(int64_t) * 2 * (L + 1));
   tab(sizeof(float) * 3 * (int64_t)S * c.max_steps_per_call);
   e->tables_bytes = tb;
@@ -294,6 +298,7 @@ static void build_problems(iql_engine* e) {
     ph.count = (int)e->h_probs.size() - ph.first;
     ph.K = (l >= 1) ? H : 0;
     ph.umma_ok = (l >= 1 && l < L);
+    ph.epi = (l < L) ? EPI_RELU : EPI_LINEAR;
     e->fwd_phases.push_back(ph);
   }
   // ---- backward phases ----
@@ -303,6 +308,7 @@ static void build_problems(iql_engine* e) {
   for (int l = L; l >= 0; --l) {
     // weight gradient  dW_l = G_l^T H_l   (TN)
     Phase pw; pw.mode = 2; pw.first = (int)e->h_probs.size(); pw.maxM = 0; pw.maxN = 0; pw.K = B; pw.umma_ok = (l >= 1 && l < L);
+    pw.epi = EPI_NONE;
     for (int m = 0; m < S; ++m)
       for (int t = 0; t < 4; ++t) {
         const int net = tr[t].net, f = tr[t].pass;
@@ -329,6 +335,7 @@ static void build_problems(iql_engine* e) {
     if (l == 0) break;
     // activation gradient  G_{l-1} = (G_l W_l) * [H_l > 0]   (NN)
     Phase px; px.mode = 1; px.first = (int)e->h_probs.size(); px.maxM = B; px.maxN = H; px.K = (l < L) ? H : 0; px.umma_ok = (l < L);
+    px.epi = EPI_DRELU;
     for (int m = 0; m < S; ++m)
       for (int t = 0; t < 4; ++t) {
         const int net = tr[t].net, f = tr[t].pass;
@@ -373,11 +380,21 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   e->d_counters = (iql_counters*)tab(sizeof(iql_counters) * S);
   e->d_replay = (ReplayBinding*)tab(sizeof(ReplayBinding) * S);
   e->d_probs = (GemmProb*)tab(sizeof(GemmProb) * nprob);
+  e->d_maps = tab(128 * 2 * nprob);
   e->d_act_off = (int64_t*)tab(sizeof(int64_t) * 2 * (L + 1));
   e->d_loss_ring = (float*)tab(sizeof(float) * 3 * (int64_t)S * e->cfg.max_steps_per_call);
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
   if ((int64_t)e->h_probs.size() != nprob) return fail(e, IQL_ERR_STATE, "internal: problem count mismatch");
+  e->h_maps.assign((size_t)128 * 2 * nprob, 0);
+  if (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) {
+    auto encode = [&](const Phase& ph) {
+      if (!ph.umma_ok || !umma_phase_supported(ph.mode, e->cfg.batch_size, e->cfg.hidden_dim)) return 0;
+      return umma_encode_maps(ph.mode, e->h_probs.data() + ph.first, ph.count, e->h_maps.data() + (size_t)256 * ph.first);
+    };
+    for (const Phase& ph : e->fwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (forward phase)");
+    for (const Phase& ph : e->bwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward phase)");
+  }
   e->bound = true;
   e->tables_dirty = e->scalars_dirty = e->counters_dirty = e->replay_dirty = true;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);
@@ -389,6 +406,7 @@ static int flush_tables(iql_engine* e, cudaStream_t st) {
   const int S = e->cfg.n_members, L = e->cfg.n_hidden;
   if (e->tables_dirty) {
     CUDA_TRY(e, cudaMemcpyAsync(e->d_probs, e->h_probs.data(), sizeof(GemmProb) * e->h_probs.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_maps, e->h_maps.data(), e->h_maps.size(), cudaMemcpyHostToDevice, st));
     std::vector<int64_t> off(2 * (L + 1));
     for (int l = 0; l <= L; ++l) {
       off[l] = e->w_off[IQL_NET_ACTOR][l];
@@ -476,7 +494,9 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   if (gather) { launch_gather(ctx, e->d_ws_f, e->wl.member_floats, e->wl.xrow, st); ++launches; }
   auto run_phase = [&](const Phase& ph) {
     if (tf32 && ph.umma_ok && umma_phase_supported(ph.mode, e->cfg.batch_size, e->cfg.hidden_dim)) {
-      launch_umma_gemm(ph.mode, e->d_probs + ph.first, ph.count, ph.maxM, ph.maxN, ph.K, ctx, st);
+      launch_umma_gemm(ph.mode, e->d_probs + ph.first, e->d_maps + (size_t)256 * ph.first, ph.epi, ph.count, ph.maxM,
+                       ph.maxN, ctx, st);
+      if (ph.mode == 2) { launch_colsum(e->d_probs + ph.first, ph.count, ph.maxM, st); ++launches; }
     } else {
       launch_simt_gemm(ph.mode, e->d_probs + ph.first, ph.count, ph.maxM, ph.maxN, ctx, st);
     }
@@ -579,5 +599,34 @@ extern "C" int iql_act(iql_engine* e, int32_t member, const float* states, int64
   launch_act(ctx, e->params + (int64_t)member * e->layout.param_floats, e->d_act_off, e->d_act_off + (L + 1), states, n,
              max_action, out_actions, (cudaStream_t)stream);
   CUDA_TRY(e, cudaGetLastError());
+  return IQL_OK;
+}
+
+// Self-test of the tcgen05 GEMM on one dense problem (tests/test_gpu_umma.py):
+// C[M,N] = op(A) op(B) with the operand layouts of `mode` (0 NT, 1 NN, 2 TN), plain store.
+extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
+                                      const float* B, int32_t ldb, float* C, int32_t ldc, void* scratch,
+                                      size_t scratch_bytes, void* stream) {
+  if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0 || (M % 256) || (N % 256) || (K % 32))
+    return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: M, N multiples of 256 and K multiple of 32 required");
+  if (!A || !B || !C || !scratch || scratch_bytes < 1024 || ((uintptr_t)scratch & 127))
+    return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: null pointer or scratch < 1024 B / unaligned");
+  GemmProb p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  p.epi = EPI_NONE; p.drop_layer = -1;
+  alignas(64) char maps[256];
+  if (umma_encode_maps(mode, &p, 1, maps)) return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: cuTensorMapEncodeTiled failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* d = (char*)scratch;
+  if (cudaMemcpyAsync(d, maps, 256, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(d + 256, &p, sizeof(p), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: upload failed");
+  StepCtx ctx;
+  memset(&ctx, 0, sizeof(ctx));
+  launch_umma_gemm(mode, (const GemmProb*)(d + 256), d, EPI_NONE, 1, M, N, ctx, st);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(nullptr, IQL_ERR_CUDA, std::string("iql_selftest_umma_gemm: ") + cudaGetErrorString(err));
   return IQL_OK;
 }

@@ -1,7 +1,392 @@
-// placeholder until the tcgen05 kernel lands: nothing is eligible, so the
-// TF32 mode currently runs the FP32 kernels.
+// tcgen05 (UMMA) TF32 grouped GEMM for the hidden-layer GEMMs of the IQL step
+// (IQL_MATH_TF32_TCGEN05).  sm_100a only.
+//
+//   mode 0  NT  C[M,N] = A[M,K] * B[N,K]^T   forward  H' = relu(H W^T + b)      A,B K-major
+//   mode 1  NN  C[M,N] = A[M,K] * B[K,N]     dgrad    G' = (G W) * [H > 0]      A K-major, B MN-major
+//   mode 2  TN  C[M,N] = A[K,M]^T * B[K,N]   wgrad    dW = G^T H                A,B MN-major
+//
+// One CTA computes a 256 x 256 output tile as two M=128 UMMA accumulators that
+// fill the 512 TMEM columns; the B tile is staged once and feeds both halves.
+// Operands arrive by TMA (one elected thread) into a 3-stage ring of
+// 128B-swizzled shared-memory tiles (32 K-elements = 128 B per row), the MMA
+// is issued by one elected thread (tcgen05.mma.cta_group::1.kind::tf32, FP32
+// accumulate in TMEM), completion is tracked with tcgen05.commit -> mbarrier,
+// and four epilogue warps read the accumulators with tcgen05.ld, transpose
+// through shared memory and apply the fused epilogue with coalesced global
+// accesses (bias+ReLU(+dropout) / ReLU-mask / plain store).
+//
+// Shared-memory / descriptor conventions (cute/atom/mma_traits_sm100.hpp):
+//   K-major  : rows of 128 B, SWIZZLE_128B (16 B atoms), SBO = 1024 B between
+//              8-row groups, K advance of one UMMA (8 tf32) = +32 B.
+//   MN-major : tf32 requires SWIZZLE_128B_BASE32B; slabs of 32 MN-elements
+//              ([32 k-rows][128 B]), LBO = slab stride, SBO = 512 B between
+//              4-row groups, K advance of one UMMA (8 k-rows) = +1024 B.
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
 #include "umma_gemm.h"
+
 namespace iql {
-bool umma_phase_supported(int, int, int) { return false; }
-void launch_umma_gemm(int, const GemmProb*, int, int, int, int, const StepCtx&, cudaStream_t) {}
+
+constexpr int TILE_M = 256, TILE_N = 256, TILE_K = 32, UMMA_K = 8, N_STAGES = 3;
+constexpr int STAGE_A_BYTES = TILE_M * TILE_K * 4;  // 32 KB
+constexpr int STAGE_B_BYTES = TILE_N * TILE_K * 4;  // 32 KB
+constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int N_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a mis-programmed TMA / MMA traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 24)) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)(layout & 7) << 61);
+}
+
+struct UmmaParams {
+  // per-operand descriptor fields, host-computed (16-byte units unless noted)
+  uint32_t a_lbo, a_sbo, a_layout, a_kstep, a_half;  // a_half: offset of the second M=128 half (16 B units)
+  uint32_t b_lbo, b_sbo, b_layout, b_kstep;
+  uint32_t idesc;
+  int a_mn, b_mn;  // operand majors (0 K-major, 1 MN-major)
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(N_THREADS, 1)
+umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restrict__ maps, UmmaParams up, StepCtx ctx) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bars = base + N_STAGES * STAGE_BYTES;  // full[3], empty[3], tmem_full, tmem slot
+  const uint32_t full0 = bars, empty0 = bars + 8 * N_STAGES, tfull = bars + 16 * N_STAGES, tslot = tfull + 8;
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + N_STAGES * STAGE_BYTES + 16 * N_STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.z;
+  const GemmProb p = probs[prob];
+  const int m0 = blockIdx.y * TILE_M, n0 = blockIdx.x * TILE_N;
+  if (m0 >= p.M || n0 >= p.N) return;  // uniform per CTA
+  const CUtensorMap* mapA = maps + 2 * prob;
+  const CUtensorMap* mapB = mapA + 1;
+  const int num_kb = p.K / TILE_K;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < N_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (1 CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tslot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
+        const uint32_t fb = full0 + 8 * stage;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const int k0 = kb * TILE_K;
+        if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
+        else tma_load_2d(sa, mapA, fb, k0, m0);
+        if (up.b_mn) tma_load_3d(sb, mapB, fb, 0, k0, n0 >> 5);
+        else tma_load_2d(sb, mapB, fb, k0, n0);
+        if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
+        const uint64_t adesc0 = make_desc(sa, up.a_lbo, up.a_sbo, up.a_layout);
+        const uint64_t bdesc0 = make_desc(sb, up.b_lbo, up.b_sbo, up.b_layout);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int ks = 0; ks < TILE_K / UMMA_K; ++ks) {
+            const uint64_t ad = adesc0 + (uint64_t)(h * up.a_half + ks * up.a_kstep);
+            const uint64_t bd = bdesc0 + (uint64_t)(ks * up.b_kstep);
+            umma_tf32(tmem_base + h * 256, ad, bd, up.idesc, (kb | ks) != 0);
+          }
+        }
+        umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
+        if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull);  // accumulators complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    // all MMAs are complete, so the operand ring is free: use it as the transpose staging area
+    float* stg = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    const MemberScalars* sc = ctx.scalars + p.member;
+    float dscale = 1.0f;
+    bool philox_drop = false;
+    uint64_t dstep = 0;
+    if (EPI == EPI_DRELU) dscale = (p.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
+    if (EPI == EPI_RELU) {
+      philox_drop = p.drop_layer >= 0 && sc->drop_threshold != 0u;
+      if (philox_drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
+    }
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int row_base = m0 + h * 128 + q * 32;
+#pragma unroll 1
+      for (int c = 0; c < TILE_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int col = n0 + c * 32 + lane;
+        float bias = 0.f;
+        if (EPI == EPI_RELU || EPI == EPI_LINEAR) bias = p.bias[col];
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int row = row_base + rr;
+          float v = stg[rr * 33 + lane];
+          if (EPI == EPI_RELU) {
+            v = fmaxf(v + bias, 0.f);
+            if (philox_drop) {
+              if (ctx.dropout_masks) {
+                const uint8_t* mk = ctx.dropout_masks +
+                                    ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H;
+                v = mk[col] ? v * sc->drop_scale : 0.f;
+              } else {
+                const int64_t e = (int64_t)row * p.N + col;
+                const Philox4 ph = philox_dropout_quad(sc->seed, dstep, (uint32_t)p.drop_layer, (uint32_t)(e >> 2));
+                const uint32_t wsel = (e & 3) == 0 ? ph.x : (e & 3) == 1 ? ph.y : (e & 3) == 2 ? ph.z : ph.w;
+                v = (wsel >= sc->drop_threshold) ? v * sc->drop_scale : 0.f;
+              }
+            }
+          } else if (EPI == EPI_LINEAR) {
+            v += bias;
+          } else if (EPI == EPI_DRELU) {
+            v = (p.mask[(int64_t)row * p.ldmask + col] > 0.f) ? v * dscale : 0.f;
+          }
+          p.C[(int64_t)row * p.ldc + col] = v;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// bias gradient of the wgrad phases: dbias[m] = sum_k A[k][m]  (A = G, [K=B rows][M] row-major)
+__global__ void __launch_bounds__(256) colsum_kernel(const GemmProb* __restrict__ probs) {
+  const GemmProb p = probs[blockIdx.y];
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= p.M || p.dbias == nullptr) return;
+  float s = 0.f;
+  for (int k = 0; k < p.K; ++k) s += p.A[(int64_t)k * p.lda + m];
+  p.dbias[m] = s;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* s = getenv(name);
+  return s ? (uint32_t)strtoul(s, nullptr, 0) : dflt;
+}
+
+bool umma_phase_supported(int mode, int batch, int hidden) {
+  (void)mode;
+  static int disabled = -1;
+  if (disabled < 0) disabled = getenv("IQL_B200_NO_UMMA") ? 1 : 0;
+  return !disabled && batch == TILE_M && hidden >= 256 && hidden % 256 == 0;
+}
+
+// K-major operand [rows][K] (ld floats): 2-D map {K, rows}, box {32, 256}, SWIZZLE_128B
+static int encode_kmajor(CUtensorMap* out, const float* ptr, int rows, int K, int ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 1;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {TILE_K, 256};
+  cuuint32_t es[2] = {1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
+}
+
+// MN-major operand [K rows][MN] (ld floats): 3-D map {32, K, MN/32}, box {32, 32, 8}, SWIZZLE_128B_ATOM_32B
+static int encode_mnmajor(CUtensorMap* out, const float* ptr, int mn, int K, int ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 1;
+  cuuint64_t gdim[3] = {32, (cuuint64_t)K, (cuuint64_t)(mn / 32)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t box[3] = {32, TILE_K, 8};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = (CUtensorMapSwizzle)env_u32("IQL_UMMA_MN_TMA_SWIZZLE", (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
+}
+
+int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, void* h_maps_out) {
+  CUtensorMap* maps = (CUtensorMap*)h_maps_out;
+  for (int i = 0; i < nprob; ++i) {
+    const GemmProb& p = h_probs[i];
+    int rc;
+    if (mode == 2) rc = encode_mnmajor(&maps[2 * i], p.A, p.M, p.K, p.lda);
+    else rc = encode_kmajor(&maps[2 * i], p.A, p.M, p.K, p.lda);
+    if (rc) return rc;
+    if (mode == 0) rc = encode_kmajor(&maps[2 * i + 1], p.B, p.N, p.K, p.ldb);
+    else rc = encode_mnmajor(&maps[2 * i + 1], p.B, p.N, p.K, p.ldb);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static UmmaParams make_params(int mode) {
+  UmmaParams u;
+  const int a_mn = (mode == 2), b_mn = (mode != 0);
+  u.a_mn = a_mn;
+  u.b_mn = b_mn;
+  // K-major SW128: LBO unused (1), SBO 1024 B, layout 2, K step 32 B, second half = 128 rows * 128 B
+  // MN-major SW128/32B: LBO = slab stride 4096 B, SBO 512 B, layout 1, K step 1024 B, second half = 4 slabs
+  u.a_lbo = a_mn ? env_u32("IQL_UMMA_MN_LBO", 4096 >> 4) : 1;
+  u.a_sbo = a_mn ? env_u32("IQL_UMMA_MN_SBO", 512 >> 4) : (1024 >> 4);
+  u.a_layout = a_mn ? env_u32("IQL_UMMA_MN_LAYOUT", 1) : 2;
+  u.a_kstep = a_mn ? env_u32("IQL_UMMA_MN_KSTEP", 1024 >> 4) : (32 >> 4);
+  u.a_half = (128 * 128) >> 4;  // both layouts: 16 KB
+  u.b_lbo = b_mn ? env_u32("IQL_UMMA_MN_LBO", 4096 >> 4) : 1;
+  u.b_sbo = b_mn ? env_u32("IQL_UMMA_MN_SBO", 512 >> 4) : (1024 >> 4);
+  u.b_layout = b_mn ? env_u32("IQL_UMMA_MN_LAYOUT", 1) : 2;
+  u.b_kstep = b_mn ? env_u32("IQL_UMMA_MN_KSTEP", 1024 >> 4) : (32 >> 4);
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
+  // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+  u.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+            ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  return u;
+}
+
+void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, int epi, int nprob, int maxM, int maxN,
+                      const StepCtx& ctx, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_DRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_set = true;
+  }
+  const UmmaParams up = make_params(mode);
+  dim3 grid((maxN + TILE_N - 1) / TILE_N, (maxM + TILE_M - 1) / TILE_M, nprob);
+  const CUtensorMap* m = (const CUtensorMap*)maps;
+  if (epi == EPI_RELU) umma_gemm_kernel<EPI_RELU><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, up, ctx);
+  else if (epi == EPI_DRELU) umma_gemm_kernel<EPI_DRELU><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, up, ctx);
+  else if (epi == EPI_LINEAR) umma_gemm_kernel<EPI_LINEAR><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, up, ctx);
+  else umma_gemm_kernel<EPI_NONE><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, up, ctx);
+}
+
+void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st) {
+  dim3 grid((maxM + 255) / 256, nprob);
+  colsum_kernel<<<grid, 256, 0, st>>>(probs);
+}
+
 }  // namespace iql

@@ -1,0 +1,60 @@
+"""tcgen05 TF32 GEMM building block vs a plain PyTorch fp32 reference of the same op."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(mode, M, N, K, seed=0):
+    from jsrl_corl_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pad = 8  # exercise leading dimensions larger than the logical width
+    if mode == 0:
+        A = torch.randn(M, K + pad, device="cuda", generator=g)[:, :K]
+        B = torch.randn(N, K + pad, device="cuda", generator=g)[:, :K]
+        ref = A.double() @ B.double().T
+    elif mode == 1:
+        A = torch.randn(M, K + pad, device="cuda", generator=g)[:, :K]
+        B = torch.randn(K, N + pad, device="cuda", generator=g)[:, :N]
+        ref = A.double() @ B.double()
+    else:
+        A = torch.randn(K, M + pad, device="cuda", generator=g)[:, :M]
+        B = torch.randn(K, N + pad, device="cuda", generator=g)[:, :N]
+        ref = A.double().T @ B.double()
+    Cout = torch.full((M, N + pad), float("nan"), device="cuda")
+    scratch = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        rc = L.iql_selftest_umma_gemm(mode, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                      Cout.data_ptr(), Cout.stride(0), scratch.data_ptr(), scratch.numel(), st.cuda_stream)
+    _lib.check(rc, None, "iql_selftest_umma_gemm")
+    st.synchronize()
+    out = Cout[:, :N].double()
+    err = (out - ref).norm() / ref.norm()
+    return float(err), out, ref
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(256, 256, 256), (512, 256, 64), (256, 768, 128)])
+def test_umma_gemm_matches_fp32_matmul(mode, shape):
+    M, N, K = shape
+    err, out, ref = _run(mode, M, N, K)
+    # TF32 operands (10-bit mantissa), fp32 accumulation: ~5e-4 relative per product, averaged over K
+    assert err < 1.5e-3, (mode, shape, err)
+    assert torch.isfinite(out).all()
+
+
+def test_umma_gemm_rejects_bad_shapes():
+    from jsrl_corl_b200 import _lib
+
+    L = _lib.lib()
+    x = torch.zeros(256, 256, device="cuda")
+    s = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    rc = L.iql_selftest_umma_gemm(0, 100, 256, 256, x.data_ptr(), 256, x.data_ptr(), 256, x.data_ptr(), 256,
+                                  s.data_ptr(), 4096, None)
+    assert rc == _lib.IQL_ERR_INVALID
