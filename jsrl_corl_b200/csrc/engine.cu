@@ -29,7 +29,9 @@ struct Phase {
   int K;         // common K of the phase (0 if mixed)
   bool umma_ok;  // eligible for the tcgen05 kernel
   int epi;       // common epilogue of the phase
+  int kind;      // PH_*: dedicated skinny-layer kernel, or generic grouped GEMM
 };
+enum { PH_GENERIC = 0, PH_FIRST_FWD = 1, PH_OUT_FWD = 2, PH_LAST_WGRAD = 3, PH_LAST_DGRAD = 4, PH_FIRST_WGRAD = 5 };
 
 struct iql_engine {
   iql_config cfg;
@@ -299,6 +301,7 @@ static void build_problems(iql_engine* e) {
     ph.K = (l >= 1) ? H : 0;
     ph.umma_ok = (l >= 1 && l < L);
     ph.epi = (l < L) ? EPI_RELU : EPI_LINEAR;
+    ph.kind = (l == 0) ? PH_FIRST_FWD : (l == L ? PH_OUT_FWD : PH_GENERIC);
     e->fwd_phases.push_back(ph);
   }
   // ---- backward phases ----
@@ -309,6 +312,7 @@ static void build_problems(iql_engine* e) {
     // weight gradient  dW_l = G_l^T H_l   (TN)
     Phase pw; pw.mode = 2; pw.first = (int)e->h_probs.size(); pw.maxM = 0; pw.maxN = 0; pw.K = B; pw.umma_ok = (l >= 1 && l < L);
     pw.epi = EPI_NONE;
+    pw.kind = (l == L) ? PH_LAST_WGRAD : (l == 0 ? PH_FIRST_WGRAD : PH_GENERIC);
     for (int m = 0; m < S; ++m)
       for (int t = 0; t < 4; ++t) {
         const int net = tr[t].net, f = tr[t].pass;
@@ -336,6 +340,7 @@ static void build_problems(iql_engine* e) {
     // activation gradient  G_{l-1} = (G_l W_l) * [H_l > 0]   (NN)
     Phase px; px.mode = 1; px.first = (int)e->h_probs.size(); px.maxM = B; px.maxN = H; px.K = (l < L) ? H : 0; px.umma_ok = (l < L);
     px.epi = EPI_DRELU;
+    px.kind = (l == L) ? PH_LAST_DGRAD : PH_GENERIC;
     for (int m = 0; m < S; ++m)
       for (int t = 0; t < 4; ++t) {
         const int net = tr[t].net, f = tr[t].pass;
@@ -492,20 +497,50 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   int launches = 0;
   const bool tf32 = e->cfg.math_mode == IQL_MATH_TF32_TCGEN05;
   if (gather) { launch_gather(ctx, e->d_ws_f, e->wl.member_floats, e->wl.xrow, st); ++launches; }
-  auto run_phase = [&](const Phase& ph) {
-    if (tf32 && ph.umma_ok && umma_phase_supported(ph.mode, e->cfg.batch_size, e->cfg.hidden_dim)) {
-      launch_umma_gemm(ph.mode, e->d_probs + ph.first, e->d_maps + (size_t)256 * ph.first, ph.epi, ph.count, ph.maxM,
-                       ph.maxN, ctx, st);
-      if (ph.mode == 2) { launch_colsum(e->d_probs + ph.first, ph.count, ph.maxM, st); ++launches; }
+  const iql_config& c = e->cfg;
+  const int B = c.batch_size, H = c.hidden_dim, A = c.action_dim, K0 = c.state_dim + c.action_dim;
+  // the skinny-layer kernels keep one operand in shared memory; fall back to the generic GEMM when it does not fit
+  static const bool no_skinny = getenv("IQL_B200_NO_SKINNY") != nullptr;
+  auto kpad = [](int k) { return k <= 24 ? 24 : (k <= 40 ? 40 : 72); };
+  auto apad = [](int a) { return a <= 1 ? 1 : (a <= 8 ? 8 : 24); };
+  const bool first_ok = !no_skinny && K0 <= 72;
+  const bool first_wgrad_ok = first_ok && ((size_t)B * kpad(K0) + 512 * (kpad(K0) + 1)) * 4 <= 200 * 1024;
+  const bool out_ok = !no_skinny && A <= 64 && (size_t)(A <= 1 ? 1 : (A <= 8 ? 8 : (A <= 24 ? 24 : 64))) * H * 4 <= 200 * 1024;
+  const bool last_ok = !no_skinny && A <= 24 && ((size_t)B * apad(A) + 256 * apad(A)) * 4 <= 200 * 1024;
+  bool skip_next = false, skip_colsum = false;
+  auto run_phase = [&](const Phase& ph, const Phase* next, const Phase* next2) {
+    if (skip_next) { skip_next = false; return; }
+    const GemmProb* pp = e->d_probs + ph.first;
+    if (ph.kind == PH_FIRST_FWD && first_ok) {
+      launch_first_fwd(pp, ph.count, B, H, K0, ctx, st);
+    } else if (ph.kind == PH_OUT_FWD && out_ok) {
+      launch_out_fwd(pp, ph.count, B, H, A, st);
+    } else if (ph.kind == PH_LAST_WGRAD && last_ok && next && next->kind == PH_LAST_DGRAD) {
+      // fused wgrad + dgrad of the output layer; it also emits db_{L-1} when layer L-1 is a hidden-layer
+      // tcgen05 wgrad phase (whose kernel does not produce bias gradients)
+      const bool emit_db = next2 && next2->kind == PH_GENERIC && tf32 && next2->umma_ok && umma_phase_supported(2, B, H);
+      launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st);
+      skip_next = true;
+      skip_colsum = emit_db;
+    } else if (ph.kind == PH_FIRST_WGRAD && first_wgrad_ok) {
+      launch_first_wgrad(pp, ph.count, B, H, K0, st);
+    } else if (tf32 && ph.umma_ok && umma_phase_supported(ph.mode, B, H)) {
+      launch_umma_gemm(ph.mode, pp, e->d_maps + (size_t)256 * ph.first, ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st);
+      if (ph.mode == 2) {
+        if (skip_colsum) skip_colsum = false;  // db already written by the fused output-layer backward
+        else { launch_colsum(pp, ph.count, ph.maxM, st); ++launches; }
+      }
     } else {
-      launch_simt_gemm(ph.mode, e->d_probs + ph.first, ph.count, ph.maxM, ph.maxN, ctx, st);
+      launch_simt_gemm(ph.mode, pp, ph.count, ph.maxM, ph.maxN, ctx, st);
     }
     ++launches;
   };
-  for (const Phase& ph : e->fwd_phases) run_phase(ph);
+  for (const Phase& ph : e->fwd_phases) run_phase(ph, nullptr, nullptr);
   launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, st);
   ++launches;
-  for (const Phase& ph : e->bwd_phases) run_phase(ph);
+  for (size_t i = 0; i < e->bwd_phases.size(); ++i)
+    run_phase(e->bwd_phases[i], i + 1 < e->bwd_phases.size() ? &e->bwd_phases[i + 1] : nullptr,
+              i + 2 < e->bwd_phases.size() ? &e->bwd_phases[i + 2] : nullptr);
   launch_adam(ctx, e->params, e->exp_avg, e->exp_avg_sq, e->target, e->grads, st);
   ++launches;
   return launches;

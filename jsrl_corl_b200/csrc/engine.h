@@ -113,6 +113,12 @@ void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_a
 void launch_advance(const StepCtx& ctx, int K, cudaStream_t st);
 void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float* s, const float* a, const float* r,
                        const float* s2, const float* d, cudaStream_t st);
+// skinny-layer kernels (kernels_skinny.cu)
+void launch_first_fwd(const GemmProb* probs, int nprob, int B, int H, int kmax, const StepCtx& ctx, cudaStream_t st);
+void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cudaStream_t st);
+void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
+                     int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st);
+void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax, cudaStream_t st);
 void launch_act(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
                 const float* states, int64_t n, float max_action, float* out, cudaStream_t st);
 

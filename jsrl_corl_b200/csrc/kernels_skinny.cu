@@ -1,0 +1,333 @@
+// CUDA-core kernels for the "skinny" ends of the MLPs: first layer (K = obs or
+// obs+act, 11..69) and last layer (N = 1 or act_dim).  These GEMMs carry < 10 %
+// of the FLOPs but have no tensor-core shape; they are HBM/L2-bound row
+// streams, so each kernel makes ONE coalesced pass over the big [B, H] operand
+// with the small operand held in registers / shared memory, and sums in a
+// fixed order (deterministic, fp32).
+//
+//   first_fwd   H1 = drop(relu(X W0^T + b0))                      (iql.py:329-333 forward)
+//   out_fwd     y  = H_L W_L^T + b_L                               (output Linear)
+//   last_bwd    dW_L = G_L^T H_L, db_L = colsum(G_L),
+//               G_{L-1} = (G_L W_L) * [H_L > 0] * scale            (autograd of the output Linear + ReLU/Dropout)
+//   first_wgrad dW_0 = G_0^T X, db_0 = colsum(G_0)
+#include "common.cuh"
+#include "engine.h"
+
+namespace iql {
+
+// ---------------------------------------------------------------------------
+// first layer forward.  grid (nprob, ceil(B/64), ceil(H/256)), 256 threads.
+// thread = one output column n; W0[n][:] in registers; X rows broadcast from smem.
+// ---------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(256) first_fwd_kernel(const GemmProb* __restrict__ probs, StepCtx ctx) {
+  constexpr int RT = 64;
+  __shared__ __align__(16) float xs[RT][KMAX];
+  const GemmProb p = probs[blockIdx.x];
+  const int r0 = blockIdx.y * RT;
+  const int n = blockIdx.z * 256 + threadIdx.x;
+  const int K = p.K;
+  if (r0 >= p.M) return;
+  for (int i = threadIdx.x; i < RT * KMAX; i += 256) {
+    const int r = i / KMAX, k = i - r * KMAX;
+    float v = 0.f;
+    if (r0 + r < p.M && k < K) v = p.A[(int64_t)(r0 + r) * p.lda + k];
+    xs[r][k] = v;
+  }
+  float w[KMAX];
+  float bias = 0.f;
+  if (n < p.N) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) w[k] = (k < K) ? p.B[(int64_t)n * p.ldb + k] : 0.f;
+    bias = p.bias[n];
+  } else {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) w[k] = 0.f;
+  }
+  __syncthreads();
+  if (n >= p.N) return;
+  const MemberScalars* sc = ctx.scalars + p.member;
+  const bool drop = p.drop_layer >= 0 && sc->drop_threshold != 0u;
+  uint64_t dstep = 0;
+  if (drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
+  const int rows = min(RT, p.M - r0);
+  for (int r = 0; r < rows; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k4 = 0; k4 < KMAX; k4 += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(&xs[r][k4]);
+      acc = fmaf(x.x, w[k4], acc);
+      acc = fmaf(x.y, w[k4 + 1], acc);
+      acc = fmaf(x.z, w[k4 + 2], acc);
+      acc = fmaf(x.w, w[k4 + 3], acc);
+    }
+    float v = fmaxf(acc + bias, 0.f);
+    const int row = r0 + r;
+    if (drop) {
+      if (ctx.dropout_masks) {
+        const uint8_t* mk = ctx.dropout_masks +
+                            ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H;
+        v = mk[n] ? v * sc->drop_scale : 0.f;
+      } else {
+        const int64_t e = (int64_t)row * p.N + n;
+        const Philox4 ph = philox_dropout_quad(sc->seed, dstep, (uint32_t)p.drop_layer, (uint32_t)(e >> 2));
+        const uint32_t ws = (e & 3) == 0 ? ph.x : (e & 3) == 1 ? ph.y : (e & 3) == 2 ? ph.z : ph.w;
+        v = (ws >= sc->drop_threshold) ? v * sc->drop_scale : 0.f;
+      }
+    }
+    p.C[(int64_t)row * p.ldc + n] = v;
+  }
+}
+
+void launch_first_fwd(const GemmProb* probs, int nprob, int B, int H, int kmax, const StepCtx& ctx, cudaStream_t st) {
+  dim3 grid(nprob, (B + 63) / 64, (H + 255) / 256);
+  if (kmax <= 24) first_fwd_kernel<24><<<grid, 256, 0, st>>>(probs, ctx);
+  else if (kmax <= 40) first_fwd_kernel<40><<<grid, 256, 0, st>>>(probs, ctx);
+  else first_fwd_kernel<72><<<grid, 256, 0, st>>>(probs, ctx);
+}
+
+// ---------------------------------------------------------------------------
+// output layer forward.  grid (nprob, ceil(B/32)), 256 threads = 8 warps, one
+// warp per row (4 rows per warp), lanes stride the hidden dimension.
+// ---------------------------------------------------------------------------
+template <int AMAX>
+__global__ void __launch_bounds__(256) out_fwd_kernel(const GemmProb* __restrict__ probs) {
+  extern __shared__ float wsm[];  // [N][K]
+  const GemmProb p = probs[blockIdx.x];
+  const int K = p.K, N = p.N;
+  for (int i = threadIdx.x; i < N * K; i += 256) wsm[i] = p.B[(int64_t)(i / K) * p.ldb + (i % K)];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = 0; rr < 4; ++rr) {
+    const int row = blockIdx.y * 32 + warp * 4 + rr;
+    if (row >= p.M) break;
+    float acc[AMAX];
+#pragma unroll
+    for (int m = 0; m < AMAX; ++m) acc[m] = 0.f;
+    const float* h = p.A + (int64_t)row * p.lda;
+    for (int k = lane; k < K; k += 32) {
+      const float x = h[k];
+#pragma unroll
+      for (int m = 0; m < AMAX; ++m)
+        if (m < N) acc[m] = fmaf(x, wsm[m * K + k], acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < AMAX; ++m) {
+      if (m < N) {
+        float v = acc[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) p.C[(int64_t)row * p.ldc + m] = v + p.bias[m];
+      }
+    }
+  }
+}
+
+void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cudaStream_t st) {
+  dim3 grid(nprob, (B + 31) / 32);
+  const size_t sm = (size_t)amax * H * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(out_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  if (amax <= 1) out_fwd_kernel<1><<<grid, 256, sm, st>>>(probs);
+  else if (amax <= 8) out_fwd_kernel<8><<<grid, 256, sm, st>>>(probs);
+  else if (amax <= 24) out_fwd_kernel<24><<<grid, 256, sm, st>>>(probs);
+  else out_fwd_kernel<64><<<grid, 256, sm, st>>>(probs);
+}
+
+// ---------------------------------------------------------------------------
+// last layer backward (fused wgrad + dgrad + ReLU/dropout mask).
+// grid (nprob, ceil(H/64)), 256 threads = 64 columns x 4 row groups.
+//   pn: the dgrad problem  (A = G_L [B][ldg], K = A_out, B = W_L [A_out][H], C = G_{L-1}, mask = H_L)
+//   pw: the wgrad problem  (C = dW_L [A_out][H], dbias = db_L)
+// ---------------------------------------------------------------------------
+template <int AMAX>
+__global__ void __launch_bounds__(256) last_bwd_kernel(const GemmProb* __restrict__ probs_dgrad,
+                                                       const GemmProb* __restrict__ probs_wgrad,
+                                                       const GemmProb* __restrict__ probs_prev_wgrad, StepCtx ctx) {
+  extern __shared__ float sm[];  // G tile [B][AMAX] then reduction scratch [4][64][AMAX]
+  const GemmProb pn = probs_dgrad[blockIdx.x];
+  const GemmProb pw = probs_wgrad[blockIdx.x];
+  // bias gradient of layer L-1 (the wgrad problem of the NEXT backward phase), when that layer is a hidden one
+  float* dbias_prev = probs_prev_wgrad ? probs_prev_wgrad[blockIdx.x].dbias : nullptr;
+  const int B = pn.M, H = pn.N, AO = pn.K;
+  float* gs = sm;
+  float* red = sm + (size_t)B * AMAX;
+  for (int i = threadIdx.x; i < B * AMAX; i += 256) {
+    const int b = i / AMAX, m = i - b * AMAX;
+    gs[i] = (m < AO) ? pn.A[(int64_t)b * pn.lda + m] : 0.f;
+  }
+  const int tn = threadIdx.x & 63, bg = threadIdx.x >> 6;
+  const int n = blockIdx.y * 64 + tn;
+  float w[AMAX], dw[AMAX];
+#pragma unroll
+  for (int m = 0; m < AMAX; ++m) {
+    w[m] = (m < AO && n < H) ? pn.B[(int64_t)m * pn.ldb + n] : 0.f;
+    dw[m] = 0.f;
+  }
+  const MemberScalars* sc = ctx.scalars + pn.member;
+  const float dscale = (pn.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
+  __syncthreads();
+  const int rows_per = (B + 3) / 4;
+  const int b_lo = bg * rows_per, b_hi = min(B, b_lo + rows_per);
+  float csum = 0.f;  // column sum of the produced G_{L-1} = bias gradient of layer L-1
+  if (n < H) {
+    if (AO == 1) {  // scalar heads (Q, V): uniform per CTA
+      const float w0 = w[0];
+      float d0 = 0.f;
+#pragma unroll 4
+      for (int b = b_lo; b < b_hi; ++b) {
+        const float h = pn.mask[(int64_t)b * pn.ldmask + n];
+        const float g = gs[b * AMAX];
+        d0 = fmaf(g, h, d0);
+        const float o = (h > 0.f) ? (g * w0) * dscale : 0.f;
+        csum += o;
+        pn.C[(int64_t)b * pn.ldc + n] = o;
+      }
+      dw[0] = d0;
+    } else {
+      for (int b = b_lo; b < b_hi; ++b) {
+        const float h = pn.mask[(int64_t)b * pn.ldmask + n];
+        float gsum = 0.f;
+#pragma unroll
+        for (int m = 0; m < AMAX; ++m) {
+          const float g = gs[b * AMAX + m];
+          gsum = fmaf(g, w[m], gsum);
+          dw[m] = fmaf(g, h, dw[m]);
+        }
+        const float o = (h > 0.f) ? gsum * dscale : 0.f;
+        csum += o;
+        pn.C[(int64_t)b * pn.ldc + n] = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < AMAX; ++m) red[(bg * 64 + tn) * AMAX + m] = dw[m];
+  __shared__ float cred[4][64];
+  cred[bg][tn] = csum;
+  __syncthreads();
+  if (bg == 0 && n < H) {
+#pragma unroll
+    for (int m = 0; m < AMAX; ++m) {
+      if (m < AO) {
+        const float s = ((red[(0 * 64 + tn) * AMAX + m] + red[(1 * 64 + tn) * AMAX + m]) +
+                         red[(2 * 64 + tn) * AMAX + m]) + red[(3 * 64 + tn) * AMAX + m];
+        pw.C[(int64_t)m * pw.ldc + n] = s;
+      }
+    }
+    if (dbias_prev != nullptr) dbias_prev[n] = ((cred[0][tn] + cred[1][tn]) + cred[2][tn]) + cred[3][tn];
+  }
+  if (blockIdx.y == 0 && pw.dbias != nullptr && threadIdx.x < AO) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += gs[b * AMAX + threadIdx.x];
+    pw.dbias[threadIdx.x] = s;
+  }
+}
+
+void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
+                     int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st) {
+  dim3 grid(nprob, (H + 63) / 64);
+  auto smem = [&](int a) { return ((size_t)B * a + 4 * 64 * a) * sizeof(float); };
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(last_bwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(last_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(last_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  if (amax <= 1) last_bwd_kernel<1><<<grid, 256, smem(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+  else if (amax <= 8) last_bwd_kernel<8><<<grid, 256, smem(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+  else last_bwd_kernel<24><<<grid, 256, smem(24), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+}
+
+// ---------------------------------------------------------------------------
+// first layer weight gradient.  grid (nprob, ceil(H/(64*NC))), 256 threads = 64 column slots x 4 row groups,
+// NC columns per thread (the X row fetched from shared memory is reused NC times).
+//   p: TN problem (A = G_0 [B][H] (K = B rows, M = H), B = X [B][ldx] (N = K0), C = dW_0 [H][K0], dbias = db_0)
+// ---------------------------------------------------------------------------
+template <int KMAX, int NC>
+__global__ void __launch_bounds__(256) first_wgrad_kernel(const GemmProb* __restrict__ probs) {
+  extern __shared__ float sm[];  // X [B][KMAX], then reduction scratch [4][64*NC][KMAX + 1]
+  const GemmProb p = probs[blockIdx.x];
+  const int B = p.K, H = p.M, K0 = p.N;
+  constexpr int CW = 64 * NC;  // columns per CTA
+  float* xs = sm;
+  float* red = sm + (size_t)B * KMAX;
+  for (int i = threadIdx.x; i < B * KMAX; i += 256) {
+    const int b = i / KMAX, k = i - b * KMAX;
+    xs[i] = (k < K0) ? p.B[(int64_t)b * p.ldb + k] : 0.f;
+  }
+  const int tn = threadIdx.x & 63, bg = threadIdx.x >> 6;
+  const int n0 = blockIdx.y * CW + tn;
+  float acc[NC][KMAX];
+  float bsum[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    bsum[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) acc[c][k] = 0.f;
+  }
+  __syncthreads();
+  const int rows_per = (B + 3) / 4;
+  const int b_lo = bg * rows_per, b_hi = min(B, b_lo + rows_per);
+  for (int b = b_lo; b < b_hi; ++b) {
+    float g[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int n = n0 + c * 64;
+      g[c] = (n < H) ? p.A[(int64_t)b * p.lda + n] : 0.f;
+      bsum[c] += g[c];
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < KMAX; k4 += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(&xs[b * KMAX + k4]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        acc[c][k4] = fmaf(g[c], x.x, acc[c][k4]);
+        acc[c][k4 + 1] = fmaf(g[c], x.y, acc[c][k4 + 1]);
+        acc[c][k4 + 2] = fmaf(g[c], x.z, acc[c][k4 + 2]);
+        acc[c][k4 + 3] = fmaf(g[c], x.w, acc[c][k4 + 3]);
+      }
+    }
+  }
+  constexpr int RS = KMAX + 1;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float* mine = red + (size_t)(bg * CW + c * 64 + tn) * RS;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) mine[k] = acc[c][k];
+    mine[KMAX] = bsum[c];
+  }
+  __syncthreads();
+  // 256 threads cooperatively finish the CW x (K0 + 1) outputs of this column block (fixed order)
+  for (int i = threadIdx.x; i < CW * RS; i += 256) {
+    const int c = i / RS, k = i - c * RS;
+    const int nn = blockIdx.y * CW + c;
+    if (nn >= H) continue;
+    const float s = ((red[(size_t)(0 * CW + c) * RS + k] + red[(size_t)(1 * CW + c) * RS + k]) +
+                     red[(size_t)(2 * CW + c) * RS + k]) + red[(size_t)(3 * CW + c) * RS + k];
+    if (k < K0) p.C[(int64_t)nn * p.ldc + k] = s;
+    else if (k == KMAX && p.dbias != nullptr) p.dbias[nn] = s;
+  }
+}
+
+void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax, cudaStream_t st) {
+  auto smem = [&](int k, int nc) { return ((size_t)B * k + 4 * 64 * nc * (k + 1)) * sizeof(float); };
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(first_wgrad_kernel<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(first_wgrad_kernel<40, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(first_wgrad_kernel<72, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  if (kmax <= 24) first_wgrad_kernel<24, 2><<<dim3(nprob, (H + 127) / 128), 256, smem(24, 2), st>>>(probs);
+  else if (kmax <= 40) first_wgrad_kernel<40, 2><<<dim3(nprob, (H + 127) / 128), 256, smem(40, 2), st>>>(probs);
+  else first_wgrad_kernel<72, 1><<<dim3(nprob, (H + 63) / 64), 256, smem(72, 1), st>>>(probs);
+}
+
+}  // namespace iql

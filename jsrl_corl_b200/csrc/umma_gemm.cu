@@ -11,9 +11,9 @@
 // 128B-swizzled shared-memory tiles (32 K-elements = 128 B per row), the MMA
 // is issued by one elected thread (tcgen05.mma.cta_group::1.kind::tf32, FP32
 // accumulate in TMEM), completion is tracked with tcgen05.commit -> mbarrier,
-// and four epilogue warps read the accumulators with tcgen05.ld, transpose
-// through shared memory and apply the fused epilogue with coalesced global
-// accesses (bias+ReLU(+dropout) / ReLU-mask / plain store).
+// and eight epilogue warps read the accumulators with tcgen05.ld, transpose
+// through shared memory and apply the fused epilogue with coalesced 16-byte
+// global accesses (bias+ReLU(+dropout) / ReLU-mask / plain store).
 //
 // Shared-memory / descriptor conventions (cute/atom/mma_traits_sm100.hpp):
 //   K-major  : rows of 128 B, SWIZZLE_128B (16 B atoms), SBO = 1024 B between
@@ -35,7 +35,7 @@ constexpr int STAGE_A_BYTES = TILE_M * TILE_K * 4;  // 32 KB
 constexpr int STAGE_B_BYTES = TILE_N * TILE_K * 4;  // 32 KB
 constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
 constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int N_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int N_THREADS = 320;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-9 epilogue (2 per TMEM lane quarter)
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -197,59 +197,79 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
       umma_commit(tfull);  // accumulators complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a quarter and split the columns.
+    const int q = warp & 3;
+    const int ch = (warp - 2) >> 2;  // column half handled by this warp
     mbar_wait(tfull, 0);
     tc_fence_after();
     // all MMAs are complete, so the operand ring is free: use it as the transpose staging area
-    float* stg = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);
     const MemberScalars* sc = ctx.scalars + p.member;
     float dscale = 1.0f;
-    bool philox_drop = false;
+    bool drop = false;
     uint64_t dstep = 0;
     if (EPI == EPI_DRELU) dscale = (p.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
     if (EPI == EPI_RELU) {
-      philox_drop = p.drop_layer >= 0 && sc->drop_threshold != 0u;
-      if (philox_drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
+      drop = p.drop_layer >= 0 && sc->drop_threshold != 0u;
+      if (drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
     }
+    const int lr = lane >> 3;        // row within a group of 4
+    const int lc = (lane & 7) * 4;   // first of this lane's 4 columns
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int row_base = m0 + h * 128 + q * 32;
 #pragma unroll 1
-      for (int c = 0; c < TILE_N / 32; ++c) {
+      for (int cc = 0; cc < TILE_N / 64; ++cc) {
+        const int c = ch * (TILE_N / 64) + cc;
+        const int col = n0 + c * 32 + lc;
+        float4 mk[8];
+        if (EPI == EPI_DRELU) {  // issue the activation-mask loads before waiting on TMEM
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            mk[i] = __ldg(reinterpret_cast<const float4*>(p.mask + (int64_t)(row_base + i * 4 + lr) * p.ldmask + col));
+        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == EPI_RELU || EPI == EPI_LINEAR) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + c * 32), r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(&stg[lane * 36 + 4 * j]) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
         __syncwarp();
-        const int col = n0 + c * 32 + lane;
-        float bias = 0.f;
-        if (EPI == EPI_RELU || EPI == EPI_LINEAR) bias = p.bias[col];
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int row = row_base + rr;
-          float v = stg[rr * 33 + lane];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + lr;
+          const int row = row_base + rl;
+          float4 v = *reinterpret_cast<const float4*>(&stg[rl * 36 + lc]);
           if (EPI == EPI_RELU) {
-            v = fmaxf(v + bias, 0.f);
-            if (philox_drop) {
+            v.x = fmaxf(v.x + b4.x, 0.f); v.y = fmaxf(v.y + b4.y, 0.f);
+            v.z = fmaxf(v.z + b4.z, 0.f); v.w = fmaxf(v.w + b4.w, 0.f);
+            if (drop) {
               if (ctx.dropout_masks) {
-                const uint8_t* mk = ctx.dropout_masks +
-                                    ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H;
-                v = mk[col] ? v * sc->drop_scale : 0.f;
+                const uint8_t* mkb = ctx.dropout_masks +
+                                     ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H + col;
+                v.x = mkb[0] ? v.x * sc->drop_scale : 0.f; v.y = mkb[1] ? v.y * sc->drop_scale : 0.f;
+                v.z = mkb[2] ? v.z * sc->drop_scale : 0.f; v.w = mkb[3] ? v.w * sc->drop_scale : 0.f;
               } else {
-                const int64_t e = (int64_t)row * p.N + col;
-                const Philox4 ph = philox_dropout_quad(sc->seed, dstep, (uint32_t)p.drop_layer, (uint32_t)(e >> 2));
-                const uint32_t wsel = (e & 3) == 0 ? ph.x : (e & 3) == 1 ? ph.y : (e & 3) == 2 ? ph.z : ph.w;
-                v = (wsel >= sc->drop_threshold) ? v * sc->drop_scale : 0.f;
+                const uint32_t quad = (uint32_t)(((int64_t)row * p.N + col) >> 2);
+                const Philox4 ph = philox_dropout_quad(sc->seed, dstep, (uint32_t)p.drop_layer, quad);
+                v.x = (ph.x >= sc->drop_threshold) ? v.x * sc->drop_scale : 0.f;
+                v.y = (ph.y >= sc->drop_threshold) ? v.y * sc->drop_scale : 0.f;
+                v.z = (ph.z >= sc->drop_threshold) ? v.z * sc->drop_scale : 0.f;
+                v.w = (ph.w >= sc->drop_threshold) ? v.w * sc->drop_scale : 0.f;
               }
             }
           } else if (EPI == EPI_LINEAR) {
-            v += bias;
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           } else if (EPI == EPI_DRELU) {
-            v = (p.mask[(int64_t)row * p.ldmask + col] > 0.f) ? v * dscale : 0.f;
+            v.x = mk[i].x > 0.f ? v.x * dscale : 0.f; v.y = mk[i].y > 0.f ? v.y * dscale : 0.f;
+            v.z = mk[i].z > 0.f ? v.z * dscale : 0.f; v.w = mk[i].w > 0.f ? v.w * dscale : 0.f;
           }
-          p.C[(int64_t)row * p.ldc + col] = v;
+          *reinterpret_cast<float4*>(p.C + (int64_t)row * p.ldc + col) = v;
         }
         __syncwarp();
       }
