@@ -116,7 +116,7 @@ typedef struct iql_tensor_info {
   int32_t layer; /* Linear index 0..n_hidden */
   int32_t kind;  /* IQL_KIND_* */
   int32_t rows, cols; /* weight [rows, cols]; bias/log_std [rows], cols = 1 */
-  int32_t reserved;
+  int32_t ld;         /* row stride in floats (>= cols, multiple of 4 so that every row is 16-byte aligned for TMA) */
   int64_t offset; /* float offset inside the member block */
 } iql_tensor_info;
 
@@ -187,7 +187,8 @@ int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float
             float* out_actions, void* stream);
 /* Self-test hook for the tcgen05 TF32 GEMM building block (no reference
  * counterpart): C[M,N] = op(A) op(B), mode 0 NT (A[M,K], B[N,K]), 1 NN (A[M,K],
- * B[K,N]), 2 TN (A[K,M], B[K,N]); M, N multiples of 256, K multiple of 32;
+ * B[K,N]), 2 TN (A[K,M], B[K,N]); M multiple of 256, N <= 256 or a multiple of
+ * 256, any K (TMA zero-fills tails), lda/ldb multiples of 4;
  * scratch: >= 1024 B of 128-byte aligned device memory. */
 int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
                            const float* B, int32_t ldb, float* C, int32_t ldc, void* scratch,

@@ -69,7 +69,7 @@ class Layout(C.Structure):
 class TensorInfo(C.Structure):
     _fields_ = [
         ("net", C.c_int32), ("layer", C.c_int32), ("kind", C.c_int32),
-        ("rows", C.c_int32), ("cols", C.c_int32), ("reserved", C.c_int32),
+        ("rows", C.c_int32), ("cols", C.c_int32), ("ld", C.c_int32),
         ("offset", C.c_int64),
     ]
 

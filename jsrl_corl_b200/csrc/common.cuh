@@ -78,6 +78,19 @@ __host__ __device__ __forceinline__ uint32_t dropout_threshold(double p) {
   return (uint32_t)t;
 }
 
+// Round-to-nearest TF32 (10-bit mantissa).  tcgen05 kind::tf32 TRUNCATES the low 13 mantissa bits of its fp32
+// operands, a systematic shrink of ~1e-3 per GEMM; operands that were rounded to nearest beforehand pass through
+// the truncation unchanged, which turns the bias into zero-mean rounding noise.
+__device__ __forceinline__ float round_tf32(float x) {
+#ifdef __CUDA_ARCH__
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+#else
+  return x;
+#endif
+}
+
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 }  // namespace iql

@@ -39,6 +39,7 @@ struct iql_engine {
   WorkspaceLayout wl;
   std::vector<iql_tensor_info> tensors;
   int64_t w_off[4][16], b_off[4][16];
+  int w_ld[4][16];
   int64_t log_std_off = 0;
   // bound device memory
   float *params = nullptr, *exp_avg = nullptr, *exp_avg_sq = nullptr, *target = nullptr, *grads = nullptr;
@@ -53,6 +54,8 @@ struct iql_engine {
   std::vector<char> h_maps;
   int64_t* d_act_off = nullptr;  // [2][L+1]
   float* d_loss_ring = nullptr;
+  float* d_wshadow = nullptr;    // [S][P]  TF32-rounded params  (tcgen05 mode)
+  float* d_tshadow = nullptr;    // [S][PQ] TF32-rounded target
   float* d_ws_f = nullptr;       // activation area
   int64_t tables_bytes = 0;
   // host shadows
@@ -101,8 +104,11 @@ static void build_layout(iql_engine* e) {
     iql_tensor_info t;
     memset(&t, 0, sizeof(t));
     t.net = net; t.layer = layer; t.kind = kind; t.rows = rows; t.cols = cols; t.offset = off;
+    // weight rows are padded to a multiple of 4 floats: 16-byte aligned rows are what TMA needs to
+    // stream the first-layer weights (K = 11..69) into the tcgen05 pipeline; padding stays zero
+    t.ld = (kind == IQL_KIND_WEIGHT) ? (int)round_up(cols, 4) : 1;
     e->tensors.push_back(t);
-    off = round_up(off + (int64_t)rows * cols, 32);  // every tensor starts 128-byte aligned
+    off = round_up(off + (int64_t)rows * t.ld, 32);  // every tensor starts 128-byte aligned
     return t.offset;
   };
   // order == reference optimizer parameter order: qf.parameters() = q1 then q2 (iql.py:422-423),
@@ -118,6 +124,7 @@ static void build_layout(iql_engine* e) {
       const int in = (l == 0) ? net_in_dim(c, net) : H;
       const int out = (l == L) ? net_out_dim(c, net) : H;
       e->w_off[net][l] = add(net, l, IQL_KIND_WEIGHT, out, in);
+      e->w_ld[net][l] = (int)round_up(in, 4);
       e->b_off[net][l] = add(net, l, IQL_KIND_BIAS, out, 1);
     }
   }
@@ -152,6 +159,10 @@ static void build_layout(iql_engine* e) {
   tab(128 * 2 * nprob);
   tab(sizeof(int64_t) * 2 * (L + 1));
   tab(sizeof(float) * 3 * (int64_t)S * c.max_steps_per_call);
+  if (c.math_mode == IQL_MATH_TF32_TCGEN05) {
+    tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
+    tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
+  }
   e->tables_bytes = tb;
   e->layout.workspace_bytes = tb + (int64_t)S * wl.member_floats * (int64_t)sizeof(float);
 }
@@ -170,6 +181,7 @@ extern "C" int iql_create(const iql_config* cfg, iql_engine** out) {
   memset(&e->layout, 0, sizeof(e->layout));
   memset(e->w_off, 0, sizeof(e->w_off));
   memset(e->b_off, 0, sizeof(e->b_off));
+  memset(e->w_ld, 0, sizeof(e->w_ld));
   build_layout(e);
   const int S = cfg->n_members;
   e->h_scalars.resize(S);
@@ -255,6 +267,7 @@ static void build_problems(iql_engine* e) {
   const int ROW = e->layout.row.row_floats;
   const WorkspaceLayout& wl = e->wl;
   const int64_t P = e->layout.param_floats, PQ = e->layout.q_floats;
+  const bool use_shadow = c.math_mode == IQL_MATH_TF32_TCGEN05 && umma_phase_supported(0, B, H);
   e->h_probs.clear();
   e->fwd_phases.clear();
   e->bwd_phases.clear();
@@ -284,11 +297,15 @@ static void build_problems(iql_engine* e) {
         if (l == 0) { p.A = wsm(m) + wl.xrow + pd.in_off; p.lda = ROW; p.K = pd.k0; }
         else { p.A = actp(m, f, l - 1); p.lda = H; p.K = H; }
         p.B = blk + e->w_off[pd.net][l];
-        p.ldb = p.K;
+        if (use_shadow && l >= 1 && l < L)  // hidden-layer weights feed tcgen05: use the TF32-rounded copy
+          p.B = (pd.tgt ? e->d_tshadow + (int64_t)m * PQ : e->d_wshadow + (int64_t)m * P) + e->w_off[pd.net][l];
+        p.ldb = e->w_ld[pd.net][l];
         p.bias = blk + e->b_off[pd.net][l];
         if (l < L) {
           p.N = H; p.C = actp(m, f, l); p.ldc = H; p.epi = EPI_RELU;
           p.drop_layer = (f == PASS_PI) ? l : -1;
+          // H_L of the forward-only passes (V(s'), target Q) is consumed only by the fused output Linear
+          p.no_store = (l == L - 1 && (f == PASS_V_NEXT || f == PASS_TQ1 || f == PASS_TQ2)) ? 1 : 0;
         } else if (f == PASS_PI) {
           p.N = c.action_dim; p.C = wsm(m) + wl.zpi; p.ldc = wl.Ald; p.epi = EPI_LINEAR;
         } else {
@@ -299,7 +316,7 @@ static void build_problems(iql_engine* e) {
       }
     ph.count = (int)e->h_probs.size() - ph.first;
     ph.K = (l >= 1) ? H : 0;
-    ph.umma_ok = (l >= 1 && l < L);
+    ph.umma_ok = true;  // every forward layer has a tcgen05 form (K tails / N < 32 are zero-filled by TMA)
     ph.epi = (l < L) ? EPI_RELU : EPI_LINEAR;
     ph.kind = (l == 0) ? PH_FIRST_FWD : (l == L ? PH_OUT_FWD : PH_GENERIC);
     e->fwd_phases.push_back(ph);
@@ -310,7 +327,7 @@ static void build_problems(iql_engine* e) {
   auto ghp = [&](int m, int t, int which) { return wsm(m) + wl.gh + ((int64_t)(t * 2 + which)) * B * H; };
   for (int l = L; l >= 0; --l) {
     // weight gradient  dW_l = G_l^T H_l   (TN)
-    Phase pw; pw.mode = 2; pw.first = (int)e->h_probs.size(); pw.maxM = 0; pw.maxN = 0; pw.K = B; pw.umma_ok = (l >= 1 && l < L);
+    Phase pw; pw.mode = 2; pw.first = (int)e->h_probs.size(); pw.maxM = 0; pw.maxN = 0; pw.K = B; pw.umma_ok = (l < L);
     pw.epi = EPI_NONE;
     pw.kind = (l == L) ? PH_LAST_WGRAD : (l == 0 ? PH_FIRST_WGRAD : PH_GENERIC);
     for (int m = 0; m < S; ++m)
@@ -327,7 +344,7 @@ static void build_problems(iql_engine* e) {
         if (l == 0) { p.B = wsm(m) + wl.xrow + pd.in_off; p.ldb = ROW; p.N = pd.k0; }
         else { p.B = actp(m, f, l - 1); p.ldb = H; p.N = H; }
         p.C = e->grads + (int64_t)m * P + e->w_off[net][l];
-        p.ldc = p.N;
+        p.ldc = e->w_ld[net][l];
         p.dbias = e->grads + (int64_t)m * P + e->b_off[net][l];
         p.epi = EPI_NONE;
         if (p.M > pw.maxM) pw.maxM = p.M;
@@ -351,8 +368,8 @@ static void build_problems(iql_engine* e) {
           if (t == 3) { p.A = wsm(m) + wl.gpi; p.lda = wl.Ald; p.K = c.action_dim; }
           else { p.A = wsm(m) + wl.gy + (int64_t)t * B; p.lda = 1; p.K = 1; }
         } else { p.A = ghp(m, t, (L - 1 - l) & 1); p.lda = H; p.K = H; }
-        p.B = e->params + (int64_t)m * P + e->w_off[net][l];
-        p.ldb = H;
+        p.B = ((use_shadow && l < L) ? e->d_wshadow : e->params) + (int64_t)m * P + e->w_off[net][l];
+        p.ldb = e->w_ld[net][l];
         p.C = ghp(m, t, (L - l) & 1);
         p.ldc = H;
         p.mask = actp(m, f, l - 1);
@@ -388,6 +405,10 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   e->d_maps = tab(128 * 2 * nprob);
   e->d_act_off = (int64_t*)tab(sizeof(int64_t) * 2 * (L + 1));
   e->d_loss_ring = (float*)tab(sizeof(float) * 3 * (int64_t)S * e->cfg.max_steps_per_call);
+  if (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) {
+    e->d_wshadow = (float*)tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
+    e->d_tshadow = (float*)tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
+  }
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
   if ((int64_t)e->h_probs.size() != nprob) return fail(e, IQL_ERR_STATE, "internal: problem count mismatch");
@@ -395,7 +416,8 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   if (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) {
     auto encode = [&](const Phase& ph) {
       if (!ph.umma_ok || !umma_phase_supported(ph.mode, e->cfg.batch_size, e->cfg.hidden_dim)) return 0;
-      return umma_encode_maps(ph.mode, e->h_probs.data() + ph.first, ph.count, e->h_maps.data() + (size_t)256 * ph.first);
+      return umma_encode_maps(ph.mode, e->h_probs.data() + ph.first, ph.count, umma_tile_n(ph.maxN),
+                              e->h_maps.data() + (size_t)256 * ph.first);
     };
     for (const Phase& ph : e->fwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (forward phase)");
     for (const Phase& ph : e->bwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward phase)");
@@ -451,6 +473,9 @@ static StepCtx make_ctx(const iql_engine* e) {
   c.scalars = e->d_scalars; c.counters = e->d_counters; c.replay = e->d_replay;
   c.loss_ring = e->d_loss_ring;
   c.k_max = e->cfg.max_steps_per_call;
+  c.tf32 = (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) && umma_phase_supported(0, e->cfg.batch_size, e->cfg.hidden_dim);
+  c.w_shadow = e->d_wshadow;
+  c.t_shadow = e->d_tshadow;
   return c;
 }
 
@@ -511,31 +536,47 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   auto run_phase = [&](const Phase& ph, const Phase* next, const Phase* next2) {
     if (skip_next) { skip_next = false; return; }
     const GemmProb* pp = e->d_probs + ph.first;
-    if (ph.kind == PH_FIRST_FWD && first_ok) {
+    // Mixed precision: the input layer (observations, K = 11..69) and the output heads run in FP32 on CUDA
+    // cores; every hidden-layer GEMM and the first-layer weight gradient run as TF32 tcgen05 GEMMs.  TF32 on the
+    // input layer doubles the value-loss error (measured 1.2e-3 -> 2.6e-3) for < 10 % of the step time.
+    static const bool tf32_first = getenv("IQL_B200_TF32_FIRST") != nullptr;
+    const bool umma = tf32 && ph.umma_ok && umma_phase_supported(ph.mode, B, H) &&
+                      !(ph.kind == PH_FIRST_FWD && !tf32_first && first_ok);
+    if (umma && ph.kind == PH_OUT_FWD) {
+      // the heads stay in FP32: TF32 rounding of Q and V would be amplified by adv = q - v and exp(beta * adv)
+      if (out_ok) launch_out_fwd(pp, ph.count, B, H, A, st);
+      else launch_simt_gemm(ph.mode, pp, ph.count, ph.maxM, ph.maxN, ctx, st);
+    } else if (umma && ph.kind != PH_LAST_WGRAD) {
+      // forward, last hidden layer: fuse the FP32 output Linear into the epilogue and skip the next phase
+      const bool fuse = ph.mode == 0 && ph.epi == EPI_RELU && next && next->kind == PH_OUT_FWD && H == 256 &&
+                        umma_can_fuse_out(A);
+      launch_umma_gemm(ph.mode, pp, e->d_maps + (size_t)256 * ph.first, fuse ? e->d_probs + next->first : nullptr,
+                       ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st);
+      if (fuse) skip_next = true;
+      if (ph.mode == 2) {
+        if (skip_colsum) skip_colsum = false;  // db already written by the fused output-layer backward
+        else { launch_colsum(pp, ph.count, ph.maxM, st); ++launches; }
+      }
+    } else if (ph.kind == PH_FIRST_FWD && first_ok) {
       launch_first_fwd(pp, ph.count, B, H, K0, ctx, st);
     } else if (ph.kind == PH_OUT_FWD && out_ok) {
       launch_out_fwd(pp, ph.count, B, H, A, st);
     } else if (ph.kind == PH_LAST_WGRAD && last_ok && next && next->kind == PH_LAST_DGRAD) {
       // fused wgrad + dgrad of the output layer; it also emits db_{L-1} when layer L-1 is a hidden-layer
       // tcgen05 wgrad phase (whose kernel does not produce bias gradients)
-      const bool emit_db = next2 && next2->kind == PH_GENERIC && tf32 && next2->umma_ok && umma_phase_supported(2, B, H);
+      const bool emit_db = next2 && tf32 && next2->umma_ok && umma_phase_supported(2, B, H);
       launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st);
       skip_next = true;
       skip_colsum = emit_db;
     } else if (ph.kind == PH_FIRST_WGRAD && first_wgrad_ok) {
       launch_first_wgrad(pp, ph.count, B, H, K0, st);
-    } else if (tf32 && ph.umma_ok && umma_phase_supported(ph.mode, B, H)) {
-      launch_umma_gemm(ph.mode, pp, e->d_maps + (size_t)256 * ph.first, ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st);
-      if (ph.mode == 2) {
-        if (skip_colsum) skip_colsum = false;  // db already written by the fused output-layer backward
-        else { launch_colsum(pp, ph.count, ph.maxM, st); ++launches; }
-      }
     } else {
       launch_simt_gemm(ph.mode, pp, ph.count, ph.maxM, ph.maxN, ctx, st);
     }
     ++launches;
   };
-  for (const Phase& ph : e->fwd_phases) run_phase(ph, nullptr, nullptr);
+  for (size_t i = 0; i < e->fwd_phases.size(); ++i)
+    run_phase(e->fwd_phases[i], i + 1 < e->fwd_phases.size() ? &e->fwd_phases[i + 1] : nullptr, nullptr);
   launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, st);
   ++launches;
   for (size_t i = 0; i < e->bwd_phases.size(); ++i)
@@ -573,6 +614,7 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
 
   StepCtx ctx = make_ctx(e);
   ctx.K = k_steps;
+  if (ctx.tf32) launch_refresh_shadow(ctx, e->params, e->target, st);
   ctx.indices = (sample_mode == IQL_SAMPLE_INDICES) ? indices : nullptr;
   ctx.dropout_masks = dropout_masks;
   ctx.idx_out = idx_out;
@@ -642,8 +684,9 @@ extern "C" int iql_act(iql_engine* e, int32_t member, const float* states, int64
 extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
                                       const float* B, int32_t ldb, float* C, int32_t ldc, void* scratch,
                                       size_t scratch_bytes, void* stream) {
-  if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0 || (M % 256) || (N % 256) || (K % 32))
-    return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: M, N multiples of 256 and K multiple of 32 required");
+  if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0 || (M % 256) || (N > 256 && (N % 256)))
+    return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: M multiple of 256 and N <= 256 or a multiple of 256 required");
+  if ((lda & 3) || (ldb & 3)) return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: lda, ldb must be multiples of 4 (TMA row alignment)");
   if (!A || !B || !C || !scratch || scratch_bytes < 1024 || ((uintptr_t)scratch & 127))
     return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: null pointer or scratch < 1024 B / unaligned");
   GemmProb p;
@@ -651,7 +694,7 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.epi = EPI_NONE; p.drop_layer = -1;
   alignas(64) char maps[256];
-  if (umma_encode_maps(mode, &p, 1, maps)) return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: cuTensorMapEncodeTiled failed");
+  if (umma_encode_maps(mode, &p, 1, umma_tile_n(N), maps)) return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: cuTensorMapEncodeTiled failed");
   cudaStream_t st = (cudaStream_t)stream;
   char* d = (char*)scratch;
   if (cudaMemcpyAsync(d, maps, 256, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -660,7 +703,7 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
     return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: upload failed");
   StepCtx ctx;
   memset(&ctx, 0, sizeof(ctx));
-  launch_umma_gemm(mode, (const GemmProb*)(d + 256), d, EPI_NONE, 1, M, N, ctx, st);
+  launch_umma_gemm(mode, (const GemmProb*)(d + 256), d, nullptr, EPI_NONE, 1, M, N, ctx, st);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(nullptr, IQL_ERR_CUDA, std::string("iql_selftest_umma_gemm: ") + cudaGetErrorString(err));
   return IQL_OK;

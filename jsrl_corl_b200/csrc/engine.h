@@ -32,7 +32,7 @@ struct GemmProb {
   int epi;
   int member;
   int drop_layer;      // >= 0: hidden-layer index whose dropout applies (actor only)
-  int pad0;
+  int no_store;        // 1: C is consumed only by a fused follow-up (forward-only passes), skip the store
 };
 
 // Per-member scalars derived on the host the way torch derives them
@@ -80,6 +80,9 @@ struct StepCtx {
   int64_t* idx_out;              // [S][K][B] or null
   float* loss_ring;              // [S][Kmax][3]
   int k_max;
+  int tf32;                      // 1: tcgen05 path; producers round GEMM operands to nearest TF32
+  float* w_shadow;               // [S][P]  TF32-rounded copy of params (tcgen05 B operands), tf32 mode only
+  float* t_shadow;               // [S][PQ] TF32-rounded copy of the target network
 };
 
 struct TensorDesc {
@@ -111,6 +114,7 @@ void launch_loss(const StepCtx& ctx, float* ws, int64_t ws_member_floats, const 
 void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_avg_sq, float* target,
                  const float* grads, cudaStream_t st);
 void launch_advance(const StepCtx& ctx, int K, cudaStream_t st);
+void launch_refresh_shadow(const StepCtx& ctx, const float* params, const float* target, cudaStream_t st);
 void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float* s, const float* a, const float* r,
                        const float* s2, const float* d, cudaStream_t st);
 // skinny-layer kernels (kernels_skinny.cu)

@@ -406,6 +406,9 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
     p[j] = fmaf(as.neg_step_size, __fdiv_rn(mm[j], denom), p[j]);         // addcdiv_
   }
   *reinterpret_cast<float4*>(params + off) = make_float4(p[0], p[1], p[2], p[3]);
+  if (ctx.tf32)
+    *reinterpret_cast<float4*>(ctx.w_shadow + off) =
+        make_float4(round_tf32(p[0]), round_tf32(p[1]), round_tf32(p[2]), round_tf32(p[3]));
   *reinterpret_cast<float4*>(exp_avg + off) = make_float4(mm[0], mm[1], mm[2], mm[3]);
   *reinterpret_cast<float4*>(exp_avg_sq + off) = make_float4(vv[0], vv[1], vv[2], vv[3]);
   if (opt == 0) {
@@ -416,7 +419,33 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
 #pragma unroll
     for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(sc.one_minus_tau, t[j]), __fmul_rn(sc.tau, p[j]));
     *reinterpret_cast<float4*>(target + toff) = make_float4(t[0], t[1], t[2], t[3]);
+    if (ctx.tf32)
+      *reinterpret_cast<float4*>(ctx.t_shadow + toff) =
+          make_float4(round_tf32(t[0]), round_tf32(t[1]), round_tf32(t[2]), round_tf32(t[3]));
   }
+}
+
+// TF32-rounded operand copies of params / target, rebuilt at the start of every engine call so that weights
+// written from outside (checkpoint loads, parameter surgery through the torch views) are always picked up.
+__global__ void __launch_bounds__(256) refresh_shadow_kernel(StepCtx ctx, const float* __restrict__ params,
+                                                             const float* __restrict__ target) {
+  const int m = blockIdx.y;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i < ctx.P) {
+    const float4 v = *reinterpret_cast<const float4*>(params + m * ctx.P + i);
+    *reinterpret_cast<float4*>(ctx.w_shadow + m * ctx.P + i) =
+        make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+  }
+  if (i < ctx.PQ) {
+    const float4 v = *reinterpret_cast<const float4*>(target + m * ctx.PQ + i);
+    *reinterpret_cast<float4*>(ctx.t_shadow + m * ctx.PQ + i) =
+        make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+  }
+}
+
+void launch_refresh_shadow(const StepCtx& ctx, const float* params, const float* target, cudaStream_t st) {
+  dim3 grid((unsigned)((ctx.P / 4 + 255) / 256), ctx.n_members);
+  refresh_shadow_kernel<<<grid, 256, 0, st>>>(ctx, params, target);
 }
 
 void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_avg_sq, float* target,
@@ -466,7 +495,8 @@ __global__ void __launch_bounds__(256) act_kernel(int S, int A, int H, int L, co
     const float* bias = block + b_off[l];
     for (int j = warp; j < out_dim; j += nwarp) {
       float acc = 0.f;
-      for (int k = lane; k < in_dim; k += 32) acc = fmaf(W[(int64_t)j * in_dim + k], cur[k], acc);
+      const int ldw = (in_dim + 3) & ~3;  // weight rows are padded to a multiple of 4 floats
+      for (int k = lane; k < in_dim; k += 32) acc = fmaf(W[(int64_t)j * ldw + k], cur[k], acc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) {

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(const GemmProb* __restri
         v = (ws >= sc->drop_threshold) ? v * sc->drop_scale : 0.f;
       }
     }
-    p.C[(int64_t)row * p.ldc + n] = v;
+    p.C[(int64_t)row * p.ldc + n] = ctx.tf32 ? round_tf32(v) : v;  // A operand of the next (tcgen05) layer
   }
 }
 
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(const GemmProb* __restric
         d0 = fmaf(g, h, d0);
         const float o = (h > 0.f) ? (g * w0) * dscale : 0.f;
         csum += o;
-        pn.C[(int64_t)b * pn.ldc + n] = o;
+        pn.C[(int64_t)b * pn.ldc + n] = ctx.tf32 ? round_tf32(o) : o;
       }
       dw[0] = d0;
     } else {
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(const GemmProb* __restric
         }
         const float o = (h > 0.f) ? gsum * dscale : 0.f;
         csum += o;
-        pn.C[(int64_t)b * pn.ldc + n] = o;
+        pn.C[(int64_t)b * pn.ldc + n] = ctx.tf32 ? round_tf32(o) : o;
       }
     }
   }

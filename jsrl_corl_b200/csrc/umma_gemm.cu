@@ -30,7 +30,7 @@
 
 namespace iql {
 
-constexpr int TILE_M = 256, TILE_N = 256, TILE_K = 32, UMMA_K = 8, N_STAGES = 3;
+constexpr int TILE_M = 256, TILE_N = 256 /* maximum; the N tile is a launch parameter */, TILE_K = 32, UMMA_K = 8, N_STAGES = 3;
 constexpr int STAGE_A_BYTES = TILE_M * TILE_K * 4;  // 32 KB
 constexpr int STAGE_B_BYTES = TILE_N * TILE_K * 4;  // 32 KB
 constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
@@ -116,11 +116,17 @@ struct UmmaParams {
   uint32_t b_lbo, b_sbo, b_layout, b_kstep;
   uint32_t idesc;
   int a_mn, b_mn;  // operand majors (0 K-major, 1 MN-major)
+  int tile_n;      // UMMA N of this launch: multiple of 32, <= 256 (B tile = tile_n * 128 B per stage)
 };
 
-template <int EPI>
+// FUSE_OUT (forward, last hidden layer): the output Linear y = H_L W_L^T + b_L (N = 1 or act_dim <= 8) is
+// evaluated in the epilogue, in FP32, on the FP32 accumulators -- the Q/V/policy heads never see TF32 rounding
+// and H_L makes no extra trip through HBM.  `probs_out` is the problem table of the output-layer phase.
+constexpr int FUSE_AMAX = 8;
+template <int EPI, bool FUSE_OUT>
 __global__ void __launch_bounds__(N_THREADS, 1)
-umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restrict__ maps, UmmaParams up, StepCtx ctx) {
+umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restrict__ maps,
+                 const GemmProb* __restrict__ probs_out, UmmaParams up, StepCtx ctx) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
@@ -132,11 +138,12 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.z;
   const GemmProb p = probs[prob];
-  const int m0 = blockIdx.y * TILE_M, n0 = blockIdx.x * TILE_N;
+  const int tile_n = up.tile_n;
+  const int m0 = blockIdx.y * TILE_M, n0 = blockIdx.x * tile_n;
   if (m0 >= p.M || n0 >= p.N) return;  // uniform per CTA
   const CUtensorMap* mapA = maps + 2 * prob;
   const CUtensorMap* mapB = mapA + 1;
-  const int num_kb = p.K / TILE_K;
+  const int num_kb = (p.K + TILE_K - 1) / TILE_K;  // TMA zero-fills the K tail
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < N_STAGES; ++s) {
@@ -163,7 +170,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
         const uint32_t fb = full0 + 8 * stage;
-        mbar_expect_tx(fb, STAGE_BYTES);
+        mbar_expect_tx(fb, STAGE_A_BYTES + tile_n * TILE_K * 4);
         const int k0 = kb * TILE_K;
         if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
         else tma_load_2d(sa, mapA, fb, k0, m0);
@@ -216,13 +223,25 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     }
     const int lr = lane >> 3;        // row within a group of 4
     const int lc = (lane & 7) * 4;   // first of this lane's 4 columns
+    GemmProb po;
+    int a_out = 0;
+    float* ypart = reinterpret_cast<float*>(smem) + 8 * (32 * 36);  // [2 column halves][256 rows][FUSE_AMAX]
+    if (FUSE_OUT) { po = probs_out[prob]; a_out = po.N; }
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int row_base = m0 + h * 128 + q * 32;
+      float yacc[8][FUSE_AMAX];
+      if (FUSE_OUT) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int m = 0; m < FUSE_AMAX; ++m) yacc[i][m] = 0.f;
+      }
 #pragma unroll 1
-      for (int cc = 0; cc < TILE_N / 64; ++cc) {
-        const int c = ch * (TILE_N / 64) + cc;
+      for (int c = ch; c < (tile_n >> 5); c += 2) {
         const int col = n0 + c * 32 + lc;
+        // full 16-byte accesses when this lane's 4 columns exist and rows are 16-byte aligned
+        const bool vec = (col + 3 < p.N) && ((p.ldc & 3) == 0);
         float4 mk[8];
         if (EPI == EPI_DRELU) {  // issue the activation-mask loads before waiting on TMEM
 #pragma unroll
@@ -230,7 +249,13 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
             mk[i] = __ldg(reinterpret_cast<const float4*>(p.mask + (int64_t)(row_base + i * 4 + lr) * p.ldmask + col));
         }
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EPI == EPI_RELU || EPI == EPI_LINEAR) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (EPI == EPI_RELU) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (EPI == EPI_LINEAR) {  // output layer: N = 1 or act_dim, guarded
+          b4.x = col < p.N ? p.bias[col] : 0.f;
+          b4.y = col + 1 < p.N ? p.bias[col + 1] : 0.f;
+          b4.z = col + 2 < p.N ? p.bias[col + 2] : 0.f;
+          b4.w = col + 3 < p.N ? p.bias[col + 3] : 0.f;
+        }
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + c * 32), r);
         tmem_ld_wait();
@@ -269,10 +294,51 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
             v.x = mk[i].x > 0.f ? v.x * dscale : 0.f; v.y = mk[i].y > 0.f ? v.y * dscale : 0.f;
             v.z = mk[i].z > 0.f ? v.z * dscale : 0.f; v.w = mk[i].w > 0.f ? v.w * dscale : 0.f;
           }
-          *reinterpret_cast<float4*>(p.C + (int64_t)row * p.ldc + col) = v;
+          if (FUSE_OUT) {
+#pragma unroll
+            for (int m = 0; m < FUSE_AMAX; ++m) {
+              if (m < a_out) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(po.B + (int64_t)m * po.ldb + col));
+                yacc[i][m] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, yacc[i][m]))));
+              }
+            }
+            if (p.no_store) continue;
+          }
+          if (EPI == EPI_RELU || EPI == EPI_DRELU) {  // these outputs are operands of later tcgen05 GEMMs
+            v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+          }
+          float* crow = p.C + (int64_t)row * p.ldc + col;
+          if (vec) {
+            *reinterpret_cast<float4*>(crow) = v;
+          } else {
+            if (col < p.N) crow[0] = v.x;
+            if (col + 1 < p.N) crow[1] = v.y;
+            if (col + 2 < p.N) crow[2] = v.z;
+            if (col + 3 < p.N) crow[3] = v.w;
+          }
         }
         __syncwarp();
       }
+      if (FUSE_OUT) {  // reduce the 8 lanes that share a row, park the per-column-half partial sums
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int m = 0; m < FUSE_AMAX; ++m) {
+            if (m < a_out) {
+              float t = yacc[i][m];
+              t += __shfl_xor_sync(0xffffffffu, t, 1);
+              t += __shfl_xor_sync(0xffffffffu, t, 2);
+              t += __shfl_xor_sync(0xffffffffu, t, 4);
+              if ((lane & 7) == 0) ypart[(ch * 256 + h * 128 + q * 32 + i * 4 + lr) * FUSE_AMAX + m] = t;
+            }
+          }
+      }
+    }
+    if (FUSE_OUT) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
+      const int t = threadIdx.x - 64;                  // 0..255 = row of the tile
+      for (int m = 0; m < a_out; ++m)
+        po.C[(int64_t)(m0 + t) * po.ldc + m] = (ypart[t * FUSE_AMAX + m] + ypart[(256 + t) * FUSE_AMAX + m]) + po.bias[m];
     }
   }
   tc_fence_before();
@@ -316,54 +382,62 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 }
 
 bool umma_phase_supported(int mode, int batch, int hidden) {
-  (void)mode;
+  (void)mode;  // every tcgen05 phase has M in {batch, hidden}: both must be multiples of the 256-row tile
   static int disabled = -1;
   if (disabled < 0) disabled = getenv("IQL_B200_NO_UMMA") ? 1 : 0;
   return !disabled && batch == TILE_M && hidden >= 256 && hidden % 256 == 0;
 }
 
-// K-major operand [rows][K] (ld floats): 2-D map {K, rows}, box {32, 256}, SWIZZLE_128B
-static int encode_kmajor(CUtensorMap* out, const float* ptr, int rows, int K, int ld) {
+// K-major operand [rows][K] (ld floats): 2-D map {K, rows}, box {32, box_rows}, SWIZZLE_128B.
+// Rows / K beyond the extents are zero-filled by TMA (K tails, output layers with N = 1 or act_dim).
+static int encode_kmajor(CUtensorMap* out, const float* ptr, int rows, int K, int ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return 1;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {TILE_K, 256};
+  cuuint32_t box[2] = {TILE_K, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
 }
 
-// MN-major operand [K rows][MN] (ld floats): 3-D map {32, K, MN/32}, box {32, 32, 8}, SWIZZLE_128B_ATOM_32B
-static int encode_mnmajor(CUtensorMap* out, const float* ptr, int mn, int K, int ld) {
+// MN-major operand [K rows][MN] (ld floats): 3-D map {32, K, ceil(MN/32)}, box {32, 32, slabs},
+// SWIZZLE_128B_ATOM_32B.  MN < 32 shrinks the inner extent so the missing columns are zero-filled.
+static int encode_mnmajor(CUtensorMap* out, const float* ptr, int mn, int K, int ld, int slabs) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return 1;
-  cuuint64_t gdim[3] = {32, (cuuint64_t)K, (cuuint64_t)(mn / 32)};
+  cuuint64_t gdim[3] = {(cuuint64_t)(mn < 32 ? mn : 32), (cuuint64_t)K, (cuuint64_t)((mn + 31) / 32)};
   cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, 128};
-  cuuint32_t box[3] = {32, TILE_K, 8};
+  cuuint32_t box[3] = {32, TILE_K, (cuuint32_t)slabs};
   cuuint32_t es[3] = {1, 1, 1};
   const CUtensorMapSwizzle sw = (CUtensorMapSwizzle)env_u32("IQL_UMMA_MN_TMA_SWIZZLE", (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS;
 }
 
-int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, void* h_maps_out) {
+int umma_tile_n(int maxN) {
+  const int t = (maxN + 31) / 32 * 32;
+  return t > TILE_N ? TILE_N : t;
+}
+
+int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, void* h_maps_out) {
   CUtensorMap* maps = (CUtensorMap*)h_maps_out;
   for (int i = 0; i < nprob; ++i) {
     const GemmProb& p = h_probs[i];
     int rc;
-    if (mode == 2) rc = encode_mnmajor(&maps[2 * i], p.A, p.M, p.K, p.lda);
-    else rc = encode_kmajor(&maps[2 * i], p.A, p.M, p.K, p.lda);
+    if (mode == 2) rc = encode_mnmajor(&maps[2 * i], p.A, p.M, p.K, p.lda, TILE_M / 32);
+    else rc = encode_kmajor(&maps[2 * i], p.A, p.M, p.K, p.lda, TILE_M);
     if (rc) return rc;
-    if (mode == 0) rc = encode_kmajor(&maps[2 * i + 1], p.B, p.N, p.K, p.ldb);
-    else rc = encode_mnmajor(&maps[2 * i + 1], p.B, p.N, p.K, p.ldb);
+    if (mode == 0) rc = encode_kmajor(&maps[2 * i + 1], p.B, p.N, p.K, p.ldb, tile_n);
+    else rc = encode_mnmajor(&maps[2 * i + 1], p.B, p.N, p.K, p.ldb, tile_n / 32);
     if (rc) return rc;
   }
   return 0;
 }
 
-static UmmaParams make_params(int mode) {
+static UmmaParams make_params(int mode, int tile_n) {
   UmmaParams u;
+  u.tile_n = tile_n;
   const int a_mn = (mode == 2), b_mn = (mode != 0);
   u.a_mn = a_mn;
   u.b_mn = b_mn;
@@ -381,27 +455,32 @@ static UmmaParams make_params(int mode) {
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
   // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
   u.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-            ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   return u;
 }
 
-void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, int epi, int nprob, int maxM, int maxN,
-                      const StepCtx& ctx, cudaStream_t st) {
+bool umma_can_fuse_out(int act_dim) { return act_dim <= FUSE_AMAX && getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
+
+void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_DRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_RELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_DRELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI_LINEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     attr_set = true;
   }
-  const UmmaParams up = make_params(mode);
-  dim3 grid((maxN + TILE_N - 1) / TILE_N, (maxM + TILE_M - 1) / TILE_M, nprob);
+  const int tile_n = umma_tile_n(maxN);
+  const UmmaParams up = make_params(mode, tile_n);
+  dim3 grid((maxN + tile_n - 1) / tile_n, (maxM + TILE_M - 1) / TILE_M, nprob);
   const CUtensorMap* m = (const CUtensorMap*)maps;
-  if (epi == EPI_RELU) umma_gemm_kernel<EPI_RELU><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, up, ctx);
-  else if (epi == EPI_DRELU) umma_gemm_kernel<EPI_DRELU><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, up, ctx);
-  else if (epi == EPI_LINEAR) umma_gemm_kernel<EPI_LINEAR><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, up, ctx);
-  else umma_gemm_kernel<EPI_NONE><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, up, ctx);
+  if (epi == EPI_RELU && probs_out) umma_gemm_kernel<EPI_RELU, true><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, probs_out, up, ctx);
+  else if (epi == EPI_RELU) umma_gemm_kernel<EPI_RELU, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
+  else if (epi == EPI_DRELU) umma_gemm_kernel<EPI_DRELU, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
+  else if (epi == EPI_LINEAR) umma_gemm_kernel<EPI_LINEAR, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
+  else umma_gemm_kernel<EPI_NONE, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
 }
 
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st) {

@@ -8,9 +8,14 @@ namespace iql {
 bool umma_phase_supported(int mode, int batch, int hidden);
 // Encode the two TMA tensor maps (A, B) of every problem into h_maps_out
 // (2 * nprob CUtensorMap, 128 B each).  Returns 0 on success.
-int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, void* h_maps_out);
-void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, int epi, int nprob, int maxM, int maxN,
-                      const StepCtx& ctx, cudaStream_t st);
+// tile_n = umma_tile_n(max N of the phase): the UMMA N / B-tile height used by the launch.
+int umma_tile_n(int maxN);
+int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, void* h_maps_out);
+// probs_out != null (forward, last hidden layer, EPI_RELU): the output-layer problems whose Linear is
+// evaluated in FP32 inside the epilogue (see umma_can_fuse_out).
+bool umma_can_fuse_out(int act_dim);
+void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st);
 // bias gradients of a wgrad phase: dbias[m] = sum_k A[k][m]
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st);
 }  // namespace iql

@@ -44,7 +44,7 @@ def query_layout(n_members, state_dim, action_dim, hidden_dim, n_hidden, batch_s
         for i in range(lay.n_tensors):
             t = TensorInfo()
             _lib.check(L.iql_tensor_at(h, i, C.byref(t)), h)
-            tensors.append((t.net, t.layer, t.kind, t.rows, t.cols, t.offset))
+            tensors.append((t.net, t.layer, t.kind, t.rows, t.cols, t.offset, t.ld))
     finally:
         L.iql_destroy(h)
     return lay, tensors
@@ -144,10 +144,11 @@ class EnsembleEngine:
                 continue
             if limit is not None and t.offset >= limit:
                 continue
-            n = t.rows * t.cols
-            v = block[t.offset:t.offset + n]
             if t.kind == _lib.KIND_WEIGHT:
-                v = v.view(t.rows, t.cols)
+                # rows are padded to a multiple of 4 floats (16-byte aligned rows for TMA); the view hides the padding
+                v = block[t.offset:t.offset + t.rows * t.ld].view(t.rows, t.ld)[:, :t.cols]
+            else:
+                v = block[t.offset:t.offset + t.rows]
             if t.net in (_lib.NET_Q1, _lib.NET_Q2):
                 grp, key = "qf", f"q{1 if t.net == _lib.NET_Q1 else 2}.net.{q_idx[t.layer]}."
             elif t.net == _lib.NET_V:

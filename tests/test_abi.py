@@ -79,13 +79,14 @@ def test_layout_follows_reference_checkpoint_order(S, A, H, L, det, dropout):
     expected = []  # optimizer parameter order == module.parameters() order (log_std first for the Gaussian actor)
     for mod in (q, v, actor):
         expected += [tuple(p.shape) for p in mod.parameters()]
-    got = [(r, c) if kind == _lib.KIND_WEIGHT else (r,) for (_, _, kind, r, c, _) in tensors]
+    got = [(r, c) if kind == _lib.KIND_WEIGHT else (r,) for (_, _, kind, r, c, _, _) in tensors]
+    assert all(ld % 4 == 0 and ld >= c for (_, _, kind, r, c, _, ld) in tensors if kind == _lib.KIND_WEIGHT)
     assert got == expected
     offs = [t[5] for t in tensors]
     assert offs == sorted(offs) and all(o % 32 == 0 for o in offs)  # 128-byte aligned tensors
     assert lay.q_floats == lay.v_begin and lay.v_end == lay.actor_begin and lay.actor_end == lay.param_floats
     n_q = sum(p.numel() for p in q.parameters())
-    assert lay.q_floats >= n_q and lay.q_floats - n_q < 32 * len(list(q.parameters()))
+    assert lay.q_floats >= n_q and lay.q_floats - n_q < (32 + 3 * H) * len(list(q.parameters()))
     # dropout shifts the Sequential indices to 0,3,6 (reference iql.py:329-333)
     idx = linear_indices(L, dropout > 0)
     assert [k for k in actor.state_dict() if k.endswith("weight")] == [f"net.net.{i}.weight" for i in idx]

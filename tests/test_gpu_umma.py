@@ -13,19 +13,22 @@ def _run(mode, M, N, K, seed=0):
     L = _lib.lib()
     g = torch.Generator(device="cuda").manual_seed(seed)
     pad = 8  # exercise leading dimensions larger than the logical width
+    pad_k = pad + (-K) % 4  # leading dimensions must stay multiples of 4 floats (TMA row alignment)
+    pad_m = pad + (-M) % 4
+    pad_n = pad + (-N) % 4
     if mode == 0:
-        A = torch.randn(M, K + pad, device="cuda", generator=g)[:, :K]
-        B = torch.randn(N, K + pad, device="cuda", generator=g)[:, :K]
+        A = torch.randn(M, K + pad_k, device="cuda", generator=g)[:, :K]
+        B = torch.randn(N, K + pad_k, device="cuda", generator=g)[:, :K]
         ref = A.double() @ B.double().T
     elif mode == 1:
-        A = torch.randn(M, K + pad, device="cuda", generator=g)[:, :K]
-        B = torch.randn(K, N + pad, device="cuda", generator=g)[:, :N]
+        A = torch.randn(M, K + pad_k, device="cuda", generator=g)[:, :K]
+        B = torch.randn(K, N + pad_n, device="cuda", generator=g)[:, :N]
         ref = A.double() @ B.double()
     else:
-        A = torch.randn(K, M + pad, device="cuda", generator=g)[:, :M]
-        B = torch.randn(K, N + pad, device="cuda", generator=g)[:, :N]
+        A = torch.randn(K, M + pad_m, device="cuda", generator=g)[:, :M]
+        B = torch.randn(K, N + pad_n, device="cuda", generator=g)[:, :N]
         ref = A.double().T @ B.double()
-    Cout = torch.full((M, N + pad), float("nan"), device="cuda")
+    Cout = torch.full((M, N + 5), float("nan"), device="cuda")
     scratch = torch.zeros(4096, dtype=torch.uint8, device="cuda")
     st = torch.cuda.Stream()
     st.wait_stream(torch.cuda.current_stream())
@@ -34,6 +37,7 @@ def _run(mode, M, N, K, seed=0):
                                       Cout.data_ptr(), Cout.stride(0), scratch.data_ptr(), scratch.numel(), st.cuda_stream)
     _lib.check(rc, None, "iql_selftest_umma_gemm")
     st.synchronize()
+    assert torch.isnan(Cout[:, N:]).all(), "the kernel wrote outside its N columns"
     out = Cout[:, :N].double()
     err = (out - ref).norm() / ref.norm()
     return float(err), out, ref
@@ -47,6 +51,15 @@ def test_umma_gemm_matches_fp32_matmul(mode, shape):
     # TF32 operands (10-bit mantissa), fp32 accumulation: ~5e-4 relative per product, averaged over K
     assert err < 1.5e-3, (mode, shape, err)
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("mode,shape", [(0, (256, 256, 23)), (0, (256, 6, 256)), (0, (256, 1, 256)), (0, (256, 256, 69)),
+                                        (2, (256, 23, 256)), (2, (256, 37, 256)), (2, (256, 69, 256)), (1, (256, 64, 40))])
+def test_umma_gemm_skinny_shapes_and_tails(mode, shape):
+    """First-layer (K = obs dims) and output-layer (N = 1 / act_dim) shapes: TMA zero-fill of K tails and of N < 32."""
+    M, N, K = shape
+    err, out, ref = _run(mode, M, N, K)
+    assert err < 1.5e-3, (mode, shape, err)
 
 
 def test_umma_gemm_rejects_bad_shapes():
