@@ -16,74 +16,82 @@
 namespace iql {
 
 // ---------------------------------------------------------------------------
-// first layer forward.  grid (nprob, ceil(B/64), ceil(H/256)), 256 threads.
-// thread = one output column n; W0[n][:] in registers; X rows broadcast from smem.
+// first layer forward.  grid (nprob, ceil(B/64), ceil(H/(128*NC))), 128 threads.
+// thread = NC output columns; their W0 rows live in registers; X rows are broadcast from smem
+// (one LDS.128 feeds 4*NC FMAs).
 // ---------------------------------------------------------------------------
-template <int KMAX>
-__global__ void __launch_bounds__(256) first_fwd_kernel(const GemmProb* __restrict__ probs, StepCtx ctx) {
+template <int KMAX, int NC>
+__global__ void __launch_bounds__(128) first_fwd_kernel(const GemmProb* __restrict__ probs, StepCtx ctx) {
   constexpr int RT = 64;
   __shared__ __align__(16) float xs[RT][KMAX];
   const GemmProb p = probs[blockIdx.x];
   const int r0 = blockIdx.y * RT;
-  const int n = blockIdx.z * 256 + threadIdx.x;
+  const int nb = blockIdx.z * 128 * NC + threadIdx.x;
   const int K = p.K;
   if (r0 >= p.M) return;
-  for (int i = threadIdx.x; i < RT * KMAX; i += 256) {
+  for (int i = threadIdx.x; i < RT * KMAX; i += 128) {
     const int r = i / KMAX, k = i - r * KMAX;
     float v = 0.f;
     if (r0 + r < p.M && k < K) v = p.A[(int64_t)(r0 + r) * p.lda + k];
     xs[r][k] = v;
   }
-  float w[KMAX];
-  float bias = 0.f;
-  if (n < p.N) {
+  float w[NC][KMAX];
+  float bias[NC];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) w[k] = (k < K) ? p.B[(int64_t)n * p.ldb + k] : 0.f;
-    bias = p.bias[n];
-  } else {
+  for (int c = 0; c < NC; ++c) {
+    const int n = nb + c * 128;
+    bias[c] = (n < p.N) ? p.bias[n] : 0.f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) w[k] = 0.f;
+    for (int k = 0; k < KMAX; ++k) w[c][k] = (n < p.N && k < K) ? p.B[(int64_t)n * p.ldb + k] : 0.f;
   }
   __syncthreads();
-  if (n >= p.N) return;
   const MemberScalars* sc = ctx.scalars + p.member;
   const bool drop = p.drop_layer >= 0 && sc->drop_threshold != 0u;
   uint64_t dstep = 0;
   if (drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
   const int rows = min(RT, p.M - r0);
   for (int r = 0; r < rows; ++r) {
-    float acc = 0.f;
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.f;
 #pragma unroll
     for (int k4 = 0; k4 < KMAX; k4 += 4) {
       const float4 x = *reinterpret_cast<const float4*>(&xs[r][k4]);
-      acc = fmaf(x.x, w[k4], acc);
-      acc = fmaf(x.y, w[k4 + 1], acc);
-      acc = fmaf(x.z, w[k4 + 2], acc);
-      acc = fmaf(x.w, w[k4 + 3], acc);
-    }
-    float v = fmaxf(acc + bias, 0.f);
-    const int row = r0 + r;
-    if (drop) {
-      if (ctx.dropout_masks) {
-        const uint8_t* mk = ctx.dropout_masks +
-                            ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H;
-        v = mk[n] ? v * sc->drop_scale : 0.f;
-      } else {
-        const int64_t e = (int64_t)row * p.N + n;
-        const Philox4 ph = philox_dropout_quad(sc->seed, dstep, (uint32_t)p.drop_layer, (uint32_t)(e >> 2));
-        const uint32_t ws = (e & 3) == 0 ? ph.x : (e & 3) == 1 ? ph.y : (e & 3) == 2 ? ph.z : ph.w;
-        v = (ws >= sc->drop_threshold) ? v * sc->drop_scale : 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        acc[c] = fmaf(x.x, w[c][k4], acc[c]);
+        acc[c] = fmaf(x.y, w[c][k4 + 1], acc[c]);
+        acc[c] = fmaf(x.z, w[c][k4 + 2], acc[c]);
+        acc[c] = fmaf(x.w, w[c][k4 + 3], acc[c]);
       }
     }
-    p.C[(int64_t)row * p.ldc + n] = ctx.tf32 ? round_tf32(v) : v;  // A operand of the next (tcgen05) layer
+    const int row = r0 + r;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int n = nb + c * 128;
+      if (n >= p.N) continue;
+      float v = fmaxf(acc[c] + bias[c], 0.f);
+      if (drop) {
+        if (ctx.dropout_masks) {
+          const uint8_t* mk = ctx.dropout_masks +
+                              ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H;
+          v = mk[n] ? v * sc->drop_scale : 0.f;
+        } else {
+          const int64_t e = (int64_t)row * p.N + n;
+          const Philox4 ph = philox_dropout_quad(sc->seed, dstep, (uint32_t)p.drop_layer, (uint32_t)(e >> 2));
+          const uint32_t ws = (e & 3) == 0 ? ph.x : (e & 3) == 1 ? ph.y : (e & 3) == 2 ? ph.z : ph.w;
+          v = (ws >= sc->drop_threshold) ? v * sc->drop_scale : 0.f;
+        }
+      }
+      p.C[(int64_t)row * p.ldc + n] = ctx.tf32 ? round_tf32(v) : v;  // A operand of the next (tcgen05) layer
+    }
   }
 }
 
 void launch_first_fwd(const GemmProb* probs, int nprob, int B, int H, int kmax, const StepCtx& ctx, cudaStream_t st) {
-  dim3 grid(nprob, (B + 63) / 64, (H + 255) / 256);
-  if (kmax <= 24) first_fwd_kernel<24><<<grid, 256, 0, st>>>(probs, ctx);
-  else if (kmax <= 40) first_fwd_kernel<40><<<grid, 256, 0, st>>>(probs, ctx);
-  else first_fwd_kernel<72><<<grid, 256, 0, st>>>(probs, ctx);
+  if (kmax <= 24) first_fwd_kernel<24, 2><<<dim3(nprob, (B + 63) / 64, (H + 255) / 256), 128, 0, st>>>(probs, ctx);
+  else if (kmax <= 40) first_fwd_kernel<40, 2><<<dim3(nprob, (B + 63) / 64, (H + 255) / 256), 128, 0, st>>>(probs, ctx);
+  else first_fwd_kernel<72, 1><<<dim3(nprob, (B + 63) / 64, (H + 127) / 128), 128, 0, st>>>(probs, ctx);
 }
 
 // ---------------------------------------------------------------------------
@@ -177,32 +185,46 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(const GemmProb* __restric
   const int b_lo = bg * rows_per, b_hi = min(B, b_lo + rows_per);
   float csum = 0.f;  // column sum of the produced G_{L-1} = bias gradient of layer L-1
   if (n < H) {
+    constexpr int RB = 8;  // rows per batch: 8 independent loads in flight per thread
     if (AO == 1) {  // scalar heads (Q, V): uniform per CTA
       const float w0 = w[0];
       float d0 = 0.f;
-#pragma unroll 4
-      for (int b = b_lo; b < b_hi; ++b) {
-        const float h = pn.mask[(int64_t)b * pn.ldmask + n];
-        const float g = gs[b * AMAX];
-        d0 = fmaf(g, h, d0);
-        const float o = (h > 0.f) ? (g * w0) * dscale : 0.f;
-        csum += o;
-        pn.C[(int64_t)b * pn.ldc + n] = ctx.tf32 ? round_tf32(o) : o;
+      for (int b0 = b_lo; b0 < b_hi; b0 += RB) {
+        float hv[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) hv[j] = (b0 + j < b_hi) ? __ldg(pn.mask + (int64_t)(b0 + j) * pn.ldmask + n) : 0.f;
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          if (b0 + j < b_hi) {
+            const float g = gs[(b0 + j) * AMAX];
+            d0 = fmaf(g, hv[j], d0);
+            const float o = (hv[j] > 0.f) ? (g * w0) * dscale : 0.f;
+            csum += o;
+            pn.C[(int64_t)(b0 + j) * pn.ldc + n] = ctx.tf32 ? round_tf32(o) : o;
+          }
+        }
       }
       dw[0] = d0;
     } else {
-      for (int b = b_lo; b < b_hi; ++b) {
-        const float h = pn.mask[(int64_t)b * pn.ldmask + n];
-        float gsum = 0.f;
+      for (int b0 = b_lo; b0 < b_hi; b0 += RB) {
+        float hv[RB];
 #pragma unroll
-        for (int m = 0; m < AMAX; ++m) {
-          const float g = gs[b * AMAX + m];
-          gsum = fmaf(g, w[m], gsum);
-          dw[m] = fmaf(g, h, dw[m]);
+        for (int j = 0; j < RB; ++j) hv[j] = (b0 + j < b_hi) ? __ldg(pn.mask + (int64_t)(b0 + j) * pn.ldmask + n) : 0.f;
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          if (b0 + j < b_hi) {
+            float gsum = 0.f;
+#pragma unroll
+            for (int m = 0; m < AMAX; ++m) {
+              const float g = gs[(b0 + j) * AMAX + m];
+              gsum = fmaf(g, w[m], gsum);
+              dw[m] = fmaf(g, hv[j], dw[m]);
+            }
+            const float o = (hv[j] > 0.f) ? gsum * dscale : 0.f;
+            csum += o;
+            pn.C[(int64_t)(b0 + j) * pn.ldc + n] = ctx.tf32 ? round_tf32(o) : o;
+          }
         }
-        const float o = (h > 0.f) ? gsum * dscale : 0.f;
-        csum += o;
-        pn.C[(int64_t)b * pn.ldc + n] = ctx.tf32 ? round_tf32(o) : o;
       }
     }
   }

@@ -256,6 +256,13 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           b4.z = col + 2 < p.N ? p.bias[col + 2] : 0.f;
           b4.w = col + 3 < p.N ? p.bias[col + 3] : 0.f;
         }
+        float4 w4[FUSE_AMAX];
+        if (FUSE_OUT) {  // this lane's 4 columns of every head row, once per chunk
+#pragma unroll
+          for (int m = 0; m < FUSE_AMAX; ++m)
+            w4[m] = (m < a_out) ? __ldg(reinterpret_cast<const float4*>(po.B + (int64_t)m * po.ldb + col))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + c * 32), r);
         tmem_ld_wait();
@@ -297,10 +304,8 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           if (FUSE_OUT) {
 #pragma unroll
             for (int m = 0; m < FUSE_AMAX; ++m) {
-              if (m < a_out) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(po.B + (int64_t)m * po.ldb + col));
-                yacc[i][m] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, yacc[i][m]))));
-              }
+              if (m < a_out)
+                yacc[i][m] = fmaf(v.x, w4[m].x, fmaf(v.y, w4[m].y, fmaf(v.z, w4[m].z, fmaf(v.w, w4[m].w, yacc[i][m]))));
             }
             if (p.no_store) continue;
           }
