@@ -291,23 +291,44 @@ def run_ours(args, w, rank, world, local_rank):
         ms_e2e = float(t.item())
     e2e_value = world * S_local * inner * e2e_steps / (ms_e2e * 1e-3)
 
+    # per-kernel CUDA-event timing of the step (events on the engine's launch stream), after the timed region
+    kernels = eng.profile_step(reps=5) if rank == 0 else []
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        tf32_peak = measure_tf32_peak(torch, device) if args.math == "tf32" else None
+        tf32_peak = measure_tf32_peak(torch, device) if args.math == "tf32" else 148 * 128 * 2 * 1.965e9 / 1e12
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         fl = flops_per_step(w)
-        achieved_tflops = (S_local * inner * args.steps * fl) / (ms * 1e-3) / 1e12  # per GPU
-        if args.math == "tf32":
-            roof = {"bound": "tensor", "achieved": achieved_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": achieved_tflops / tf32_peak, "traffic": None,
-                    "kernel": "whole fused K-step update (all kernels of the step)",
-                    "peak_source": "cuBLAS TF32 8192^3 measured live (MEASURED_PEAKS.json has no TF32 entry); "
-                                   f"bf16 {peak_src}: {peaks.get('bf16_tflops')}"}
-        else:
-            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-            roof = {"bound": "tensor", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": achieved_tflops / fp32_peak, "traffic": None,
-                    "kernel": "whole fused K-step update, FP32 CUDA-core validation path",
-                    "peak_source": "nominal FP32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz"}
+        achieved_tflops = (S_local * inner * args.steps * fl) / (ms * 1e-3) / 1e12  # per GPU, whole step
+        traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+        traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+        table = []
+        for kq in kernels:
+            t = kq["ms"] * 1e-3
+            tf, gb = kq["flops"] / t / 1e12, kq["bytes"] / t / 1e9
+            bound = "tensor" if kq["flops"] / (tf32_peak * 1e12) > kq["bytes"] / (hbm_peak * 1e9) else "hbm"
+            table.append({"kernel": kq["label"], "us": round(kq["ms"] * 1e3, 2), "bound": bound, "tflops": round(tf, 2),
+                          "gbs": round(gb, 1), "frac": round(tf / tf32_peak if bound == "tensor" else gb / hbm_peak, 4)})
+        step_us = sum(r["us"] for r in table)
+        dom = max(table, key=lambda r: r["us"]) if table else None
+        roof = None
+        if dom is not None:
+            dk = next(kq for kq in kernels if kq["label"] == dom["kernel"])
+            roof = {"bound": dom["bound"], "achieved": dom["tflops"] if dom["bound"] == "tensor" else dom["gbs"],
+                    "peak": tf32_peak if dom["bound"] == "tensor" else hbm_peak,
+                    "unit": "TFLOP/s" if dom["bound"] == "tensor" else "GB/s", "frac": dom["frac"],
+                    "traffic": traffic.get(dom["kernel"]),
+                    "kernel": dom["kernel"], "kernel_us": dom["us"], "kernel_share_of_step": round(dom["us"] / step_us, 3),
+                    "algorithmic_bytes_per_launch": dk["bytes"], "algorithmic_flops_per_launch": dk["flops"],
+                    "peak_source": (f"HBM {peak_src} (MEASURED_PEAKS.json)" if dom["bound"] == "hbm" else
+                                    "cuBLAS TF32 8192^3 measured live (MEASURED_PEAKS.json has no TF32 entry)"),
+                    "how": "CUDA events on the engine's launch stream around every kernel of the step, 5 reps, "
+                           "after the timed region (iql_profile_step)"}
+        step_view = {"step_us_sum_of_kernels": round(step_us, 1),
+                     "whole_step_tflops": round(achieved_tflops, 2), "tf32_peak_tflops": round(tf32_peak, 1),
+                     "whole_step_frac_of_tensor_peak": round(achieved_tflops / tf32_peak, 4),
+                     "whole_step_hbm_gbs": round(sum(kq["bytes"] for kq in kernels) / (step_us * 1e-6) / 1e9, 1) if step_us else None,
+                     "hbm_peak_gbs": hbm_peak, "bf16_peak_tflops": peaks.get("bf16_tflops"), "peak_source": peak_src}
         cpu = None
         if not args.no_cpu_baseline:
             sps, dt, cores = cpu_reference_steps_per_sec(w, args.cpu_steps, 5)
@@ -329,7 +350,9 @@ def run_ours(args, w, rank, world, local_rank):
                     "note": "host-drawn int64 sample indices in, loss scalars out, one sync per bench step"},
             "gpu_launches": launches,
             "roofline": roof,
-            "hbm": {"gather_bytes_per_member_step": gather_bytes_per_step(w), "hbm_peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
+            "step_roofline": step_view,
+            "kernels": table,
+            "hbm": {"gather_bytes_per_member_step": gather_bytes_per_step(w)},
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
             "flop_per_member_step": fl,

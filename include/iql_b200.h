@@ -193,6 +193,12 @@ int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float
 int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
                            const float* B, int32_t ldb, float* C, int32_t ldc, void* scratch,
                            size_t scratch_bytes, void* stream);
+/* Measurement hook (bench.py roofline): run `reps` update steps with CUDA events recorded on `stream`
+ * around every kernel launch of the step.  For launch slot i < *n_slots: avg_ms[i], the algorithmic
+ * FLOPs and bytes of that launch (2MNK; every operand read once, every output written once) and a
+ * 32-byte label at labels + 32*i.  Advances the learners by `reps` steps. */
+int iql_profile_step(iql_engine* e, int32_t reps, int32_t max_slots, int32_t* n_slots, float* avg_ms,
+                     double* flops, double* bytes, char* labels, void* stream);
 /* number of kernel launches issued by the last iql_train_steps call */
 int64_t iql_last_launch_count(const iql_engine* e);
 

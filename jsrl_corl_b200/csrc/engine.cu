@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -20,6 +21,29 @@
 using namespace iql;
 
 static thread_local std::string g_create_error;
+
+// Optional per-launch instrumentation of one update step (iql_profile_step).
+struct StepTimer {
+  std::vector<cudaEvent_t> ev;       // ev[i] recorded BEFORE launch i; one extra at the end
+  std::vector<std::string> label;
+  std::vector<double> flops, bytes;  // algorithmic work of the launch
+  cudaStream_t st = nullptr;
+  void mark(const char* name, double fl, double by) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    label.push_back(name);
+    flops.push_back(fl);
+    bytes.push_back(by);
+  }
+  void finish() {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+  }
+};
 
 struct Phase {
   int mode;      // 0 NT, 1 NN, 2 TN
@@ -518,10 +542,15 @@ extern "C" int iql_load_batch(iql_engine* e, int32_t member, const float* states
 }
 
 // one update step for all members; returns number of launches
-static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t st) {
+static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t st, StepTimer* tm = nullptr) {
   int launches = 0;
   const bool tf32 = e->cfg.math_mode == IQL_MATH_TF32_TCGEN05;
-  if (gather) { launch_gather(ctx, e->d_ws_f, e->wl.member_floats, e->wl.xrow, st); ++launches; }
+  const double S_d = e->cfg.n_members;
+  if (gather) {
+    if (tm) tm->mark("gather", 0, 2.0 * S_d * e->cfg.batch_size * e->layout.row.row_floats * 4);
+    launch_gather(ctx, e->d_ws_f, e->wl.member_floats, e->wl.xrow, st);
+    ++launches;
+  }
   const iql_config& c = e->cfg;
   const int B = c.batch_size, H = c.hidden_dim, A = c.action_dim, K0 = c.state_dim + c.action_dim;
   // the skinny-layer kernels keep one operand in shared memory; fall back to the generic GEMM when it does not fit
@@ -536,6 +565,27 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   auto run_phase = [&](const Phase& ph, const Phase* next, const Phase* next2) {
     if (skip_next) { skip_next = false; return; }
     const GemmProb* pp = e->d_probs + ph.first;
+    if (tm) {  // algorithmic work: 2MNK flops; each operand read once, the output written once
+      double fl = 0, by = 0;
+      auto add = [&](const Phase& q) {
+        for (int i = 0; i < q.count; ++i) {
+          const GemmProb& g = e->h_probs[q.first + i];
+          fl += 2.0 * g.M * g.N * g.K;
+          by += 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (g.no_store ? 0.0 : (double)g.M * g.N) + (g.mask ? (double)g.M * g.N : 0.0));
+        }
+      };
+      add(ph);
+      const bool fuse_next = next && ((ph.kind == PH_LAST_WGRAD && next->kind == PH_LAST_DGRAD) ||
+                                      (next->kind == PH_OUT_FWD && ph.mode == 0 && ph.epi == EPI_RELU && tf32 && H == 256 &&
+                                       umma_can_fuse_out(A) && umma_phase_supported(0, B, H)));
+      if (fuse_next) add(*next);
+      static const char* kinds[] = {"gemm", "first_fwd", "out_fwd", "last_bwd", "last_dgrad", "first_wgrad"};
+      static const char* modes[] = {"fwd", "dgrad", "wgrad"};
+      char nm[32];
+      snprintf(nm, sizeof(nm), "%s_%s%s", ph.kind == PH_GENERIC ? "hidden" : kinds[ph.kind], modes[ph.mode],
+               (tf32 && ph.umma_ok && umma_phase_supported(ph.mode, B, H)) ? "" : "");
+      tm->mark(nm, fl, by);
+    }
     // Mixed precision: the input layer (observations, K = 11..69) and the output heads run in FP32 on CUDA
     // cores; every hidden-layer GEMM and the first-layer weight gradient run as TF32 tcgen05 GEMMs.  TF32 on the
     // input layer doubles the value-loss error (measured 1.2e-3 -> 2.6e-3) for < 10 % of the step time.
@@ -577,13 +627,18 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   };
   for (size_t i = 0; i < e->fwd_phases.size(); ++i)
     run_phase(e->fwd_phases[i], i + 1 < e->fwd_phases.size() ? &e->fwd_phases[i + 1] : nullptr, nullptr);
+  if (tm) tm->mark("loss", 0, S_d * e->cfg.batch_size * 4.0 * (8 + 3 * e->wl.Ald));
   launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, st);
   ++launches;
   for (size_t i = 0; i < e->bwd_phases.size(); ++i)
     run_phase(e->bwd_phases[i], i + 1 < e->bwd_phases.size() ? &e->bwd_phases[i + 1] : nullptr,
               i + 2 < e->bwd_phases.size() ? &e->bwd_phases[i + 2] : nullptr);
+  // Adam: read g, p, m, v + target; write p, m, v + target (+ the TF32 shadow copies in tcgen05 mode)
+  if (tm) tm->mark("adam_polyak", 0, S_d * 4.0 * ((7.0 + (ctx.tf32 ? 1 : 0)) * e->layout.param_floats +
+                                                  (2.0 + (ctx.tf32 ? 1 : 0)) * e->layout.q_floats));
   launch_adam(ctx, e->params, e->exp_avg, e->exp_avg_sq, e->target, e->grads, st);
   ++launches;
+  if (tm) tm->finish();
   return launches;
 }
 
@@ -706,5 +761,53 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
   launch_umma_gemm(mode, (const GemmProb*)(d + 256), d, nullptr, EPI_NONE, 1, M, N, ctx, st);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(nullptr, IQL_ERR_CUDA, std::string("iql_selftest_umma_gemm: ") + cudaGetErrorString(err));
+  return IQL_OK;
+}
+
+extern "C" int iql_profile_step(iql_engine* e, int32_t reps, int32_t max_slots, int32_t* n_slots, float* avg_ms,
+                                double* flops, double* bytes, char* labels, void* stream) {
+  if (!e || !n_slots || !avg_ms || !flops || !bytes || !labels || reps <= 0 || max_slots <= 0)
+    return fail(e, IQL_ERR_INVALID, "iql_profile_step: null or non-positive argument");
+  if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_profile_step: state not bound");
+  for (int m = 0; m < e->cfg.n_members; ++m)
+    if (!e->h_replay[m].rows || e->h_replay[m].size <= 0) return fail(e, IQL_ERR_STATE, "iql_profile_step: replay buffer not bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = flush_tables(e, st);
+  if (rc != IQL_OK) return rc;
+  StepCtx ctx = make_ctx(e);
+  ctx.K = 1;
+  if (ctx.tf32) launch_refresh_shadow(ctx, e->params, e->target, st);
+  std::vector<double> acc;
+  StepTimer last;
+  for (int r = 0; r < reps; ++r) {
+    StepTimer tm;
+    tm.st = st;
+    ctx.k = 0;
+    enqueue_step(e, ctx, true, st, &tm);
+    launch_advance(ctx, 1, st);
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+    for (int m = 0; m < e->cfg.n_members; ++m) {
+      iql_counters& c = e->h_counters[m];
+      c.v_step++; c.q_step++; c.actor_step++; c.total_it++; c.sample_step++;
+      if (e->h_hparams[m].cosine_t_max > 0) c.sched_epoch++;
+    }
+    if (acc.empty()) acc.assign(tm.label.size(), 0.0);
+    for (size_t i = 0; i + 1 < tm.ev.size() && i < acc.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]);
+      acc[i] += ms;
+    }
+    for (cudaEvent_t ev : tm.ev) cudaEventDestroy(ev);
+    tm.ev.clear();
+    last = tm;
+  }
+  const int n = (int)std::min<size_t>(acc.size(), (size_t)max_slots);
+  *n_slots = n;
+  for (int i = 0; i < n; ++i) {
+    avg_ms[i] = (float)(acc[i] / reps);
+    flops[i] = last.flops[i];
+    bytes[i] = last.bytes[i];
+    snprintf(labels + 32 * i, 32, "%s", last.label[i].c_str());
+  }
   return IQL_OK;
 }

@@ -269,6 +269,27 @@ class EnsembleEngine:
         self._keep2 = (indices, dropout_masks)
         return (out, idx_out) if return_indices else out
 
+    def profile_step(self, reps: int = 5):
+        """Per-kernel CUDA-event timing of the update step (measurement hook).  Returns a list of dicts
+        {label, ms, flops, bytes} in launch order; advances the learners by `reps` steps."""
+        n = C.c_int32(0)
+        cap = 64
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        by = (C.c_double * cap)()
+        labels = C.create_string_buffer(32 * cap)
+        st = self._enter()
+        try:
+            _lib.check(self._L.iql_profile_step(self._h, reps, cap, C.byref(n), ms, fl, by, labels, st.cuda_stream),
+                       self._h, "iql_profile_step")
+        finally:
+            self._exit()
+        out = []
+        for i in range(n.value):
+            out.append({"label": labels.raw[32 * i:32 * (i + 1)].split(b"\0")[0].decode(), "ms": float(ms[i]),
+                        "flops": float(fl[i]), "bytes": float(by[i])})
+        return out
+
     def last_launch_count(self) -> int:
         return int(self._L.iql_last_launch_count(self._h))
 
