@@ -175,7 +175,7 @@ def cpu_reference_steps_per_sec(w, steps, warmup, n_rows=200_000):
 def run_reference_arm(args, w, rank):
     if rank != 0:
         return
-    inner = args.inner if args.inner else 25
+    inner = args.inner if args.inner else 250  # ~1 s of CPU work per bench step
     steps_total = max(1, args.steps) * inner
     sps, dt, cores = cpu_reference_steps_per_sec(w, steps_total, max(3, args.warmup))
     line = {
@@ -223,7 +223,9 @@ def run_ours(args, w, rank, world, local_rank):
         ens.engine.target[1:] = ens.engine.target[0]
     data = synthetic_dataset(N_ROWS, w["S"], w["A"], 0, antmaze_rewards=w["antmaze"])
     rb = ReplayBuffer(w["S"], w["A"], N_ROWS, device)
-    rb.load_d4rl_dataset(data)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # the reference-compatible "Dataset size" print must not reach stdout
+        rb.load_d4rl_dataset(data)
     ens.bind_replay(rb)
     eng = ens.engine
     losses = torch.empty(S_local, inner, 3, dtype=torch.float32, device=device)
@@ -373,7 +375,7 @@ def main():
     ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--inner", type=int, default=0, help="updates per engine call (0 = workload default)")
     ap.add_argument("--members", type=int, default=0, help="override members per GPU")
-    ap.add_argument("--cpu-steps", type=int, default=1500)
+    ap.add_argument("--cpu-steps", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-init", action="store_true")
     args = ap.parse_args()
