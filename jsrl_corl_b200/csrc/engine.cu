@@ -400,6 +400,9 @@ static void build_problems(iql_engine* e) {
         p.ldmask = H;
         p.epi = EPI_DRELU;
         p.drop_layer = (t == 3) ? (l - 1) : -1;
+        // bias gradient of the layer below = column sums of the gradient this problem produces
+        // (written by the tcgen05 dgrad epilogue; the FP32 kernels compute it in their wgrad instead)
+        p.dbias = e->grads + (int64_t)m * P + e->b_off[net][l - 1];
         e->h_probs.push_back(p);
       }
     px.count = (int)e->h_probs.size() - px.first;
@@ -603,6 +606,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       launch_umma_gemm(ph.mode, pp, e->d_maps + (size_t)256 * ph.first, fuse ? e->d_probs + next->first : nullptr,
                        ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st);
       if (fuse) skip_next = true;
+      if (ph.mode == 1) skip_colsum = true;  // the dgrad epilogue wrote the bias gradient of the layer below
       if (ph.mode == 2) {
         if (skip_colsum) skip_colsum = false;  // db already written by the fused output-layer backward
         else { launch_colsum(pp, ph.count, ph.maxM, st); ++launches; }

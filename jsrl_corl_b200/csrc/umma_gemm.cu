@@ -5,15 +5,16 @@
 //   mode 1  NN  C[M,N] = A[M,K] * B[K,N]     dgrad    G' = (G W) * [H > 0]      A K-major, B MN-major
 //   mode 2  TN  C[M,N] = A[K,M]^T * B[K,N]   wgrad    dW = G^T H                A,B MN-major
 //
-// One CTA computes a 256 x 256 output tile as two M=128 UMMA accumulators that
-// fill the 512 TMEM columns; the B tile is staged once and feeds both halves.
-// Operands arrive by TMA (one elected thread) into a 3-stage ring of
-// 128B-swizzled shared-memory tiles (32 K-elements = 128 B per row), the MMA
-// is issued by one elected thread (tcgen05.mma.cta_group::1.kind::tf32, FP32
-// accumulate in TMEM), completion is tracked with tcgen05.commit -> mbarrier,
-// and eight epilogue warps read the accumulators with tcgen05.ld, transpose
-// through shared memory and apply the fused epilogue with coalesced 16-byte
-// global accesses (bias+ReLU(+dropout) / ReLU-mask / plain store).
+// Persistent kernel, one CTA per SM, looping over 128 x tile_n output tiles (tile_n <= 256).  The FP32
+// accumulator of a tile is one M=128 `tcgen05.mma.cta_group::1.kind::tf32` block of 256 TMEM columns; the 512
+// columns hold TWO such accumulators, so the epilogue of tile i overlaps the TMA + MMA main loop of tile
+// i+1.  Warp 0 lane 0 issues TMA (cp.async.bulk.tensor, 128-byte swizzle) into a 3-stage ring and runs
+// ahead across tile boundaries; warp 1 lane 0 issues the MMAs, `tcgen05.commit`s every stage to the
+// ring's empty barrier and the last one of a tile to the accumulator-full barrier; warps 2-9 (two per
+// TMEM lane quarter, splitting the columns) drain the accumulator with tcgen05.ld, release it through
+// the accumulator-empty barrier, transpose through a private staging tile and apply the fused epilogue
+// (bias + ReLU + dropout, ReLU mask, or plain store; optionally the FP32 output heads) with coalesced
+// 16-byte global accesses.
 //
 // Shared-memory / descriptor conventions (cute/atom/mma_traits_sm100.hpp):
 //   K-major  : rows of 128 B, SWIZZLE_128B (16 B atoms), SBO = 1024 B between
@@ -30,11 +31,15 @@
 
 namespace iql {
 
-constexpr int TILE_M = 256, TILE_N = 256 /* maximum; the N tile is a launch parameter */, TILE_K = 32, UMMA_K = 8, N_STAGES = 3;
-constexpr int STAGE_A_BYTES = TILE_M * TILE_K * 4;  // 32 KB
+constexpr int TILE_M = 128, TILE_N = 256 /* maximum; the N tile is a launch parameter */, TILE_K = 32, UMMA_K = 8, N_STAGES = 3;
+constexpr int STAGE_A_BYTES = TILE_M * TILE_K * 4;  // 16 KB
 constexpr int STAGE_B_BYTES = TILE_N * TILE_K * 4;  // 32 KB
 constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int N_EPI_WARPS = 8;
+constexpr int STG_FLOATS = 32 * 36;                                   // per-warp transpose tile
+constexpr int FUSE_AMAX = 8;                                          // head rows evaluated in the epilogue
+constexpr int EPI_SMEM_BYTES = N_EPI_WARPS * STG_FLOATS * 4 + 2 * 2 * TILE_M * FUSE_AMAX * 4;  // staging + 2x head partials
+constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int N_THREADS = 320;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-9 epilogue (2 per TMEM lane quarter)
 
 // ---------------------------------------------------------------------------
@@ -44,6 +49,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -112,17 +120,35 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, ui
 
 struct UmmaParams {
   // per-operand descriptor fields, host-computed (16-byte units unless noted)
-  uint32_t a_lbo, a_sbo, a_layout, a_kstep, a_half;  // a_half: offset of the second M=128 half (16 B units)
+  uint32_t a_lbo, a_sbo, a_layout, a_kstep;
   uint32_t b_lbo, b_sbo, b_layout, b_kstep;
   uint32_t idesc;
   int a_mn, b_mn;  // operand majors (0 K-major, 1 MN-major)
   int tile_n;      // UMMA N of this launch: multiple of 32, <= 256 (B tile = tile_n * 128 B per stage)
+  int tiles_m, tiles_n, total_tiles;  // tile grid per problem and over the whole launch
+  // Work units handed to CTAs round-robin.  Default: one unit = one tile.  prob_major (dgrad with fused bias
+  // gradient): one unit = all M tiles of one (problem, N tile), so that the column sums of the produced
+  // gradient are completed inside one CTA in a fixed order -- no atomics, no zero-fill.
+  int prob_major, units, tiles_per_unit;
 };
+
+__device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int j, int& prob, int& m0, int& n0) {
+  if (up.prob_major) {
+    prob = unit / up.tiles_n;
+    n0 = (unit - prob * up.tiles_n) * up.tile_n;
+    m0 = j * TILE_M;
+  } else {
+    const int per = up.tiles_m * up.tiles_n;
+    prob = unit / per;
+    const int rem = unit - prob * per;
+    m0 = (rem / up.tiles_n) * TILE_M;
+    n0 = (rem % up.tiles_n) * up.tile_n;
+  }
+}
 
 // FUSE_OUT (forward, last hidden layer): the output Linear y = H_L W_L^T + b_L (N = 1 or act_dim <= 8) is
 // evaluated in the epilogue, in FP32, on the FP32 accumulators -- the Q/V/policy heads never see TF32 rounding
 // and H_L makes no extra trip through HBM.  `probs_out` is the problem table of the output-layer phase.
-constexpr int FUSE_AMAX = 8;
 template <int EPI, bool FUSE_OUT>
 __global__ void __launch_bounds__(N_THREADS, 1)
 umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restrict__ maps,
@@ -131,29 +157,29 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t bars = base + N_STAGES * STAGE_BYTES;  // full[3], empty[3], tmem_full, tmem slot
-  const uint32_t full0 = bars, empty0 = bars + 8 * N_STAGES, tfull = bars + 16 * N_STAGES, tslot = tfull + 8;
-  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + N_STAGES * STAGE_BYTES + 16 * N_STAGES + 8);
+  constexpr int RING = N_STAGES * STAGE_BYTES;
+  float* epi_smem = reinterpret_cast<float*>(smem + RING);
+  // barriers: full[3], empty[3], tmem_full[2], tmem_empty[2], tmem slot
+  const uint32_t bars = base + RING + EPI_SMEM_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * N_STAGES, tfull0 = bars + 16 * N_STAGES, tempty0 = tfull0 + 16;
+  const uint32_t tslot = tempty0 + 16;
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + RING + EPI_SMEM_BYTES + 16 * N_STAGES + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int prob = blockIdx.z;
-  const GemmProb p = probs[prob];
   const int tile_n = up.tile_n;
-  const int m0 = blockIdx.y * TILE_M, n0 = blockIdx.x * tile_n;
-  if (m0 >= p.M || n0 >= p.N) return;  // uniform per CTA
-  const CUtensorMap* mapA = maps + 2 * prob;
-  const CUtensorMap* mapB = mapA + 1;
-  const int num_kb = (p.K + TILE_K - 1) / TILE_K;  // TMA zero-fills the K tail
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < N_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tfull, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, N_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (1 CTA per SM)
+  if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (1 CTA per SM) = two accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -166,70 +192,86 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
-        const uint32_t fb = full0 + 8 * stage;
-        mbar_expect_tx(fb, STAGE_A_BYTES + tile_n * TILE_K * 4);
-        const int k0 = kb * TILE_K;
-        if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
-        else tma_load_2d(sa, mapA, fb, k0, m0);
-        if (up.b_mn) tma_load_3d(sb, mapB, fb, 0, k0, n0 >> 5);
-        else tma_load_2d(sb, mapB, fb, k0, n0);
-        if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+      for (int u = blockIdx.x; u < up.units; u += gridDim.x)
+      for (int j = 0; j < up.tiles_per_unit; ++j) {
+        int prob, m0, n0;
+        decode_tile(up, u, j, prob, m0, n0);
+        const int K = probs[prob].K;
+        const CUtensorMap* mapA = maps + 2 * prob;
+        const CUtensorMap* mapB = mapA + 1;
+        const int num_kb = (K + TILE_K - 1) / TILE_K;  // TMA zero-fills the K tail
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
+          const uint32_t fb = full0 + 8 * stage;
+          mbar_expect_tx(fb, STAGE_A_BYTES + tile_n * TILE_K * 4);
+          const int k0 = kb * TILE_K;
+          if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
+          else tma_load_2d(sa, mapA, fb, k0, m0);
+          if (up.b_mn) tma_load_3d(sb, mapB, fb, 0, k0, n0 >> 5);
+          else tma_load_2d(sb, mapB, fb, k0, n0);
+          if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full0 + 8 * stage, phase);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int u = blockIdx.x; u < up.units; u += gridDim.x)
+      for (int j = 0; j < up.tiles_per_unit; ++j, ++it) {
+        int prob, m0, n0;
+        decode_tile(up, u, j, prob, m0, n0);
+        const int num_kb = (probs[prob].K + TILE_K - 1) / TILE_K;
+        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty0 + 8 * buf, acc_phase ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
-        const uint64_t adesc0 = make_desc(sa, up.a_lbo, up.a_sbo, up.a_layout);
-        const uint64_t bdesc0 = make_desc(sb, up.b_lbo, up.b_sbo, up.b_layout);
+        const uint32_t tacc = tmem_base + buf * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
+          const uint64_t adesc0 = make_desc(sa, up.a_lbo, up.a_sbo, up.a_layout);
+          const uint64_t bdesc0 = make_desc(sb, up.b_lbo, up.b_sbo, up.b_layout);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int ks = 0; ks < TILE_K / UMMA_K; ++ks) {
-            const uint64_t ad = adesc0 + (uint64_t)(h * up.a_half + ks * up.a_kstep);
-            const uint64_t bd = bdesc0 + (uint64_t)(ks * up.b_kstep);
-            umma_tf32(tmem_base + h * 256, ad, bd, up.idesc, (kb | ks) != 0);
-          }
+          for (int ks = 0; ks < TILE_K / UMMA_K; ++ks)
+            umma_tf32(tacc, adesc0 + (uint64_t)(ks * up.a_kstep), bdesc0 + (uint64_t)(ks * up.b_kstep), up.idesc,
+                      (kb | ks) != 0);
+          umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
+          if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
-        if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(tfull0 + 8 * buf);  // accumulator complete
       }
-      umma_commit(tfull);  // accumulators complete
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a quarter and split the columns.
     const int q = warp & 3;
     const int ch = (warp - 2) >> 2;  // column half handled by this warp
-    mbar_wait(tfull, 0);
-    tc_fence_after();
-    // all MMAs are complete, so the operand ring is free: use it as the transpose staging area
-    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);
-    const MemberScalars* sc = ctx.scalars + p.member;
-    float dscale = 1.0f;
-    bool drop = false;
-    uint64_t dstep = 0;
-    if (EPI == EPI_DRELU) dscale = (p.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
-    if (EPI == EPI_RELU) {
-      drop = p.drop_layer >= 0 && sc->drop_threshold != 0u;
-      if (drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
-    }
+    float* stg = epi_smem + (warp - 2) * STG_FLOATS;
+    float* ypart_all = epi_smem + N_EPI_WARPS * STG_FLOATS;  // [2 tile parities][2 column halves][128 rows][FUSE_AMAX]
     const int lr = lane >> 3;        // row within a group of 4
     const int lc = (lane & 7) * 4;   // first of this lane's 4 columns
-    GemmProb po;
-    int a_out = 0;
-    float* ypart = reinterpret_cast<float*>(smem) + 8 * (32 * 36);  // [2 column halves][256 rows][FUSE_AMAX]
-    if (FUSE_OUT) { po = probs_out[prob]; a_out = po.N; }
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      const int row_base = m0 + h * 128 + q * 32;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < up.units; u += gridDim.x)
+    for (int j = 0; j < up.tiles_per_unit; ++j, ++it) {
+      int prob, m0, n0;
+      decode_tile(up, u, j, prob, m0, n0);
+      const GemmProb p = probs[prob];
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      const MemberScalars* sc = ctx.scalars + p.member;
+      float dscale = 1.0f;
+      bool drop = false;
+      uint64_t dstep = 0;
+      if (EPI == EPI_DRELU) dscale = (p.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
+      if (EPI == EPI_RELU) {
+        drop = p.drop_layer >= 0 && sc->drop_threshold != 0u;
+        if (drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
+      }
+      GemmProb po;
+      int a_out = 0;
+      float* ypart = ypart_all + (it & 1) * (2 * TILE_M * FUSE_AMAX);
+      if (FUSE_OUT) { po = probs_out[prob]; a_out = po.N; }
       float yacc[8][FUSE_AMAX];
       if (FUSE_OUT) {
 #pragma unroll
@@ -237,41 +279,71 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
 #pragma unroll
           for (int m = 0; m < FUSE_AMAX; ++m) yacc[i][m] = 0.f;
       }
+      const int row_base = m0 + q * 32;
+      const int n_chunks = tile_n >> 5;
+      // fused bias gradient (dgrad): column sums of the produced G over all rows of the problem
+      const bool do_csum = (EPI == EPI_DRELU) && up.prob_major && p.dbias != nullptr;
+      float* csum_s = ypart_all;  // [4 quarters][TILE_N]; the head-partial area is unused by dgrad launches
+      // Operand prefetch for the epilogue, one chunk ahead: the ReLU mask (dgrad), the bias (forward) and the
+      // head weights do not depend on the accumulator, so the first chunk's loads are in flight while this
+      // warp still waits for the MMAs, and chunk c+2's loads are issued before chunk c is processed.
+      float4 mk[8], mk_n[8];
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), b4_n = b4;
+      float4 w4[FUSE_AMAX], w4_n[FUSE_AMAX];
+      auto prefetch = [&](int c, float4* mkd, float4& bd, float4* wd) {
+        const int col = n0 + c * 32 + lc;
+        if (EPI == EPI_DRELU) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            mkd[i] = __ldg(reinterpret_cast<const float4*>(p.mask + (int64_t)(row_base + i * 4 + lr) * p.ldmask + col));
+        }
+        if (EPI == EPI_RELU) bd = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (EPI == EPI_LINEAR) {  // output layer: N = 1 or act_dim, guarded
+          bd.x = col < p.N ? p.bias[col] : 0.f;
+          bd.y = col + 1 < p.N ? p.bias[col + 1] : 0.f;
+          bd.z = col + 2 < p.N ? p.bias[col + 2] : 0.f;
+          bd.w = col + 3 < p.N ? p.bias[col + 3] : 0.f;
+        }
+        if (FUSE_OUT) {
+          if (a_out == 1) {
+            wd[0] = __ldg(reinterpret_cast<const float4*>(po.B + col));
+          } else {
+#pragma unroll
+            for (int m = 0; m < FUSE_AMAX; ++m)
+              wd[m] = (m < a_out) ? __ldg(reinterpret_cast<const float4*>(po.B + (int64_t)m * po.ldb + col))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      if (ch < n_chunks) prefetch(ch, mk_n, b4_n, w4_n);
+      mbar_wait(tfull0 + 8 * buf, acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c = ch; c < (tile_n >> 5); c += 2) {
+      for (int c = ch; c < n_chunks; c += 2) {
         const int col = n0 + c * 32 + lc;
         // full 16-byte accesses when this lane's 4 columns exist and rows are 16-byte aligned
         const bool vec = (col + 3 < p.N) && ((p.ldc & 3) == 0);
-        float4 mk[8];
-        if (EPI == EPI_DRELU) {  // issue the activation-mask loads before waiting on TMEM
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            mk[i] = __ldg(reinterpret_cast<const float4*>(p.mask + (int64_t)(row_base + i * 4 + lr) * p.ldmask + col));
-        }
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EPI == EPI_RELU) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        if (EPI == EPI_LINEAR) {  // output layer: N = 1 or act_dim, guarded
-          b4.x = col < p.N ? p.bias[col] : 0.f;
-          b4.y = col + 1 < p.N ? p.bias[col + 1] : 0.f;
-          b4.z = col + 2 < p.N ? p.bias[col + 2] : 0.f;
-          b4.w = col + 3 < p.N ? p.bias[col + 3] : 0.f;
-        }
-        float4 w4[FUSE_AMAX];
-        if (FUSE_OUT) {  // this lane's 4 columns of every head row, once per chunk
+        for (int i = 0; i < 8; ++i) mk[i] = mk_n[i];
+        b4 = b4_n;
 #pragma unroll
-          for (int m = 0; m < FUSE_AMAX; ++m)
-            w4[m] = (m < a_out) ? __ldg(reinterpret_cast<const float4*>(po.B + (int64_t)m * po.ldb + col))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int m = 0; m < FUSE_AMAX; ++m) w4[m] = w4_n[m];
+        if (c + 2 < n_chunks) prefetch(c + 2, mk_n, b4_n, w4_n);
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + c * 32), r);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + c * 32), r);
         tmem_ld_wait();
+        if (c + 2 >= n_chunks) {  // last TMEM read of this warp for this tile: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(&stg[lane * 36 + 4 * j]) =
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                           __uint_as_float(r[4 * j + 3]));
         __syncwarp();
+        float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + lr;
@@ -300,11 +372,14 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           } else if (EPI == EPI_DRELU) {
             v.x = mk[i].x > 0.f ? v.x * dscale : 0.f; v.y = mk[i].y > 0.f ? v.y * dscale : 0.f;
             v.z = mk[i].z > 0.f ? v.z * dscale : 0.f; v.w = mk[i].w > 0.f ? v.w * dscale : 0.f;
+            cs4.x += v.x; cs4.y += v.y; cs4.z += v.z; cs4.w += v.w;
           }
           if (FUSE_OUT) {
+            if (a_out == 1) {  // scalar heads (Q, V): the common case, warp-uniform
+              yacc[i][0] = fmaf(v.x, w4[0].x, fmaf(v.y, w4[0].y, fmaf(v.z, w4[0].z, fmaf(v.w, w4[0].w, yacc[i][0]))));
+            } else {
 #pragma unroll
-            for (int m = 0; m < FUSE_AMAX; ++m) {
-              if (m < a_out)
+              for (int m = 0; m < FUSE_AMAX; ++m)
                 yacc[i][m] = fmaf(v.x, w4[m].x, fmaf(v.y, w4[m].y, fmaf(v.z, w4[m].z, fmaf(v.w, w4[m].w, yacc[i][m]))));
             }
             if (p.no_store) continue;
@@ -322,28 +397,63 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
             if (col + 3 < p.N) crow[3] = v.w;
           }
         }
+        if (do_csum) {  // 32-row partial of this warp: add the 4 row groups, accumulate across the M tiles
+          cs4.x += __shfl_xor_sync(0xffffffffu, cs4.x, 8);  cs4.y += __shfl_xor_sync(0xffffffffu, cs4.y, 8);
+          cs4.z += __shfl_xor_sync(0xffffffffu, cs4.z, 8);  cs4.w += __shfl_xor_sync(0xffffffffu, cs4.w, 8);
+          cs4.x += __shfl_xor_sync(0xffffffffu, cs4.x, 16); cs4.y += __shfl_xor_sync(0xffffffffu, cs4.y, 16);
+          cs4.z += __shfl_xor_sync(0xffffffffu, cs4.z, 16); cs4.w += __shfl_xor_sync(0xffffffffu, cs4.w, 16);
+          if (lane < 8) {
+            float4* dst = reinterpret_cast<float4*>(&csum_s[q * TILE_N + c * 32 + lc]);
+            float4 acc = (j == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : *dst;
+            acc.x += cs4.x; acc.y += cs4.y; acc.z += cs4.z; acc.w += cs4.w;
+            *dst = acc;
+          }
+        }
         __syncwarp();
       }
-      if (FUSE_OUT) {  // reduce the 8 lanes that share a row, park the per-column-half partial sums
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int m = 0; m < FUSE_AMAX; ++m) {
-            if (m < a_out) {
-              float t = yacc[i][m];
-              t += __shfl_xor_sync(0xffffffffu, t, 1);
-              t += __shfl_xor_sync(0xffffffffu, t, 2);
-              t += __shfl_xor_sync(0xffffffffu, t, 4);
-              if ((lane & 7) == 0) ypart[(ch * 256 + h * 128 + q * 32 + i * 4 + lr) * FUSE_AMAX + m] = t;
-            }
-          }
+      if (do_csum && j == up.tiles_per_unit - 1) {  // all rows of the problem seen: combine the quarters
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int tc = threadIdx.x - 64;  // 0..255 = column of this N tile
+        if (tc < tile_n && n0 + tc < p.N)
+          p.dbias[n0 + tc] = ((csum_s[tc] + csum_s[TILE_N + tc]) + csum_s[2 * TILE_N + tc]) + csum_s[3 * TILE_N + tc];
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // csum_s is reused by the next unit
       }
-    }
-    if (FUSE_OUT) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
-      const int t = threadIdx.x - 64;                  // 0..255 = row of the tile
-      for (int m = 0; m < a_out; ++m)
-        po.C[(int64_t)(m0 + t) * po.ldc + m] = (ypart[t * FUSE_AMAX + m] + ypart[(256 + t) * FUSE_AMAX + m]) + po.bias[m];
+      if (n_chunks <= ch) {  // this warp had no chunk (tile_n == 32 and ch == 1): still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      }
+      if (FUSE_OUT) {
+        // reduce the 8 lanes that share a row, park the per-column-half partial sums, combine the halves
+        if (a_out == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float tsum = yacc[i][0];
+            tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+            tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+            tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
+            if ((lane & 7) == 0) ypart[(ch * TILE_M + q * 32 + i * 4 + lr) * FUSE_AMAX] = tsum;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int m = 0; m < FUSE_AMAX; ++m) {
+              if (m < a_out) {  // warp-uniform
+                float tsum = yacc[i][m];
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+                tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
+                if ((lane & 7) == 0) ypart[(ch * TILE_M + q * 32 + i * 4 + lr) * FUSE_AMAX + m] = tsum;
+              }
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
+        const int tr = threadIdx.x - 64;                // 0..255
+        if (tr < TILE_M)
+          for (int m = 0; m < a_out; ++m)
+            po.C[(int64_t)(m0 + tr) * po.ldc + m] = (ypart[tr * FUSE_AMAX + m] + ypart[(TILE_M + tr) * FUSE_AMAX + m]) + po.bias[m];
+      }
     }
   }
   tc_fence_before();
@@ -390,7 +500,7 @@ bool umma_phase_supported(int mode, int batch, int hidden) {
   (void)mode;  // every tcgen05 phase has M in {batch, hidden}: both must be multiples of the 256-row tile
   static int disabled = -1;
   if (disabled < 0) disabled = getenv("IQL_B200_NO_UMMA") ? 1 : 0;
-  return !disabled && batch == TILE_M && hidden >= 256 && hidden % 256 == 0;
+  return !disabled && batch == 256 && hidden >= 256 && hidden % 256 == 0;
 }
 
 // K-major operand [rows][K] (ld floats): 2-D map {K, rows}, box {32, box_rows}, SWIZZLE_128B.
@@ -430,7 +540,7 @@ int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, v
   for (int i = 0; i < nprob; ++i) {
     const GemmProb& p = h_probs[i];
     int rc;
-    if (mode == 2) rc = encode_mnmajor(&maps[2 * i], p.A, p.M, p.K, p.lda, TILE_M / 32);
+    if (mode == 2) rc = encode_mnmajor(&maps[2 * i], p.A, p.M, p.K, p.lda, TILE_M / 32);  // 4 slabs = 128 rows
     else rc = encode_kmajor(&maps[2 * i], p.A, p.M, p.K, p.lda, TILE_M);
     if (rc) return rc;
     if (mode == 0) rc = encode_kmajor(&maps[2 * i + 1], p.B, p.N, p.K, p.ldb, tile_n);
@@ -452,7 +562,6 @@ static UmmaParams make_params(int mode, int tile_n) {
   u.a_sbo = a_mn ? env_u32("IQL_UMMA_MN_SBO", 512 >> 4) : (1024 >> 4);
   u.a_layout = a_mn ? env_u32("IQL_UMMA_MN_LAYOUT", 1) : 2;
   u.a_kstep = a_mn ? env_u32("IQL_UMMA_MN_KSTEP", 1024 >> 4) : (32 >> 4);
-  u.a_half = (128 * 128) >> 4;  // both layouts: 16 KB
   u.b_lbo = b_mn ? env_u32("IQL_UMMA_MN_LBO", 4096 >> 4) : 1;
   u.b_sbo = b_mn ? env_u32("IQL_UMMA_MN_SBO", 512 >> 4) : (1024 >> 4);
   u.b_layout = b_mn ? env_u32("IQL_UMMA_MN_LAYOUT", 1) : 2;
@@ -478,8 +587,21 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
     attr_set = true;
   }
   const int tile_n = umma_tile_n(maxN);
-  const UmmaParams up = make_params(mode, tile_n);
-  dim3 grid((maxN + tile_n - 1) / tile_n, (maxM + TILE_M - 1) / TILE_M, nprob);
+  UmmaParams up = make_params(mode, tile_n);
+  up.tiles_m = (maxM + TILE_M - 1) / TILE_M;
+  up.tiles_n = (maxN + tile_n - 1) / tile_n;
+  up.total_tiles = nprob * up.tiles_m * up.tiles_n;
+  up.prob_major = (epi == EPI_DRELU) ? 1 : 0;
+  up.tiles_per_unit = up.prob_major ? up.tiles_m : 1;
+  up.units = up.total_tiles / up.tiles_per_unit;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  dim3 grid(up.units < n_sm ? up.units : n_sm);  // persistent: one CTA per SM
   const CUtensorMap* m = (const CUtensorMap*)maps;
   if (epi == EPI_RELU && probs_out) umma_gemm_kernel<EPI_RELU, true><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, probs_out, up, ctx);
   else if (epi == EPI_RELU) umma_gemm_kernel<EPI_RELU, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
