@@ -80,6 +80,11 @@ struct iql_engine {
   float* d_loss_ring = nullptr;
   float* d_wshadow = nullptr;    // [S][P]  TF32-rounded params  (tcgen05 mode)
   float* d_tshadow = nullptr;    // [S][PQ] TF32-rounded target
+  float* d_wshadow_lo = nullptr; // lo parts (first-layer ranges) for the 3xTF32 input layer
+  float* d_tshadow_lo = nullptr;
+  char* d_maps_first = nullptr;  // [4 * S * N_PASS] CUtensorMap: Xhi, Whi, Xlo, Wlo of the input-layer forward
+  std::vector<char> h_maps_first;
+  bool split_first = false;      // input layer runs as 3xTF32 tcgen05 GEMM
   float* d_ws_f = nullptr;       // activation area
   int64_t tables_bytes = 0;
   // host shadows
@@ -170,6 +175,11 @@ static void build_layout(iql_engine* e) {
   wl.gy = region(3 * B);
   wl.gpi = region(B * wl.Ald);
   wl.gh = region((int64_t)4 * 2 * B * H);
+  wl.xhi = wl.xlo = 0;
+  if (c.math_mode == IQL_MATH_TF32_TCGEN05) {
+    wl.xhi = region(B * e->layout.row.row_floats);
+    wl.xlo = region(B * e->layout.row.row_floats);
+  }
   wl.member_floats = w;
 
   const int S = c.n_members;
@@ -186,6 +196,9 @@ static void build_layout(iql_engine* e) {
   if (c.math_mode == IQL_MATH_TF32_TCGEN05) {
     tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
     tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
+    tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
+    tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
+    tab((int64_t)128 * 4 * S * N_PASS);
   }
   e->tables_bytes = tb;
   e->layout.workspace_bytes = tb + (int64_t)S * wl.member_floats * (int64_t)sizeof(float);
@@ -435,6 +448,9 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   if (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) {
     e->d_wshadow = (float*)tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
     e->d_tshadow = (float*)tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
+    e->d_wshadow_lo = (float*)tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
+    e->d_tshadow_lo = (float*)tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
+    e->d_maps_first = tab((int64_t)128 * 4 * S * N_PASS);
   }
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
@@ -447,6 +463,30 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
                               e->h_maps.data() + (size_t)256 * ph.first);
     };
     for (const Phase& ph : e->fwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (forward phase)");
+    // 3xTF32 input layer: hi / lo operand maps of the first forward phase
+    e->split_first = umma_phase_supported(0, e->cfg.batch_size, e->cfg.hidden_dim) && getenv("IQL_B200_NO_SPLIT_FIRST") == nullptr;
+    if (e->split_first) {
+      const Phase& ph = e->fwd_phases[0];
+      std::vector<GemmProb> hi(e->h_probs.begin() + ph.first, e->h_probs.begin() + ph.first + ph.count), lo = hi;
+      const int64_t P = e->layout.param_floats, PQ = e->layout.q_floats;
+      for (int i = 0; i < ph.count; ++i) {
+        const GemmProb& g = e->h_probs[ph.first + i];
+        const int m = g.member;
+        const float* wsm = e->d_ws_f + (int64_t)m * e->wl.member_floats;
+        const int64_t a_off = g.A - (wsm + e->wl.xrow);  // column offset of this pass's input inside the row
+        hi[i].A = wsm + e->wl.xhi + a_off;
+        lo[i].A = wsm + e->wl.xlo + a_off;
+        const float* pblk = e->params + (int64_t)m * P;
+        const float* tblk = e->target + (int64_t)m * PQ;
+        const bool tgt = (g.B >= tblk && g.B < tblk + PQ);
+        const int64_t w_off = tgt ? (g.B - tblk) : (g.B - pblk);
+        hi[i].B = (tgt ? e->d_tshadow + (int64_t)m * PQ : e->d_wshadow + (int64_t)m * P) + w_off;
+        lo[i].B = (tgt ? e->d_tshadow_lo + (int64_t)m * PQ : e->d_wshadow_lo + (int64_t)m * P) + w_off;
+      }
+      e->h_maps_first.assign((size_t)128 * 4 * ph.count, 0);
+      if (umma_encode_maps_split(hi.data(), lo.data(), ph.count, umma_tile_n(ph.maxN), e->h_maps_first.data()))
+        return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (3xTF32 input layer)");
+    }
     for (const Phase& ph : e->bwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward phase)");
   }
   e->bound = true;
@@ -461,6 +501,8 @@ static int flush_tables(iql_engine* e, cudaStream_t st) {
   if (e->tables_dirty) {
     CUDA_TRY(e, cudaMemcpyAsync(e->d_probs, e->h_probs.data(), sizeof(GemmProb) * e->h_probs.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(e, cudaMemcpyAsync(e->d_maps, e->h_maps.data(), e->h_maps.size(), cudaMemcpyHostToDevice, st));
+    if (!e->h_maps_first.empty())
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_first, e->h_maps_first.data(), e->h_maps_first.size(), cudaMemcpyHostToDevice, st));
     std::vector<int64_t> off(2 * (L + 1));
     for (int l = 0; l <= L; ++l) {
       off[l] = e->w_off[IQL_NET_ACTOR][l];
@@ -503,6 +545,15 @@ static StepCtx make_ctx(const iql_engine* e) {
   c.tf32 = (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) && umma_phase_supported(0, e->cfg.batch_size, e->cfg.hidden_dim);
   c.w_shadow = e->d_wshadow;
   c.t_shadow = e->d_tshadow;
+  c.w_shadow_lo = e->d_wshadow_lo;
+  c.t_shadow_lo = e->d_tshadow_lo;
+  for (int n = 0; n < 4; ++n) {
+    c.first_w_begin[n] = e->split_first ? e->w_off[n][0] : 0;
+    c.first_w_end[n] = e->split_first ? e->w_off[n][0] + (int64_t)e->cfg.hidden_dim * e->w_ld[n][0] : 0;
+  }
+  c.xrow_off_ = e->wl.xrow;
+  c.xhi_off = (c.tf32 && e->split_first) ? e->wl.xhi : 0;
+  c.xlo_off = (c.tf32 && e->split_first) ? e->wl.xlo : 0;
   return c;
 }
 
@@ -592,9 +643,9 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     // Mixed precision: the input layer (observations, K = 11..69) and the output heads run in FP32 on CUDA
     // cores; every hidden-layer GEMM and the first-layer weight gradient run as TF32 tcgen05 GEMMs.  TF32 on the
     // input layer doubles the value-loss error (measured 1.2e-3 -> 2.6e-3) for < 10 % of the step time.
-    static const bool tf32_first = getenv("IQL_B200_TF32_FIRST") != nullptr;
+    const bool split = ph.kind == PH_FIRST_FWD && e->split_first;  // 3xTF32: FP32-accurate on tensor cores
     const bool umma = tf32 && ph.umma_ok && umma_phase_supported(ph.mode, B, H) &&
-                      !(ph.kind == PH_FIRST_FWD && !tf32_first && first_ok);
+                      !(ph.kind == PH_FIRST_FWD && !split && first_ok);
     if (umma && ph.kind == PH_OUT_FWD) {
       // the heads stay in FP32: TF32 rounding of Q and V would be amplified by adv = q - v and exp(beta * adv)
       if (out_ok) launch_out_fwd(pp, ph.count, B, H, A, st);
@@ -603,8 +654,8 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       // forward, last hidden layer: fuse the FP32 output Linear into the epilogue and skip the next phase
       const bool fuse = ph.mode == 0 && ph.epi == EPI_RELU && next && next->kind == PH_OUT_FWD && H == 256 &&
                         umma_can_fuse_out(A);
-      launch_umma_gemm(ph.mode, pp, e->d_maps + (size_t)256 * ph.first, fuse ? e->d_probs + next->first : nullptr,
-                       ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st);
+      launch_umma_gemm(ph.mode, pp, split ? e->d_maps_first : e->d_maps + (size_t)256 * ph.first,
+                       fuse ? e->d_probs + next->first : nullptr, ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st, split);
       if (fuse) skip_next = true;
       if (ph.mode == 1) skip_colsum = true;  // the dgrad epilogue wrote the bias gradient of the layer below
       if (ph.mode == 2) {

@@ -83,6 +83,13 @@ struct StepCtx {
   int tf32;                      // 1: tcgen05 path; producers round GEMM operands to nearest TF32
   float* w_shadow;               // [S][P]  TF32-rounded copy of params (tcgen05 B operands), tf32 mode only
   float* t_shadow;               // [S][PQ] TF32-rounded copy of the target network
+  // 3xTF32 input layer: x = hi + lo with both parts TF32-exact, so X W0^T = Xhi Whi + Xlo Whi + Xhi Wlo
+  // runs on the tensor cores at FP32 accuracy.  lo parts of the first-layer weights / of the gathered rows:
+  float* w_shadow_lo;            // [S][P]  (only the first-layer weight ranges are maintained)
+  float* t_shadow_lo;            // [S][PQ]
+  int64_t first_w_begin[4], first_w_end[4];  // first-layer weight ranges of q1, q2, v, actor inside a member block
+  int64_t xrow_off_;             // per-member workspace offset of the gathered rows
+  int64_t xhi_off, xlo_off;      // per-member workspace offsets of the hi / lo copies of the gathered rows (0 = off)
 };
 
 struct TensorDesc {
@@ -98,6 +105,7 @@ struct WorkspaceLayout {
   int64_t gy;        // [3][B]        dL/dy of V, q1, q2
   int64_t gpi;       // [B][Ald]      dL/dz of actor
   int64_t gh;        // [4][2][B][H]  ping-pong activation gradients of the 4 trainable nets
+  int64_t xhi, xlo;  // [B][ROW] each: TF32 hi / lo split of the gathered rows (tcgen05 mode)
   int64_t member_floats;
   int Ald;
 };

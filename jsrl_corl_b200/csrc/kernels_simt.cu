@@ -191,7 +191,14 @@ __global__ void __launch_bounds__(256) gather_kernel(StepCtx ctx, float* __restr
   }
   if (q == 0 && ctx.idx_out) ctx.idx_out[((int64_t)m * ctx.K + ctx.k) * ctx.B + b] = idx;
   const float4 v = __ldg(reinterpret_cast<const float4*>(rb.rows + idx * RF) + q);
-  reinterpret_cast<float4*>(ws + m * ws_member_floats + xrow_off + (int64_t)b * RF)[q] = v;
+  float* wm = ws + m * ws_member_floats;
+  reinterpret_cast<float4*>(wm + xrow_off + (int64_t)b * RF)[q] = v;
+  if (ctx.xhi_off) {  // TF32 hi / lo split of the row for the 3xTF32 input layer
+    const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    reinterpret_cast<float4*>(wm + ctx.xhi_off + (int64_t)b * RF)[q] = hi;
+    reinterpret_cast<float4*>(wm + ctx.xlo_off + (int64_t)b * RF)[q] =
+        make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+  }
 }
 
 void launch_gather(const StepCtx& ctx, float* ws, int64_t ws_member_floats, int64_t xrow_off, cudaStream_t st) {
@@ -200,7 +207,8 @@ void launch_gather(const StepCtx& ctx, float* ws, int64_t ws_member_floats, int6
   gather_kernel<<<grid, 256, 0, st>>>(ctx, ws, ws_member_floats, xrow_off);
 }
 
-__global__ void load_batch_kernel(iql_row_layout lay, int B, float* __restrict__ xrow, const float* __restrict__ s,
+__global__ void load_batch_kernel(iql_row_layout lay, int B, float* __restrict__ xrow, float* __restrict__ xhi,
+                                  float* __restrict__ xlo, const float* __restrict__ s,
                                   const float* __restrict__ a, const float* __restrict__ r,
                                   const float* __restrict__ s2, const float* __restrict__ d) {
   const int RF = lay.row_floats, S = lay.state_dim, A = lay.action_dim;
@@ -214,13 +222,21 @@ __global__ void load_batch_kernel(iql_row_layout lay, int B, float* __restrict__
   else if (c == lay.off_reward) v = r[row];
   else if (c == lay.off_done) v = d[row];
   xrow[i] = v;
+  if (xhi) {
+    const float hi = round_tf32(v);
+    xhi[i] = hi;
+    xlo[i] = round_tf32(v - hi);
+  }
 }
 
 void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float* s, const float* a, const float* r,
                        const float* s2, const float* d, cudaStream_t st) {
   (void)member;
   const int n = ctx.B * ctx.row.row_floats;
-  load_batch_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx.row, ctx.B, xrow, s, a, r, s2, d);
+  // xrow points at this member's gathered-row region; the hi / lo copies live at fixed offsets from it
+  float* xhi = ctx.xhi_off ? xrow + (ctx.xhi_off - ctx.xrow_off_) : nullptr;
+  float* xlo = ctx.xhi_off ? xrow + (ctx.xlo_off - ctx.xrow_off_) : nullptr;
+  load_batch_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx.row, ctx.B, xrow, xhi, xlo, s, a, r, s2, d);
 }
 
 // ===========================================================================
@@ -406,9 +422,16 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
     p[j] = fmaf(as.neg_step_size, __fdiv_rn(mm[j], denom), p[j]);         // addcdiv_
   }
   *reinterpret_cast<float4*>(params + off) = make_float4(p[0], p[1], p[2], p[3]);
-  if (ctx.tf32)
-    *reinterpret_cast<float4*>(ctx.w_shadow + off) =
-        make_float4(round_tf32(p[0]), round_tf32(p[1]), round_tf32(p[2]), round_tf32(p[3]));
+  bool first_layer = false;
+  if (ctx.tf32) {
+    const float4 hi = make_float4(round_tf32(p[0]), round_tf32(p[1]), round_tf32(p[2]), round_tf32(p[3]));
+    *reinterpret_cast<float4*>(ctx.w_shadow + off) = hi;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) first_layer |= (i >= ctx.first_w_begin[r] && i < ctx.first_w_end[r]);
+    if (first_layer)
+      *reinterpret_cast<float4*>(ctx.w_shadow_lo + off) =
+          make_float4(round_tf32(p[0] - hi.x), round_tf32(p[1] - hi.y), round_tf32(p[2] - hi.z), round_tf32(p[3] - hi.w));
+  }
   *reinterpret_cast<float4*>(exp_avg + off) = make_float4(mm[0], mm[1], mm[2], mm[3]);
   *reinterpret_cast<float4*>(exp_avg_sq + off) = make_float4(vv[0], vv[1], vv[2], vv[3]);
   if (opt == 0) {
@@ -419,9 +442,13 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
 #pragma unroll
     for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(sc.one_minus_tau, t[j]), __fmul_rn(sc.tau, p[j]));
     *reinterpret_cast<float4*>(target + toff) = make_float4(t[0], t[1], t[2], t[3]);
-    if (ctx.tf32)
-      *reinterpret_cast<float4*>(ctx.t_shadow + toff) =
-          make_float4(round_tf32(t[0]), round_tf32(t[1]), round_tf32(t[2]), round_tf32(t[3]));
+    if (ctx.tf32) {
+      const float4 hi = make_float4(round_tf32(t[0]), round_tf32(t[1]), round_tf32(t[2]), round_tf32(t[3]));
+      *reinterpret_cast<float4*>(ctx.t_shadow + toff) = hi;
+      if (first_layer)
+        *reinterpret_cast<float4*>(ctx.t_shadow_lo + toff) =
+            make_float4(round_tf32(t[0] - hi.x), round_tf32(t[1] - hi.y), round_tf32(t[2] - hi.z), round_tf32(t[3] - hi.w));
+    }
   }
 }
 
@@ -431,15 +458,24 @@ __global__ void __launch_bounds__(256) refresh_shadow_kernel(StepCtx ctx, const 
                                                              const float* __restrict__ target) {
   const int m = blockIdx.y;
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  bool first_layer = false;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) first_layer |= (i >= ctx.first_w_begin[r] && i < ctx.first_w_end[r]);
   if (i < ctx.P) {
     const float4 v = *reinterpret_cast<const float4*>(params + m * ctx.P + i);
-    *reinterpret_cast<float4*>(ctx.w_shadow + m * ctx.P + i) =
-        make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    *reinterpret_cast<float4*>(ctx.w_shadow + m * ctx.P + i) = hi;
+    if (first_layer)
+      *reinterpret_cast<float4*>(ctx.w_shadow_lo + m * ctx.P + i) =
+          make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
   }
   if (i < ctx.PQ) {
     const float4 v = *reinterpret_cast<const float4*>(target + m * ctx.PQ + i);
-    *reinterpret_cast<float4*>(ctx.t_shadow + m * ctx.PQ + i) =
-        make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    *reinterpret_cast<float4*>(ctx.t_shadow + m * ctx.PQ + i) = hi;
+    if (first_layer)
+      *reinterpret_cast<float4*>(ctx.t_shadow_lo + m * ctx.PQ + i) =
+          make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
   }
 }
 

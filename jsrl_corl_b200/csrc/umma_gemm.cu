@@ -130,6 +130,9 @@ struct UmmaParams {
   // gradient): one unit = all M tiles of one (problem, N tile), so that the column sums of the produced
   // gradient are completed inside one CTA in a fixed order -- no atomics, no zero-fill.
   int prob_major, units, tiles_per_unit;
+  // 3xTF32 input layer: the K loop runs n_split passes over K, pass j taking A from map a_sel[j] and B from
+  // map b_sel[j] of the problem's maps_per_prob tensor maps: (Xhi,Whi), (Xlo,Whi), (Xhi,Wlo).
+  int n_split, maps_per_prob, a_sel[3], b_sel[3];
 };
 
 __device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int j, int& prob, int& m0, int& n0) {
@@ -197,15 +200,18 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
         int prob, m0, n0;
         decode_tile(up, u, j, prob, m0, n0);
         const int K = probs[prob].K;
-        const CUtensorMap* mapA = maps + 2 * prob;
-        const CUtensorMap* mapB = mapA + 1;
-        const int num_kb = (K + TILE_K - 1) / TILE_K;  // TMA zero-fills the K tail
+        const CUtensorMap* pmaps = maps + up.maps_per_prob * prob;
+        const int nkb = (K + TILE_K - 1) / TILE_K;  // TMA zero-fills the K tail
+        const int num_kb = nkb * up.n_split;
         for (int kb = 0; kb < num_kb; ++kb) {
+          const int sj = kb / nkb;
+          const CUtensorMap* mapA = pmaps + up.a_sel[sj];
+          const CUtensorMap* mapB = pmaps + up.b_sel[sj];
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
           const uint32_t fb = full0 + 8 * stage;
           mbar_expect_tx(fb, STAGE_A_BYTES + tile_n * TILE_K * 4);
-          const int k0 = kb * TILE_K;
+          const int k0 = (kb - sj * nkb) * TILE_K;
           if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
           else tma_load_2d(sa, mapA, fb, k0, m0);
           if (up.b_mn) tma_load_3d(sb, mapB, fb, 0, k0, n0 >> 5);
@@ -222,7 +228,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
       for (int j = 0; j < up.tiles_per_unit; ++j, ++it) {
         int prob, m0, n0;
         decode_tile(up, u, j, prob, m0, n0);
-        const int num_kb = (probs[prob].K + TILE_K - 1) / TILE_K;
+        const int num_kb = ((probs[prob].K + TILE_K - 1) / TILE_K) * up.n_split;
         const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(tempty0 + 8 * buf, acc_phase ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
@@ -553,6 +559,10 @@ int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, v
 static UmmaParams make_params(int mode, int tile_n) {
   UmmaParams u;
   u.tile_n = tile_n;
+  u.n_split = 1;
+  u.maps_per_prob = 2;
+  u.a_sel[0] = u.a_sel[1] = u.a_sel[2] = 0;
+  u.b_sel[0] = u.b_sel[1] = u.b_sel[2] = 1;
   const int a_mn = (mode == 2), b_mn = (mode != 0);
   u.a_mn = a_mn;
   u.b_mn = b_mn;
@@ -573,10 +583,24 @@ static UmmaParams make_params(int mode, int tile_n) {
   return u;
 }
 
+// 3xTF32 forward of the input layer: 4 maps per problem = [Xhi, Whi, Xlo, Wlo] (all K-major)
+int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out) {
+  CUtensorMap* maps = (CUtensorMap*)h_maps_out;
+  for (int i = 0; i < nprob; ++i) {
+    const GemmProb& a = h_hi[i];
+    const GemmProb& b = h_lo[i];
+    if (encode_kmajor(&maps[4 * i + 0], a.A, a.M, a.K, a.lda, TILE_M)) return 1;
+    if (encode_kmajor(&maps[4 * i + 1], a.B, a.N, a.K, a.ldb, tile_n)) return 1;
+    if (encode_kmajor(&maps[4 * i + 2], b.A, b.M, b.K, b.lda, TILE_M)) return 1;
+    if (encode_kmajor(&maps[4 * i + 3], b.B, b.N, b.K, b.ldb, tile_n)) return 1;
+  }
+  return 0;
+}
+
 bool umma_can_fuse_out(int act_dim) { return act_dim <= FUSE_AMAX && getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
 
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
-                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st) {
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(umma_gemm_kernel<EPI_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -591,6 +615,13 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
   up.tiles_m = (maxM + TILE_M - 1) / TILE_M;
   up.tiles_n = (maxN + tile_n - 1) / tile_n;
   up.total_tiles = nprob * up.tiles_m * up.tiles_n;
+  if (split3) {  // passes: Xhi Whi, Xlo Whi, Xhi Wlo
+    up.n_split = 3;
+    up.maps_per_prob = 4;
+    up.a_sel[0] = 0; up.b_sel[0] = 1;
+    up.a_sel[1] = 2; up.b_sel[1] = 1;
+    up.a_sel[2] = 0; up.b_sel[2] = 3;
+  }
   up.prob_major = (epi == EPI_DRELU) ? 1 : 0;
   up.tiles_per_unit = up.prob_major ? up.tiles_m : 1;
   up.units = up.total_tiles / up.tiles_per_unit;
