@@ -324,8 +324,9 @@ static void build_problems(iql_engine* e) {
   // ---- forward phases, layer 0..L ----
   for (int l = 0; l <= L; ++l) {
     Phase ph; ph.mode = 0; ph.first = (int)e->h_probs.size(); ph.maxM = B; ph.maxN = 0; ph.K = 0; ph.umma_ok = false;
-    for (int m = 0; m < S; ++m)
-      for (int f = 0; f < N_PASS; ++f) {
+    // pass-major order: the six scalar-head passes of all members first, the policy pass last
+    for (int f = 0; f < N_PASS; ++f)
+      for (int m = 0; m < S; ++m) {
         const PassDef& pd = passes[f];
         const float* blk = pd.tgt ? e->target + (int64_t)m * PQ : e->params + (int64_t)m * P;
         GemmProb p = blank();
@@ -654,9 +655,17 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       // forward, last hidden layer: fuse the FP32 output Linear into the epilogue and skip the next phase
       const bool fuse = ph.mode == 0 && ph.epi == EPI_RELU && next && next->kind == PH_OUT_FWD && H == 256 &&
                         umma_can_fuse_out(A);
+      const int n_scalar = (N_PASS - 1) * e->cfg.n_members;  // problems with a scalar head (V, Q passes)
       launch_umma_gemm(ph.mode, pp, split ? e->d_maps_first : e->d_maps + (size_t)256 * ph.first,
-                       fuse ? e->d_probs + next->first : nullptr, ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st, split);
-      if (fuse) skip_next = true;
+                       fuse ? e->d_probs + next->first : nullptr, ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st, split,
+                       n_scalar);
+      if (fuse) {  // the policy head (N = act_dim) stays with the FP32 output-layer kernel
+        const GemmProb* pa = e->d_probs + next->first + n_scalar;
+        if (out_ok) launch_out_fwd(pa, ph.count - n_scalar, B, H, A, st);
+        else launch_simt_gemm(0, pa, ph.count - n_scalar, B, A, ctx, st);
+        ++launches;
+        skip_next = true;
+      }
       if (ph.mode == 1) skip_colsum = true;  // the dgrad epilogue wrote the bias gradient of the layer below
       if (ph.mode == 2) {
         if (skip_colsum) skip_colsum = false;  // db already written by the fused output-layer backward

@@ -35,12 +35,14 @@ constexpr int TILE_M = 128, TILE_N = 256 /* maximum; the N tile is a launch para
 constexpr int STAGE_A_BYTES = TILE_M * TILE_K * 4;  // 16 KB
 constexpr int STAGE_B_BYTES = TILE_N * TILE_K * 4;  // 32 KB
 constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-constexpr int N_EPI_WARPS = 8;
+constexpr int N_EPI_WARPS = 16;                                       // 4 column groups x 4 TMEM lane quarters
+constexpr int N_CGROUPS = N_EPI_WARPS / 4;
 constexpr int STG_FLOATS = 32 * 36;                                   // per-warp transpose tile
-constexpr int FUSE_AMAX = 8;                                          // head rows evaluated in the epilogue
-constexpr int EPI_SMEM_BYTES = N_EPI_WARPS * STG_FLOATS * 4 + 2 * 2 * TILE_M * FUSE_AMAX * 4;  // staging + 2x head partials
+constexpr int AUX_FLOATS = 2 * N_CGROUPS * TILE_M;                    // head partials [2 parities][4 groups][128]; also
+                                                                      // the bias-gradient sums [4 quarters][256]
+constexpr int EPI_SMEM_BYTES = N_EPI_WARPS * STG_FLOATS * 4 + (AUX_FLOATS > 4 * TILE_N ? AUX_FLOATS : 4 * TILE_N) * 4;
 constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int N_THREADS = 320;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-9 epilogue (2 per TMEM lane quarter)
+constexpr int N_THREADS = 576;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-17 epilogue (4 per TMEM lane quarter)
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -133,6 +135,7 @@ struct UmmaParams {
   // 3xTF32 input layer: the K loop runs n_split passes over K, pass j taking A from map a_sel[j] and B from
   // map b_sel[j] of the problem's maps_per_prob tensor maps: (Xhi,Whi), (Xlo,Whi), (Xhi,Wlo).
   int n_split, maps_per_prob, a_sel[3], b_sel[3];
+  int fuse_count;  // FUSE_OUT: problems [0, fuse_count) have a scalar head evaluated in the epilogue
 };
 
 __device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int j, int& prob, int& m0, int& n0) {
@@ -149,9 +152,11 @@ __device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int 
   }
 }
 
-// FUSE_OUT (forward, last hidden layer): the output Linear y = H_L W_L^T + b_L (N = 1 or act_dim <= 8) is
-// evaluated in the epilogue, in FP32, on the FP32 accumulators -- the Q/V/policy heads never see TF32 rounding
-// and H_L makes no extra trip through HBM.  `probs_out` is the problem table of the output-layer phase.
+// FUSE_OUT (forward, last hidden layer): the scalar heads y = H_L w^T + b (Q, V: N = 1) of the first
+// `up.fuse_count` problems are evaluated in the epilogue, in FP32, on the FP32 accumulators -- Q and V never see
+// TF32 rounding and H_L makes no extra trip through HBM (for the forward-only passes it is never stored).
+// `probs_out` is the problem table of the output-layer phase; the policy head (N = act_dim) of the remaining
+// problems is left to the FP32 output-layer kernel.
 template <int EPI, bool FUSE_OUT>
 __global__ void __launch_bounds__(N_THREADS, 1)
 umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restrict__ maps,
@@ -253,9 +258,9 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     // ===================== epilogue (warps 2..9) =====================
     // warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a quarter and split the columns.
     const int q = warp & 3;
-    const int ch = (warp - 2) >> 2;  // column half handled by this warp
+    const int ch = (warp - 2) >> 2;  // column group (0..3) handled by this warp: chunks ch, ch+4
     float* stg = epi_smem + (warp - 2) * STG_FLOATS;
-    float* ypart_all = epi_smem + N_EPI_WARPS * STG_FLOATS;  // [2 tile parities][2 column halves][128 rows][FUSE_AMAX]
+    float* ypart_all = epi_smem + N_EPI_WARPS * STG_FLOATS;  // [2 tile parities][4 column groups][128 rows]
     const int lr = lane >> 3;        // row within a group of 4
     const int lc = (lane & 7) * 4;   // first of this lane's 4 columns
     uint32_t it = 0;
@@ -265,26 +270,28 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
       decode_tile(up, u, j, prob, m0, n0);
       const GemmProb p = probs[prob];
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      // per-member scalars are read ONCE per tile into registers: inside the store loop the compiler would
+      // have to reload them after every global store (possible aliasing), exposing a DRAM latency per row
       const MemberScalars* sc = ctx.scalars + p.member;
+      const uint32_t drop_thr = (p.drop_layer >= 0) ? sc->drop_threshold : 0u;
+      const float drop_scale = sc->drop_scale;
+      const uint64_t drop_seed = sc->seed;
       float dscale = 1.0f;
       bool drop = false;
       uint64_t dstep = 0;
-      if (EPI == EPI_DRELU) dscale = (p.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
+      if (EPI == EPI_DRELU) dscale = (drop_thr != 0u) ? drop_scale : 1.0f;
       if (EPI == EPI_RELU) {
-        drop = p.drop_layer >= 0 && sc->drop_threshold != 0u;
+        drop = drop_thr != 0u;
         if (drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
       }
       GemmProb po;
-      int a_out = 0;
-      float* ypart = ypart_all + (it & 1) * (2 * TILE_M * FUSE_AMAX);
-      if (FUSE_OUT) { po = probs_out[prob]; a_out = po.N; }
-      float yacc[8][FUSE_AMAX];
-      if (FUSE_OUT) {
+      const bool fuse = FUSE_OUT && prob < up.fuse_count;
+      float* ypart = ypart_all + (it & 1) * (N_CGROUPS * TILE_M);
+      if (fuse) po = probs_out[prob];
+      const bool skip_store = fuse && p.no_store;
+      float yacc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int m = 0; m < FUSE_AMAX; ++m) yacc[i][m] = 0.f;
-      }
+      for (int i = 0; i < 8; ++i) yacc[i] = 0.f;
       const int row_base = m0 + q * 32;
       const int n_chunks = tile_n >> 5;
       // fused bias gradient (dgrad): column sums of the produced G over all rows of the problem
@@ -293,16 +300,11 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
       // Operand prefetch for the epilogue, one chunk ahead: the ReLU mask (dgrad), the bias (forward) and the
       // head weights do not depend on the accumulator, so the first chunk's loads are in flight while this
       // warp still waits for the MMAs, and chunk c+2's loads are issued before chunk c is processed.
-      float4 mk[8], mk_n[8];
+      float4 mk[8];
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), b4_n = b4;
-      float4 w4[FUSE_AMAX], w4_n[FUSE_AMAX];
-      auto prefetch = [&](int c, float4* mkd, float4& bd, float4* wd) {
+      float4 w4 = b4, w4_n = b4;
+      auto prefetch = [&](int c, float4& bd, float4& wd) {
         const int col = n0 + c * 32 + lc;
-        if (EPI == EPI_DRELU) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            mkd[i] = __ldg(reinterpret_cast<const float4*>(p.mask + (int64_t)(row_base + i * 4 + lr) * p.ldmask + col));
-        }
         if (EPI == EPI_RELU) bd = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         if (EPI == EPI_LINEAR) {  // output layer: N = 1 or act_dim, guarded
           bd.x = col < p.N ? p.bias[col] : 0.f;
@@ -310,35 +312,28 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           bd.z = col + 2 < p.N ? p.bias[col + 2] : 0.f;
           bd.w = col + 3 < p.N ? p.bias[col + 3] : 0.f;
         }
-        if (FUSE_OUT) {
-          if (a_out == 1) {
-            wd[0] = __ldg(reinterpret_cast<const float4*>(po.B + col));
-          } else {
-#pragma unroll
-            for (int m = 0; m < FUSE_AMAX; ++m)
-              wd[m] = (m < a_out) ? __ldg(reinterpret_cast<const float4*>(po.B + (int64_t)m * po.ldb + col))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
+        if (fuse) wd = __ldg(reinterpret_cast<const float4*>(po.B + col));
       };
-      if (ch < n_chunks) prefetch(ch, mk_n, b4_n, w4_n);
+      if (ch < n_chunks) prefetch(ch, b4_n, w4_n);
       mbar_wait(tfull0 + 8 * buf, acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = ch; c < n_chunks; c += 2) {
+      for (int c = ch; c < n_chunks; c += N_CGROUPS) {
         const int col = n0 + c * 32 + lc;
         // full 16-byte accesses when this lane's 4 columns exist and rows are 16-byte aligned
         const bool vec = (col + 3 < p.N) && ((p.ldc & 3) == 0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mk[i] = mk_n[i];
         b4 = b4_n;
+        w4 = w4_n;
+        if (c + N_CGROUPS < n_chunks) prefetch(c + N_CGROUPS, b4_n, w4_n);
+        if (EPI == EPI_DRELU) {  // ReLU mask of this chunk: in flight during the TMEM read and the transpose
 #pragma unroll
-        for (int m = 0; m < FUSE_AMAX; ++m) w4[m] = w4_n[m];
-        if (c + 2 < n_chunks) prefetch(c + 2, mk_n, b4_n, w4_n);
+          for (int i = 0; i < 8; ++i)
+            mk[i] = __ldg(reinterpret_cast<const float4*>(p.mask + (int64_t)(row_base + i * 4 + lr) * p.ldmask + col));
+        }
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + c * 32), r);
         tmem_ld_wait();
-        if (c + 2 >= n_chunks) {  // last TMEM read of this warp for this tile: hand the accumulator back
+        if (c + N_CGROUPS >= n_chunks) {  // last TMEM read of this warp for this tile: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -362,15 +357,15 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
               if (ctx.dropout_masks) {
                 const uint8_t* mkb = ctx.dropout_masks +
                                      ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H + col;
-                v.x = mkb[0] ? v.x * sc->drop_scale : 0.f; v.y = mkb[1] ? v.y * sc->drop_scale : 0.f;
-                v.z = mkb[2] ? v.z * sc->drop_scale : 0.f; v.w = mkb[3] ? v.w * sc->drop_scale : 0.f;
+                v.x = mkb[0] ? v.x * drop_scale : 0.f; v.y = mkb[1] ? v.y * drop_scale : 0.f;
+                v.z = mkb[2] ? v.z * drop_scale : 0.f; v.w = mkb[3] ? v.w * drop_scale : 0.f;
               } else {
                 const uint32_t quad = (uint32_t)(((int64_t)row * p.N + col) >> 2);
-                const Philox4 ph = philox_dropout_quad(sc->seed, dstep, (uint32_t)p.drop_layer, quad);
-                v.x = (ph.x >= sc->drop_threshold) ? v.x * sc->drop_scale : 0.f;
-                v.y = (ph.y >= sc->drop_threshold) ? v.y * sc->drop_scale : 0.f;
-                v.z = (ph.z >= sc->drop_threshold) ? v.z * sc->drop_scale : 0.f;
-                v.w = (ph.w >= sc->drop_threshold) ? v.w * sc->drop_scale : 0.f;
+                const Philox4 ph = philox_dropout_quad(drop_seed, dstep, (uint32_t)p.drop_layer, quad);
+                v.x = (ph.x >= drop_thr) ? v.x * drop_scale : 0.f;
+                v.y = (ph.y >= drop_thr) ? v.y * drop_scale : 0.f;
+                v.z = (ph.z >= drop_thr) ? v.z * drop_scale : 0.f;
+                v.w = (ph.w >= drop_thr) ? v.w * drop_scale : 0.f;
               }
             }
           } else if (EPI == EPI_LINEAR) {
@@ -380,15 +375,9 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
             v.z = mk[i].z > 0.f ? v.z * dscale : 0.f; v.w = mk[i].w > 0.f ? v.w * dscale : 0.f;
             cs4.x += v.x; cs4.y += v.y; cs4.z += v.z; cs4.w += v.w;
           }
-          if (FUSE_OUT) {
-            if (a_out == 1) {  // scalar heads (Q, V): the common case, warp-uniform
-              yacc[i][0] = fmaf(v.x, w4[0].x, fmaf(v.y, w4[0].y, fmaf(v.z, w4[0].z, fmaf(v.w, w4[0].w, yacc[i][0]))));
-            } else {
-#pragma unroll
-              for (int m = 0; m < FUSE_AMAX; ++m)
-                yacc[i][m] = fmaf(v.x, w4[m].x, fmaf(v.y, w4[m].y, fmaf(v.z, w4[m].z, fmaf(v.w, w4[m].w, yacc[i][m]))));
-            }
-            if (p.no_store) continue;
+          if (fuse) {
+            yacc[i] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, yacc[i]))));
+            if (skip_store) continue;
           }
           if (EPI == EPI_RELU || EPI == EPI_DRELU) {  // these outputs are operands of later tcgen05 GEMMs
             v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
@@ -418,47 +407,35 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
         __syncwarp();
       }
       if (do_csum && j == up.tiles_per_unit - 1) {  // all rows of the problem seen: combine the quarters
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int tc = threadIdx.x - 64;  // 0..255 = column of this N tile
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const int tc = threadIdx.x - 64;  // 0..511; the first tile_n threads own one column each
         if (tc < tile_n && n0 + tc < p.N)
           p.dbias[n0 + tc] = ((csum_s[tc] + csum_s[TILE_N + tc]) + csum_s[2 * TILE_N + tc]) + csum_s[3 * TILE_N + tc];
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // csum_s is reused by the next unit
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // csum_s is reused by the next unit
       }
-      if (n_chunks <= ch) {  // this warp had no chunk (tile_n == 32 and ch == 1): still release the accumulator
+      if (n_chunks <= ch) {  // this warp had no chunk (tile_n < 128): still release the accumulator
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
       }
       if (FUSE_OUT) {
-        // reduce the 8 lanes that share a row, park the per-column-half partial sums, combine the halves
-        if (a_out == 1) {
+        // scalar heads: reduce the 8 lanes that share a row, park the per-column-group partials, combine them.
+        // Every epilogue warp takes part in the barrier (tiles without a fused head just pass through).
+        if (fuse) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float tsum = yacc[i][0];
+            float tsum = yacc[i];
             tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
             tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
             tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
-            if ((lane & 7) == 0) ypart[(ch * TILE_M + q * 32 + i * 4 + lr) * FUSE_AMAX] = tsum;
+            if ((lane & 7) == 0) ypart[ch * TILE_M + q * 32 + i * 4 + lr] = tsum;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int m = 0; m < FUSE_AMAX; ++m) {
-              if (m < a_out) {  // warp-uniform
-                float tsum = yacc[i][m];
-                tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
-                tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
-                tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
-                if ((lane & 7) == 0) ypart[(ch * TILE_M + q * 32 + i * 4 + lr) * FUSE_AMAX + m] = tsum;
-              }
-            }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps
-        const int tr = threadIdx.x - 64;                // 0..255
-        if (tr < TILE_M)
-          for (int m = 0; m < a_out; ++m)
-            po.C[(int64_t)(m0 + tr) * po.ldc + m] = (ypart[tr * FUSE_AMAX + m] + ypart[(TILE_M + tr) * FUSE_AMAX + m]) + po.bias[m];
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // the 16 epilogue warps
+        const int tr = threadIdx.x - 64;                // 0..511
+        if (fuse && tr < TILE_M)
+          po.C[(int64_t)(m0 + tr) * po.ldc] =
+              (((ypart[tr] + ypart[TILE_M + tr]) + ypart[2 * TILE_M + tr]) + ypart[3 * TILE_M + tr]) + po.bias[0];
       }
     }
   }
@@ -560,6 +537,7 @@ static UmmaParams make_params(int mode, int tile_n) {
   UmmaParams u;
   u.tile_n = tile_n;
   u.n_split = 1;
+  u.fuse_count = 0;
   u.maps_per_prob = 2;
   u.a_sel[0] = u.a_sel[1] = u.a_sel[2] = 0;
   u.b_sel[0] = u.b_sel[1] = u.b_sel[2] = 1;
@@ -597,10 +575,10 @@ int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob
   return 0;
 }
 
-bool umma_can_fuse_out(int act_dim) { return act_dim <= FUSE_AMAX && getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
+bool umma_can_fuse_out(int act_dim) { (void)act_dim; return getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
 
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
-                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3) {
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3, int fuse_count) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(umma_gemm_kernel<EPI_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -622,6 +600,7 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
     up.a_sel[1] = 2; up.b_sel[1] = 1;
     up.a_sel[2] = 0; up.b_sel[2] = 3;
   }
+  up.fuse_count = probs_out ? fuse_count : 0;
   up.prob_major = (epi == EPI_DRELU) ? 1 : 0;
   up.tiles_per_unit = up.prob_major ? up.tiles_m : 1;
   up.units = up.total_tiles / up.tiles_per_unit;

@@ -11,12 +11,12 @@ bool umma_phase_supported(int mode, int batch, int hidden);
 // tile_n = umma_tile_n(max N of the phase): the UMMA N / B-tile height used by the launch.
 int umma_tile_n(int maxN);
 int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, void* h_maps_out);
-// probs_out != null (forward, last hidden layer, EPI_RELU): the output-layer problems whose Linear is
-// evaluated in FP32 inside the epilogue (see umma_can_fuse_out).
+// probs_out != null (forward, last hidden layer, EPI_RELU): the output-layer problem table; the scalar heads
+// of its first `fuse_count` problems are evaluated in FP32 inside the epilogue.
 bool umma_can_fuse_out(int act_dim);
 // split3: 3xTF32 input layer; `maps` then holds 4 maps per problem (umma_encode_maps_split).
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
-                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3 = false);
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3 = false, int fuse_count = 0);
 int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out);
 // bias gradients of a wgrad phase: dbias[m] = sum_k A[k][m]
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st);

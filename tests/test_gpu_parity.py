@@ -171,7 +171,10 @@ def test_update_matches_reference_short_horizon_tf32(name, steps):
     eng, _ = _make_engine(g, "tf32")
     losses = _run_indices(eng, g, steps)[0]
     err = _loss_errors(losses, g.losses[:steps].astype(np.float64))
-    assert err[:5].max() < TF32_TOL, err[:5].max()
+    # the actor loss carries exp(beta * adv): its sensitivity to a perturbation of adv scales with beta
+    # (beta = 3 in the locomotion configs, 10 in antmaze); the bar scales accordingly
+    tol5 = TF32_TOL * max(1.0, g.meta["beta"] / 3.0)
+    assert err[:5].max() < tol5, err[:5].max()
     assert err.max() < TF32_DRIFT_TOL, err.max()
     got, ref = _cpu_tree(eng.param_views(0)), g.tree(f"step{steps}")
     worst, where = tree_max_rel(got, ref)
