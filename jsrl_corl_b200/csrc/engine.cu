@@ -666,7 +666,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
         ++launches;
         skip_next = true;
       }
-      if (ph.mode == 1) skip_colsum = true;  // the dgrad epilogue wrote the bias gradient of the layer below
+      if (ph.mode == 1 && umma_dgrad_writes_dbias(B)) skip_colsum = true;  // the dgrad epilogue wrote db of the layer below
       if (ph.mode == 2) {
         if (skip_colsum) skip_colsum = false;  // db already written by the fused output-layer backward
         else { launch_colsum(pp, ph.count, ph.maxM, st); ++launches; }

@@ -446,14 +446,27 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
   }
 }
 
-// bias gradient of the wgrad phases: dbias[m] = sum_k A[k][m]  (A = G, [K=B rows][M] row-major)
+// bias gradient of the wgrad phases: dbias[m] = sum_k A[k][m]  (A = G, [K = batch rows][M] row-major).
+// 256 threads = 32 columns x 8 row groups: coalesced 128-byte row segments, fixed summation order.
 __global__ void __launch_bounds__(256) colsum_kernel(const GemmProb* __restrict__ probs) {
+  __shared__ float part[8][33];
   const GemmProb p = probs[blockIdx.y];
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= p.M || p.dbias == nullptr) return;
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int m = blockIdx.x * 32 + c;
   float s = 0.f;
-  for (int k = 0; k < p.K; ++k) s += p.A[(int64_t)k * p.lda + m];
-  p.dbias[m] = s;
+  if (m < p.M && p.dbias != nullptr) {
+    int k = g;
+    for (; k + 24 < p.K; k += 32) {  // 4 independent loads in flight
+      const float a0 = p.A[(int64_t)k * p.lda + m], a1 = p.A[(int64_t)(k + 8) * p.lda + m];
+      const float a2 = p.A[(int64_t)(k + 16) * p.lda + m], a3 = p.A[(int64_t)(k + 24) * p.lda + m];
+      s += (a0 + a1) + (a2 + a3);
+    }
+    for (; k < p.K; k += 8) s += p.A[(int64_t)k * p.lda + m];
+  }
+  part[g][c] = s;
+  __syncthreads();
+  if (g == 0 && m < p.M && p.dbias != nullptr)
+    p.dbias[m] = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) + ((part[4][c] + part[5][c]) + (part[6][c] + part[7][c]));
 }
 
 // ---------------------------------------------------------------------------
@@ -483,7 +496,7 @@ bool umma_phase_supported(int mode, int batch, int hidden) {
   (void)mode;  // every tcgen05 phase has M in {batch, hidden}: both must be multiples of the 256-row tile
   static int disabled = -1;
   if (disabled < 0) disabled = getenv("IQL_B200_NO_UMMA") ? 1 : 0;
-  return !disabled && batch == 256 && hidden >= 256 && hidden % 256 == 0;
+  return !disabled && batch >= 128 && batch % 128 == 0 && hidden >= 256 && hidden % 256 == 0;
 }
 
 // K-major operand [rows][K] (ld floats): 2-D map {K, rows}, box {32, box_rows}, SWIZZLE_128B.
@@ -575,6 +588,8 @@ int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob
   return 0;
 }
 
+bool umma_dgrad_writes_dbias(int batch) { return (batch + TILE_M - 1) / TILE_M <= 2; }
+
 bool umma_can_fuse_out(int act_dim) { (void)act_dim; return getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
 
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
@@ -601,7 +616,9 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
     up.a_sel[2] = 0; up.b_sel[2] = 3;
   }
   up.fuse_count = probs_out ? fuse_count : 0;
-  up.prob_major = (epi == EPI_DRELU) ? 1 : 0;
+  // fused bias gradient needs all M tiles of a problem in one CTA: only worth it while that leaves enough
+  // independent units to fill the GPU (batch <= 256); larger batches use tile-major order + colsum_kernel
+  up.prob_major = (epi == EPI_DRELU && up.tiles_m <= 2) ? 1 : 0;
   up.tiles_per_unit = up.prob_major ? up.tiles_m : 1;
   up.units = up.total_tiles / up.tiles_per_unit;
   static int n_sm = 0;
@@ -621,7 +638,7 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
 }
 
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st) {
-  dim3 grid((maxM + 255) / 256, nprob);
+  dim3 grid((maxM + 31) / 32, nprob);
   colsum_kernel<<<grid, 256, 0, st>>>(probs);
 }
 

@@ -14,6 +14,8 @@ int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, v
 // probs_out != null (forward, last hidden layer, EPI_RELU): the output-layer problem table; the scalar heads
 // of its first `fuse_count` problems are evaluated in FP32 inside the epilogue.
 bool umma_can_fuse_out(int act_dim);
+// true when the dgrad epilogue also produces the bias gradient of the layer below (else run launch_colsum)
+bool umma_dgrad_writes_dbias(int batch);
 // split3: 3xTF32 input layer; `maps` then holds 4 maps per problem (umma_encode_maps_split).
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
                       int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3 = false, int fuse_count = 0);

@@ -405,3 +405,33 @@ def test_philox_dropout_masks_equal_cpu_restatement_and_oracle(math_mode, H, B):
     assert _loss_errors(la[0], np.array(ref)).max() < tol
     worst, where = tree_max_rel(wa, orc.state())
     assert worst < (FP32_TOL if math_mode == "fp32" else TF32_W30_TOL), (worst, where)
+
+
+@pytest.mark.parametrize("B,H,L,A", [(384, 512, 3, 3), (128, 256, 1, 6), (512, 256, 2, 24)])
+def test_tcgen05_path_general_shapes_match_oracle(B, H, L, A):
+    """Batch sizes that are multiples of 128, hidden widths that are multiples of 256 (several N tiles and
+    M tiles per problem), one to three hidden layers, wide action spaces: TF32 path vs the numpy oracle."""
+    from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
+    from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
+    from oracle.philox import philox_indices
+
+    S_dim, n_rows, steps = 11, 3000, 3
+    ens = IQLEnsemble(2, S_dim, A, H, L, B, deterministic=False, math_mode="tf32", seeds=[5, 6], max_steps_per_call=4,
+                      hparams=[dict(cosine_t_max=50)] * 2)
+    data = synthetic_dataset(n_rows, S_dim, A, 1)
+    rb = ReplayBuffer(S_dim, A, n_rows, "cuda")
+    rb.load_d4rl_dataset(data)
+    ens.bind_replay(rb)
+    init = [{g: {k: v.copy() for k, v in d.items()} for g, d in _cpu_tree(ens.engine.param_views(m)).items()} for m in range(2)]
+    losses = ens.train_steps(steps).cpu().numpy()
+    for m in range(2):
+        orc = NumpyIQL(OracleConfig(S_dim, A, H, L, False, 0.0, max_steps=50), init[m], np.float32)
+        ref = []
+        for k in range(steps):
+            lo = orc.train(batch_from(data, philox_indices(ens.seeds[m], k, n_rows, B)))
+            ref.append([lo["value_loss"], lo["q_loss"], lo["actor_loss"]])
+        # deeper / wider stacks accumulate proportionally more TF32 rounding (two 512-wide TF32 layers here)
+        tol = TF32_TOL * max(1, L - 1) * max(1.0, (H / 256) ** 0.5) * 1.5
+        assert _loss_errors(losses[m], np.array(ref)).max() < tol, (m, _loss_errors(losses[m], np.array(ref)).max())
+        worst, where = tree_max_rel(_cpu_tree(ens.engine.param_views(m)), orc.state())
+        assert worst < TF32_W30_TOL, (worst, where)
