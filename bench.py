@@ -143,11 +143,14 @@ def cpu_reference_steps_per_sec(w, steps, warmup, n_rows=200_000):
     from jsrl_corl_b200.ensemble import reference_init
     from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
 
+    # all host threads (torchrun pins OMP_NUM_THREADS=1 in the workers' environment; undo that for this arm)
+    cores = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores)
         cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
-        cores = os.cpu_count() or 1
+        pass
     data = synthetic_dataset(n_rows, w["S"], w["A"], 0, antmaze_rewards=w["antmaze"])
     q, v, actor = reference_init(0, w["S"], w["A"], w["H"], w["L"], w["det"], w["dropout"])
     init = {g: {k: t.detach().numpy().copy() for k, t in mod.state_dict().items()} for g, mod in (("qf", q), ("vf", v), ("actor", actor))}

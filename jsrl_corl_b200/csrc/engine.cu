@@ -739,11 +739,14 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
   ctx.idx_out = idx_out;
   const bool gather = sample_mode != IQL_SAMPLE_PRELOADED;
   // the legacy default stream cannot be captured; the facade runs the engine on its own stream
-  const bool graphable = e->use_graphs && st != nullptr && sample_mode == IQL_SAMPLE_PHILOX && !dropout_masks &&
-                         !idx_out && k_steps > 1;
+  // Graphs: the K-step Philox loop, and the single preloaded step of the drop-in `train(batch)` path (its ~11
+  // launches would otherwise be launch-latency bound).  Keyed by K, negative for the preloaded variant.
+  const bool graphable = e->use_graphs && st != nullptr && !dropout_masks && !idx_out &&
+                         ((sample_mode == IQL_SAMPLE_PHILOX && k_steps > 1) || sample_mode == IQL_SAMPLE_PRELOADED);
+  const int graph_key = (sample_mode == IQL_SAMPLE_PRELOADED) ? -k_steps : k_steps;
   int64_t launches = 0;
   if (graphable) {
-    auto it = e->graphs.find(k_steps);
+    auto it = e->graphs.find(graph_key);
     if (it == e->graphs.end()) {
       cudaGraph_t graph = nullptr;
       CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -755,7 +758,7 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
       cudaGraphExec_t exec = nullptr;
       CUDA_TRY(e, cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
-      it = e->graphs.emplace(k_steps, std::make_pair(exec, launches)).first;
+      it = e->graphs.emplace(graph_key, std::make_pair(exec, launches)).first;
     }
     CUDA_TRY(e, cudaGraphLaunch(it->second.first, st));
     launches = it->second.second;
