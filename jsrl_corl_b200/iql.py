@@ -471,6 +471,8 @@ class ImplicitQLearning:
         self._pushed = None
         self._total_it = 0
         self._steps = {"v": 0, "q": 0, "actor": 0}
+        self._step_tensors: Dict[str, torch.Tensor] = {}
+        self._published = False
         S, A, H, L = self.qf.state_dim, self.qf.action_dim, self.qf.hidden_dim, self.qf.n_hidden
         if (self.vf.state_dim, self.vf.hidden_dim, self.vf.n_hidden) != (S, H, L) or \
                 (self.actor.state_dim, self.actor.hidden_dim, self.actor.n_hidden) != (S, H, L):
@@ -528,6 +530,7 @@ class ImplicitQLearning:
                 p.data = view
         self._engine = eng
         self._pushed = None
+        self._published = False
         self._push_counters()
         self._publish_optimizer_state()
         return eng
@@ -552,10 +555,16 @@ class ImplicitQLearning:
             steps = self._steps[{"qf": "q", "vf": "v", "actor": "actor"}[grp]]
             if steps == 0:
                 continue  # torch creates Adam state lazily at the first step
+            # one CPU step tensor per optimizer, shared by its parameters and updated in place after every
+            # update, so `optimizer.state_dict()` is current even when called directly on the optimizer
+            step_t = self._step_tensors.setdefault(grp, torch.tensor(0.0))
+            step_t.fill_(float(steps))
             for name in m_views[grp]:
                 p = mod.get_parameter(name)
-                opt.state[p] = {"step": torch.tensor(float(steps)), "exp_avg": m_views[grp][name],
-                                "exp_avg_sq": v_views[grp][name]}
+                st = opt.state.get(p)
+                if st is None or st.get("exp_avg") is not m_views[grp][name] or st.get("step") is not step_t:
+                    opt.state[p] = {"step": step_t, "exp_avg": m_views[grp][name], "exp_avg_sq": v_views[grp][name]}
+        self._published = len(self._step_tensors) == 3  # every optimizer has stepped at least once
 
     def _push_hparams(self):
         gq, gv, ga = _adam_group(self.q_optimizer), _adam_group(self.v_optimizer), _adam_group(self.actor_optimizer)
@@ -609,6 +618,11 @@ class ImplicitQLearning:
         self._total_it += 1
         for k in self._steps:
             self._steps[k] += 1
+        if self._published:
+            for grp, key in (("qf", "q"), ("vf", "v"), ("actor", "actor")):
+                self._step_tensors[grp].fill_(float(self._steps[key]))
+        else:
+            self._publish_optimizer_state()
         self._advance_schedule(1)
         v_loss, q_loss, a_loss = losses[0, 0].tolist()  # one D2H sync (the reference does three .item())
         return {"value_loss": v_loss, "q_loss": q_loss, "actor_loss": a_loss}

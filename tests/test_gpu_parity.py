@@ -435,3 +435,60 @@ def test_tcgen05_path_general_shapes_match_oracle(B, H, L, A):
         assert _loss_errors(losses[m], np.array(ref)).max() < tol, (m, _loss_errors(losses[m], np.array(ref)).max())
         worst, where = tree_max_rel(_cpu_tree(ens.engine.param_views(m)), orc.state())
         assert worst < TF32_W30_TOL, (worst, where)
+
+
+def test_facade_batch_size_change_and_partial_load_keep_state():
+    """The drop-in trainer sizes its engine from the first batch; a different batch size later migrates the
+    whole state (weights, Adam moments, counters).  partial_load_state_dict copies networks only."""
+    g = Golden("small_gauss")
+    m = g.meta
+    tr, rb = _facade_trainer(g, "fp32")
+    np.random.seed(3)
+    for _ in range(5):
+        tr.train(rb.sample(m["B"]))
+    before = {k: v.clone() for k, v in tr.qf.state_dict().items()}
+    m1 = tr.q_optimizer.state_dict()["state"][0]["exp_avg"].clone()
+    tr.train(rb.sample(16))  # new batch size -> new engine, same state
+    assert tr.total_it == 6 and float(tr.q_optimizer.state_dict()["state"][0]["step"]) == 6.0
+    after = tr.qf.state_dict()
+    # one Adam step moves every weight by at most ~lr
+    assert all((after[k] - before[k]).abs().max() < 2e-3 for k in before)
+    assert (tr.q_optimizer.state_dict()["state"][0]["exp_avg"] - 0.9 * m1).abs().max() < 1.0  # moments carried over
+    assert not torch.equal(tr.q_optimizer.state_dict()["state"][0]["exp_avg"], torch.zeros_like(m1))
+    tr2, _ = _facade_trainer(g, "fp32")
+    tr2.partial_load_state_dict(tr.state_dict())
+    assert tr2.total_it == 6
+    for k, v in tr.qf.state_dict().items():
+        assert torch.equal(v, tr2.qf.state_dict()[k]) and torch.equal(v, tr2.q_target.state_dict()[k])
+    assert tr2.q_optimizer.state_dict()["state"] == {}  # optimizers untouched (iql.py:595-606)
+    assert tr2.actor_lr_schedule.last_epoch == tr.actor_lr_schedule.last_epoch == 6
+
+
+def test_replay_offline_semantics_and_ensemble_shared_vs_private_buffers():
+    from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
+    from oracle.iql_numpy import synthetic_dataset
+
+    # offline/iql.py:173 samples from min(_size, _pointer); identical to _size right after load_d4rl_dataset
+    rb = ReplayBuffer(5, 2, 50, "cuda", offline_semantics=True)
+    rb.load_d4rl_dataset(synthetic_dataset(40, 5, 2, 0))
+    assert rb._high() == 40
+    np.random.seed(0)
+    a = rb.sample(8)
+    np.random.seed(0)
+    idx = np.random.randint(0, 40, size=8)
+    assert np.array_equal(a[0].cpu().numpy(), synthetic_dataset(40, 5, 2, 0)["observations"][idx])
+    # an ensemble bound to per-member buffers trains each member on its own data
+    data = [synthetic_dataset(300, 5, 2, s) for s in (1, 2)]
+    bufs = []
+    for d in data:
+        b = ReplayBuffer(5, 2, 300, "cuda")
+        b.load_d4rl_dataset(d)
+        bufs.append(b)
+    ens = IQLEnsemble(2, 5, 2, 32, 2, 16, math_mode="fp32", seeds=[7, 7])  # same seed: same init, same index stream
+    ens.bind_replay(bufs)
+    losses = ens.train_steps(3).cpu().numpy()
+    assert not np.allclose(losses[0], losses[1])  # different data
+    ens2 = IQLEnsemble(2, 5, 2, 32, 2, 16, math_mode="fp32", seeds=[7, 7])
+    ens2.bind_replay(bufs[0])
+    l2 = ens2.train_steps(3).cpu().numpy()
+    assert np.array_equal(l2[0], l2[1]) and np.array_equal(l2[0], losses[0])
