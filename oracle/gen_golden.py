@@ -184,8 +184,44 @@ def sampler_golden():
     print(f"sampler: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def resume_golden():
+    """A checkpoint written by the reference (torch.save(trainer.state_dict())) after 20 steps, and the losses of
+    the next 20 steps of a FRESH reference trainer that loaded it (load_state_dict re-clones q_target, iql.py:584)."""
+    ref = load_reference_iql("finetune")
+    S, A, H, L, B, n_rows = 11, 3, 64, 2, 32, 10000
+
+    def build():
+        torch.manual_seed(0)
+        q, v = ref.TwinQ(S, A, H, L), ref.ValueFunction(S, H, L)
+        actor = ref.GaussianPolicy(S, A, 1.0, H, L)
+        vo, qo, ao = (torch.optim.Adam(m.parameters(), lr=3e-4) for m in (v, q, actor))
+        return ref.ImplicitQLearning(1.0, actor, ao, q, qo, v, vo, max_steps=40, device="cpu")
+
+    data = synthetic_dataset(n_rows, S, A, 0)
+    rb = ref.ReplayBuffer(S, A, n_rows, "cpu")
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        rb.load_d4rl_dataset(data)
+    np.random.seed(1)
+    tr = build()
+    for _ in range(20):
+        tr.train(rb.sample(B))
+    path = os.path.join(OUT, "reference_checkpoint_19.pt")
+    torch.save(tr.state_dict(), path)
+    tr2 = build()
+    tr2.load_state_dict(torch.load(path))
+    losses = []
+    for _ in range(20):
+        log = tr2.train(rb.sample(B))
+        losses.append([log["value_loss"], log["q_loss"], log["actor_loss"]])
+    np.savez_compressed(os.path.join(OUT, "resume.npz"), losses_after_resume=np.array(losses, dtype=np.float32),
+                        dims=np.array([S, A, H, L, B, n_rows]), total_it=np.array(tr2.total_it))
+    print(f"resume: checkpoint {os.path.getsize(path) / 1e6:.2f} MB, final losses {losses[-1]}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    resume_golden()
     torch.set_num_threads(8)
     sampler_golden()
     # small Gaussian config with full optimizer state (teacher-forced single-step checks)

@@ -492,3 +492,31 @@ def test_replay_offline_semantics_and_ensemble_shared_vs_private_buffers():
     ens2.bind_replay(bufs[0])
     l2 = ens2.train_steps(3).cpu().numpy()
     assert np.array_equal(l2[0], l2[1]) and np.array_equal(l2[0], losses[0])
+
+
+def test_resume_from_reference_written_checkpoint():
+    """Load a checkpoint_19.pt written by the REFERENCE trainer (torch.save(trainer.state_dict())), continue for 20
+    steps on the same index stream, compare with what a fresh reference trainer did after loading the same file."""
+    import jsrl_corl_b200 as J
+    from oracle.iql_numpy import synthetic_dataset
+
+    z = np.load(GOLDEN + "/resume.npz")
+    S, A, H, L, B, n_rows = [int(x) for x in z["dims"]]
+    torch.manual_seed(123)  # different init on purpose: everything must come from the checkpoint
+    q, v, actor = J.TwinQ(S, A, H, L).cuda(), J.ValueFunction(S, H, L).cuda(), J.GaussianPolicy(S, A, 1.0, H, L).cuda()
+    vo, qo, ao = (torch.optim.Adam(m.parameters(), lr=3e-4) for m in (v, q, actor))
+    tr = J.ImplicitQLearning(1.0, actor, ao, q, qo, v, vo, max_steps=40, device="cuda", math_mode="fp32")
+    tr.load_state_dict(torch.load(GOLDEN + "/reference_checkpoint_19.pt", map_location="cuda"))
+    assert tr.total_it == 20 and tr.actor_lr_schedule.last_epoch == 20
+    rb = J.ReplayBuffer(S, A, n_rows, "cuda")
+    rb.load_d4rl_dataset(synthetic_dataset(n_rows, S, A, 0))
+    np.random.seed(1)
+    for _ in range(20):
+        np.random.randint(0, n_rows, size=B)  # the 20 batches consumed before the checkpoint
+    losses = []
+    for _ in range(20):
+        log = tr.train(rb.sample(B))
+        losses.append([log["value_loss"], log["q_loss"], log["actor_loss"]])
+    np.testing.assert_allclose(np.array(losses), z["losses_after_resume"], rtol=2e-5, atol=1e-8)
+    assert tr.total_it == int(z["total_it"]) == 40
+    assert abs(ao.param_groups[0]["lr"]) < 1e-12  # cosine schedule with T_max = 40 has reached eta_min = 0
