@@ -182,7 +182,8 @@ int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mode, const i
                     void* stream);
 /* replaces: actor(obs).mean / DeterministicPolicy.forward as used by
  * GaussianPolicy.act / DeterministicPolicy.act iql.py:371-379,403-413 in eval
- * mode: out[n,A] = clamp(max_action * tanh(MLP(states[n,S]))). */
+ * mode: out[n,A] = clamp(max_action * tanh(MLP(states[n,S]))).  member = -1 evaluates every member's
+ * policy on its own block of rows (vectorised envs): states [S][n][state_dim] -> out [S][n][action_dim]. */
 int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float max_action,
             float* out_actions, void* stream);
 /* Self-test hook for the tcgen05 TF32 GEMM building block (no reference

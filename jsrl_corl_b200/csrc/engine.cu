@@ -787,7 +787,7 @@ extern "C" int64_t iql_last_launch_count(const iql_engine* e) { return e ? e->la
 
 extern "C" int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float max_action,
                        float* out_actions, void* stream) {
-  if (!e || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_act: bad member");
+  if (!e || member < -1 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_act: bad member");
   if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_act: state not bound");
   if (!states || !out_actions || n < 0) return fail(e, IQL_ERR_INVALID, "iql_act: null or negative n");
   if (n == 0) return IQL_OK;
@@ -795,8 +795,10 @@ extern "C" int iql_act(iql_engine* e, int32_t member, const float* states, int64
   if (rc != IQL_OK) return rc;
   StepCtx ctx = make_ctx(e);
   const int L = e->cfg.n_hidden;
-  launch_act(ctx, e->params + (int64_t)member * e->layout.param_floats, e->d_act_off, e->d_act_off + (L + 1), states, n,
-             max_action, out_actions, (cudaStream_t)stream);
+  // member == -1: all members at once, states [S][n][state_dim] -> actions [S][n][action_dim]
+  const int first = member < 0 ? 0 : member, count = member < 0 ? e->cfg.n_members : 1;
+  launch_act(ctx, e->params + (int64_t)first * e->layout.param_floats, count, e->d_act_off, e->d_act_off + (L + 1), states,
+             n, max_action, out_actions, (cudaStream_t)stream);
   CUDA_TRY(e, cudaGetLastError());
   return IQL_OK;
 }

@@ -131,7 +131,7 @@ void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cu
 void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
                      int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st);
 void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax, cudaStream_t st);
-void launch_act(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
-                const float* states, int64_t n, float max_action, float* out, cudaStream_t st);
+void launch_act(const StepCtx& ctx, const float* actor_block, int n_members, const int64_t* w_off,
+                const int64_t* b_off, const float* states, int64_t n, float max_action, float* out, cudaStream_t st);
 
 }  // namespace iql

@@ -511,8 +511,8 @@ void launch_advance(const StepCtx& ctx, int K, cudaStream_t st) {
 // actor inference (eval mode): out = clamp(max_action * tanh(MLP(s)))
 // one CTA per state row, one warp per output neuron, activations in smem
 // ===========================================================================
-__global__ void __launch_bounds__(256) act_kernel(int S, int A, int H, int L, const float* __restrict__ block,
-                                                  const int64_t* __restrict__ w_off,
+__global__ void __launch_bounds__(256) act_kernel(int S, int A, int H, int L, const float* __restrict__ block0,
+                                                  int64_t member_stride, const int64_t* __restrict__ w_off,
                                                   const int64_t* __restrict__ b_off,
                                                   const float* __restrict__ states, float max_action,
                                                   float* __restrict__ out) {
@@ -520,7 +520,9 @@ __global__ void __launch_bounds__(256) act_kernel(int S, int A, int H, int L, co
   const int width = H > S ? H : S;
   float* cur = sm;
   float* nxt = sm + width;
-  const int64_t row = blockIdx.x;
+  // blockIdx.y = ensemble member (vectorised-env mode: every member's policy on its own rows), blockIdx.x = row
+  const float* block = block0 + blockIdx.y * member_stride;
+  const int64_t row = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
   for (int i = threadIdx.x; i < S; i += blockDim.x) cur[i] = states[row * S + i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -547,11 +549,12 @@ __global__ void __launch_bounds__(256) act_kernel(int S, int A, int H, int L, co
   }
 }
 
-void launch_act(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
-                const float* states, int64_t n, float max_action, float* out, cudaStream_t st) {
+void launch_act(const StepCtx& ctx, const float* actor_block, int n_members, const int64_t* w_off,
+                const int64_t* b_off, const float* states, int64_t n, float max_action, float* out, cudaStream_t st) {
   const int width = ctx.H > ctx.S_dim ? ctx.H : ctx.S_dim;
-  act_kernel<<<(unsigned)n, 256, 2 * width * sizeof(float), st>>>(ctx.S_dim, ctx.A_dim, ctx.H, ctx.L, actor_block,
-                                                                  w_off, b_off, states, max_action, out);
+  dim3 grid((unsigned)n, (unsigned)n_members);
+  act_kernel<<<grid, 256, 2 * width * sizeof(float), st>>>(ctx.S_dim, ctx.A_dim, ctx.H, ctx.L, actor_block, ctx.P, w_off,
+                                                           b_off, states, max_action, out);
 }
 
 }  // namespace iql

@@ -345,6 +345,8 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
                           __uint_as_float(r[4 * j + 3]));
         __syncwarp();
         float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* const cbase = p.C + (int64_t)(row_base + lr) * p.ldc + col;  // row i*4+lr is 4*i*ldc floats further
+        const int cstep = 4 * p.ldc;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + lr;
@@ -382,7 +384,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           if (EPI == EPI_RELU || EPI == EPI_DRELU) {  // these outputs are operands of later tcgen05 GEMMs
             v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
           }
-          float* crow = p.C + (int64_t)row * p.ldc + col;
+          float* crow = cbase + i * cstep;
           if (vec) {
             *reinterpret_cast<float4*>(crow) = v;
           } else {

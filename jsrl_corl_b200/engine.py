@@ -294,11 +294,19 @@ class EnsembleEngine:
         return int(self._L.iql_last_launch_count(self._h))
 
     def act(self, member: int, states: torch.Tensor, max_action: float = 1.0) -> torch.Tensor:
-        states = self._dense(states).view(-1, self.state_dim)
-        out = torch.empty(states.shape[0], self.action_dim, dtype=torch.float32, device=self.device)
+        """Eval-mode policy actions.  member >= 0: states [n, S] -> [n, A].  member == -1: every member acts on
+        its own rows, states [n_members, n, S] -> [n_members, n, A] (one launch, vectorised envs)."""
+        if member < 0:
+            states = self._dense(states).view(self.n_members, -1, self.state_dim)
+            n = states.shape[1]
+            out = torch.empty(self.n_members, n, self.action_dim, dtype=torch.float32, device=self.device)
+        else:
+            states = self._dense(states).view(-1, self.state_dim)
+            n = states.shape[0]
+            out = torch.empty(n, self.action_dim, dtype=torch.float32, device=self.device)
         st = self._enter()
         try:
-            _lib.check(self._L.iql_act(self._h, member, states.data_ptr(), states.shape[0], float(max_action),
+            _lib.check(self._L.iql_act(self._h, member, states.data_ptr(), n, float(max_action),
                                        out.data_ptr(), st.cuda_stream), self._h, "iql_act")
         finally:
             self._exit()

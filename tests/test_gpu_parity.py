@@ -520,3 +520,21 @@ def test_resume_from_reference_written_checkpoint():
     np.testing.assert_allclose(np.array(losses), z["losses_after_resume"], rtol=2e-5, atol=1e-8)
     assert tr.total_it == int(z["total_it"]) == 40
     assert abs(ao.param_groups[0]["lr"]) < 1e-12  # cosine schedule with T_max = 40 has reached eta_min = 0
+
+
+def test_batched_act_all_members_matches_per_member_and_torch():
+    from jsrl_corl_b200 import IQLEnsemble
+    import jsrl_corl_b200 as J
+
+    ens = IQLEnsemble(3, 17, 6, 256, 2, 256, math_mode="fp32", seeds=[1, 2, 3])
+    states = torch.randn(3, 5, 17, device="cuda")
+    all_a = ens.engine.act(-1, states, max_action=0.7)
+    assert all_a.shape == (3, 5, 6)
+    for m in range(3):
+        one = ens.engine.act(m, states[m], max_action=0.7)
+        assert torch.equal(one, all_a[m])
+        pol = J.GaussianPolicy(17, 6, 0.7, 256, 2).cuda()
+        pol.load_state_dict({k: v for k, v in ens.engine.param_views(m)["actor"].items()})
+        pol.eval()
+        ref = torch.clamp(0.7 * pol(states[m]).mean, -0.7, 0.7)
+        assert torch.allclose(one, ref, rtol=1e-5, atol=1e-6)
