@@ -213,6 +213,8 @@ extern "C" int iql_create(const iql_config* cfg, iql_engine** out) {
   if (cfg->math_mode != IQL_MATH_FP32_SIMT && cfg->math_mode != IQL_MATH_TF32_TCGEN05)
     return fail(nullptr, IQL_ERR_INVALID, "iql_create: unknown math_mode");
   if (cfg->max_steps_per_call <= 0) return fail(nullptr, IQL_ERR_INVALID, "iql_create: max_steps_per_call must be positive");
+  if (!cfg->deterministic && cfg->action_dim > 64)
+    return fail(nullptr, IQL_ERR_INVALID, "iql_create: Gaussian policies support action_dim <= 64");
   iql_engine* e = new iql_engine();
   e->cfg = *cfg;
   memset(&e->layout, 0, sizeof(e->layout));

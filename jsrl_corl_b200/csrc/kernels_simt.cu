@@ -244,24 +244,20 @@ void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float*
 //   value_loss  iql.py:489-490,301-302     q_loss  iql.py:506-508
 //   actor_loss  iql.py:524-534 (+ torch Normal.log_prob)
 // ===========================================================================
-__device__ __forceinline__ float block_sum_256(float v, float* red) {
+__device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) red[w] = v;
-  __syncthreads();
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s += red[i];
-  return s;
+  return v;
 }
+
+constexpr int LOSS_MAX_A = 64;  // log_std gradient slots reduced in shared memory
 
 __global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restrict__ ws, int64_t ws_member_floats,
                                                    WorkspaceLayout wl, const float* __restrict__ params,
                                                    float* __restrict__ grads) {
-  extern __shared__ float e_s[];  // [B] exp_adv / B
-  __shared__ float red[8];
+  // per-warp partial sums: [0..3] = value / q1 / q2 / actor loss terms, [4 + a] = d loss / d log_std[a].
+  // One shuffle tree per quantity and ONE block barrier; summation order is fixed (rows by lane, warps 0..7).
+  __shared__ float red[8][4 + LOSS_MAX_A];
   const int m = blockIdx.x;
   const int B = ctx.B, A = ctx.A_dim, RF = ctx.row.row_floats, Ald = wl.Ald;
   float* w = ws + m * ws_member_floats;
@@ -275,85 +271,100 @@ __global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restric
   const float w_neg = fabsf(sc.iql_tau - 1.0f), w_pos = fabsf(sc.iql_tau);
   const float* log_std = params + m * ctx.P + ctx.log_std_off;
   constexpr float HALF_LOG_2PI = 0.9189385332046727f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gauss = !ctx.deterministic;
+  for (int j = lane; j < 4 + LOSS_MAX_A; j += 32) red[warp][j] = 0.f;
+  __syncwarp();
 
   float v_acc = 0.f, q1_acc = 0.f, q2_acc = 0.f, a_acc = 0.f;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const float next_v = yq[PASS_V_NEXT * B + b];
-    const float v = yq[PASS_V * B + b];
-    const float tq = fminf(yq[PASS_TQ1 * B + b], yq[PASS_TQ2 * B + b]);
-    const float q1 = yq[PASS_Q1 * B + b], q2 = yq[PASS_Q2 * B + b];
-    const float* xr = xrow + (int64_t)b * RF;
-    const float r = xr[ctx.row.off_reward], d = xr[ctx.row.off_done];
-    // --- V (expectile) ---
-    const float adv = tq - v;
-    const float wt = adv < 0.f ? w_neg : w_pos;
-    v_acc += wt * (adv * adv);
-    gy[0 * B + b] = -((wt * inv_b) * (2.0f * adv));
-    // --- Q (TD) ---
-    const float target = r + ((1.0f - d) * sc.discount) * next_v;
-    const float d1 = q1 - target, d2 = q2 - target;
-    q1_acc += d1 * d1;
-    q2_acc += d2 * d2;
-    gy[1 * B + b] = d1 * (2.0f * inv_b) * 0.5f;
-    gy[2 * B + b] = d2 * (2.0f * inv_b) * 0.5f;
-    // --- policy (AWR) ---
-    const float e = fminf(expf(sc.beta * adv), 100.0f);
-    const float eb = e * inv_b;
-    e_s[b] = eb;
+  for (int b0 = 0; b0 < B; b0 += blockDim.x) {  // uniform trip count: every lane takes part in the shuffles
+    const int b = b0 + threadIdx.x;
+    const bool valid = b < B;
+    float adv = 0.f, e = 0.f, eb = 0.f;
+    const float* xr = xrow + (int64_t)(valid ? b : 0) * RF;
+    if (valid) {
+      const float next_v = yq[PASS_V_NEXT * B + b];
+      const float v = yq[PASS_V * B + b];
+      const float tq = fminf(yq[PASS_TQ1 * B + b], yq[PASS_TQ2 * B + b]);
+      const float q1 = yq[PASS_Q1 * B + b], q2 = yq[PASS_Q2 * B + b];
+      const float r = xr[ctx.row.off_reward], d = xr[ctx.row.off_done];
+      // --- V (expectile) ---
+      adv = tq - v;
+      const float wt = adv < 0.f ? w_neg : w_pos;
+      v_acc += wt * (adv * adv);
+      gy[0 * B + b] = -((wt * inv_b) * (2.0f * adv));
+      // --- Q (TD) ---
+      const float target = r + ((1.0f - d) * sc.discount) * next_v;
+      const float d1 = q1 - target, d2 = q2 - target;
+      q1_acc += d1 * d1;
+      q2_acc += d2 * d2;
+      gy[1 * B + b] = d1 * (2.0f * inv_b) * 0.5f;
+      gy[2 * B + b] = d2 * (2.0f * inv_b) * 0.5f;
+      // --- policy (AWR) weight ---
+      e = fminf(expf(sc.beta * adv), 100.0f);
+      eb = e * inv_b;
+    }
     float bc = 0.f;
     for (int a = 0; a < A; ++a) {
-      const float mu = tanhf(zpi[(int64_t)b * Ald + a]);
-      const float act = xr[ctx.row.off_action + a];
-      float gmu;
-      if (ctx.deterministic) {
-        const float diff = mu - act;
-        bc += diff * diff;
-        gmu = eb * (2.0f * diff);
-      } else {
-        const float ls = fminf(fmaxf(log_std[a], -20.0f), 2.0f);
-        const float sd = expf(ls);
-        const float var = sd * sd;
-        const float diff = act - mu;
-        const float logp = -(diff * diff) / (2.0f * var) - logf(sd) - HALF_LOG_2PI;
-        bc -= logp;
-        gmu = -eb * diff / var;
+      float dls = 0.f;
+      if (valid) {
+        const float mu = tanhf(zpi[(int64_t)b * Ald + a]);
+        const float act = xr[ctx.row.off_action + a];
+        float gmu;
+        if (!gauss) {
+          const float diff = mu - act;
+          bc += diff * diff;
+          gmu = eb * (2.0f * diff);
+        } else {
+          const float ls = fminf(fmaxf(log_std[a], -20.0f), 2.0f);
+          const float sd = expf(ls);
+          const float var = sd * sd;
+          const float diff = act - mu;
+          const float logp = -(diff * diff) / (2.0f * var) - logf(sd) - HALF_LOG_2PI;
+          bc -= logp;
+          gmu = -eb * diff / var;
+          dls = eb * (1.0f - diff * diff / var);
+        }
+        gpi[(int64_t)b * Ald + a] = gmu * (1.0f - mu * mu);
       }
-      gpi[(int64_t)b * Ald + a] = gmu * (1.0f - mu * mu);
+      if (gauss && a < LOSS_MAX_A) {
+        dls = warp_sum(dls);
+        if (lane == 0) red[warp][4 + a] += dls;
+      }
     }
     a_acc += e * bc;
   }
-  const float v_sum = block_sum_256(v_acc, red);
-  const float q1_sum = block_sum_256(q1_acc, red);
-  const float q2_sum = block_sum_256(q2_acc, red);
-  const float a_sum = block_sum_256(a_acc, red);
+  v_acc = warp_sum(v_acc);
+  q1_acc = warp_sum(q1_acc);
+  q2_acc = warp_sum(q2_acc);
+  a_acc = warp_sum(a_acc);
+  if (lane == 0) {
+    red[warp][0] = v_acc; red[warp][1] = q1_acc; red[warp][2] = q2_acc; red[warp][3] = a_acc;
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  if (j < 4 + (gauss ? min(A, LOSS_MAX_A) : 0)) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][j];
+    red[0][j] = s;  // slot j is only read by thread j before this write
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     float* out = ctx.loss_ring + ((int64_t)m * ctx.k_max + ctx.k) * 3;
-    out[0] = v_sum * inv_b;
-    out[1] = (q1_sum * inv_b + q2_sum * inv_b) * 0.5f;
-    out[2] = a_sum * inv_b;
+    out[0] = red[0][0] * inv_b;
+    out[1] = (red[0][1] * inv_b + red[0][2] * inv_b) * 0.5f;
+    out[2] = red[0][3] * inv_b;
   }
-  if (!ctx.deterministic) {
-    __syncthreads();
-    for (int a = 0; a < A; ++a) {
-      const float lsr = log_std[a];
-      const float ls = fminf(fmaxf(lsr, -20.0f), 2.0f);
-      const float sd = expf(ls);
-      const float var = sd * sd;
-      float part = 0.f;
-      for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        const float mu = tanhf(zpi[(int64_t)b * Ald + a]);
-        const float diff = xrow[(int64_t)b * RF + ctx.row.off_action + a] - mu;
-        part += e_s[b] * (1.0f - diff * diff / var);
-      }
-      const float tot = block_sum_256(part, red);
-      if (threadIdx.x == 0) grads[m * ctx.P + ctx.log_std_off + a] = (lsr >= -20.0f && lsr <= 2.0f) ? tot : 0.f;
-    }
+  if (gauss && j < min(A, LOSS_MAX_A)) {
+    const float lsr = log_std[j];
+    grads[m * ctx.P + ctx.log_std_off + j] = (lsr >= -20.0f && lsr <= 2.0f) ? red[0][4 + j] : 0.f;
   }
 }
 
 void launch_loss(const StepCtx& ctx, float* ws, int64_t ws_member_floats, const WorkspaceLayout& wl,
                  const float* params, float* grads, cudaStream_t st) {
-  loss_kernel<<<ctx.n_members, 256, ctx.B * sizeof(float), st>>>(ctx, ws, ws_member_floats, wl, params, grads);
+  loss_kernel<<<ctx.n_members, 256, 0, st>>>(ctx, ws, ws_member_floats, wl, params, grads);
 }
 
 // ===========================================================================
