@@ -31,7 +31,8 @@
 
 namespace iql {
 
-constexpr int TILE_M = 128, TILE_N = 256 /* maximum; the N tile is a launch parameter */, TILE_K = 32, UMMA_K = 8, N_STAGES = 3;
+constexpr int TILE_M = 128, TILE_N = 256 /* maximum; the N tile is a launch parameter */, TILE_K = 32, UMMA_K = 8, N_STAGES = 3 /* ring size in MAX-size stages */,
+              MAX_STAGES = 8;  // narrow N tiles use more, smaller stages: same bytes in flight
 constexpr int STAGE_A_BYTES = TILE_M * TILE_K * 4;  // 16 KB
 constexpr int STAGE_B_BYTES = TILE_N * TILE_K * 4;  // 32 KB
 constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
@@ -41,7 +42,7 @@ constexpr int STG_FLOATS = 32 * 36;                                   // per-war
 constexpr int AUX_FLOATS = 2 * N_CGROUPS * TILE_M;                    // head partials [2 parities][4 groups][128]; also
                                                                       // the bias-gradient sums [4 quarters][256]
 constexpr int EPI_SMEM_BYTES = N_EPI_WARPS * STG_FLOATS * 4 + (AUX_FLOATS > 4 * TILE_N ? AUX_FLOATS : 4 * TILE_N) * 4;
-constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr int N_THREADS = 576;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-17 epilogue (4 per TMEM lane quarter)
 
 // ---------------------------------------------------------------------------
@@ -136,6 +137,7 @@ struct UmmaParams {
   // map b_sel[j] of the problem's maps_per_prob tensor maps: (Xhi,Whi), (Xlo,Whi), (Xhi,Wlo).
   int n_split, maps_per_prob, a_sel[3], b_sel[3];
   int fuse_count;  // FUSE_OUT: problems [0, fuse_count) have a scalar head evaluated in the epilogue
+  int n_stages, stage_bytes;  // TMA ring geometry for this tile_n
 };
 
 __device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int j, int& prob, int& m0, int& n0) {
@@ -167,17 +169,19 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int RING = N_STAGES * STAGE_BYTES;
   float* epi_smem = reinterpret_cast<float*>(smem + RING);
-  // barriers: full[3], empty[3], tmem_full[2], tmem_empty[2], tmem slot
+  // barriers: full[8], empty[8], tmem_full[2], tmem_empty[2], tmem slot
   const uint32_t bars = base + RING + EPI_SMEM_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 8 * N_STAGES, tfull0 = bars + 16 * N_STAGES, tempty0 = tfull0 + 16;
+  const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
   const uint32_t tslot = tempty0 + 16;
-  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + RING + EPI_SMEM_BYTES + 16 * N_STAGES + 32);
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + RING + EPI_SMEM_BYTES + 16 * MAX_STAGES + 32);
+  const int n_stages = up.n_stages;                      // RING / stage_bytes, capped at MAX_STAGES
+  const uint32_t stage_bytes = (uint32_t)up.stage_bytes;  // 16 KB of A + tile_n * 128 B of B, 1024-byte multiple
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_n = up.tile_n;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < N_STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
@@ -213,7 +217,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           const CUtensorMap* mapA = pmaps + up.a_sel[sj];
           const CUtensorMap* mapB = pmaps + up.b_sel[sj];
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
+          const uint32_t sa = base + stage * stage_bytes, sb = sa + STAGE_A_BYTES;
           const uint32_t fb = full0 + 8 * stage;
           mbar_expect_tx(fb, STAGE_A_BYTES + tile_n * TILE_K * 4);
           const int k0 = (kb - sj * nkb) * TILE_K;
@@ -221,7 +225,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           else tma_load_2d(sa, mapA, fb, k0, m0);
           if (up.b_mn) tma_load_3d(sb, mapB, fb, 0, k0, n0 >> 5);
           else tma_load_2d(sb, mapB, fb, k0, n0);
-          if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -241,7 +245,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + STAGE_A_BYTES;
+          const uint32_t sa = base + stage * stage_bytes, sb = sa + STAGE_A_BYTES;
           const uint64_t adesc0 = make_desc(sa, up.a_lbo, up.a_sbo, up.a_layout);
           const uint64_t bdesc0 = make_desc(sb, up.b_lbo, up.b_sbo, up.b_layout);
 #pragma unroll
@@ -249,7 +253,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
             umma_tf32(tacc, adesc0 + (uint64_t)(ks * up.a_kstep), bdesc0 + (uint64_t)(ks * up.b_kstep), up.idesc,
                       (kb | ks) != 0);
           umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
-          if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull0 + 8 * buf);  // accumulator complete
       }
@@ -618,6 +622,9 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
     up.a_sel[2] = 0; up.b_sel[2] = 3;
   }
   up.fuse_count = probs_out ? fuse_count : 0;
+  up.stage_bytes = STAGE_A_BYTES + tile_n * TILE_K * 4;  // multiples of 4 KB: swizzle-atom alignment holds
+  up.n_stages = (N_STAGES * STAGE_BYTES) / up.stage_bytes;
+  if (up.n_stages > MAX_STAGES) up.n_stages = MAX_STAGES;
   // fused bias gradient needs all M tiles of a problem in one CTA: only worth it while that leaves enough
   // independent units to fill the GPU (batch <= 256); larger batches use tile-major order + colsum_kernel
   up.prob_major = (epi == EPI_DRELU && up.tiles_m <= 2) ? 1 : 0;
