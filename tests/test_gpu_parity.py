@@ -538,3 +538,53 @@ def test_batched_act_all_members_matches_per_member_and_torch():
         pol.eval()
         ref = torch.clamp(0.7 * pol(states[m]).mean, -0.7, 0.7)
         assert torch.allclose(one, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_full_size_properties_64_members_1m_rows():
+    """BASELINE configs[2] at full size (64 members, 1M-row buffer, 2x256, batch 256), size-independent properties:
+    (1) the rows gathered in-kernel are exactly the buffer rows at the Philox indices; (2) a run is bit-reproducible;
+    (3) splitting the ensemble over two engines (= two GPUs) leaves every member bit-identical; (4) K steps in one
+    call == the same steps in several calls."""
+    from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
+    from oracle.iql_numpy import synthetic_dataset
+    from oracle.philox import philox_indices
+
+    S_dim, A_dim, n_rows, B, members, K = 17, 6, 1_000_000, 256, 64, 6
+    data = synthetic_dataset(n_rows, S_dim, A_dim, 0)
+    rb = ReplayBuffer(S_dim, A_dim, n_rows, "cuda")
+    rb.load_d4rl_dataset(data)
+
+    def make(seeds):
+        ens = IQLEnsemble(len(seeds), S_dim, A_dim, 256, 2, B, math_mode="tf32", seeds=seeds, max_steps_per_call=8)
+        ens.bind_replay(rb)
+        return ens
+
+    seeds = list(range(100, 100 + members))
+    full = make(seeds)
+    losses, idx = full.train_steps(K, return_indices=True)
+    losses, idx = losses.cpu().numpy(), idx.cpu().numpy()
+    assert np.isfinite(losses).all()
+    for m in (0, 17, 63):
+        for k in (0, K - 1):
+            assert np.array_equal(idx[m, k], philox_indices(seeds[m], k, n_rows, B))
+    # (1) the standalone gather of the same indices returns exactly the dataset rows
+    rb_p = ReplayBuffer(S_dim, A_dim, 8, "cuda", sampler="philox", seed=seeds[17])
+    rb_p._rows, rb_p._size, rb_p._pointer = rb._rows, n_rows, n_rows  # share the 1M-row storage
+    s, a, r, s2, d = [t.cpu().numpy() for t in rb_p.sample(B)]
+    assert np.array_equal(s, data["observations"][idx[17, 0]]) and np.array_equal(a, data["actions"][idx[17, 0]])
+    assert np.array_equal(r[:, 0], data["rewards"][idx[17, 0]]) and np.array_equal(s2, data["next_observations"][idx[17, 0]])
+    # (2) reproducible
+    again = make(seeds)
+    l2 = again.train_steps(K).cpu().numpy()
+    assert np.array_equal(l2, losses)
+    # (3) sharded == unsharded, member by member
+    half_a, half_b = make(seeds[:32]), make(seeds[32:])
+    la, lb = half_a.train_steps(K).cpu().numpy(), half_b.train_steps(K).cpu().numpy()
+    assert np.array_equal(np.concatenate([la, lb]), losses)
+    pa = half_b.engine.param_views(5)["qf"]["q2.net.2.weight"]
+    pf = full.engine.param_views(37)["qf"]["q2.net.2.weight"]
+    assert torch.equal(pa, pf)
+    # (4) K fused == K split
+    split = make(seeds)
+    ls = np.concatenate([split.train_steps(2).cpu().numpy(), split.train_steps(4).cpu().numpy()], axis=1)
+    assert np.array_equal(ls, losses)
