@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -99,7 +100,7 @@ struct iql_engine {
   int64_t last_launches = 0;
   std::string err;
   // CUDA graphs of the K-step sequence, keyed by K (Philox sampling mode only)
-  std::map<int, std::pair<cudaGraphExec_t, int64_t>> graphs;
+  std::map<std::tuple<int, int, uintptr_t>, std::pair<cudaGraphExec_t, int64_t>> graphs;
   bool use_graphs = true;
 };
 
@@ -743,9 +744,16 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
   // the legacy default stream cannot be captured; the facade runs the engine on its own stream
   // Graphs: the K-step Philox loop, and the single preloaded step of the drop-in `train(batch)` path (its ~11
   // launches would otherwise be launch-latency bound).  Keyed by K, negative for the preloaded variant.
+  // (the index pointer is baked into the captured kernels, so the INDICES variant is keyed by it: callers that
+  // reuse one staging buffer -- the Python facade does -- replay one graph; at most 16 graphs are kept)
   const bool graphable = e->use_graphs && st != nullptr && !dropout_masks && !idx_out &&
-                         ((sample_mode == IQL_SAMPLE_PHILOX && k_steps > 1) || sample_mode == IQL_SAMPLE_PRELOADED);
-  const int graph_key = (sample_mode == IQL_SAMPLE_PRELOADED) ? -k_steps : k_steps;
+                         (k_steps > 1 || sample_mode == IQL_SAMPLE_PRELOADED);
+  const auto graph_key = std::make_tuple((int)sample_mode, (int)k_steps,
+                                         sample_mode == IQL_SAMPLE_INDICES ? (uintptr_t)indices : (uintptr_t)0);
+  if (graphable && e->graphs.size() >= 16 && e->graphs.find(graph_key) == e->graphs.end()) {
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);
+    e->graphs.clear();
+  }
   int64_t launches = 0;
   if (graphable) {
     auto it = e->graphs.find(graph_key);

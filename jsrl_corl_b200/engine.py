@@ -91,6 +91,7 @@ class EnsembleEngine:
                                           self.workspace.data_ptr(), self.workspace.numel()), self._h, "iql_bind_state")
         self._hparams = [self._default_hparams(m) for m in range(n_members)]
         self._replay_refs: Dict[int, torch.Tensor] = {}
+        self._idx_stage: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------
     def __del__(self):
@@ -245,10 +246,21 @@ class EnsembleEngine:
         if smode == _lib.SAMPLE_INDICES:
             if indices is None:
                 raise ValueError("mode='indices' needs an int64 tensor [S, K, B]")
-            indices = indices.to(device=self.device, dtype=torch.int64).contiguous()
             if indices.numel() != S * k_steps * B:
                 raise ValueError("indices must have S*K*B elements")
-            idx_ptr = indices.data_ptr()
+            # stage into a persistent device buffer (one per K): the engine's CUDA graph is keyed by this pointer,
+            # and host (pinned) index tensors are uploaded straight into it on the engine's stream
+            stage = self._idx_stage.get(k_steps)
+            if stage is None:
+                stage = self._idx_stage[k_steps] = torch.empty(S * k_steps * B, dtype=torch.int64, device=self.device)
+            src = indices.reshape(-1)
+            if src.dtype != torch.int64:
+                src = src.to(torch.int64)
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                stage.copy_(src, non_blocking=True)
+            indices = stage
+            idx_ptr = stage.data_ptr()
         mask_ptr = None
         if dropout_masks is not None:
             dropout_masks = dropout_masks.to(device=self.device, dtype=torch.uint8).contiguous()
