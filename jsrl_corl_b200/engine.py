@@ -225,7 +225,33 @@ class EnsembleEngine:
             self._exit()
         self._keep = (s, a, r, s2, d)
 
+    def train_on_batch(self, batch, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """S = 1 drop-in step: stage an externally sampled batch and run one update, under a single stream
+        hand-over (the `ImplicitQLearning.train(batch)` path).  Returns losses [1, 1, 3] on the device."""
+        s, a, r, s2, d = [self._dense(b) for b in batch]
+        B = self.batch_size
+        if s.shape != (B, self.state_dim) or s2.shape != (B, self.state_dim):
+            raise ValueError(f"states must be [{B}, {self.state_dim}]")
+        if a.shape != (B, self.action_dim):
+            raise RuntimeError("Actions shape missmatch")  # iql.py:530
+        if r.numel() != B or d.numel() != B:
+            raise ValueError("rewards / dones must have batch_size elements")
+        if out is None:
+            out = torch.empty(self.n_members, 1, 3, dtype=torch.float32, device=self.device)
+        st = self._enter()
+        try:
+            _lib.check(self._L.iql_load_batch(self._h, 0, s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr(),
+                                              d.data_ptr(), st.cuda_stream), self._h, "iql_load_batch")
+            _lib.check(self._L.iql_train_steps(self._h, 1, _lib.SAMPLE_PRELOADED, None, None, out.data_ptr(), None,
+                                               st.cuda_stream), self._h, "iql_train_steps")
+        finally:
+            self._exit()
+        self._keep = (s, a, r, s2, d)
+        return out
+
     def _dense(self, t: torch.Tensor) -> torch.Tensor:
+        if t.device == self.device and t.dtype == torch.float32 and t.is_contiguous():
+            return t
         return t.to(device=self.device, dtype=torch.float32).contiguous()
 
     def _enter(self) -> torch.cuda.Stream:

@@ -473,6 +473,7 @@ class ImplicitQLearning:
         self._steps = {"v": 0, "q": 0, "actor": 0}
         self._step_tensors: Dict[str, torch.Tensor] = {}
         self._published = False
+        self._loss_buf: Optional[torch.Tensor] = None
         S, A, H, L = self.qf.state_dim, self.qf.action_dim, self.qf.hidden_dim, self.qf.n_hidden
         if (self.vf.state_dim, self.vf.hidden_dim, self.vf.n_hidden) != (S, H, L) or \
                 (self.actor.state_dim, self.actor.hidden_dim, self.actor.n_hidden) != (S, H, L):
@@ -613,8 +614,9 @@ class ImplicitQLearning:
             raise RuntimeError("Actions shape missmatch")
         eng = self._ensure_engine(int(observations.shape[0]))
         self._push_hparams()
-        eng.load_batch(0, (observations, actions, rewards, next_observations, dones))
-        losses = eng.train_steps(1, mode="preloaded")
+        if self._loss_buf is None or self._loss_buf.device != eng.device:
+            self._loss_buf = torch.empty(1, 1, 3, dtype=torch.float32, device=eng.device)
+        losses = eng.train_on_batch((observations, actions, rewards, next_observations, dones), out=self._loss_buf)
         self._total_it += 1
         for k in self._steps:
             self._steps[k] += 1
@@ -624,7 +626,7 @@ class ImplicitQLearning:
         else:
             self._publish_optimizer_state()
         self._advance_schedule(1)
-        v_loss, q_loss, a_loss = losses[0, 0].tolist()  # one D2H sync (the reference does three .item())
+        v_loss, q_loss, a_loss = losses.view(3).tolist()  # one D2H sync (the reference does three .item())
         return {"value_loss": v_loss, "q_loss": q_loss, "actor_loss": a_loss}
 
     # ---- checkpoints (iql.py:565-606) --------------------------------------
