@@ -69,6 +69,12 @@ def main(tag="r01"):
                           f"{d['value']:.0f} | {d['e2e']['value']:.0f} | {100 * d['step_roofline']['whole_step_frac_of_tensor_peak']:.1f} % | "
                           f"{d['step_roofline']['whole_step_hbm_gbs']:.0f} |")
     sr = b["step_roofline"]
+    dr = os.path.join(G, f"dropin_rate_{tag}.txt")
+    dropin = ""
+    if os.path.exists(dr):
+        lines = [l.split("  last=")[0] for l in open(dr).read().splitlines() if "steps/s" in l]
+        dropin = ("Drop-in loop `batch = rb.sample(256); log = trainer.train(batch)` (S = 1, K = 1, one host sync per step, "
+                  "`tools/dropin_rate.py`): " + "; ".join(lines) + ".\n")
     md = f"""# Round 1 profile summary (B200, TF32 tcgen05 path)
 
 Default bench workload = BASELINE.json configs[2]: halfcheetah-medium-replay shape (obs 17, act 6, 2x256, Gaussian
@@ -103,6 +109,7 @@ Dominant kernel: `{b['roofline']['kernel']}` ({b['roofline']['kernel_us']} us, {
 |---|---|---|---|---|---|---|---|
 {chr(10).join(others)}
 
+{dropin}
 The stress shape (4x1024, batch 4096) is the compute-bound regime of the same kernels: its hidden-layer GEMMs run at
 80-86 % of the measured cuBLAS TF32 peak and the whole update step at about half of it.
 
