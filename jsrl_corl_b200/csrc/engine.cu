@@ -51,6 +51,8 @@ struct Phase {
   int first;     // index into problem table
   int count;
   int maxM, maxN;
+  int maxK = 0;  // largest K over the problems of the phase
+  bool cta2 = false;  // tcgen05 kernel runs this phase on CTA pairs (decided when the tensor maps are encoded)
   int K;         // common K of the phase (0 if mixed)
   bool umma_ok;  // eligible for the tcgen05 kernel
   int epi;       // common epilogue of the phase
@@ -458,13 +460,19 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   }
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
+  for (auto* phases : {&e->fwd_phases, &e->bwd_phases})
+    for (Phase& ph : *phases) {
+      ph.maxK = 0;
+      for (int i = 0; i < ph.count; ++i) ph.maxK = std::max(ph.maxK, e->h_probs[ph.first + i].K);
+      ph.cta2 = ph.umma_ok && umma_cta2(ph.mode, ph.count, ph.maxM, ph.maxN, ph.maxK);
+    }
   if ((int64_t)e->h_probs.size() != nprob) return fail(e, IQL_ERR_STATE, "internal: problem count mismatch");
   e->h_maps.assign((size_t)128 * 2 * nprob, 0);
   if (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) {
     auto encode = [&](const Phase& ph) {
       if (!ph.umma_ok || !umma_phase_supported(ph.mode, e->cfg.batch_size, e->cfg.hidden_dim)) return 0;
       return umma_encode_maps(ph.mode, e->h_probs.data() + ph.first, ph.count, umma_tile_n(ph.maxN),
-                              e->h_maps.data() + (size_t)256 * ph.first);
+                              e->h_maps.data() + (size_t)256 * ph.first, ph.cta2);
     };
     for (const Phase& ph : e->fwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (forward phase)");
     // 3xTF32 input layer: hi / lo operand maps of the first forward phase
@@ -488,7 +496,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
         lo[i].B = (tgt ? e->d_tshadow_lo + (int64_t)m * PQ : e->d_wshadow_lo + (int64_t)m * P) + w_off;
       }
       e->h_maps_first.assign((size_t)128 * 4 * ph.count, 0);
-      if (umma_encode_maps_split(hi.data(), lo.data(), ph.count, umma_tile_n(ph.maxN), e->h_maps_first.data()))
+      if (umma_encode_maps_split(hi.data(), lo.data(), ph.count, umma_tile_n(ph.maxN), e->h_maps_first.data(), ph.cta2))
         return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (3xTF32 input layer)");
     }
     for (const Phase& ph : e->bwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward phase)");
@@ -661,7 +669,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       const int n_scalar = (N_PASS - 1) * e->cfg.n_members;  // problems with a scalar head (V, Q passes)
       launch_umma_gemm(ph.mode, pp, split ? e->d_maps_first : e->d_maps + (size_t)256 * ph.first,
                        fuse ? e->d_probs + next->first : nullptr, ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st, split,
-                       n_scalar);
+                       n_scalar, ph.cta2, ph.maxK);
       if (fuse) {  // the policy head (N = act_dim) stays with the FP32 output-layer kernel
         const GemmProb* pa = e->d_probs + next->first + n_scalar;
         if (out_ok) launch_out_fwd(pa, ph.count - n_scalar, B, H, A, st);
@@ -818,6 +826,8 @@ extern "C" int iql_act(iql_engine* e, int32_t member, const float* states, int64
 extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda,
                                       const float* B, int32_t ldb, float* C, int32_t ldc, void* scratch,
                                       size_t scratch_bytes, void* stream) {
+  const bool allow_pair = !(mode & 0x100);  // test hook: mode | 0x100 keeps the single-CTA kernel
+  mode &= 0xFF;
   if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0 || (M % 256) || (N > 256 && (N % 256)))
     return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: M multiple of 256 and N <= 256 or a multiple of 256 required");
   if ((lda & 3) || (ldb & 3)) return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: lda, ldb must be multiples of 4 (TMA row alignment)");
@@ -828,7 +838,8 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.epi = EPI_NONE; p.drop_layer = -1;
   alignas(64) char maps[256];
-  if (umma_encode_maps(mode, &p, 1, umma_tile_n(N), maps)) return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: cuTensorMapEncodeTiled failed");
+  const bool cta2 = allow_pair && umma_cta2_ok(M, N);
+  if (umma_encode_maps(mode, &p, 1, umma_tile_n(N), maps, cta2)) return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: cuTensorMapEncodeTiled failed");
   cudaStream_t st = (cudaStream_t)stream;
   char* d = (char*)scratch;
   if (cudaMemcpyAsync(d, maps, 256, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -837,7 +848,7 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
     return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: upload failed");
   StepCtx ctx;
   memset(&ctx, 0, sizeof(ctx));
-  launch_umma_gemm(mode, (const GemmProb*)(d + 256), d, nullptr, EPI_NONE, 1, M, N, ctx, st);
+  launch_umma_gemm(mode, (const GemmProb*)(d + 256), d, nullptr, EPI_NONE, 1, M, N, ctx, st, false, 0, cta2, K);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(nullptr, IQL_ERR_CUDA, std::string("iql_selftest_umma_gemm: ") + cudaGetErrorString(err));
   return IQL_OK;

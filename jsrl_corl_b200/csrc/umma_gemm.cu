@@ -16,6 +16,14 @@
 // (bias + ReLU + dropout, ReLU mask, or plain store; optionally the FP32 output heads) with coalesced
 // 16-byte global accesses.
 //
+// CTA pairs (CTA2 = true): when M is a multiple of 256 and the N tile is 256 wide the kernel is launched as
+// 2-CTA clusters and one `tcgen05.mma.cta_group::2` covers a 256 x 256 tile: each CTA of the pair stages its
+// own 128 rows of A and HALF of the B tile (the tensor cores of both SMs read both halves), so a tile costs
+// 32 KB instead of 48 KB of operand delivery per k-block and SM.  Both CTAs issue TMA (`.cta_group::2`,
+// completing on the leader's full barrier), only the leader (cluster rank 0) issues the MMAs and commits
+// with `.multicast::cluster` to the ring/accumulator barriers of both CTAs; each CTA drains its own 128 TMEM
+// lanes and the epilogue warps of both release the accumulator on the leader's barrier.
+//
 // Shared-memory / descriptor conventions (cute/atom/mma_traits_sm100.hpp):
 //   K-major  : rows of 128 B, SWIZZLE_128B (16 B atoms), SBO = 1024 B between
 //              8-row groups, K advance of one UMMA (8 tf32) = +32 B.
@@ -41,7 +49,9 @@ constexpr int N_CGROUPS = N_EPI_WARPS / 4;
 constexpr int STG_FLOATS = 32 * 36;                                   // per-warp transpose tile
 constexpr int AUX_FLOATS = 2 * N_CGROUPS * TILE_M;                    // head partials [2 parities][4 groups][128]; also
                                                                       // the bias-gradient sums [4 quarters][256]
-constexpr int EPI_SMEM_BYTES = N_EPI_WARPS * STG_FLOATS * 4 + (AUX_FLOATS > 4 * TILE_N ? AUX_FLOATS : 4 * TILE_N) * 4;
+constexpr int AUX_BYTES = (AUX_FLOATS > 4 * TILE_N ? AUX_FLOATS : 4 * TILE_N) * 4;
+constexpr int PEER_CSUM_SLOTS = 3;                                    // CTA pair: ring of bias-gradient partials sent by the peer
+constexpr int EPI_SMEM_BYTES = N_EPI_WARPS * STG_FLOATS * 4 + AUX_BYTES + PEER_CSUM_SLOTS * TILE_N * 4;
 constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr int N_THREADS = 576;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-17 epilogue (4 per TMEM lane quarter)
 
@@ -86,6 +96,68 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// ---- CTA-pair (cluster of 2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 24)) __trap();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA loads of a CTA pair: the transaction bytes complete on `cluster_bar`, a barrier of the LEADER CTA
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(uint32_t dst, const void* tmap, uint32_t cluster_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -128,6 +200,7 @@ struct UmmaParams {
   uint32_t idesc;
   int a_mn, b_mn;  // operand majors (0 K-major, 1 MN-major)
   int tile_n;      // UMMA N of this launch: multiple of 32, <= 256 (B tile = tile_n * 128 B per stage)
+  int tile_m;      // rows of one work tile: 128, or 256 for a CTA pair (each CTA owns 128 of them)
   int tiles_m, tiles_n, total_tiles;  // tile grid per problem and over the whole launch
   // Work units handed to CTAs round-robin.  Default: one unit = one tile.  prob_major (dgrad with fused bias
   // gradient): one unit = all M tiles of one (problem, N tile), so that the column sums of the produced
@@ -138,18 +211,23 @@ struct UmmaParams {
   int n_split, maps_per_prob, a_sel[3], b_sel[3];
   int fuse_count;  // FUSE_OUT: problems [0, fuse_count) have a scalar head evaluated in the epilogue
   int n_stages, stage_bytes;  // TMA ring geometry for this tile_n
+  int k_max;  // largest K of the phase: every problem runs ceil(k_max / 32) k-blocks (TMA zero-fills beyond its own K)
+  // IQL_UMMA_DBG, profiling experiments only (tools/umma_probe.sh; the results of the step are WRONG):
+  // 1 no global stores, 2 operands of 4 problems only (L2 hits), 4 no epilogue, 8 no MMAs, 16 no TMA loads,
+  // 32 no tensor-map prefetch
+  int dbg;
 };
 
 __device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int j, int& prob, int& m0, int& n0) {
   if (up.prob_major) {
     prob = unit / up.tiles_n;
     n0 = (unit - prob * up.tiles_n) * up.tile_n;
-    m0 = j * TILE_M;
+    m0 = j * up.tile_m;
   } else {
     const int per = up.tiles_m * up.tiles_n;
     prob = unit / per;
     const int rem = unit - prob * per;
-    m0 = (rem / up.tiles_n) * TILE_M;
+    m0 = (rem / up.tiles_n) * up.tile_m;
     n0 = (rem % up.tiles_n) * up.tile_n;
   }
 }
@@ -159,7 +237,7 @@ __device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int 
 // TF32 rounding and H_L makes no extra trip through HBM (for the forward-only passes it is never stored).
 // `probs_out` is the problem table of the output-layer phase; the policy head (N = act_dim) of the remaining
 // problems is left to the FP32 output-layer kernel.
-template <int EPI, bool FUSE_OUT>
+template <int EPI, bool FUSE_OUT, bool CTA2>
 __global__ void __launch_bounds__(N_THREADS, 1)
 umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restrict__ maps,
                  const GemmProb* __restrict__ probs_out, UmmaParams up, StepCtx ctx) {
@@ -169,10 +247,16 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int RING = N_STAGES * STAGE_BYTES;
   float* epi_smem = reinterpret_cast<float*>(smem + RING);
-  // barriers: full[8], empty[8], tmem_full[2], tmem_empty[2], tmem slot
+  // barriers: full[8], empty[8], tmem_full[2], tmem_empty[2], tmem slot, peer-csum full[3]
   const uint32_t bars = base + RING + EPI_SMEM_BYTES;
   const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES, tfull0 = bars + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
   const uint32_t tslot = tempty0 + 16;
+  const uint32_t csfull0 = tslot + 8;
+  // CTA pair: rank 0 leads (issues the MMAs, owns the full / accumulator-empty barriers); work is dealt to pairs
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_off = (int)rank * TILE_M;  // this CTA's rows inside the pair's 256-row tile
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + RING + EPI_SMEM_BYTES + 16 * MAX_STAGES + 32);
   const int n_stages = up.n_stages;                      // RING / stage_bytes, capped at MAX_STAGES
   const uint32_t stage_bytes = (uint32_t)up.stage_bytes;  // 16 KB of A + tile_n * 128 B of B, 1024-byte multiple
@@ -187,16 +271,24 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, N_EPI_WARPS);
+      mbar_init(tempty0 + 8 * b, CTA2 ? 2 * N_EPI_WARPS : N_EPI_WARPS);  // pair: the epilogue warps of both CTAs
     }
+    for (int b = 0; b < PEER_CSUM_SLOTS; ++b) mbar_init(csfull0 + 8 * b, TILE_N);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncwarp();
   if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (1 CTA per SM) = two accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {     // the same warp of BOTH CTAs of the pair allocates
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync();  // the peer's barriers and TMEM must exist before anything is sent to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
 
@@ -204,58 +296,92 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int u = blockIdx.x; u < up.units; u += gridDim.x)
+      const int b_rows = CTA2 ? (tile_n >> 1) : tile_n;  // pair: this CTA stages half of the B tile
+      const uint32_t tx_bytes = (uint32_t)(CTA2 ? 2 : 1) * (uint32_t)(STAGE_A_BYTES + b_rows * TILE_K * 4);
+      const uint32_t full0_lead = CTA2 ? mapa_u32(full0, 0) : full0;
+      for (int u = worker; u < up.units; u += n_workers)
       for (int j = 0; j < up.tiles_per_unit; ++j) {
         int prob, m0, n0;
         decode_tile(up, u, j, prob, m0, n0);
-        const int K = probs[prob].K;
-        const CUtensorMap* pmaps = maps + up.maps_per_prob * prob;
-        const int nkb = (K + TILE_K - 1) / TILE_K;  // TMA zero-fills the K tail
+        m0 += m_off;
+        n0 += (int)rank * b_rows;
+        const CUtensorMap* pmaps = maps + up.maps_per_prob * ((up.dbg & 2) ? (prob & 3) : prob);
+        const int nkb = (up.k_max + TILE_K - 1) / TILE_K;  // TMA zero-fills the K tail
         const int num_kb = nkb * up.n_split;
+        if (up.dbg & 16) continue;
+        if (!(up.dbg & 32)) {  // descriptors of the NEXT tile: fetched while this tile's k-blocks stream in
+          int un = u, jn = j + 1;
+          if (jn == up.tiles_per_unit) { jn = 0; un += n_workers; }
+          if (un < up.units) {
+            int prob2, m2, n2;
+            decode_tile(up, un, jn, prob2, m2, n2);
+            if (prob2 != prob) {
+              const CUtensorMap* nm = maps + up.maps_per_prob * ((up.dbg & 2) ? (prob2 & 3) : prob2);
+              for (int i = 0; i < up.maps_per_prob; ++i)
+                asm volatile("prefetch.tensormap [%0];" ::"l"(nm + i) : "memory");
+            }
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           const int sj = kb / nkb;
           const CUtensorMap* mapA = pmaps + up.a_sel[sj];
           const CUtensorMap* mapB = pmaps + up.b_sel[sj];
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * stage_bytes, sb = sa + STAGE_A_BYTES;
-          const uint32_t fb = full0 + 8 * stage;
-          mbar_expect_tx(fb, STAGE_A_BYTES + tile_n * TILE_K * 4);
           const int k0 = (kb - sj * nkb) * TILE_K;
-          if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
-          else tma_load_2d(sa, mapA, fb, k0, m0);
-          if (up.b_mn) tma_load_3d(sb, mapB, fb, 0, k0, n0 >> 5);
-          else tma_load_2d(sb, mapB, fb, k0, n0);
+          if (CTA2) {  // the leader arms its barrier for the loads of both CTAs; the peer's bytes land on it too
+            const uint32_t fb = full0_lead + 8 * stage;
+            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, tx_bytes);
+            if (up.a_mn) tma_load_3d_cg2(sa, mapA, fb, 0, k0, m0 >> 5);
+            else tma_load_2d_cg2(sa, mapA, fb, k0, m0);
+            if (up.b_mn) tma_load_3d_cg2(sb, mapB, fb, 0, k0, n0 >> 5);
+            else tma_load_2d_cg2(sb, mapB, fb, k0, n0);
+          } else {
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, tx_bytes);
+            if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
+            else tma_load_2d(sa, mapA, fb, k0, m0);
+            if (up.b_mn) tma_load_3d(sb, mapB, fb, 0, k0, n0 >> 5);
+            else tma_load_2d(sb, mapB, fb, k0, n0);
+          }
           if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int u = blockIdx.x; u < up.units; u += gridDim.x)
+      for (int u = worker; u < up.units; u += n_workers)
       for (int j = 0; j < up.tiles_per_unit; ++j, ++it) {
         int prob, m0, n0;
         decode_tile(up, u, j, prob, m0, n0);
-        const int num_kb = ((probs[prob].K + TILE_K - 1) / TILE_K) * up.n_split;
+        const int num_kb = ((up.k_max + TILE_K - 1) / TILE_K) * up.n_split;
         const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(tempty0 + 8 * buf, acc_phase ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * 256;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full0 + 8 * stage, phase);
+          if (!(up.dbg & 16)) mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = base + stage * stage_bytes, sb = sa + STAGE_A_BYTES;
           const uint64_t adesc0 = make_desc(sa, up.a_lbo, up.a_sbo, up.a_layout);
           const uint64_t bdesc0 = make_desc(sb, up.b_lbo, up.b_sbo, up.b_layout);
 #pragma unroll
-          for (int ks = 0; ks < TILE_K / UMMA_K; ++ks)
-            umma_tf32(tacc, adesc0 + (uint64_t)(ks * up.a_kstep), bdesc0 + (uint64_t)(ks * up.b_kstep), up.idesc,
-                      (kb | ks) != 0);
-          umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
+          for (int ks = 0; ks < TILE_K / UMMA_K; ++ks) {
+            if (up.dbg & 8) break;
+            if (CTA2) umma_tf32_cg2(tacc, adesc0 + (uint64_t)(ks * up.a_kstep), bdesc0 + (uint64_t)(ks * up.b_kstep), up.idesc,
+                                    (kb | ks) != 0);
+            else umma_tf32(tacc, adesc0 + (uint64_t)(ks * up.a_kstep), bdesc0 + (uint64_t)(ks * up.b_kstep), up.idesc,
+                           (kb | ks) != 0);
+          }
+          // frees the smem slot (of both CTAs of a pair) when these MMAs have read it
+          if (CTA2) umma_commit_cg2(empty0 + 8 * stage);
+          else umma_commit(empty0 + 8 * stage);
           if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull0 + 8 * buf);  // accumulator complete
+        if (CTA2) umma_commit_cg2(tfull0 + 8 * buf);  // accumulator complete (both halves)
+        else umma_commit(tfull0 + 8 * buf);
       }
     }
   } else {
@@ -267,11 +393,18 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     float* ypart_all = epi_smem + N_EPI_WARPS * STG_FLOATS;  // [2 tile parities][4 column groups][128 rows]
     const int lr = lane >> 3;        // row within a group of 4
     const int lc = (lane & 7) * 4;   // first of this lane's 4 columns
-    uint32_t it = 0;
-    for (int u = blockIdx.x; u < up.units; u += gridDim.x)
+    uint32_t it = 0, ucount = 0;
+    const uint32_t tempty0_lead = CTA2 ? mapa_u32(tempty0, 0) : tempty0;
+    float* peer_csum = epi_smem + N_EPI_WARPS * STG_FLOATS + AUX_BYTES / 4;  // [PEER_CSUM_SLOTS][TILE_N], written by the peer
+    auto acc_release = [&](uint32_t buf) {  // this warp has read its part of the accumulator
+      if (CTA2) mbar_arrive_cluster(tempty0_lead + 8 * buf);
+      else mbar_arrive(tempty0 + 8 * buf);
+    };
+    for (int u = worker; u < up.units; u += n_workers, ++ucount)
     for (int j = 0; j < up.tiles_per_unit; ++j, ++it) {
       int prob, m0, n0;
       decode_tile(up, u, j, prob, m0, n0);
+      m0 += m_off;
       const GemmProb p = probs[prob];
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
       // per-member scalars are read ONCE per tile into registers: inside the store loop the compiler would
@@ -321,6 +454,12 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
       if (ch < n_chunks) prefetch(ch, b4_n, w4_n);
       mbar_wait(tfull0 + 8 * buf, acc_phase);
       tc_fence_after();
+      if (up.dbg & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) acc_release(buf);
+        continue;
+      }
 #pragma unroll 1
       for (int c = ch; c < n_chunks; c += N_CGROUPS) {
         const int col = n0 + c * 32 + lc;
@@ -340,7 +479,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
         if (c + N_CGROUPS >= n_chunks) {  // last TMEM read of this warp for this tile: hand the accumulator back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+          if (lane == 0) acc_release(buf);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -389,6 +528,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
             v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
           }
           float* crow = cbase + i * cstep;
+          if (up.dbg & 1) continue;
           if (vec) {
             *reinterpret_cast<float4*>(crow) = v;
           } else {
@@ -415,14 +555,29 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
       if (do_csum && j == up.tiles_per_unit - 1) {  // all rows of the problem seen: combine the quarters
         asm volatile("bar.sync 1, 512;" ::: "memory");
         const int tc = threadIdx.x - 64;  // 0..511; the first tile_n threads own one column each
-        if (tc < tile_n && n0 + tc < p.N)
-          p.dbias[n0 + tc] = ((csum_s[tc] + csum_s[TILE_N + tc]) + csum_s[2 * TILE_N + tc]) + csum_s[3 * TILE_N + tc];
+        if (tc < tile_n) {
+          float own = ((csum_s[tc] + csum_s[TILE_N + tc]) + csum_s[2 * TILE_N + tc]) + csum_s[3 * TILE_N + tc];
+          if (CTA2) {
+            // the peer sends the sums of its 128 rows into the leader's ring slot and arrives (release.cluster)
+            // on the slot's barrier.  Slot reuse is safe with 3 slots: the peer can only reach unit i+3 after the
+            // MMAs of i+3, which wait for every leader epilogue warp to have started unit i+1, i.e. finished i.
+            const uint32_t slot = ucount % PEER_CSUM_SLOTS, par = (ucount / PEER_CSUM_SLOTS) & 1u;
+            if (rank != 0) {
+              st_cluster_f32(mapa_u32(smem_u32(&peer_csum[slot * TILE_N + tc]), 0), own);
+              mbar_arrive_cluster(mapa_u32(csfull0 + 8 * slot, 0));
+            } else {
+              mbar_wait_cluster(csfull0 + 8 * slot, par);
+              own += peer_csum[slot * TILE_N + tc];
+            }
+          }
+          if (rank == 0 && n0 + tc < p.N) p.dbias[n0 + tc] = own;
+        }
         asm volatile("bar.sync 1, 512;" ::: "memory");  // csum_s is reused by the next unit
       }
       if (n_chunks <= ch) {  // this warp had no chunk (tile_n < 128): still release the accumulator
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        if (lane == 0) acc_release(buf);
       }
       if (FUSE_OUT) {
         // scalar heads: reduce the 8 lanes that share a row, park the per-column-group partials, combine them.
@@ -446,9 +601,12 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CTA2) cluster_sync();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrivals are in flight
+  else __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -537,8 +695,29 @@ int umma_tile_n(int maxN) {
   return t > TILE_N ? TILE_N : t;
 }
 
-int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, void* h_maps_out) {
+// CTA pairs: every M of the phase a multiple of 256 (two 128-row halves), a full 256-wide N tile; the fused
+// bias gradient of the dgrad epilogue is exchanged inside the pair, which covers one 256-row tile per problem.
+bool umma_dgrad_writes_dbias(int batch);
+
+bool umma_cta2_ok(int maxM, int maxN) {
+  return getenv("IQL_B200_NO_CTA2") == nullptr && maxM > 0 && (maxM % (2 * TILE_M)) == 0 && maxN >= TILE_N &&
+         (maxN % TILE_N) == 0;
+}
+
+// Where pairs pay (measured, profiles/r01_cta_pair.md): long K loops (hidden >= 512 forward, batch >= 512 weight
+// gradients) where operand delivery per MMA matters, and dgrad launches with too few problems to give every SM a
+// tile of its own.  At 2x256 / batch 256 with 64 members the phases are bound by HBM traffic, which pairs do not
+// change, and the coupling of the two epilogues costs ~8 %.
+bool umma_cta2(int mode, int nprob, int maxM, int maxN, int maxK) {
+  if (!umma_cta2_ok(maxM, maxN)) return false;
+  if (getenv("IQL_B200_FORCE_CTA2")) return true;  // tests: run every eligible phase on pairs
+  if (mode == 1) return umma_dgrad_writes_dbias(maxM) && nprob * (maxN / TILE_N) <= 74;
+  return maxK >= 512;
+}
+
+int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, void* h_maps_out, bool cta2) {
   CUtensorMap* maps = (CUtensorMap*)h_maps_out;
+  if (cta2) tile_n >>= 1;  // each CTA of a pair stages half of the B tile
   for (int i = 0; i < nprob; ++i) {
     const GemmProb& p = h_probs[i];
     int rc;
@@ -552,9 +731,10 @@ int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, v
   return 0;
 }
 
-static UmmaParams make_params(int mode, int tile_n) {
+static UmmaParams make_params(int mode, int tile_n, bool cta2) {
   UmmaParams u;
   u.tile_n = tile_n;
+  u.tile_m = cta2 ? 2 * TILE_M : TILE_M;
   u.n_split = 1;
   u.fuse_count = 0;
   u.maps_per_prob = 2;
@@ -576,13 +756,14 @@ static UmmaParams make_params(int mode, int tile_n) {
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
   // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
   u.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-            ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(u.tile_m >> 4) << 24);
   return u;
 }
 
 // 3xTF32 forward of the input layer: 4 maps per problem = [Xhi, Whi, Xlo, Wlo] (all K-major)
-int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out) {
+int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out, bool cta2) {
   CUtensorMap* maps = (CUtensorMap*)h_maps_out;
+  if (cta2) tile_n >>= 1;
   for (int i = 0; i < nprob; ++i) {
     const GemmProb& a = h_hi[i];
     const GemmProb& b = h_lo[i];
@@ -598,20 +779,41 @@ bool umma_dgrad_writes_dbias(int batch) { return (batch + TILE_M - 1) / TILE_M <
 
 bool umma_can_fuse_out(int act_dim) { (void)act_dim; return getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
 
-void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
-                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3, int fuse_count) {
+template <int EPI, bool FUSE_OUT>
+static void launch_variant(bool cta2, int workers, const GemmProb* probs, const CUtensorMap* maps, const GemmProb* probs_out,
+                           const UmmaParams& up, const StepCtx& ctx, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_NONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_RELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_DRELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI_LINEAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     attr_set = true;
   }
+  if (!cta2) {
+    umma_gemm_kernel<EPI, FUSE_OUT, false><<<workers, N_THREADS, SMEM_BYTES, st>>>(probs, maps, probs_out, up, ctx);
+    return;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * workers);
+  cfg.blockDim = dim3(N_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, FUSE_OUT, true>, probs, maps, probs_out, up, ctx);
+}
+
+void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3, int fuse_count, bool cta2,
+                      int maxK) {
   const int tile_n = umma_tile_n(maxN);
-  UmmaParams up = make_params(mode, tile_n);
-  up.tiles_m = (maxM + TILE_M - 1) / TILE_M;
+  UmmaParams up = make_params(mode, tile_n, cta2);
+  up.tiles_m = (maxM + up.tile_m - 1) / up.tile_m;
   up.tiles_n = (maxN + tile_n - 1) / tile_n;
   up.total_tiles = nprob * up.tiles_m * up.tiles_n;
   if (split3) {  // passes: Xhi Whi, Xlo Whi, Xhi Wlo
@@ -622,12 +824,15 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
     up.a_sel[2] = 0; up.b_sel[2] = 3;
   }
   up.fuse_count = probs_out ? fuse_count : 0;
-  up.stage_bytes = STAGE_A_BYTES + tile_n * TILE_K * 4;  // multiples of 4 KB: swizzle-atom alignment holds
+  // per-CTA stage: 16 KB of A + the B rows this CTA stages (multiples of 4 KB: swizzle-atom alignment holds)
+  up.stage_bytes = STAGE_A_BYTES + (cta2 ? tile_n / 2 : tile_n) * TILE_K * 4;
   up.n_stages = (N_STAGES * STAGE_BYTES) / up.stage_bytes;
   if (up.n_stages > MAX_STAGES) up.n_stages = MAX_STAGES;
-  // fused bias gradient needs all M tiles of a problem in one CTA: only worth it while that leaves enough
-  // independent units to fill the GPU (batch <= 256); larger batches use tile-major order + colsum_kernel
-  up.prob_major = (epi == EPI_DRELU && up.tiles_m <= 2) ? 1 : 0;
+  // fused bias gradient needs all rows of a problem in one CTA (or CTA pair): only worth it while that leaves
+  // enough independent units to fill the GPU (batch <= 256); larger batches use tile-major order + colsum_kernel
+  up.k_max = maxK;
+  up.dbg = (int)env_u32("IQL_UMMA_DBG", 0);
+  up.prob_major = (epi == EPI_DRELU && umma_dgrad_writes_dbias(maxM)) ? 1 : 0;
   up.tiles_per_unit = up.prob_major ? up.tiles_m : 1;
   up.units = up.total_tiles / up.tiles_per_unit;
   static int n_sm = 0;
@@ -637,13 +842,14 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  dim3 grid(up.units < n_sm ? up.units : n_sm);  // persistent: one CTA per SM
+  const int max_workers = cta2 ? n_sm / 2 : n_sm;  // persistent: one CTA per SM
+  const int workers = up.units < max_workers ? up.units : max_workers;
   const CUtensorMap* m = (const CUtensorMap*)maps;
-  if (epi == EPI_RELU && probs_out) umma_gemm_kernel<EPI_RELU, true><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, probs_out, up, ctx);
-  else if (epi == EPI_RELU) umma_gemm_kernel<EPI_RELU, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
-  else if (epi == EPI_DRELU) umma_gemm_kernel<EPI_DRELU, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
-  else if (epi == EPI_LINEAR) umma_gemm_kernel<EPI_LINEAR, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
-  else umma_gemm_kernel<EPI_NONE, false><<<grid, N_THREADS, SMEM_BYTES, st>>>(probs, m, nullptr, up, ctx);
+  if (epi == EPI_RELU && probs_out) launch_variant<EPI_RELU, true>(cta2, workers, probs, m, probs_out, up, ctx, st);
+  else if (epi == EPI_RELU) launch_variant<EPI_RELU, false>(cta2, workers, probs, m, nullptr, up, ctx, st);
+  else if (epi == EPI_DRELU) launch_variant<EPI_DRELU, false>(cta2, workers, probs, m, nullptr, up, ctx, st);
+  else if (epi == EPI_LINEAR) launch_variant<EPI_LINEAR, false>(cta2, workers, probs, m, nullptr, up, ctx, st);
+  else launch_variant<EPI_NONE, false>(cta2, workers, probs, m, nullptr, up, ctx, st);
 }
 
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st) {

@@ -10,7 +10,12 @@ bool umma_phase_supported(int mode, int batch, int hidden);
 // (2 * nprob CUtensorMap, 128 B each).  Returns 0 on success.
 // tile_n = umma_tile_n(max N of the phase): the UMMA N / B-tile height used by the launch.
 int umma_tile_n(int maxN);
-int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, void* h_maps_out);
+// CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, each CTA staging half of the B tile): umma_cta2_ok says
+// whether the shape allows them, umma_cta2 whether the phase should use them; the tensor maps and the launch
+// must be given the same answer (the engine stores it per phase when the state is bound).
+bool umma_cta2_ok(int maxM, int maxN);
+bool umma_cta2(int mode, int nprob, int maxM, int maxN, int maxK);
+int umma_encode_maps(int mode, const GemmProb* h_probs, int nprob, int tile_n, void* h_maps_out, bool cta2);
 // probs_out != null (forward, last hidden layer, EPI_RELU): the output-layer problem table; the scalar heads
 // of its first `fuse_count` problems are evaluated in FP32 inside the epilogue.
 bool umma_can_fuse_out(int act_dim);
@@ -18,8 +23,9 @@ bool umma_can_fuse_out(int act_dim);
 bool umma_dgrad_writes_dbias(int batch);
 // split3: 3xTF32 input layer; `maps` then holds 4 maps per problem (umma_encode_maps_split).
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
-                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3 = false, int fuse_count = 0);
-int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out);
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3 = false, int fuse_count = 0,
+                      bool cta2 = false, int maxK = 0);
+int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out, bool cta2);
 // bias gradients of a wgrad phase: dbias[m] = sum_k A[k][m]
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st);
 }  // namespace iql

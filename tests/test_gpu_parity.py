@@ -165,8 +165,13 @@ def test_update_matches_reference_short_horizon_fp32(name, steps):
     assert worst < FP32_TOL, (worst, where)
 
 
+@pytest.mark.parametrize("pairs", [False, True], ids=["policy", "forced_cta_pairs"])
 @pytest.mark.parametrize("name,steps", CASES)
-def test_update_matches_reference_short_horizon_tf32(name, steps):
+def test_update_matches_reference_short_horizon_tf32(name, steps, pairs, monkeypatch):
+    """pairs=True runs every eligible tcgen05 phase (3xTF32 input layer, hidden forward with the fused heads,
+    dgrad with the bias gradient exchanged through DSMEM, wgrad) on CTA pairs (cta_group::2)."""
+    if pairs:
+        monkeypatch.setenv("IQL_B200_FORCE_CTA2", "1")  # read when the engine state is bound
     g = Golden(name)
     eng, _ = _make_engine(g, "tf32")
     losses = _run_indices(eng, g, steps)[0]
@@ -407,7 +412,7 @@ def test_philox_dropout_masks_equal_cpu_restatement_and_oracle(math_mode, H, B):
     assert worst < (FP32_TOL if math_mode == "fp32" else TF32_W30_TOL), (worst, where)
 
 
-@pytest.mark.parametrize("B,H,L,A", [(384, 512, 3, 3), (128, 256, 1, 6), (512, 256, 2, 24)])
+@pytest.mark.parametrize("B,H,L,A", [(384, 512, 3, 3), (128, 256, 1, 6), (512, 256, 2, 24), (256, 512, 2, 4)])
 def test_tcgen05_path_general_shapes_match_oracle(B, H, L, A):
     """Batch sizes that are multiples of 128, hidden widths that are multiples of 256 (several N tiles and
     M tiles per problem), one to three hidden layers, wide action spaces: TF32 path vs the numpy oracle."""

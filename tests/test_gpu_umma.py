@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(mode, M, N, K, seed=0):
+def _run(mode, M, N, K, seed=0, single_cta=False):
     from jsrl_corl_b200 import _lib
 
     L = _lib.lib()
@@ -33,7 +33,7 @@ def _run(mode, M, N, K, seed=0):
     st = torch.cuda.Stream()
     st.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(st):
-        rc = L.iql_selftest_umma_gemm(mode, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+        rc = L.iql_selftest_umma_gemm(mode | (0x100 if single_cta else 0), M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
                                       Cout.data_ptr(), Cout.stride(0), scratch.data_ptr(), scratch.numel(), st.cuda_stream)
     _lib.check(rc, None, "iql_selftest_umma_gemm")
     st.synchronize()
@@ -43,11 +43,14 @@ def _run(mode, M, N, K, seed=0):
     return float(err), out, ref
 
 
+@pytest.mark.parametrize("single_cta", [False, True], ids=["cta_pair", "single_cta"])
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("shape", [(256, 256, 256), (512, 256, 64), (256, 768, 128)])
-def test_umma_gemm_matches_fp32_matmul(mode, shape):
+@pytest.mark.parametrize("shape", [(256, 256, 256), (512, 256, 64), (256, 768, 128), (1024, 512, 96)])
+def test_umma_gemm_matches_fp32_matmul(mode, shape, single_cta):
+    """N a multiple of 256 runs on CTA pairs (tcgen05 cta_group::2) unless mode | 0x100 asks for the single-CTA kernel;
+    the two must agree bit for bit (same products, same accumulation order inside the tensor core)."""
     M, N, K = shape
-    err, out, ref = _run(mode, M, N, K)
+    err, out, ref = _run(mode, M, N, K, single_cta=single_cta)
     # TF32 operands (10-bit mantissa), fp32 accumulation: ~5e-4 relative per product, averaged over K
     assert err < 1.5e-3, (mode, shape, err)
     assert torch.isfinite(out).all()
@@ -60,6 +63,13 @@ def test_umma_gemm_skinny_shapes_and_tails(mode, shape):
     M, N, K = shape
     err, out, ref = _run(mode, M, N, K)
     assert err < 1.5e-3, (mode, shape, err)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_umma_cta_pair_equals_single_cta(mode):
+    _, pair, _ = _run(mode, 512, 512, 160, seed=3)
+    _, single, _ = _run(mode, 512, 512, 160, seed=3, single_cta=True)
+    assert torch.equal(pair, single)
 
 
 def test_umma_gemm_rejects_bad_shapes():
