@@ -202,6 +202,11 @@ int iql_profile_step(iql_engine* e, int32_t reps, int32_t max_slots, int32_t* n_
                      double* flops, double* bytes, char* labels, void* stream);
 /* number of kernel launches issued by the last iql_train_steps call */
 int64_t iql_last_launch_count(const iql_engine* e);
+/* Measurement hook (tools/fused_trace.py): with IQL_FUSED_TRACE set in the environment, CTA 0 of the fused
+ * forward kernel records clock64 stamps of its TMA / MMA / epilogue roles for its first 8 tiles; this copies the
+ * stamps of the last launch, [3 roles][8 tiles][4 layers][4 stamps] int64, to the host.  Returns the number of
+ * words written, < 0 when tracing is off or `max_words` is too small. */
+int iql_debug_fused_trace(long long* out, int32_t max_words);
 
 #ifdef __cplusplus
 }

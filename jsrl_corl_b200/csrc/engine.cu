@@ -88,6 +88,7 @@ struct iql_engine {
   char* d_maps_first = nullptr;  // [4 * S * N_PASS] CUtensorMap: Xhi, Whi, Xlo, Wlo of the input-layer forward
   std::vector<char> h_maps_first;
   bool split_first = false;      // input layer runs as 3xTF32 tcgen05 GEMM
+  bool fused_fwd = false;        // whole forward (hidden layers + scalar heads) runs as one fused tcgen05 launch
   float* d_ws_f = nullptr;       // activation area
   int64_t tables_bytes = 0;
   // host shadows
@@ -460,11 +461,17 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   }
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
+  const bool tc_mode = e->cfg.math_mode == IQL_MATH_TF32_TCGEN05 && umma_phase_supported(0, e->cfg.batch_size, e->cfg.hidden_dim);
+  // 3xTF32 input layer, and on top of it the fused forward (all hidden layers of a tile chained through TMEM)
+  e->split_first = tc_mode && getenv("IQL_B200_NO_SPLIT_FIRST") == nullptr;
+  e->fused_fwd = e->split_first && umma_can_fuse_out(e->cfg.action_dim) &&
+                 fused_fwd_supported(e->cfg.batch_size, e->cfg.hidden_dim, e->cfg.n_hidden, e->cfg.state_dim + e->cfg.action_dim);
   for (auto* phases : {&e->fwd_phases, &e->bwd_phases})
     for (Phase& ph : *phases) {
       ph.maxK = 0;
       for (int i = 0; i < ph.count; ++i) ph.maxK = std::max(ph.maxK, e->h_probs[ph.first + i].K);
-      ph.cta2 = ph.umma_ok && umma_cta2(ph.mode, ph.count, ph.maxM, ph.maxN, ph.maxK);
+      const bool in_fused = e->fused_fwd && ph.mode == 0 && ph.kind != PH_OUT_FWD;  // the fused kernel loads full B tiles
+      ph.cta2 = ph.umma_ok && !in_fused && umma_cta2(ph.mode, ph.count, ph.maxM, ph.maxN, ph.maxK);
     }
   if ((int64_t)e->h_probs.size() != nprob) return fail(e, IQL_ERR_STATE, "internal: problem count mismatch");
   e->h_maps.assign((size_t)128 * 2 * nprob, 0);
@@ -476,7 +483,6 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
     };
     for (const Phase& ph : e->fwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (forward phase)");
     // 3xTF32 input layer: hi / lo operand maps of the first forward phase
-    e->split_first = umma_phase_supported(0, e->cfg.batch_size, e->cfg.hidden_dim) && getenv("IQL_B200_NO_SPLIT_FIRST") == nullptr;
     if (e->split_first) {
       const Phase& ph = e->fwd_phases[0];
       std::vector<GemmProb> hi(e->h_probs.begin() + ph.first, e->h_probs.begin() + ph.first + ph.count), lo = hi;
@@ -700,8 +706,42 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     }
     ++launches;
   };
-  for (size_t i = 0; i < e->fwd_phases.size(); ++i)
-    run_phase(e->fwd_phases[i], i + 1 < e->fwd_phases.size() ? &e->fwd_phases[i + 1] : nullptr, nullptr);
+  if (tf32 && e->fused_fwd) {
+    // one launch for layers 0..L-1 + scalar heads; the policy head (N = act_dim) stays with the FP32 output kernel
+    const int L = c.n_hidden;
+    const int n_scalar = (N_PASS - 1) * c.n_members;
+    const Phase& pout = e->fwd_phases[L];
+    FusedFwdArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    for (int l = 0; l < L; ++l) {
+      fa.probs[l] = e->d_probs + e->fwd_phases[l].first;
+      fa.maps[l] = (l == 0) ? (const void*)e->d_maps_first : (const void*)(e->d_maps + (size_t)256 * e->fwd_phases[l].first);
+    }
+    fa.probs_out = e->d_probs + pout.first;
+    fa.L = L; fa.nprob = e->fwd_phases[0].count; fa.batch = B; fa.fuse_count = n_scalar; fa.k0_max = e->fwd_phases[0].maxK;
+    if (tm) {  // operands read once, the activations of the training passes written once
+      double fl = 0, by = 0;
+      for (int l = 0; l <= L; ++l) {
+        const Phase& q = e->fwd_phases[l];
+        for (int i = 0; i < q.count; ++i) {
+          const GemmProb& g = e->h_probs[q.first + i];
+          const bool kept = e->h_probs[e->fwd_phases[L - 1].first + i].no_store == 0;
+          fl += 2.0 * g.M * g.N * g.K * (l == 0 ? 3.0 : 1.0);
+          by += 4.0 * ((l == 0 ? (double)g.M * g.K : 0.0) + (double)g.N * g.K + ((l == L || kept) ? (double)g.M * g.N : 0.0));
+        }
+      }
+      tm->mark("fused_fwd", fl, by);
+    }
+    launch_fused_fwd(fa, ctx, st);
+    ++launches;
+    const GemmProb* pa = e->d_probs + pout.first + n_scalar;
+    if (out_ok) launch_out_fwd(pa, pout.count - n_scalar, B, H, A, st);
+    else launch_simt_gemm(0, pa, pout.count - n_scalar, B, A, ctx, st);
+    ++launches;
+  } else {
+    for (size_t i = 0; i < e->fwd_phases.size(); ++i)
+      run_phase(e->fwd_phases[i], i + 1 < e->fwd_phases.size() ? &e->fwd_phases[i + 1] : nullptr, nullptr);
+  }
   if (tm) tm->mark("loss", 0, S_d * e->cfg.batch_size * 4.0 * (8 + 3 * e->wl.Ald));
   launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, st);
   ++launches;

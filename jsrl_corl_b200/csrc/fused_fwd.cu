@@ -1,0 +1,373 @@
+// Fused forward of one MLP (all hidden layers + scalar head) per 128-row batch tile, hidden width 256.
+// sm_100a only.  Replaces the per-layer forward launches of the tcgen05 path (first_fwd + hidden_fwd):
+// the hidden activations of a tile never leave the SM between layers.
+//
+//   layer 0   D0[128,256] = X W0^T as 3xTF32 (Xhi Whi + Xlo Whi + Xhi Wlo), operands by TMA into the ring
+//   epilogue  H1 = drop(relu(D0 + b0)), rounded to TF32, written BACK into the same 256 TMEM columns
+//             (tcgen05.st) and, for the passes that train, to global memory for the backward pass
+//   layer l   Dl = Hl Wl^T with A = Hl read straight from tensor memory (tcgen05.mma, A in TMEM) and only
+//             the weight k-blocks streamed through the ring; Dl lands in the other 256 columns
+//   ...       the two 256-column regions alternate, so any depth fits the 512 columns
+//   last      H_L epilogue + the FP32 scalar head y = H_L w + b (Q, V passes) or the store of H_L for the
+//             policy head kernel (actor pass)
+//
+// Per tile this removes the write + read of every intermediate H_l of the forward-only passes (V(s'), target
+// Q) and the read of H_l of the training passes, and the activation operand traffic L2 -> SM of every layer
+// but the first (128 KB of the 384 KB a 128x256x256 tile used to load).
+//
+// Roles: warp 0 lane 0 TMA producer (runs ahead across layers and tiles), warp 1 lane 0 MMA issuer, warps
+// 2-17 epilogue (4 per TMEM lane quarter x 4 column groups).  Barriers: ring full / empty, tfull[2]
+// (accumulator of forward event e = tile * L + l complete; alternating so a barrier is never lapped),
+// edone[l] (epilogue of layer l done: H_{l+1} is in tensor memory, or the last layer's region is drained).
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include "umma_gemm.h"
+
+namespace iql {
+
+namespace {
+
+constexpr int FT_M = 128, FT_N = 256, FT_K = 32, F_UMMA_K = 8;
+constexpr int F_STAGE_A = FT_M * FT_K * 4;  // 16 KB (layer 0 only)
+constexpr int F_STAGE_B = FT_N * FT_K * 4;  // 32 KB
+constexpr int F_STAGE = F_STAGE_A + F_STAGE_B;
+constexpr int F_STAGES = 3;
+constexpr int F_EPI_WARPS = 16, F_CGROUPS = 4;
+constexpr int F_STG_FLOATS = 32 * 36;
+constexpr int F_RING = F_STAGES * F_STAGE;
+constexpr int F_STG_BYTES = F_EPI_WARPS * F_STG_FLOATS * 4;
+constexpr int F_VEC_BYTES = 2 * FT_N * 4 /*bias, 2 parities*/ + 2 * FT_N * 4 /*head weights*/ + 2 * F_CGROUPS * FT_M * 4 /*head partials*/;
+constexpr int F_SMEM = F_RING + F_STG_BYTES + F_VEC_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int F_THREADS = 576;
+constexpr int FUSED_TRACE_TILES = 8;
+constexpr int FUSED_TRACE_WORDS = 3 * FUSED_TRACE_TILES * FUSED_MAX_LAYERS * 4;
+
+struct FusedParams {
+  const GemmProb* probs[FUSED_MAX_LAYERS];   // hidden layer l: problem table of forward phase l (device)
+  const CUtensorMap* maps[FUSED_MAX_LAYERS]; // l = 0: 4 per problem (Xhi, W0hi, Xlo, W0lo); l >= 1: 2 per problem, [1] = W_l
+  const GemmProb* probs_out;                 // output-layer problems (scalar heads of the first fuse_count)
+  int L, nprob, tiles_m, units, fuse_count, nkb0;
+  uint32_t idesc;
+  long long* trace;  // IQL_FUSED_TRACE: clock64 stamps of CTA 0, [3 roles][FUSED_TRACE_TILES][FUSED_MAX_LAYERS][4]
+};
+
+__device__ __forceinline__ void trace_put(const FusedParams& fp, int role, uint32_t tile_it, int l, int slot) {
+  if (fp.trace && blockIdx.x == 0 && tile_it < (uint32_t)FUSED_TRACE_TILES)
+    fp.trace[((role * FUSED_TRACE_TILES + tile_it) * FUSED_MAX_LAYERS + l) * 4 + slot] = clock64();
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp, StepCtx ctx) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  float* stg_all = reinterpret_cast<float*>(smem + F_RING);
+  float* bias_s = reinterpret_cast<float*>(smem + F_RING + F_STG_BYTES);  // [2][256]
+  float* whead_s = bias_s + 2 * FT_N;                                     // [2][256]
+  float* ypart_s = whead_s + 2 * FT_N;                                    // [2][4][128]
+  const uint32_t bars = base + F_RING + F_STG_BYTES + F_VEC_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * F_STAGES, tfull0 = bars + 16 * F_STAGES, edone0 = tfull0 + 16;
+  const uint32_t tslot = edone0 + 8 * FUSED_MAX_LAYERS;
+  volatile uint32_t* tslot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + F_RING + F_STG_BYTES + F_VEC_BYTES + 16 * F_STAGES + 16 + 8 * FUSED_MAX_LAYERS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = fp.L;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < F_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull0, 1);
+    mbar_init(tfull0 + 8, 1);
+    for (int l = 0; l < FUSED_MAX_LAYERS; ++l) mbar_init(edone0 + 8 * l, F_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tslot_ptr;
+  const int nkb_h = FT_N / FT_K;  // 8 k-blocks of a hidden layer (K = 256)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, tile_it = 0;
+      for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
+        const int prob = u / fp.tiles_m;
+        const int m0 = (u - prob * fp.tiles_m) * FT_M;
+        {  // descriptors of the next tile's problem
+          const int un = u + gridDim.x;
+          if (un < fp.units) {
+            const int pn = un / fp.tiles_m;
+            if (pn != prob) {
+              for (int i = 0; i < 4; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(fp.maps[0] + 4 * pn + i) : "memory");
+              for (int l = 1; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(fp.maps[l] + 2 * pn + 1) : "memory");
+            }
+          }
+        }
+        for (int l = 0; l < L; ++l) {
+          trace_put(fp, 0, tile_it, l, 0);
+          if (l == 0) {
+            const CUtensorMap* pm = fp.maps[0] + 4 * prob;  // passes: Xhi Whi, Xlo Whi, Xhi Wlo
+            for (int sj = 0; sj < 3; ++sj) {
+              const CUtensorMap* mapA = pm + (sj == 1 ? 2 : 0);
+              const CUtensorMap* mapB = pm + (sj == 2 ? 3 : 1);
+              for (int kb = 0; kb < fp.nkb0; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t sa = base + stage * F_STAGE, sb = sa + F_STAGE_A, fb = full0 + 8 * stage;
+                mbar_expect_tx(fb, F_STAGE);
+                tma_load_2d(sa, mapA, fb, kb * FT_K, m0);
+                tma_load_2d(sb, mapB, fb, kb * FT_K, 0);
+                if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+              }
+            }
+          } else {
+            const CUtensorMap* mapB = fp.maps[l] + 2 * prob + 1;
+            for (int kb = 0; kb < nkb_h; ++kb) {
+              mbar_wait(empty0 + 8 * stage, phase ^ 1);
+              const uint32_t sb = base + stage * F_STAGE + F_STAGE_A, fb = full0 + 8 * stage;
+              mbar_expect_tx(fb, F_STAGE_B);
+              tma_load_2d(sb, mapB, fb, kb * FT_K, 0);
+              if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          trace_put(fp, 0, tile_it, l, 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, ev = 0, tile_it = 0;
+      const bool last_even = ((L - 1) & 1) == 0;  // the last layer's accumulator shares region 0 with layer 0 of the next tile
+      for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
+        for (int l = 0; l < L; ++l, ++ev) {
+          trace_put(fp, 1, tile_it, l, 0);
+          if (l == 0) {
+            if (last_even && tile_it > 0) mbar_wait(edone0 + 8 * (L - 1), (tile_it - 1) & 1);
+          } else {
+            mbar_wait(edone0 + 8 * (l - 1), tile_it & 1);  // H_l is in tensor memory
+          }
+          tc_fence_after();
+          trace_put(fp, 1, tile_it, l, 1);
+          const uint32_t tacc = tmem_base + (uint32_t)(l & 1) * 256u;
+          const uint32_t ta = tmem_base + (uint32_t)((l - 1) & 1) * 256u;
+          const int nkb = (l == 0) ? 3 * fp.nkb0 : nkb_h;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(full0 + 8 * stage, phase);
+            tc_fence_after();
+            if (kb == 0) trace_put(fp, 1, tile_it, l, 2);
+            const uint32_t sa = base + stage * F_STAGE, sb = sa + F_STAGE_A;
+            const uint64_t bdesc0 = make_desc(sb, 1, 1024 >> 4, 2);
+            if (l == 0) {
+              const uint64_t adesc0 = make_desc(sa, 1, 1024 >> 4, 2);
+#pragma unroll
+              for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
+                umma_tf32(tacc, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), fp.idesc, (kb | ks) != 0);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
+                umma_tf32_ts(tacc, ta + (uint32_t)(kb * FT_K + ks * F_UMMA_K), bdesc0 + (uint64_t)(ks * 2), fp.idesc,
+                             (kb | ks) != 0);
+            }
+            umma_commit(empty0 + 8 * stage);
+            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(tfull0 + 8 * (ev & 1));
+          trace_put(fp, 1, tile_it, l, 3);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int ch = (warp - 2) >> 2;   // column group: chunks ch and ch + 4
+    const int tr = threadIdx.x - 64;  // 0..511
+    float* stg = stg_all + (warp - 2) * F_STG_FLOATS;
+    const int lr = lane >> 3, lc = (lane & 7) * 4;
+    uint32_t ev = 0, tile_it = 0;
+    for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
+      const int prob = u / fp.tiles_m;
+      const int m0 = (u - prob * fp.tiles_m) * FT_M;
+      const bool store = fp.probs[L - 1][prob].no_store == 0;  // forward-only passes keep nothing
+      for (int l = 0; l < L; ++l, ++ev) {
+        const GemmProb p = fp.probs[l][prob];
+        const bool last = (l == L - 1);
+        const bool fuse = last && prob < fp.fuse_count;
+        const MemberScalars* sc = ctx.scalars + p.member;
+        const uint32_t drop_thr = (p.drop_layer >= 0) ? sc->drop_threshold : 0u;
+        const bool drop = drop_thr != 0u;
+        const float drop_scale = sc->drop_scale;
+        const uint64_t drop_seed = sc->seed;
+        uint64_t dstep = 0;
+        if (drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
+        GemmProb po;
+        float* bs = bias_s + (ev & 1) * FT_N;
+        float* ws = whead_s + (ev & 1) * FT_N;
+        float* ypart = ypart_s + (ev & 1) * (F_CGROUPS * FT_M);
+        if (tr < FT_N) bs[tr] = __ldg(p.bias + tr);
+        if (fuse) {
+          po = fp.probs_out[prob];
+          if (tr < FT_N) ws[tr] = __ldg(po.B + tr);
+        }
+        if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 0);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        mbar_wait(tfull0 + 8 * (ev & 1), (ev >> 1) & 1);
+        tc_fence_after();
+        if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 1);
+        const uint32_t region = tmem_base + (uint32_t)(l & 1) * 256u + ((uint32_t)(q * 32) << 16);
+        const int row = m0 + q * 32 + lane;  // the accumulator row this lane holds
+        float yacc = 0.f;
+#pragma unroll 1
+        for (int c = ch; c < FT_N / 32; c += F_CGROUPS) {
+          uint32_t r[32];
+          tmem_ld32(region + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          const float* bc = bs + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]) + bc[j], 0.f));
+          if (drop) {
+            if (ctx.dropout_masks) {
+              const uint8_t* mkb = ctx.dropout_masks +
+                                   ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H + c * 32;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const uint32_t mk4 = *reinterpret_cast<const uint32_t*>(mkb + 4 * j4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float v = __uint_as_float(r[4 * j4 + t]);
+                  r[4 * j4 + t] = __float_as_uint(((mk4 >> (8 * t)) & 0xFFu) ? v * drop_scale : 0.f);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const uint32_t quad = (uint32_t)(((int64_t)row * FT_N + c * 32 + 4 * j4) >> 2);
+                const Philox4 ph = philox_dropout_quad(drop_seed, dstep, (uint32_t)p.drop_layer, quad);
+                r[4 * j4 + 0] = __float_as_uint((ph.x >= drop_thr) ? __uint_as_float(r[4 * j4 + 0]) * drop_scale : 0.f);
+                r[4 * j4 + 1] = __float_as_uint((ph.y >= drop_thr) ? __uint_as_float(r[4 * j4 + 1]) * drop_scale : 0.f);
+                r[4 * j4 + 2] = __float_as_uint((ph.z >= drop_thr) ? __uint_as_float(r[4 * j4 + 2]) * drop_scale : 0.f);
+                r[4 * j4 + 3] = __float_as_uint((ph.w >= drop_thr) ? __uint_as_float(r[4 * j4 + 3]) * drop_scale : 0.f);
+              }
+            }
+          }
+          if (fuse) {  // FP32 head on the unrounded activations
+            const float* wc = ws + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) yacc = fmaf(__uint_as_float(r[j]), wc[j], yacc);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(__uint_as_float(r[j])));
+          if (!last) tmem_st32(region + (uint32_t)(c * 32), r);  // operand A of the next layer, in place
+          if (store) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(&stg[lane * 36 + 4 * j]) =
+                  make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                              __uint_as_float(r[4 * j + 3]));
+            __syncwarp();
+            float* const cbase = p.C + (int64_t)(m0 + q * 32 + lr) * p.ldc + c * 32 + lc;
+            const int cstep = 4 * p.ldc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(cbase + i * cstep) = *reinterpret_cast<const float4*>(&stg[(i * 4 + lr) * 36 + lc]);
+            __syncwarp();
+          }
+        }
+        if (!last) tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(edone0 + 8 * l);
+        if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 2);
+        if (fuse) {
+          ypart[ch * FT_M + q * 32 + lane] = yacc;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          if (tr < FT_M)
+            po.C[(int64_t)(m0 + tr) * po.ldc] =
+                (((ypart[tr] + ypart[FT_M + tr]) + ypart[2 * FT_M + tr]) + ypart[3 * FT_M + tr]) + __ldg(po.bias);
+        }
+        if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 3);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+}  // namespace
+
+static long long* fused_trace_buffer() {  // allocated once when IQL_FUSED_TRACE is set
+  static long long* buf = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (getenv("IQL_FUSED_TRACE") && cudaMalloc(&buf, sizeof(long long) * FUSED_TRACE_WORDS) == cudaSuccess)
+      cudaMemset(buf, 0, sizeof(long long) * FUSED_TRACE_WORDS);
+    else
+      buf = nullptr;
+  }
+  return buf;
+}
+
+bool fused_fwd_supported(int batch, int hidden, int n_hidden, int k0) {
+  fused_trace_buffer();  // allocated here (state binding), never inside a stream capture
+  return getenv("IQL_B200_NO_FUSED_FWD") == nullptr && umma_phase_supported(0, batch, hidden) && hidden == FT_N &&
+         n_hidden >= 1 && n_hidden <= FUSED_MAX_LAYERS && k0 >= 1;
+}
+
+void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+    attr_set = true;
+  }
+  FusedParams fp;
+  memset(&fp, 0, sizeof(fp));
+  for (int l = 0; l < a.L; ++l) {
+    fp.probs[l] = a.probs[l];
+    fp.maps[l] = (const CUtensorMap*)a.maps[l];
+  }
+  fp.probs_out = a.probs_out;
+  fp.L = a.L;
+  fp.nprob = a.nprob;
+  fp.tiles_m = (a.batch + FT_M - 1) / FT_M;
+  fp.units = a.nprob * fp.tiles_m;
+  fp.fuse_count = a.probs_out ? a.fuse_count : 0;
+  fp.nkb0 = (a.k0_max + FT_K - 1) / FT_K;
+  // c = F32, a = b = TF32, both K-major, N = 256, M = 128
+  fp.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FT_N >> 3) << 17) | ((uint32_t)(FT_M >> 4) << 24);
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const int grid = fp.units < n_sm ? fp.units : n_sm;
+  fp.trace = fused_trace_buffer();
+  fused_fwd_kernel<<<grid, F_THREADS, F_SMEM, st>>>(fp, ctx);
+}
+
+// measurement hook (tools/fused_trace.py): copies the clock64 stamps of the last fused_fwd launch to the host
+extern "C" int iql_debug_fused_trace(long long* out, int32_t max_words) {
+  long long* buf = fused_trace_buffer();
+  if (!buf || !out || max_words < FUSED_TRACE_WORDS) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpy(out, buf, sizeof(long long) * FUSED_TRACE_WORDS, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  return FUSED_TRACE_WORDS;
+}
+
+}  // namespace iql

@@ -26,6 +26,17 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
                       int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3 = false, int fuse_count = 0,
                       bool cta2 = false, int maxK = 0);
 int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out, bool cta2);
+// Fused forward (fused_fwd.cu): all hidden layers + scalar heads of every (member, pass) in one launch, hidden
+// activations chained through tensor memory.  Hidden width 256, 1..FUSED_MAX_LAYERS hidden layers.
+constexpr int FUSED_MAX_LAYERS = 4;
+struct FusedFwdArgs {
+  const GemmProb* probs[FUSED_MAX_LAYERS];  // device problem tables of forward phases 0..L-1 (same problem order in each)
+  const void* maps[FUSED_MAX_LAYERS];       // [0]: umma_encode_maps_split maps (4 per problem); l >= 1: umma_encode_maps maps (2 per problem)
+  const GemmProb* probs_out;                // output-layer problem table; heads of the first fuse_count problems are fused
+  int L, nprob, batch, fuse_count, k0_max;
+};
+bool fused_fwd_supported(int batch, int hidden, int n_hidden, int k0);
+void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st);
 // bias gradients of a wgrad phase: dbias[m] = sum_k A[k][m]
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st);
 }  // namespace iql
