@@ -87,6 +87,8 @@ struct iql_engine {
   float* d_tshadow_lo = nullptr;
   char* d_maps_first = nullptr;  // [4 * S * N_PASS] CUtensorMap: Xhi, Whi, Xlo, Wlo of the input-layer forward
   std::vector<char> h_maps_first;
+  char* d_maps_store = nullptr;  // [L][S * N_PASS] CUtensorMap: activation outputs of the fused forward (TMA stores)
+  std::vector<char> h_maps_store;
   bool split_first = false;      // input layer runs as 3xTF32 tcgen05 GEMM
   bool fused_fwd = false;        // whole forward (hidden layers + scalar heads) runs as one fused tcgen05 launch
   float* d_ws_f = nullptr;       // activation area
@@ -203,6 +205,7 @@ static void build_layout(iql_engine* e) {
     tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
     tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
     tab((int64_t)128 * 4 * S * N_PASS);
+    tab((int64_t)128 * L * S * N_PASS);
   }
   e->tables_bytes = tb;
   e->layout.workspace_bytes = tb + (int64_t)S * wl.member_floats * (int64_t)sizeof(float);
@@ -458,6 +461,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
     e->d_wshadow_lo = (float*)tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
     e->d_tshadow_lo = (float*)tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
     e->d_maps_first = tab((int64_t)128 * 4 * S * N_PASS);
+    e->d_maps_store = tab((int64_t)128 * L * S * N_PASS);
   }
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
@@ -506,6 +510,17 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
         return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (3xTF32 input layer)");
     }
     for (const Phase& ph : e->bwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward phase)");
+    e->h_maps_store.clear();
+    if (e->fused_fwd) {  // outputs H_1..H_L of every forward problem, stored by TMA from the fused kernel
+      const int L = e->cfg.n_hidden, np = e->fwd_phases[0].count;
+      e->h_maps_store.assign((size_t)128 * L * np, 0);
+      for (int l = 0; l < L; ++l)
+        for (int i = 0; i < np; ++i) {
+          const GemmProb& g = e->h_probs[e->fwd_phases[l].first + i];
+          if (umma_encode_store_map(e->h_maps_store.data() + (size_t)128 * (l * np + i), g.C, g.M, g.N, g.ldc))
+            return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (fused forward outputs)");
+        }
+    }
   }
   e->bound = true;
   e->tables_dirty = e->scalars_dirty = e->counters_dirty = e->replay_dirty = true;
@@ -521,6 +536,8 @@ static int flush_tables(iql_engine* e, cudaStream_t st) {
     CUDA_TRY(e, cudaMemcpyAsync(e->d_maps, e->h_maps.data(), e->h_maps.size(), cudaMemcpyHostToDevice, st));
     if (!e->h_maps_first.empty())
       CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_first, e->h_maps_first.data(), e->h_maps_first.size(), cudaMemcpyHostToDevice, st));
+    if (!e->h_maps_store.empty())
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_store, e->h_maps_store.data(), e->h_maps_store.size(), cudaMemcpyHostToDevice, st));
     std::vector<int64_t> off(2 * (L + 1));
     for (int l = 0; l <= L; ++l) {
       off[l] = e->w_off[IQL_NET_ACTOR][l];
@@ -716,6 +733,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     for (int l = 0; l < L; ++l) {
       fa.probs[l] = e->d_probs + e->fwd_phases[l].first;
       fa.maps[l] = (l == 0) ? (const void*)e->d_maps_first : (const void*)(e->d_maps + (size_t)256 * e->fwd_phases[l].first);
+      fa.store_maps[l] = e->d_maps_store + (size_t)128 * l * e->fwd_phases[0].count;
     }
     fa.probs_out = e->d_probs + pout.first;
     fa.L = L; fa.nprob = e->fwd_phases[0].count; fa.batch = B; fa.fuse_count = n_scalar; fa.k0_max = e->fwd_phases[0].maxK;

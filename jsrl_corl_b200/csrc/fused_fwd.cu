@@ -16,9 +16,12 @@
 // but the first (128 KB of the 384 KB a 128x256x256 tile used to load).
 //
 // Roles: warp 0 lane 0 TMA producer (runs ahead across layers and tiles), warp 1 lane 0 MMA issuer, warps
-// 2-17 epilogue (4 per TMEM lane quarter x 4 column groups).  Barriers: ring full / empty, tfull[2]
-// (accumulator of forward event e = tile * L + l complete; alternating so a barrier is never lapped),
-// edone[l] (epilogue of layer l done: H_{l+1} is in tensor memory, or the last layer's region is drained).
+// 2-17 epilogue (4 per TMEM lane quarter x 4 column groups), warp 18 stages the NEXT tile's biases, head
+// weights and scalars in shared memory so that no epilogue waits on a dependent global load.
+// Barriers: ring full / empty; tfull[2] (accumulator of forward event e = tile * L + l complete; alternating so
+// a barrier is never lapped); achunk[c] (the four lane quarters have written columns [32c, +32) of H_{l+1} to
+// tensor memory: the next layer's k-block c may be issued while the rest of the epilogue still runs); elast
+// (every epilogue warp has read the last layer's accumulator); recfull / recempty[2] for the per-tile records.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,21 +40,38 @@ constexpr int F_STAGE_A = FT_M * FT_K * 4;  // 16 KB (layer 0 only)
 constexpr int F_STAGE_B = FT_N * FT_K * 4;  // 32 KB
 constexpr int F_STAGE = F_STAGE_A + F_STAGE_B;
 constexpr int F_STAGES = 3;
-constexpr int F_EPI_WARPS = 16, F_CGROUPS = 4;
-constexpr int F_STG_FLOATS = 32 * 36;
+constexpr int F_EPI_WARPS = 16, F_CGROUPS = 4, F_CHUNKS = FT_N / 32;
+constexpr int F_STG_FLOATS = 32 * 32;  // per-warp staging: one 32 x 32 chunk, rows of 128 B, 128-byte swizzled (TMA store box)
 constexpr int F_RING = F_STAGES * F_STAGE;
 constexpr int F_STG_BYTES = F_EPI_WARPS * F_STG_FLOATS * 4;
-constexpr int F_VEC_BYTES = 2 * FT_N * 4 /*bias, 2 parities*/ + 2 * FT_N * 4 /*head weights*/ + 2 * F_CGROUPS * FT_M * 4 /*head partials*/;
-constexpr int F_SMEM = F_RING + F_STG_BYTES + F_VEC_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int F_THREADS = 576;
+// per-tile record written by the prefetch warp one tile ahead: biases of every layer, head weights, scalars
+constexpr int F_REC_FLOATS = FUSED_MAX_LAYERS * FT_N + FT_N + 64;
+constexpr int F_REC_BYTES = F_REC_FLOATS * 4;
+constexpr int F_YPART_BYTES = 2 * F_CGROUPS * FT_M * 4;
+constexpr int F_SMEM = F_RING + F_STG_BYTES + 2 * F_REC_BYTES + F_YPART_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int F_THREADS = 608;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-17 epilogue, warp 18 per-tile prefetch
 constexpr int FUSED_TRACE_TILES = 8;
 constexpr int FUSED_TRACE_WORDS = 3 * FUSED_TRACE_TILES * FUSED_MAX_LAYERS * 4;
+
+struct TileRec {  // the 64-float tail of a record
+  float* C[FUSED_MAX_LAYERS];
+  float* head_out;
+  unsigned long long seed, dstep;
+  float head_b, drop_scale;
+  uint32_t drop_thr;
+  int head_ldc, store, fuse, member;
+  int drop_layer[FUSED_MAX_LAYERS];
+  int ldc[FUSED_MAX_LAYERS];
+};
+static_assert(sizeof(TileRec) <= 64 * 4, "TileRec must fit the record tail");
 
 struct FusedParams {
   const GemmProb* probs[FUSED_MAX_LAYERS];   // hidden layer l: problem table of forward phase l (device)
   const CUtensorMap* maps[FUSED_MAX_LAYERS]; // l = 0: 4 per problem (Xhi, W0hi, Xlo, W0lo); l >= 1: 2 per problem, [1] = W_l
+  const CUtensorMap* smaps[FUSED_MAX_LAYERS]; // output H_{l+1} of layer l, 1 per problem (TMA store, box 32 x 32)
   const GemmProb* probs_out;                 // output-layer problems (scalar heads of the first fuse_count)
   int L, nprob, tiles_m, units, fuse_count, nkb0;
+  int ks_last0;  // UMMA_K steps that carry data in the last k-block of layer 0 (observation widths <= 24: 3 of 4)
   uint32_t idesc;
   long long* trace;  // IQL_FUSED_TRACE: clock64 stamps of CTA 0, [3 roles][FUSED_TRACE_TILES][FUSED_MAX_LAYERS][4]
 };
@@ -67,14 +87,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   float* stg_all = reinterpret_cast<float*>(smem + F_RING);
-  float* bias_s = reinterpret_cast<float*>(smem + F_RING + F_STG_BYTES);  // [2][256]
-  float* whead_s = bias_s + 2 * FT_N;                                     // [2][256]
-  float* ypart_s = whead_s + 2 * FT_N;                                    // [2][4][128]
-  const uint32_t bars = base + F_RING + F_STG_BYTES + F_VEC_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 8 * F_STAGES, tfull0 = bars + 16 * F_STAGES, edone0 = tfull0 + 16;
-  const uint32_t tslot = edone0 + 8 * FUSED_MAX_LAYERS;
-  volatile uint32_t* tslot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + F_RING + F_STG_BYTES + F_VEC_BYTES + 16 * F_STAGES + 16 + 8 * FUSED_MAX_LAYERS);
+  float* rec_s = reinterpret_cast<float*>(smem + F_RING + F_STG_BYTES);                        // [2][F_REC_FLOATS]
+  float* ypart_s = reinterpret_cast<float*>(smem + F_RING + F_STG_BYTES + 2 * F_REC_BYTES);    // [2][4][128]
+  constexpr int BAR_OFF = F_RING + F_STG_BYTES + 2 * F_REC_BYTES + F_YPART_BYTES;
+  const uint32_t bars = base + BAR_OFF;
+  // full[3] empty[3] tfull[2] elast achunk[8] recfull[2] recempty[2] | tmem slot
+  const uint32_t full0 = bars, empty0 = bars + 8 * F_STAGES, tfull0 = bars + 16 * F_STAGES, elast = tfull0 + 16;
+  const uint32_t achunk0 = elast + 8, recfull0 = achunk0 + 8 * F_CHUNKS, recempty0 = recfull0 + 16;
+  const uint32_t tslot = recempty0 + 16;
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + (tslot - bars));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = fp.L;
@@ -85,7 +106,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
     }
     mbar_init(tfull0, 1);
     mbar_init(tfull0 + 8, 1);
-    for (int l = 0; l < FUSED_MAX_LAYERS; ++l) mbar_init(edone0 + 8 * l, F_EPI_WARPS);
+    mbar_init(elast, F_EPI_WARPS);
+    for (int c = 0; c < F_CHUNKS; ++c) mbar_init(achunk0 + 8 * c, 4);  // the 4 lane quarters of chunk c
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(recfull0 + 8 * b, 32);
+      mbar_init(recempty0 + 8 * b, F_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -113,6 +139,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             if (pn != prob) {
               for (int i = 0; i < 4; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(fp.maps[0] + 4 * pn + i) : "memory");
               for (int l = 1; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(fp.maps[l] + 2 * pn + 1) : "memory");
+              for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(fp.smaps[l] + pn) : "memory");
             }
           }
         }
@@ -149,22 +176,26 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, ev = 0, tile_it = 0;
-      const bool last_even = ((L - 1) & 1) == 0;  // the last layer's accumulator shares region 0 with layer 0 of the next tile
+      uint32_t stage = 0, phase = 0, ev = 0, tile_it = 0, aev = 0;
+      // the last layer's accumulator region (L-1)&1 is still being drained by the previous tile's last epilogue
+      // when this tile reaches the first layer that writes the same region
+      const int l_guard = (L - 1) & 1;
       for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
         for (int l = 0; l < L; ++l, ++ev) {
           trace_put(fp, 1, tile_it, l, 0);
-          if (l == 0) {
-            if (last_even && tile_it > 0) mbar_wait(edone0 + 8 * (L - 1), (tile_it - 1) & 1);
-          } else {
-            mbar_wait(edone0 + 8 * (l - 1), tile_it & 1);  // H_l is in tensor memory
+          if (l == l_guard && tile_it > 0) {
+            mbar_wait(elast, (tile_it - 1) & 1);
+            tc_fence_after();
           }
-          tc_fence_after();
           trace_put(fp, 1, tile_it, l, 1);
           const uint32_t tacc = tmem_base + (uint32_t)(l & 1) * 256u;
           const uint32_t ta = tmem_base + (uint32_t)((l - 1) & 1) * 256u;
           const int nkb = (l == 0) ? 3 * fp.nkb0 : nkb_h;
           for (int kb = 0; kb < nkb; ++kb) {
+            if (l > 0) {  // columns [32 kb, +32) of H_l are in tensor memory (all four lane quarters)
+              mbar_wait(achunk0 + 8 * kb, aev & 1);
+              tc_fence_after();
+            }
             mbar_wait(full0 + 8 * stage, phase);
             tc_fence_after();
             if (kb == 0) trace_put(fp, 1, tile_it, l, 2);
@@ -172,9 +203,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             const uint64_t bdesc0 = make_desc(sb, 1, 1024 >> 4, 2);
             if (l == 0) {
               const uint64_t adesc0 = make_desc(sa, 1, 1024 >> 4, 2);
+              const int nks = ((kb % fp.nkb0) == fp.nkb0 - 1) ? fp.ks_last0 : FT_K / F_UMMA_K;  // skip all-zero K steps
 #pragma unroll
               for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
-                umma_tf32(tacc, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), fp.idesc, (kb | ks) != 0);
+                if (ks < nks) umma_tf32(tacc, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), fp.idesc, (kb | ks) != 0);
             } else {
 #pragma unroll
               for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
@@ -184,63 +216,115 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             umma_commit(empty0 + 8 * stage);
             if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
           }
+          if (l > 0) ++aev;  // one completion of every achunk barrier per non-last epilogue
           umma_commit(tfull0 + 8 * (ev & 1));
           trace_put(fp, 1, tile_it, l, 3);
         }
       }
     }
+  } else if (warp == 18) {
+    // ===================== per-tile prefetch (one tile ahead of the epilogue) =====================
+    uint32_t tile_it = 0;
+    for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
+      const int prob = u / fp.tiles_m;
+      const uint32_t b = tile_it & 1;
+      float* rec = rec_s + b * F_REC_FLOATS;
+      const bool fuse = prob < fp.fuse_count;
+      // lane l < L: problem of layer l; lane L: the head problem
+      GemmProb g;
+      memset(&g, 0, sizeof(g));
+      if (lane < L) g = fp.probs[lane][prob];
+      else if (lane == L && fuse) g = fp.probs_out[prob];
+      mbar_wait(recempty0 + 8 * b, ((tile_it >> 1) & 1) ^ 1);  // the epilogue is done with the tile that used this buffer
+      for (int l = 0; l < L; ++l) {
+        const float* bias = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)g.bias, l));
+        const float4* b4 = reinterpret_cast<const float4*>(bias);
+        reinterpret_cast<float4*>(rec + l * FT_N)[lane] = __ldg(b4 + lane);
+        reinterpret_cast<float4*>(rec + l * FT_N)[lane + 32] = __ldg(b4 + lane + 32);
+      }
+      const float* hw = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)g.B, L));
+      if (fuse) {
+        reinterpret_cast<float4*>(rec + FUSED_MAX_LAYERS * FT_N)[lane] = __ldg(reinterpret_cast<const float4*>(hw) + lane);
+        reinterpret_cast<float4*>(rec + FUSED_MAX_LAYERS * FT_N)[lane + 32] = __ldg(reinterpret_cast<const float4*>(hw) + lane + 32);
+      }
+      TileRec* tr = reinterpret_cast<TileRec*>(rec + FUSED_MAX_LAYERS * FT_N + FT_N);
+      if (lane < L) {
+        tr->C[lane] = g.C;
+        tr->ldc[lane] = g.ldc;
+        tr->drop_layer[lane] = g.drop_layer;
+      }
+      if (lane == L - 1) {
+        tr->store = g.no_store == 0;  // forward-only passes keep nothing
+        tr->member = g.member;
+        tr->fuse = fuse ? 1 : 0;
+        const MemberScalars* sc = ctx.scalars + g.member;
+        tr->drop_thr = sc->drop_threshold;
+        tr->drop_scale = sc->drop_scale;
+        tr->seed = sc->seed;
+        tr->dstep = (unsigned long long)(ctx.counters[g.member].actor_step + ctx.k);
+      }
+      if (lane == L && fuse) {
+        tr->head_out = g.C;
+        tr->head_ldc = g.ldc;
+        tr->head_b = __ldg(g.bias);
+      }
+      mbar_arrive(recfull0 + 8 * b);  // every lane releases its own writes
+    }
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int ch = (warp - 2) >> 2;   // column group: chunks ch and ch + 4
-    const int tr = threadIdx.x - 64;  // 0..511
+    const int tr_id = threadIdx.x - 64;  // 0..511
     float* stg = stg_all + (warp - 2) * F_STG_FLOATS;
-    const int lr = lane >> 3, lc = (lane & 7) * 4;
     uint32_t ev = 0, tile_it = 0;
     for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
       const int prob = u / fp.tiles_m;
       const int m0 = (u - prob * fp.tiles_m) * FT_M;
-      const bool store = fp.probs[L - 1][prob].no_store == 0;  // forward-only passes keep nothing
+      const uint32_t b = tile_it & 1;
+      const float* rec = rec_s + b * F_REC_FLOATS;
+      mbar_wait(recfull0 + 8 * b, (tile_it >> 1) & 1);
+      const TileRec* tr = reinterpret_cast<const TileRec*>(rec + FUSED_MAX_LAYERS * FT_N + FT_N);
+      const bool store = tr->store != 0;
+      const int row = m0 + q * 32 + lane;  // the accumulator row this lane holds
       for (int l = 0; l < L; ++l, ++ev) {
-        const GemmProb p = fp.probs[l][prob];
         const bool last = (l == L - 1);
-        const bool fuse = last && prob < fp.fuse_count;
-        const MemberScalars* sc = ctx.scalars + p.member;
-        const uint32_t drop_thr = (p.drop_layer >= 0) ? sc->drop_threshold : 0u;
+        const bool fuse = last && tr->fuse;
+        const int drop_layer = tr->drop_layer[l];
+        const uint32_t drop_thr = (drop_layer >= 0) ? tr->drop_thr : 0u;
         const bool drop = drop_thr != 0u;
-        const float drop_scale = sc->drop_scale;
-        const uint64_t drop_seed = sc->seed;
-        uint64_t dstep = 0;
-        if (drop) dstep = (uint64_t)(ctx.counters[p.member].actor_step + ctx.k);
-        GemmProb po;
-        float* bs = bias_s + (ev & 1) * FT_N;
-        float* ws = whead_s + (ev & 1) * FT_N;
-        float* ypart = ypart_s + (ev & 1) * (F_CGROUPS * FT_M);
-        if (tr < FT_N) bs[tr] = __ldg(p.bias + tr);
-        if (fuse) {
-          po = fp.probs_out[prob];
-          if (tr < FT_N) ws[tr] = __ldg(po.B + tr);
-        }
+        const float drop_scale = tr->drop_scale;
+        const float* bs = rec + l * FT_N;
+        const float* ws = rec + FUSED_MAX_LAYERS * FT_N;
+        float* ypart = ypart_s + (tile_it & 1) * (F_CGROUPS * FT_M);
         if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 0);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
         mbar_wait(tfull0 + 8 * (ev & 1), (ev >> 1) & 1);
         tc_fence_after();
         if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 1);
         const uint32_t region = tmem_base + (uint32_t)(l & 1) * 256u + ((uint32_t)(q * 32) << 16);
-        const int row = m0 + q * 32 + lane;  // the accumulator row this lane holds
         float yacc = 0.f;
 #pragma unroll 1
-        for (int c = ch; c < FT_N / 32; c += F_CGROUPS) {
+        for (int c = ch; c < F_CHUNKS; c += F_CGROUPS) {
           uint32_t r[32];
           tmem_ld32(region + (uint32_t)(c * 32), r);
           tmem_ld_wait();
-          const float* bc = bs + c * 32;
+          if (last && c + F_CGROUPS >= F_CHUNKS) {  // this warp's last read of the tile: the region may be overwritten
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(elast);
+          }
+          const float4* bc = reinterpret_cast<const float4*>(bs + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]) + bc[j], 0.f));
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = bc[j];
+            r[4 * j + 0] = __float_as_uint(fmaxf(__uint_as_float(r[4 * j + 0]) + b4.x, 0.f));
+            r[4 * j + 1] = __float_as_uint(fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f));
+            r[4 * j + 2] = __float_as_uint(fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f));
+            r[4 * j + 3] = __float_as_uint(fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f));
+          }
           if (drop) {
             if (ctx.dropout_masks) {
               const uint8_t* mkb = ctx.dropout_masks +
-                                   ((((int64_t)p.member * ctx.K + ctx.k) * ctx.L + p.drop_layer) * ctx.B + row) * (int64_t)ctx.H + c * 32;
+                                   ((((int64_t)tr->member * ctx.K + ctx.k) * ctx.L + drop_layer) * ctx.B + row) * (int64_t)ctx.H + c * 32;
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const uint32_t mk4 = *reinterpret_cast<const uint32_t*>(mkb + 4 * j4);
@@ -251,10 +335,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
                 }
               }
             } else {
+              const uint64_t drop_seed = tr->seed, dstep = tr->dstep;
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const uint32_t quad = (uint32_t)(((int64_t)row * FT_N + c * 32 + 4 * j4) >> 2);
-                const Philox4 ph = philox_dropout_quad(drop_seed, dstep, (uint32_t)p.drop_layer, quad);
+                const Philox4 ph = philox_dropout_quad(drop_seed, dstep, (uint32_t)drop_layer, quad);
                 r[4 * j4 + 0] = __float_as_uint((ph.x >= drop_thr) ? __uint_as_float(r[4 * j4 + 0]) * drop_scale : 0.f);
                 r[4 * j4 + 1] = __float_as_uint((ph.y >= drop_thr) ? __uint_as_float(r[4 * j4 + 1]) * drop_scale : 0.f);
                 r[4 * j4 + 2] = __float_as_uint((ph.z >= drop_thr) ? __uint_as_float(r[4 * j4 + 2]) * drop_scale : 0.f);
@@ -263,43 +348,58 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             }
           }
           if (fuse) {  // FP32 head on the unrounded activations
-            const float* wc = ws + c * 32;
+            const float4* wc = reinterpret_cast<const float4*>(ws + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) yacc = fmaf(__uint_as_float(r[j]), wc[j], yacc);
+            for (int j = 0; j < 8; ++j) {
+              const float4 w4 = wc[j];
+              yacc = fmaf(__uint_as_float(r[4 * j + 0]), w4.x, yacc);
+              yacc = fmaf(__uint_as_float(r[4 * j + 1]), w4.y, yacc);
+              yacc = fmaf(__uint_as_float(r[4 * j + 2]), w4.z, yacc);
+              yacc = fmaf(__uint_as_float(r[4 * j + 3]), w4.w, yacc);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(__uint_as_float(r[j])));
-          if (!last) tmem_st32(region + (uint32_t)(c * 32), r);  // operand A of the next layer, in place
+          if (!last) {  // columns [32 c, +32) of the next layer's operand A, in place; the MMAs of k-block c may go
+            tmem_st32(region + (uint32_t)(c * 32), r);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(achunk0 + 8 * c);
+          }
           if (store) {
+            // every lane holds one full 128-byte row of the chunk: park it (16-byte units XOR-swizzled by the row,
+            // the layout a SWIZZLE_128B tensor map expects) and let one TMA store write the 32 x 32 box -- no
+            // transposition, and no store instruction of this warp waits for the memory system
+            if (lane == 0) bulk_wait_read0();  // the previous box has left the staging tile
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(&stg[lane * 36 + 4 * j]) =
+              *reinterpret_cast<float4*>(&stg[lane * 32 + 4 * (j ^ (lane & 7))]) =
                   make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                               __uint_as_float(r[4 * j + 3]));
+            fence_async_smem();
             __syncwarp();
-            float* const cbase = p.C + (int64_t)(m0 + q * 32 + lr) * p.ldc + c * 32 + lc;
-            const int cstep = 4 * p.ldc;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(cbase + i * cstep) = *reinterpret_cast<const float4*>(&stg[(i * 4 + lr) * 36 + lc]);
-            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(fp.smaps[l] + prob, smem_u32(stg), c * 32, m0 + q * 32);
+              bulk_commit();
+            }
           }
         }
-        if (!last) tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(edone0 + 8 * l);
         if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 2);
         if (fuse) {
           ypart[ch * FT_M + q * 32 + lane] = yacc;
           asm volatile("bar.sync 1, 512;" ::: "memory");
-          if (tr < FT_M)
-            po.C[(int64_t)(m0 + tr) * po.ldc] =
-                (((ypart[tr] + ypart[FT_M + tr]) + ypart[2 * FT_M + tr]) + ypart[3 * FT_M + tr]) + __ldg(po.bias);
+          if (tr_id < FT_M)
+            tr->head_out[(int64_t)(m0 + tr_id) * tr->head_ldc] =
+                (((ypart[tr_id] + ypart[FT_M + tr_id]) + ypart[2 * FT_M + tr_id]) + ypart[3 * FT_M + tr_id]) + tr->head_b;
         }
         if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 3);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(recempty0 + 8 * b);  // this warp no longer reads the tile's record
     }
+    bulk_wait0();  // all activation stores of this thread have completed
   }
   tc_fence_before();
   __syncwarp();
@@ -339,6 +439,7 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
   for (int l = 0; l < a.L; ++l) {
     fp.probs[l] = a.probs[l];
     fp.maps[l] = (const CUtensorMap*)a.maps[l];
+    fp.smaps[l] = (const CUtensorMap*)a.store_maps[l];
   }
   fp.probs_out = a.probs_out;
   fp.L = a.L;
@@ -347,6 +448,7 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
   fp.units = a.nprob * fp.tiles_m;
   fp.fuse_count = a.probs_out ? a.fuse_count : 0;
   fp.nkb0 = (a.k0_max + FT_K - 1) / FT_K;
+  fp.ks_last0 = (a.k0_max - (fp.nkb0 - 1) * FT_K + F_UMMA_K - 1) / F_UMMA_K;
   // c = F32, a = b = TF32, both K-major, N = 256, M = 128
   fp.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FT_N >> 3) << 17) | ((uint32_t)(FT_M >> 4) << 24);
   static int n_sm = 0;

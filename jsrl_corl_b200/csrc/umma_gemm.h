@@ -32,9 +32,12 @@ constexpr int FUSED_MAX_LAYERS = 4;
 struct FusedFwdArgs {
   const GemmProb* probs[FUSED_MAX_LAYERS];  // device problem tables of forward phases 0..L-1 (same problem order in each)
   const void* maps[FUSED_MAX_LAYERS];       // [0]: umma_encode_maps_split maps (4 per problem); l >= 1: umma_encode_maps maps (2 per problem)
+  const void* store_maps[FUSED_MAX_LAYERS]; // umma_encode_store_map maps of the layer outputs, 1 per problem
   const GemmProb* probs_out;                // output-layer problem table; heads of the first fuse_count problems are fused
   int L, nprob, batch, fuse_count, k0_max;
 };
+// 2-D map of a row-major [rows][cols] fp32 output (ld floats), box 32 x 32, 128-byte swizzle (TMA store)
+int umma_encode_store_map(void* h_map_out, const float* ptr, int rows, int cols, int ld);
 bool fused_fwd_supported(int batch, int hidden, int n_hidden, int k0);
 void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st);
 // bias gradients of a wgrad phase: dbias[m] = sum_k A[k][m]
