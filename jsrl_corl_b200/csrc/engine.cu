@@ -91,6 +91,7 @@ struct iql_engine {
   std::vector<char> h_maps_store;
   bool split_first = false;      // input layer runs as 3xTF32 tcgen05 GEMM
   bool fused_fwd = false;        // whole forward (hidden layers + scalar heads) runs as one fused tcgen05 launch
+  bool fused_pair = false;       // ... on CTA pairs (cta_group::2), one pair per 256 batch rows
   float* d_ws_f = nullptr;       // activation area
   int64_t tables_bytes = 0;
   // host shadows
@@ -470,12 +471,14 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   e->split_first = tc_mode && getenv("IQL_B200_NO_SPLIT_FIRST") == nullptr;
   e->fused_fwd = e->split_first && umma_can_fuse_out(e->cfg.action_dim) &&
                  fused_fwd_supported(e->cfg.batch_size, e->cfg.hidden_dim, e->cfg.n_hidden, e->cfg.state_dim + e->cfg.action_dim);
+  e->fused_pair = e->fused_fwd && fused_fwd_pair(e->cfg.batch_size);
   for (auto* phases : {&e->fwd_phases, &e->bwd_phases})
     for (Phase& ph : *phases) {
       ph.maxK = 0;
       for (int i = 0; i < ph.count; ++i) ph.maxK = std::max(ph.maxK, e->h_probs[ph.first + i].K);
-      const bool in_fused = e->fused_fwd && ph.mode == 0 && ph.kind != PH_OUT_FWD;  // the fused kernel loads full B tiles
-      ph.cta2 = ph.umma_ok && !in_fused && umma_cta2(ph.mode, ph.count, ph.maxM, ph.maxN, ph.maxK);
+      // phases run by the fused forward: the weight boxes are full tiles, or half tiles when it runs on CTA pairs
+      const bool in_fused = e->fused_fwd && ph.mode == 0 && ph.kind != PH_OUT_FWD;
+      ph.cta2 = in_fused ? e->fused_pair : (ph.umma_ok && umma_cta2(ph.mode, ph.count, ph.maxM, ph.maxN, ph.maxK));
     }
   if ((int64_t)e->h_probs.size() != nprob) return fail(e, IQL_ERR_STATE, "internal: problem count mismatch");
   e->h_maps.assign((size_t)128 * 2 * nprob, 0);
@@ -736,6 +739,9 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       fa.store_maps[l] = e->d_maps_store + (size_t)128 * l * e->fwd_phases[0].count;
     }
     fa.probs_out = e->d_probs + pout.first;
+    fa.pair = e->fused_pair ? 1 : 0;
+    const bool pol_fused = fused_fwd_policy_head(A);
+    fa.fuse_policy = pol_fused ? 1 : 0;
     fa.L = L; fa.nprob = e->fwd_phases[0].count; fa.batch = B; fa.fuse_count = n_scalar; fa.k0_max = e->fwd_phases[0].maxK;
     if (tm) {  // operands read once, the activations of the training passes written once
       double fl = 0, by = 0;
@@ -745,6 +751,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
           const GemmProb& g = e->h_probs[q.first + i];
           const bool kept = e->h_probs[e->fwd_phases[L - 1].first + i].no_store == 0;
           fl += 2.0 * g.M * g.N * g.K * (l == 0 ? 3.0 : 1.0);
+          if (l == L && i >= n_scalar && !pol_fused) { fl -= 2.0 * g.M * g.N * g.K; continue; }  // policy head: its own launch
           by += 4.0 * ((l == 0 ? (double)g.M * g.K : 0.0) + (double)g.N * g.K + ((l == L || kept) ? (double)g.M * g.N : 0.0));
         }
       }
@@ -753,9 +760,20 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     launch_fused_fwd(fa, ctx, st);
     ++launches;
     const GemmProb* pa = e->d_probs + pout.first + n_scalar;
+    if (!pol_fused) {
+    if (tm) {
+      double fl = 0, by = 0;
+      for (int i = n_scalar; i < pout.count; ++i) {
+        const GemmProb& g = e->h_probs[pout.first + i];
+        fl += 2.0 * g.M * g.N * g.K;
+        by += 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N);
+      }
+      tm->mark("policy_head", fl, by);
+    }
     if (out_ok) launch_out_fwd(pa, pout.count - n_scalar, B, H, A, st);
     else launch_simt_gemm(0, pa, pout.count - n_scalar, B, A, ctx, st);
     ++launches;
+    }
   } else {
     for (size_t i = 0; i < e->fwd_phases.size(); ++i)
       run_phase(e->fwd_phases[i], i + 1 < e->fwd_phases.size() ? &e->fwd_phases[i + 1] : nullptr, nullptr);

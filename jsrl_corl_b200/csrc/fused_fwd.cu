@@ -40,6 +40,9 @@ constexpr int F_STAGE_A = FT_M * FT_K * 4;  // 16 KB (layer 0 only)
 constexpr int F_STAGE_B = FT_N * FT_K * 4;  // 32 KB
 constexpr int F_STAGE = F_STAGE_A + F_STAGE_B;
 constexpr int F_STAGES = 3;
+// CTA pair: the ring is cut into 16 KB granules; a layer-0 k-block takes two (own rows of X, own half of W0),
+// a hidden-layer k-block one (own half of the W_l k-block): the whole of W_l (8 granules) can be in flight
+constexpr int F_GRAN = 16 * 1024, F_NGRAN = 9, F_MAXBAR = 9;
 constexpr int F_EPI_WARPS = 16, F_CGROUPS = 4, F_CHUNKS = FT_N / 32;
 constexpr int F_STG_FLOATS = 32 * 32;  // per-warp staging: one 32 x 32 chunk, rows of 128 B, 128-byte swizzled (TMA store box)
 constexpr int F_RING = F_STAGES * F_STAGE;
@@ -50,6 +53,7 @@ constexpr int F_REC_BYTES = F_REC_FLOATS * 4;
 constexpr int F_YPART_BYTES = 2 * F_CGROUPS * FT_M * 4;
 constexpr int F_SMEM = F_RING + F_STG_BYTES + 2 * F_REC_BYTES + F_YPART_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int F_THREADS = 608;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-17 epilogue, warp 18 per-tile prefetch
+constexpr int FUSED_POL_MAX = 8;
 constexpr int FUSED_TRACE_TILES = 8;
 constexpr int FUSED_TRACE_WORDS = 3 * FUSED_TRACE_TILES * FUSED_MAX_LAYERS * 4;
 
@@ -62,6 +66,11 @@ struct TileRec {  // the 64-float tail of a record
   int head_ldc, store, fuse, member;
   int drop_layer[FUSED_MAX_LAYERS];
   int ldc[FUSED_MAX_LAYERS];
+  // policy head (actor pass, act_dim <= FUSED_POL_MAX): z = H_L Wp^T + bp, FP32, in the last epilogue
+  const float* pol_w;
+  float* pol_out;
+  int pol_a, pol_ldw, pol_ldc, pad_;
+  float pol_b[FUSED_POL_MAX];
 };
 static_assert(sizeof(TileRec) <= 64 * 4, "TileRec must fit the record tail");
 
@@ -71,6 +80,7 @@ struct FusedParams {
   const CUtensorMap* smaps[FUSED_MAX_LAYERS]; // output H_{l+1} of layer l, 1 per problem (TMA store, box 32 x 32)
   const GemmProb* probs_out;                 // output-layer problems (scalar heads of the first fuse_count)
   int L, nprob, tiles_m, units, fuse_count, nkb0;
+  int fuse_policy;  // the problems >= fuse_count (actor pass) get their N = act_dim head fused as well
   int ks_last0;  // UMMA_K steps that carry data in the last k-block of layer 0 (observation widths <= 24: 3 of 4)
   uint32_t idesc;
   long long* trace;  // IQL_FUSED_TRACE: clock64 stamps of CTA 0, [3 roles][FUSED_TRACE_TILES][FUSED_MAX_LAYERS][4]
@@ -81,6 +91,11 @@ __device__ __forceinline__ void trace_put(const FusedParams& fp, int role, uint3
     fp.trace[((role * FUSED_TRACE_TILES + tile_it) * FUSED_MAX_LAYERS + l) * 4 + slot] = clock64();
 }
 
+// Work order: table order (forward-only and critic passes first, the actor pass last).  Handing the actor tiles
+// (policy head, dropout: the longest epilogues) out first made no difference (96 vs 95 us, same box, 64-member ensemble).
+__device__ __forceinline__ int unit_prob(const FusedParams& fp, int u) { return u / fp.tiles_m; }
+
+template <bool CTA2>
 __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp, StepCtx ctx) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -92,7 +107,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   constexpr int BAR_OFF = F_RING + F_STG_BYTES + 2 * F_REC_BYTES + F_YPART_BYTES;
   const uint32_t bars = base + BAR_OFF;
   // full[3] empty[3] tfull[2] elast achunk[8] recfull[2] recempty[2] | tmem slot
-  const uint32_t full0 = bars, empty0 = bars + 8 * F_STAGES, tfull0 = bars + 16 * F_STAGES, elast = tfull0 + 16;
+  const uint32_t full0 = bars, empty0 = bars + 8 * F_MAXBAR, tfull0 = bars + 16 * F_MAXBAR, elast = tfull0 + 16;
   const uint32_t achunk0 = elast + 8, recfull0 = achunk0 + 8 * F_CHUNKS, recempty0 = recfull0 + 16;
   const uint32_t tslot = recempty0 + 16;
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + (tslot - bars));
@@ -100,14 +115,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = fp.L;
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < F_STAGES; ++s) {
+    for (int s = 0; s < F_MAXBAR; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(tfull0, 1);
     mbar_init(tfull0 + 8, 1);
-    mbar_init(elast, F_EPI_WARPS);
-    for (int c = 0; c < F_CHUNKS; ++c) mbar_init(achunk0 + 8 * c, 4);  // the 4 lane quarters of chunk c
+    // pair: the leader's barriers collect the epilogue warps of both CTAs
+    mbar_init(elast, CTA2 ? 2 * F_EPI_WARPS : F_EPI_WARPS);
+    for (int c = 0; c < F_CHUNKS; ++c) mbar_init(achunk0 + 8 * c, CTA2 ? 8 : 4);  // the lane quarters of chunk c
     for (int b = 0; b < 2; ++b) {
       mbar_init(recfull0 + 8 * b, 32);
       mbar_init(recempty0 + 8 * b, F_EPI_WARPS);
@@ -116,32 +132,68 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   }
   __syncwarp();
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
   const int nkb_h = FT_N / FT_K;  // 8 k-blocks of a hidden layer (K = 256)
+  // pair: rank 0 leads (issues the MMAs, owns full / achunk / elast); work is dealt to pairs, 256 rows per tile
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tile_rows = CTA2 ? 2 * FT_M : FT_M;
+  const int m_off = (int)rank * FT_M;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, tile_it = 0;
-      for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
-        const int prob = u / fp.tiles_m;
-        const int m0 = (u - prob * fp.tiles_m) * FT_M;
+      for (int u = worker; u < fp.units; u += n_workers, ++tile_it) {
+        const int prob = unit_prob(fp, u);
+        const int m0 = (u % fp.tiles_m) * tile_rows + m_off;
         {  // descriptors of the next tile's problem
-          const int un = u + gridDim.x;
+          const int un = u + n_workers;
           if (un < fp.units) {
-            const int pn = un / fp.tiles_m;
+            const int pn = unit_prob(fp, un);
             if (pn != prob) {
               for (int i = 0; i < 4; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(fp.maps[0] + 4 * pn + i) : "memory");
               for (int l = 1; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(fp.maps[l] + 2 * pn + 1) : "memory");
               for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(fp.smaps[l] + pn) : "memory");
             }
           }
+        }
+        if (CTA2) {
+          const uint32_t full_lead = mapa_u32(full0, 0);
+          auto put = [&](const CUtensorMap* map, int c0, int c1) {  // one 16 KB granule of this CTA
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * F_GRAN);  // the peer's granule lands on the same barrier
+            tma_load_2d_cg2(base + stage * F_GRAN, map, full_lead + 8 * stage, c0, c1);
+            if (++stage == F_NGRAN) { stage = 0; phase ^= 1; }
+          };
+          for (int l = 0; l < L; ++l) {
+            trace_put(fp, 0, tile_it, l, 0);
+            if (l == 0) {
+              const CUtensorMap* pm = fp.maps[0] + 4 * prob;
+              for (int sj = 0; sj < 3; ++sj)
+                for (int kb = 0; kb < fp.nkb0; ++kb) {
+                  put(pm + (sj == 1 ? 2 : 0), kb * FT_K, m0);               // own 128 rows of Xhi / Xlo
+                  put(pm + (sj == 2 ? 3 : 1), kb * FT_K, (int)rank * 128);  // own half of W0hi / W0lo
+                }
+            } else {
+              for (int kb = 0; kb < nkb_h; ++kb) put(fp.maps[l] + 2 * prob + 1, kb * FT_K, (int)rank * 128);
+            }
+            trace_put(fp, 0, tile_it, l, 1);
+          }
+          continue;
         }
         for (int l = 0; l < L; ++l) {
           trace_put(fp, 0, tile_it, l, 0);
@@ -175,12 +227,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, ev = 0, tile_it = 0, aev = 0;
       // the last layer's accumulator region (L-1)&1 is still being drained by the previous tile's last epilogue
       // when this tile reaches the first layer that writes the same region
       const int l_guard = (L - 1) & 1;
-      for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
+      for (int u = worker; u < fp.units; u += n_workers, ++tile_it) {
         for (int l = 0; l < L; ++l, ++ev) {
           trace_put(fp, 1, tile_it, l, 0);
           if (l == l_guard && tile_it > 0) {
@@ -191,6 +243,44 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           const uint32_t tacc = tmem_base + (uint32_t)(l & 1) * 256u;
           const uint32_t ta = tmem_base + (uint32_t)((l - 1) & 1) * 256u;
           const int nkb = (l == 0) ? 3 * fp.nkb0 : nkb_h;
+          if (CTA2) {
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (l == 0) {
+                const uint32_t ga = stage, pa = phase;
+                if (++stage == F_NGRAN) { stage = 0; phase ^= 1; }
+                const uint32_t gb = stage, pb = phase;
+                if (++stage == F_NGRAN) { stage = 0; phase ^= 1; }
+                mbar_wait(full0 + 8 * ga, pa);
+                mbar_wait(full0 + 8 * gb, pb);
+                tc_fence_after();
+                if (kb == 0) trace_put(fp, 1, tile_it, l, 2);
+                const uint64_t adesc0 = make_desc(base + ga * F_GRAN, 1, 1024 >> 4, 2);
+                const uint64_t bdesc0 = make_desc(base + gb * F_GRAN, 1, 1024 >> 4, 2);
+                const int nks = ((kb % fp.nkb0) == fp.nkb0 - 1) ? fp.ks_last0 : FT_K / F_UMMA_K;
+#pragma unroll
+                for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
+                  if (ks < nks) umma_tf32_cg2(tacc, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), fp.idesc, (kb | ks) != 0);
+                umma_commit_cg2(empty0 + 8 * ga);
+                umma_commit_cg2(empty0 + 8 * gb);
+              } else {
+                mbar_wait(achunk0 + 8 * kb, aev & 1);  // both CTAs have columns [32 kb, +32) of H_l in tensor memory
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                if (kb == 0) trace_put(fp, 1, tile_it, l, 2);
+                const uint64_t bdesc0 = make_desc(base + stage * F_GRAN, 1, 1024 >> 4, 2);
+#pragma unroll
+                for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
+                  umma_tf32_ts_cg2(tacc, ta + (uint32_t)(kb * FT_K + ks * F_UMMA_K), bdesc0 + (uint64_t)(ks * 2), fp.idesc,
+                                   (kb | ks) != 0);
+                umma_commit_cg2(empty0 + 8 * stage);
+                if (++stage == F_NGRAN) { stage = 0; phase ^= 1; }
+              }
+            }
+            if (l > 0) ++aev;
+            umma_commit_cg2(tfull0 + 8 * (ev & 1));
+            trace_put(fp, 1, tile_it, l, 3);
+            continue;
+          }
           for (int kb = 0; kb < nkb; ++kb) {
             if (l > 0) {  // columns [32 kb, +32) of H_l are in tensor memory (all four lane quarters)
               mbar_wait(achunk0 + 8 * kb, aev & 1);
@@ -225,16 +315,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   } else if (warp == 18) {
     // ===================== per-tile prefetch (one tile ahead of the epilogue) =====================
     uint32_t tile_it = 0;
-    for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
-      const int prob = u / fp.tiles_m;
+    for (int u = worker; u < fp.units; u += n_workers, ++tile_it) {
+      const int prob = unit_prob(fp, u);
       const uint32_t b = tile_it & 1;
       float* rec = rec_s + b * F_REC_FLOATS;
       const bool fuse = prob < fp.fuse_count;
       // lane l < L: problem of layer l; lane L: the head problem
       GemmProb g;
       memset(&g, 0, sizeof(g));
+      const bool pol = !fuse && fp.fuse_policy;
       if (lane < L) g = fp.probs[lane][prob];
-      else if (lane == L && fuse) g = fp.probs_out[prob];
+      else if (lane == L && (fuse || pol)) g = fp.probs_out[prob];
       mbar_wait(recempty0 + 8 * b, ((tile_it >> 1) & 1) ^ 1);  // the epilogue is done with the tile that used this buffer
       for (int l = 0; l < L; ++l) {
         const float* bias = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)g.bias, l));
@@ -268,6 +359,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
         tr->head_ldc = g.ldc;
         tr->head_b = __ldg(g.bias);
       }
+      {
+        const float* pb = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)g.bias, L));
+        const int pa = __shfl_sync(0xffffffffu, g.N, L);
+        if (lane < FUSED_POL_MAX) tr->pol_b[lane] = (pol && lane < pa) ? __ldg(pb + lane) : 0.f;
+        if (lane == L) {
+          tr->pol_a = pol ? g.N : 0;
+          tr->pol_w = g.B;
+          tr->pol_ldw = g.ldb;
+          tr->pol_out = g.C;
+          tr->pol_ldc = g.ldc;
+        }
+      }
       mbar_arrive(recfull0 + 8 * b);  // every lane releases its own writes
     }
   } else {
@@ -277,9 +380,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
     const int tr_id = threadIdx.x - 64;  // 0..511
     float* stg = stg_all + (warp - 2) * F_STG_FLOATS;
     uint32_t ev = 0, tile_it = 0;
-    for (int u = blockIdx.x; u < fp.units; u += gridDim.x, ++tile_it) {
-      const int prob = u / fp.tiles_m;
-      const int m0 = (u - prob * fp.tiles_m) * FT_M;
+    const uint32_t elast_lead = CTA2 ? mapa_u32(elast, 0) : elast;
+    const uint32_t achunk_lead = CTA2 ? mapa_u32(achunk0, 0) : achunk0;
+    for (int u = worker; u < fp.units; u += n_workers, ++tile_it) {
+      const int prob = unit_prob(fp, u);
+      const int m0 = (u % fp.tiles_m) * tile_rows + m_off;
       const uint32_t b = tile_it & 1;
       const float* rec = rec_s + b * F_REC_FLOATS;
       mbar_wait(recfull0 + 8 * b, (tile_it >> 1) & 1);
@@ -302,6 +407,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
         if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 1);
         const uint32_t region = tmem_base + (uint32_t)(l & 1) * 256u + ((uint32_t)(q * 32) << 16);
         float yacc = 0.f;
+        const int pol_a = last ? tr->pol_a : 0;  // > 0: actor pass, policy head fused
+        float pacc[FUSED_POL_MAX];
+#pragma unroll
+        for (int a = 0; a < FUSED_POL_MAX; ++a) pacc[a] = 0.f;
 #pragma unroll 1
         for (int c = ch; c < F_CHUNKS; c += F_CGROUPS) {
           uint32_t r[32];
@@ -310,7 +419,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           if (last && c + F_CGROUPS >= F_CHUNKS) {  // this warp's last read of the tile: the region may be overwritten
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(elast);
+            if (lane == 0) {
+              if (CTA2) mbar_arrive_remote(elast_lead);
+              else mbar_arrive(elast);
+            }
           }
           const float4* bc = reinterpret_cast<const float4*>(bs + c * 32);
 #pragma unroll
@@ -358,6 +470,24 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               yacc = fmaf(__uint_as_float(r[4 * j + 3]), w4.w, yacc);
             }
           }
+          if (pol_a > 0) {  // act_dim dot products per row; the weight rows are the same for every lane (L1 broadcast)
+            const float* wp = tr->pol_w + c * 32;
+            const int ldw = tr->pol_ldw;
+#pragma unroll
+            for (int a = 0; a < FUSED_POL_MAX; ++a) {
+              if (a < pol_a) {
+                const float4* wr = reinterpret_cast<const float4*>(wp + (int64_t)a * ldw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w4 = __ldg(wr + j);
+                  pacc[a] = fmaf(__uint_as_float(r[4 * j + 0]), w4.x, pacc[a]);
+                  pacc[a] = fmaf(__uint_as_float(r[4 * j + 1]), w4.y, pacc[a]);
+                  pacc[a] = fmaf(__uint_as_float(r[4 * j + 2]), w4.z, pacc[a]);
+                  pacc[a] = fmaf(__uint_as_float(r[4 * j + 3]), w4.w, pacc[a]);
+                }
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(__uint_as_float(r[j])));
           if (!last) {  // columns [32 c, +32) of the next layer's operand A, in place; the MMAs of k-block c may go
@@ -365,7 +495,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(achunk0 + 8 * c);
+            if (lane == 0) {
+              if (CTA2) mbar_arrive_remote(achunk_lead + 8 * c);
+              else mbar_arrive(achunk0 + 8 * c);
+            }
           }
           if (store) {
             // every lane holds one full 128-byte row of the chunk: park it (16-byte units XOR-swizzled by the row,
@@ -394,6 +527,29 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             tr->head_out[(int64_t)(m0 + tr_id) * tr->head_ldc] =
                 (((ypart[tr_id] + ypart[FT_M + tr_id]) + ypart[2 * FT_M + tr_id]) + ypart[3 * FT_M + tr_id]) + tr->head_b;
         }
+        if (pol_a > 0) {
+          // the four column groups park their partial sums in their (idle) staging tiles; the warps of group 0
+          // add them up in a fixed order and write z
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int a = 0; a < FUSED_POL_MAX; ++a) stg[lane * FUSED_POL_MAX + a] = pacc[a];
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          if (ch == 0) {
+            float* zrow = tr->pol_out + (int64_t)row * tr->pol_ldc;
+#pragma unroll
+            for (int a = 0; a < FUSED_POL_MAX; ++a) {
+              if (a < pol_a) {
+                const float* p0 = stg + lane * FUSED_POL_MAX + a;  // this warp is group 0 of its quarter; group g4 is 4 g4 tiles further
+                float z = 0.f;
+#pragma unroll
+                for (int g4 = 0; g4 < F_CGROUPS; ++g4) z += p0[g4 * 4 * F_STG_FLOATS];
+                zrow[a] = z + tr->pol_b[a];
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 512;" ::: "memory");  // the staging tiles go back to the activation stores
+        }
         if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 3);
       }
       __syncwarp();
@@ -403,8 +559,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   }
   tc_fence_before();
   __syncwarp();
-  __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  if (CTA2) cluster_sync();
+  else __syncthreads();
+  if (warp == 1) {
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
 }
 
 }  // namespace
@@ -428,12 +588,22 @@ bool fused_fwd_supported(int batch, int hidden, int n_hidden, int k0) {
          n_hidden >= 1 && n_hidden <= FUSED_MAX_LAYERS && k0 >= 1;
 }
 
+// CTA pairs: one pair per 256 batch rows of a problem, each CTA staging half of every weight k-block
+bool fused_fwd_pair(int batch) {
+  return getenv("IQL_B200_NO_FUSED_PAIR") == nullptr && getenv("IQL_B200_NO_CTA2") == nullptr && batch % (2 * FT_M) == 0;
+}
+
+bool fused_fwd_policy_head(int act_dim) { return act_dim >= 1 && act_dim <= FUSED_POL_MAX && getenv("IQL_B200_NO_FUSED_POLICY") == nullptr; }
+
 void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+    cudaFuncSetAttribute(fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+    cudaFuncSetAttribute(fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
     attr_set = true;
   }
+  const bool pair = a.pair != 0;
+  const int tile_rows = pair ? 2 * FT_M : FT_M;
   FusedParams fp;
   memset(&fp, 0, sizeof(fp));
   for (int l = 0; l < a.L; ++l) {
@@ -444,13 +614,14 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
   fp.probs_out = a.probs_out;
   fp.L = a.L;
   fp.nprob = a.nprob;
-  fp.tiles_m = (a.batch + FT_M - 1) / FT_M;
+  fp.tiles_m = (a.batch + tile_rows - 1) / tile_rows;
   fp.units = a.nprob * fp.tiles_m;
   fp.fuse_count = a.probs_out ? a.fuse_count : 0;
+  fp.fuse_policy = (a.probs_out && a.fuse_policy) ? 1 : 0;
   fp.nkb0 = (a.k0_max + FT_K - 1) / FT_K;
   fp.ks_last0 = (a.k0_max - (fp.nkb0 - 1) * FT_K + F_UMMA_K - 1) / F_UMMA_K;
-  // c = F32, a = b = TF32, both K-major, N = 256, M = 128
-  fp.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FT_N >> 3) << 17) | ((uint32_t)(FT_M >> 4) << 24);
+  // c = F32, a = b = TF32, both K-major, N = 256, M = 128 (256 for a CTA pair)
+  fp.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FT_N >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -458,9 +629,27 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  const int grid = fp.units < n_sm ? fp.units : n_sm;
   fp.trace = fused_trace_buffer();
-  fused_fwd_kernel<<<grid, F_THREADS, F_SMEM, st>>>(fp, ctx);
+  if (!pair) {
+    const int grid = fp.units < n_sm ? fp.units : n_sm;
+    fused_fwd_kernel<false><<<grid, F_THREADS, F_SMEM, st>>>(fp, ctx);
+    return;
+  }
+  const int workers = fp.units < n_sm / 2 ? fp.units : n_sm / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * workers);
+  cfg.blockDim = dim3(F_THREADS);
+  cfg.dynamicSmemBytes = F_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, fused_fwd_kernel<true>, fp, ctx);
 }
 
 // measurement hook (tools/fused_trace.py): copies the clock64 stamps of the last fused_fwd launch to the host

@@ -35,10 +35,14 @@ struct FusedFwdArgs {
   const void* store_maps[FUSED_MAX_LAYERS]; // umma_encode_store_map maps of the layer outputs, 1 per problem
   const GemmProb* probs_out;                // output-layer problem table; heads of the first fuse_count problems are fused
   int L, nprob, batch, fuse_count, k0_max;
+  int pair;  // run on CTA pairs (the weight maps were encoded with half-height boxes)
+  int fuse_policy;  // also fuse the policy head (problems >= fuse_count of probs_out; act_dim <= 8)
 };
 // 2-D map of a row-major [rows][cols] fp32 output (ld floats), box 32 x 32, 128-byte swizzle (TMA store)
 int umma_encode_store_map(void* h_map_out, const float* ptr, int rows, int cols, int ld);
 bool fused_fwd_supported(int batch, int hidden, int n_hidden, int k0);
+bool fused_fwd_pair(int batch);
+bool fused_fwd_policy_head(int act_dim);  // the actor's output layer fits the fused epilogue  // whether the fused forward runs on CTA pairs for this batch size
 void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st);
 // bias gradients of a wgrad phase: dbias[m] = sum_k A[k][m]
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st);
