@@ -53,6 +53,7 @@ struct Phase {
   int maxM, maxN;
   int maxK = 0;  // largest K over the problems of the phase
   bool cta2 = false;  // tcgen05 kernel runs this phase on CTA pairs (decided when the tensor maps are encoded)
+  bool rowepi = false;  // tcgen05 kernel uses the row-layout epilogue: TMA stores, ReLU sign bits as the dgrad mask
   int K;         // common K of the phase (0 if mixed)
   bool umma_ok;  // eligible for the tcgen05 kernel
   int epi;       // common epilogue of the phase
@@ -87,6 +88,8 @@ struct iql_engine {
   float* d_tshadow_lo = nullptr;
   char* d_maps_first = nullptr;  // [4 * S * N_PASS] CUtensorMap: Xhi, Whi, Xlo, Wlo of the input-layer forward
   std::vector<char> h_maps_first;
+  char* d_maps_c = nullptr;      // [nprob] CUtensorMap of the outputs of the backward tcgen05 phases (TMA stores)
+  std::vector<char> h_maps_c;
   char* d_maps_store = nullptr;  // [L][S * N_PASS] CUtensorMap: activation outputs of the fused forward (TMA stores)
   std::vector<char> h_maps_store;
   bool split_first = false;      // input layer runs as 3xTF32 tcgen05 GEMM
@@ -182,10 +185,11 @@ static void build_layout(iql_engine* e) {
   wl.gy = region(3 * B);
   wl.gpi = region(B * wl.Ald);
   wl.gh = region((int64_t)4 * 2 * B * H);
-  wl.xhi = wl.xlo = 0;
+  wl.xhi = wl.xlo = wl.bits = 0;
   if (c.math_mode == IQL_MATH_TF32_TCGEN05) {
     wl.xhi = region(B * e->layout.row.row_floats);
     wl.xlo = region(B * e->layout.row.row_floats);
+    wl.bits = region((int64_t)4 * (L > 1 ? L - 1 : 0) * B * (H / 32 + 1));
   }
   wl.member_floats = w;
 
@@ -207,6 +211,7 @@ static void build_layout(iql_engine* e) {
     tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
     tab((int64_t)128 * 4 * S * N_PASS);
     tab((int64_t)128 * L * S * N_PASS);
+    tab((int64_t)128 * nprob);
   }
   e->tables_bytes = tb;
   e->layout.workspace_bytes = tb + (int64_t)S * wl.member_floats * (int64_t)sizeof(float);
@@ -331,6 +336,10 @@ static void build_problems(iql_engine* e) {
   auto wsm = [&](int m) { return e->d_ws_f + (int64_t)m * wl.member_floats; };
   auto actp = [&](int m, int f, int l) { return wsm(m) + wl.act + ((int64_t)(f * L + l)) * B * H; };
   auto blank = [&]() { GemmProb p; memset(&p, 0, sizeof(p)); p.drop_layer = -1; return p; };
+  // sign bits of activation index a (0-based: output of forward layer a) of training pass slot t (V, q1, q2, actor)
+  auto bitsp = [&](int m, int t, int a) {
+    return reinterpret_cast<uint32_t*>(wsm(m) + wl.bits) + ((int64_t)(t * (L - 1) + a)) * B * (H / 32);
+  };
   // ---- forward phases, layer 0..L ----
   for (int l = 0; l <= L; ++l) {
     Phase ph; ph.mode = 0; ph.first = (int)e->h_probs.size(); ph.maxM = B; ph.maxN = 0; ph.K = 0; ph.umma_ok = false;
@@ -354,6 +363,8 @@ static void build_problems(iql_engine* e) {
           p.drop_layer = (f == PASS_PI) ? l : -1;
           // H_L of the forward-only passes (V(s'), target Q) is consumed only by the fused output Linear
           p.no_store = (l == L - 1 && (f == PASS_V_NEXT || f == PASS_TQ1 || f == PASS_TQ2)) ? 1 : 0;
+          const int tslot = (f == PASS_V) ? 0 : (f == PASS_Q1) ? 1 : (f == PASS_Q2) ? 2 : (f == PASS_PI) ? 3 : -1;
+          if (use_shadow && tslot >= 0 && l < L - 1) p.bits = bitsp(m, tslot, l);  // sign bits of H_{l+1}, for dgrad
         } else if (f == PASS_PI) {
           p.N = c.action_dim; p.C = wsm(m) + wl.zpi; p.ldc = wl.Ald; p.epi = EPI_LINEAR;
         } else {
@@ -422,6 +433,7 @@ static void build_problems(iql_engine* e) {
         p.ldc = H;
         p.mask = actp(m, f, l - 1);
         p.ldmask = H;
+        if (use_shadow && l < L) p.bits = bitsp(m, t, l - 1);  // same activation as p.mask, 1 bit per element
         p.epi = EPI_DRELU;
         p.drop_layer = (t == 3) ? (l - 1) : -1;
         // bias gradient of the layer below = column sums of the gradient this problem produces
@@ -463,6 +475,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
     e->d_tshadow_lo = (float*)tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
     e->d_maps_first = tab((int64_t)128 * 4 * S * N_PASS);
     e->d_maps_store = tab((int64_t)128 * L * S * N_PASS);
+    e->d_maps_c = tab((int64_t)128 * nprob);
   }
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
@@ -479,6 +492,13 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
       // phases run by the fused forward: the weight boxes are full tiles, or half tiles when it runs on CTA pairs
       const bool in_fused = e->fused_fwd && ph.mode == 0 && ph.kind != PH_OUT_FWD;
       ph.cta2 = in_fused ? e->fused_pair : (ph.umma_ok && umma_cta2(ph.mode, ph.count, ph.maxM, ph.maxN, ph.maxK));
+      // backward hidden-layer phases: row-layout epilogue (TMA stores; dgrad masks with the sign bits the fused
+      // forward wrote -- without the fused forward the bits do not exist and dgrad keeps the FP32 mask)
+      // (the same epilogue on the weight-gradient phase measured 46.4 vs 44.2 us: it stays on the transposing one)
+      const bool hidden_dgrad = tc_mode && ph.umma_ok && ph.kind == PH_GENERIC && (ph.maxN % 32) == 0 && ph.mode == 1 &&
+                                e->fused_fwd;
+      ph.rowepi = (hidden_dgrad || (ph.mode == 2 && ph.kind == PH_GENERIC && tc_mode && getenv("IQL_B200_ROWEPI_WGRAD"))) &&
+                  getenv("IQL_B200_NO_ROWEPI") == nullptr;
     }
   if ((int64_t)e->h_probs.size() != nprob) return fail(e, IQL_ERR_STATE, "internal: problem count mismatch");
   e->h_maps.assign((size_t)128 * 2 * nprob, 0);
@@ -513,6 +533,14 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
         return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (3xTF32 input layer)");
     }
     for (const Phase& ph : e->bwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward phase)");
+    e->h_maps_c.assign((size_t)128 * nprob, 0);
+    for (const Phase& ph : e->bwd_phases)
+      if (ph.rowepi)
+        for (int i = 0; i < ph.count; ++i) {
+          const GemmProb& g = e->h_probs[ph.first + i];
+          if (umma_encode_store_map(e->h_maps_c.data() + (size_t)128 * (ph.first + i), g.C, g.M, g.N, g.ldc))
+            return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward outputs)");
+        }
     e->h_maps_store.clear();
     if (e->fused_fwd) {  // outputs H_1..H_L of every forward problem, stored by TMA from the fused kernel
       const int L = e->cfg.n_hidden, np = e->fwd_phases[0].count;
@@ -539,6 +567,8 @@ static int flush_tables(iql_engine* e, cudaStream_t st) {
     CUDA_TRY(e, cudaMemcpyAsync(e->d_maps, e->h_maps.data(), e->h_maps.size(), cudaMemcpyHostToDevice, st));
     if (!e->h_maps_first.empty())
       CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_first, e->h_maps_first.data(), e->h_maps_first.size(), cudaMemcpyHostToDevice, st));
+    if (!e->h_maps_c.empty())
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_c, e->h_maps_c.data(), e->h_maps_c.size(), cudaMemcpyHostToDevice, st));
     if (!e->h_maps_store.empty())
       CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_store, e->h_maps_store.data(), e->h_maps_store.size(), cudaMemcpyHostToDevice, st));
     std::vector<int64_t> off(2 * (L + 1));
@@ -695,7 +725,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       const int n_scalar = (N_PASS - 1) * e->cfg.n_members;  // problems with a scalar head (V, Q passes)
       launch_umma_gemm(ph.mode, pp, split ? e->d_maps_first : e->d_maps + (size_t)256 * ph.first,
                        fuse ? e->d_probs + next->first : nullptr, ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st, split,
-                       n_scalar, ph.cta2, ph.maxK);
+                       n_scalar, ph.cta2, ph.maxK, ph.rowepi ? e->d_maps_c + (size_t)128 * ph.first : nullptr);
       if (fuse) {  // the policy head (N = act_dim) stays with the FP32 output-layer kernel
         const GemmProb* pa = e->d_probs + next->first + n_scalar;
         if (out_ok) launch_out_fwd(pa, ph.count - n_scalar, B, H, A, st);

@@ -33,6 +33,9 @@ struct GemmProb {
   int member;
   int drop_layer;      // >= 0: hidden-layer index whose dropout applies (actor only)
   int no_store;        // 1: C is consumed only by a fused follow-up (forward-only passes), skip the store
+  // ReLU sign bits of a hidden activation, [rows][N / 32] words, bit j of word (r, c) = H[r][32 c + j] > 0:
+  // written by the fused forward for the layers a tcgen05 dgrad phase masks with, read by that dgrad phase
+  uint32_t* bits;
 };
 
 // Per-member scalars derived on the host the way torch derives them
@@ -106,6 +109,7 @@ struct WorkspaceLayout {
   int64_t gpi;       // [B][Ald]      dL/dz of actor
   int64_t gh;        // [4][2][B][H]  ping-pong activation gradients of the 4 trainable nets
   int64_t xhi, xlo;  // [B][ROW] each: TF32 hi / lo split of the gathered rows (tcgen05 mode)
+  int64_t bits;      // [4][L-1][B][H/32] uint32: ReLU sign bits of H_1..H_{L-1} of the 4 training passes (tcgen05 mode)
   int64_t member_floats;
   int Ald;
 };

@@ -59,6 +59,7 @@ constexpr int FUSED_TRACE_WORDS = 3 * FUSED_TRACE_TILES * FUSED_MAX_LAYERS * 4;
 
 struct TileRec {  // the 64-float tail of a record
   float* C[FUSED_MAX_LAYERS];
+  uint32_t* bits[FUSED_MAX_LAYERS];  // ReLU sign bits of the layer's output for the dgrad mask (null: not needed)
   float* head_out;
   unsigned long long seed, dstep;
   float head_b, drop_scale;
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
       TileRec* tr = reinterpret_cast<TileRec*>(rec + FUSED_MAX_LAYERS * FT_N + FT_N);
       if (lane < L) {
         tr->C[lane] = g.C;
+        tr->bits[lane] = g.bits;
         tr->ldc[lane] = g.ldc;
         tr->drop_layer[lane] = g.drop_layer;
       }
@@ -490,6 +492,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(__uint_as_float(r[j])));
+          uint32_t* const bits = tr->bits[l];
+          if (store && bits != nullptr) {  // 1 bit per element for the dgrad mask (of the ROUNDED value, like the store)
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) word |= (__uint_as_float(r[j]) > 0.f ? 1u : 0u) << j;
+            bits[(int64_t)row * F_CHUNKS + c] = word;
+          }
           if (!last) {  // columns [32 c, +32) of the next layer's operand A, in place; the MMAs of k-block c may go
             tmem_st32(region + (uint32_t)(c * 32), r);
             tmem_st_wait();

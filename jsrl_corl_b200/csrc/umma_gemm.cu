@@ -100,10 +100,14 @@ __device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int 
 // TF32 rounding and H_L makes no extra trip through HBM (for the forward-only passes it is never stored).
 // `probs_out` is the problem table of the output-layer phase; the policy head (N = act_dim) of the remaining
 // problems is left to the FP32 output-layer kernel.
-template <int EPI, bool FUSE_OUT, bool CTA2>
+// ROWEPI (backward phases, EPI_NONE / EPI_DRELU): the epilogue keeps the tcgen05.ld layout (one accumulator row per
+// lane), masks with one 32-bit word of ReLU sign bits per (row, 32-column chunk) instead of 32 FP32 activations,
+// parks the chunk 128-byte-swizzled in shared memory and lets ONE TMA store per chunk write it (`cmaps`, one
+// output map per problem): no transposition, no store instruction waits for the memory system.
+template <int EPI, bool FUSE_OUT, bool CTA2, bool ROWEPI>
 __global__ void __launch_bounds__(N_THREADS, 1)
 umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restrict__ maps,
-                 const GemmProb* __restrict__ probs_out, UmmaParams up, StepCtx ctx) {
+                 const GemmProb* __restrict__ probs_out, const CUtensorMap* __restrict__ cmaps, UmmaParams up, StepCtx ctx) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
@@ -314,6 +318,67 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
         }
         if (fuse) wd = __ldg(reinterpret_cast<const float4*>(po.B + col));
       };
+      if (ROWEPI) {
+        // ---- row layout: lane = accumulator row; sign-bit mask; TMA store ----
+        float* const stgr = epi_smem + (warp - 2) * 1024;  // 4 KB per warp, 1024-byte aligned (swizzle atoms)
+        const int row = row_base + lane;
+        const int nw = p.ldmask >> 5;  // words per row of the sign-bit matrix
+        uint32_t wbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (EPI == EPI_DRELU) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c = ch + i * N_CGROUPS;
+            if (c < n_chunks) wbits[i] = __ldg(p.bits + (int64_t)row * nw + (n0 >> 5) + c);
+          }
+        }
+        mbar_wait(tfull0 + 8 * buf, acc_phase);
+        tc_fence_after();
+        if (up.dbg & 4) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) acc_release(buf);
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = ch + i * N_CGROUPS;
+          if (c >= n_chunks) break;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + c * 32), r);
+          tmem_ld_wait();
+          if (c + N_CGROUPS >= n_chunks) {  // last TMEM read of this warp for this tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) acc_release(buf);
+          }
+          if (EPI == EPI_DRELU) {
+            const uint32_t w = wbits[i];
+#pragma unroll
+            for (int j2 = 0; j2 < 32; ++j2)
+              r[j2] = ((w >> j2) & 1u) ? __float_as_uint(round_tf32(__uint_as_float(r[j2]) * dscale)) : 0u;
+          }
+          if (lane == 0) bulk_wait_read0();  // the previous chunk has left the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j2 = 0; j2 < 8; ++j2)
+            *reinterpret_cast<float4*>(&stgr[lane * 32 + 4 * (j2 ^ (lane & 7))]) =
+                make_float4(__uint_as_float(r[4 * j2]), __uint_as_float(r[4 * j2 + 1]), __uint_as_float(r[4 * j2 + 2]),
+                            __uint_as_float(r[4 * j2 + 3]));
+          fence_async_smem();
+          __syncwarp();
+          if (!(up.dbg & 1) && lane == 0) {
+            tma_store_2d(cmaps + prob, smem_u32(stgr), n0 + c * 32, row_base);
+            bulk_commit();
+          }
+          if (do_csum) {  // column `lane` of the parked chunk, summed over its 32 rows
+            float cs = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) cs += stgr[rr * 32 + 4 * ((lane >> 2) ^ (rr & 7)) + (lane & 3)];
+            float* dst = &csum_s[q * TILE_N + c * 32 + lane];
+            *dst = (j == 0) ? cs : *dst + cs;
+          }
+        }
+      } else {
       if (ch < n_chunks) prefetch(ch, b4_n, w4_n);
       mbar_wait(tfull0 + 8 * buf, acc_phase);
       tc_fence_after();
@@ -415,6 +480,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
         }
         __syncwarp();
       }
+      }  // !ROWEPI
       if (do_csum && j == up.tiles_per_unit - 1) {  // all rows of the problem seen: combine the quarters
         asm volatile("bar.sync 1, 512;" ::: "memory");
         const int tc = threadIdx.x - 64;  // 0..511; the first tile_n threads own one column each
@@ -463,6 +529,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
       }
     }
   }
+  if (ROWEPI && warp >= 2) bulk_wait0();  // this thread's TMA stores have completed
   tc_fence_before();
   __syncwarp();
   if (CTA2) cluster_sync();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrivals are in flight
@@ -654,17 +721,17 @@ bool umma_dgrad_writes_dbias(int batch) { return (batch + TILE_M - 1) / TILE_M <
 
 bool umma_can_fuse_out(int act_dim) { (void)act_dim; return getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
 
-template <int EPI, bool FUSE_OUT>
+template <int EPI, bool FUSE_OUT, bool ROWEPI>
 static void launch_variant(bool cta2, int workers, const GemmProb* probs, const CUtensorMap* maps, const GemmProb* probs_out,
-                           const UmmaParams& up, const StepCtx& ctx, cudaStream_t st) {
+                           const CUtensorMap* cmaps, const UmmaParams& up, const StepCtx& ctx, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, false, ROWEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, true, ROWEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     attr_set = true;
   }
   if (!cta2) {
-    umma_gemm_kernel<EPI, FUSE_OUT, false><<<workers, N_THREADS, SMEM_BYTES, st>>>(probs, maps, probs_out, up, ctx);
+    umma_gemm_kernel<EPI, FUSE_OUT, false, ROWEPI><<<workers, N_THREADS, SMEM_BYTES, st>>>(probs, maps, probs_out, cmaps, up, ctx);
     return;
   }
   cudaLaunchConfig_t cfg;
@@ -680,12 +747,12 @@ static void launch_variant(bool cta2, int workers, const GemmProb* probs, const 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, FUSE_OUT, true>, probs, maps, probs_out, up, ctx);
+  cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, FUSE_OUT, true, ROWEPI>, probs, maps, probs_out, cmaps, up, ctx);
 }
 
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
                       int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3, int fuse_count, bool cta2,
-                      int maxK) {
+                      int maxK, const void* cmaps) {
   const int tile_n = umma_tile_n(maxN);
   UmmaParams up = make_params(mode, tile_n, cta2);
   up.tiles_m = (maxM + up.tile_m - 1) / up.tile_m;
@@ -720,11 +787,14 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
   const int max_workers = cta2 ? n_sm / 2 : n_sm;  // persistent: one CTA per SM
   const int workers = up.units < max_workers ? up.units : max_workers;
   const CUtensorMap* m = (const CUtensorMap*)maps;
-  if (epi == EPI_RELU && probs_out) launch_variant<EPI_RELU, true>(cta2, workers, probs, m, probs_out, up, ctx, st);
-  else if (epi == EPI_RELU) launch_variant<EPI_RELU, false>(cta2, workers, probs, m, nullptr, up, ctx, st);
-  else if (epi == EPI_DRELU) launch_variant<EPI_DRELU, false>(cta2, workers, probs, m, nullptr, up, ctx, st);
-  else if (epi == EPI_LINEAR) launch_variant<EPI_LINEAR, false>(cta2, workers, probs, m, nullptr, up, ctx, st);
-  else launch_variant<EPI_NONE, false>(cta2, workers, probs, m, nullptr, up, ctx, st);
+  const CUtensorMap* cm = (const CUtensorMap*)cmaps;
+  if (epi == EPI_RELU && probs_out) launch_variant<EPI_RELU, true, false>(cta2, workers, probs, m, probs_out, nullptr, up, ctx, st);
+  else if (epi == EPI_RELU) launch_variant<EPI_RELU, false, false>(cta2, workers, probs, m, nullptr, nullptr, up, ctx, st);
+  else if (epi == EPI_DRELU && cm) launch_variant<EPI_DRELU, false, true>(cta2, workers, probs, m, nullptr, cm, up, ctx, st);
+  else if (epi == EPI_DRELU) launch_variant<EPI_DRELU, false, false>(cta2, workers, probs, m, nullptr, nullptr, up, ctx, st);
+  else if (epi == EPI_LINEAR) launch_variant<EPI_LINEAR, false, false>(cta2, workers, probs, m, nullptr, nullptr, up, ctx, st);
+  else if (cm) launch_variant<EPI_NONE, false, true>(cta2, workers, probs, m, nullptr, cm, up, ctx, st);
+  else launch_variant<EPI_NONE, false, false>(cta2, workers, probs, m, nullptr, nullptr, up, ctx, st);
 }
 
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st) {

@@ -165,10 +165,12 @@ def test_update_matches_reference_short_horizon_fp32(name, steps):
     assert worst < FP32_TOL, (worst, where)
 
 
-@pytest.mark.parametrize("variant", ["default", "cta_pairs", "per_layer_forward_cta_pairs", "per_layer_forward"])
+@pytest.mark.parametrize("variant", ["default", "cta_pairs", "per_layer_forward_cta_pairs", "per_layer_forward",
+                                     "fused_single_cta"])
 @pytest.mark.parametrize("name,steps", CASES)
 def test_update_matches_reference_short_horizon_tf32(name, steps, variant, monkeypatch):
-    """default: fused forward (hidden layers chained through tensor memory) + single-CTA backward GEMMs.
+    """default: fused forward on CTA pairs (hidden layers chained through tensor memory, policy head in the last
+    epilogue) + single-CTA backward GEMMs.
     cta_pairs: every eligible per-layer tcgen05 phase (dgrad with the bias gradient exchanged through DSMEM,
     wgrad) on CTA pairs (cta_group::2).  per_layer_forward: one launch per layer (3xTF32 input layer, hidden
     forward with the fused heads) instead of the fused forward, with and without CTA pairs."""
@@ -176,6 +178,9 @@ def test_update_matches_reference_short_horizon_tf32(name, steps, variant, monke
         monkeypatch.setenv("IQL_B200_FORCE_CTA2", "1")  # both read when the engine state is bound
     if "per_layer_forward" in variant:
         monkeypatch.setenv("IQL_B200_NO_FUSED_FWD", "1")
+    if variant == "fused_single_cta":  # fused forward on one CTA per 128 rows + separate policy-head launch
+        monkeypatch.setenv("IQL_B200_NO_FUSED_PAIR", "1")
+        monkeypatch.setenv("IQL_B200_NO_FUSED_POLICY", "1")
     g = Golden(name)
     eng, _ = _make_engine(g, "tf32")
     losses = _run_indices(eng, g, steps)[0]

@@ -28,7 +28,8 @@ def main(tag="r01"):
                          capture_output=True, text=True).stdout
     open(os.path.join(P, f"{tag}_ncu_full_summary.md"), "w").write(ncu)
     # per-kernel DRAM traffic (dram read + write of one launch) keyed by the bench's kernel labels
-    label_of = {"adam_polyak_kernel": "adam_polyak", "gather_kernel": "gather", "loss_kernel": "loss", "last_bwd_kernel": "last_bwd_wgrad"}
+    label_of = {"adam_polyak_kernel": "adam_polyak", "gather_kernel": "gather", "loss_kernel": "loss", "last_bwd_kernel": "last_bwd_wgrad",
+                "fused_fwd_kernel": "fused_fwd"}
     traffic, plain = {}, []
     for line in ncu.splitlines()[2:]:
         cells = [c.strip() for c in line.strip("|").split("|")]
@@ -69,6 +70,9 @@ def main(tag="r01"):
                           f"{d['value']:.0f} | {d['e2e']['value']:.0f} | {100 * d['step_roofline']['whole_step_frac_of_tensor_peak']:.1f} % | "
                           f"{d['step_roofline']['whole_step_hbm_gbs']:.0f} |")
     sr = b["step_roofline"]
+    ft = os.path.join(G, f"fused_trace_{tag}.txt")
+    if os.path.exists(ft):
+        shutil.copy(ft, os.path.join(P, f"{tag}_fused_trace.txt"))
     dr = os.path.join(G, f"dropin_rate_{tag}.txt")
     dropin = ""
     if os.path.exists(dr):
@@ -90,9 +94,9 @@ engine call (one CUDA graph launch).
 * clocks sampled during the timed region: {b['clocks']}
 * whole step: {sr['whole_step_tflops']} TFLOP/s of GEMM work = {100 * sr['whole_step_frac_of_tensor_peak']:.1f} % of the live-measured cuBLAS TF32 peak ({sr['tf32_peak_tflops']} TFLOP/s);
   algorithmic HBM bytes of all kernels / sum of kernel times = {sr['whole_step_hbm_gbs']} GB/s = {100 * sr['whole_step_hbm_gbs'] / sr['hbm_peak_gbs']:.0f} % of the measured HBM peak
-  ({sr['hbm_peak_gbs']} GB/s, MEASURED_PEAKS.json).  With 256-wide layers and batch 256 every GEMM of the step is a 256^3
-  problem whose operands and result (768 KB) must cross the memory system for 33.5 MFLOP: 43.7 FLOP/B, i.e. the step is
-  HBM/L2-fabric-bound by construction as long as activations and optimizer state live in HBM (DESIGN.md section 7).
+  ({sr['hbm_peak_gbs']} GB/s, MEASURED_PEAKS.json).  The forward runs as ONE fused launch (hidden layers chained through
+  tensor memory, heads in the epilogue, CTA pairs); the backward and the optimizer still move every activation
+  gradient and the whole optimizer state through HBM once per step, which is what bounds the step (DESIGN.md section 7).
 
 ## Per-kernel roofline: CUDA events inside bench.py (`kernels`), algorithmic bytes/flops per launch; traffic = ncu DRAM bytes
 
@@ -110,8 +114,10 @@ Dominant kernel: `{b['roofline']['kernel']}` ({b['roofline']['kernel_us']} us, {
 {chr(10).join(others)}
 
 {dropin}
-The stress shape (4x1024, batch 4096) is the compute-bound regime of the same kernels: its hidden-layer GEMMs run at
-80-86 % of the measured cuBLAS TF32 peak and the whole update step at about half of it.
+The stress shape (4x1024, batch 4096) is the compute-bound regime of the per-layer kernels (hidden width 1024 does not
+fit the fused forward): `tools/umma_rate.py` measures the tcgen05 GEMM building block at 575-587 TFLOP/s on one CTA per
+tile and 644-655 TFLOP/s on CTA pairs for a 8192 x 4096 x 4096 problem, all three operand layouts, against 788 TFLOP/s
+for cuBLAS TF32 on the same box.
 
 ## ncu launch list (`{tag}_launches.csv`: `--metrics gpu__time_duration.sum --clock-control none`, graphs off, cold cache, serialised)
 
@@ -121,10 +127,11 @@ The stress shape (4x1024, batch 4096) is the compute-bound regime of the same ke
 ## ncu --set full, one launch per kernel (`{tag}_ncu_full_summary.md`)
 
 {ncu}
-Reading: no GEMM launch saturates a single unit -- DRAM 35-55 %, L2 15-35 %, tensor
-pipe 10-27 % -- while the achieved operand delivery into the SMs is ~5 TB/s chip-wide; with 3 x 48 KB TMA stages
-in flight per SM that is the queueing limit of the L2->SM fabric for 128-byte-row boxes, so the remaining lever is
-bytes per FLOP (layer fusion / on-chip residency), not issue efficiency.  `adam_polyak` runs at 80-90 % of HBM peak.
+Reading (see also DESIGN.md section 5 and `{tag}_cta_pair.md`): the backward GEMM launches saturate no single unit
+(DRAM 35-55 %, L2 15-35 %, tensor pipe 10-27 %); switching parts of the kernel off (`tools/umma_probe.sh`) shows they
+are bound by the HBM traffic of the phase, not by issue efficiency.  The fused forward is bound by its tensor-pipe
+time plus the part of its epilogues that cannot overlap (`{tag}_fused_trace.txt`: clock64 timeline of one CTA pair).
+`adam_polyak` runs at 80-90 % of the measured HBM peak.
 """
     open(os.path.join(P, f"{tag}_summary.md"), "w").write(md)
     print(md[:1500])
