@@ -251,18 +251,123 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(const GemmProb* __restric
   }
 }
 
+// Vectorised variant for A_out <= 8 and H % 4 == 0: a thread owns 4 consecutive columns (16-byte loads of H_L,
+// 16-byte stores of G_{L-1}); 256 threads = 16 column quads (64 columns) x 16 row groups.
+template <int AMAX>
+__global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __restrict__ probs_dgrad,
+                                                          const GemmProb* __restrict__ probs_wgrad,
+                                                          const GemmProb* __restrict__ probs_prev_wgrad, StepCtx ctx) {
+  extern __shared__ float sm[];  // G tile [B][AMAX], then reduction scratch [16 row groups][64 columns][AMAX + 1]
+  const GemmProb pn = probs_dgrad[blockIdx.x];
+  const GemmProb pw = probs_wgrad[blockIdx.x];
+  float* dbias_prev = probs_prev_wgrad ? probs_prev_wgrad[blockIdx.x].dbias : nullptr;
+  const int B = pn.M, H = pn.N, AO = pn.K;
+  float* gs = sm;
+  float* red = sm + (size_t)B * AMAX;
+  for (int i = threadIdx.x; i < B * AMAX; i += 256) {
+    const int b = i / AMAX, m = i - b * AMAX;
+    gs[i] = (m < AO) ? pn.A[(int64_t)b * pn.lda + m] : 0.f;
+  }
+  const int tq = threadIdx.x & 15, bg = threadIdx.x >> 4;
+  const int n = blockIdx.y * 64 + tq * 4;  // first of this thread's 4 columns
+  const bool act = n < H;                  // H % 4 == 0: all four or none
+  float4 w[AMAX], dw[AMAX];
+#pragma unroll
+  for (int m = 0; m < AMAX; ++m) {
+    w[m] = (m < AO && act) ? *reinterpret_cast<const float4*>(pn.B + (int64_t)m * pn.ldb + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dw[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const MemberScalars* sc = ctx.scalars + pn.member;
+  const float dscale = (pn.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
+  const bool tf32 = ctx.tf32 != 0;
+  __syncthreads();
+  const int rows_per = (B + 15) / 16;
+  const int b_lo = bg * rows_per, b_hi = min(B, b_lo + rows_per);
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) {
+    constexpr int RB = 8;
+    for (int b0 = b_lo; b0 < b_hi; b0 += RB) {
+      float4 hv[RB];
+#pragma unroll
+      for (int j = 0; j < RB; ++j)
+        hv[j] = (b0 + j < b_hi) ? __ldg(reinterpret_cast<const float4*>(pn.mask + (int64_t)(b0 + j) * pn.ldmask + n))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        if (b0 + j < b_hi) {
+          float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (AO == 1) {  // scalar heads (Q, V): uniform per CTA
+            const float g = gs[(b0 + j) * AMAX];
+            gsum.x = g * w[0].x; gsum.y = g * w[0].y; gsum.z = g * w[0].z; gsum.w = g * w[0].w;
+            dw[0].x = fmaf(g, hv[j].x, dw[0].x); dw[0].y = fmaf(g, hv[j].y, dw[0].y);
+            dw[0].z = fmaf(g, hv[j].z, dw[0].z); dw[0].w = fmaf(g, hv[j].w, dw[0].w);
+          } else {
+#pragma unroll
+            for (int m = 0; m < AMAX; ++m) {
+              const float g = gs[(b0 + j) * AMAX + m];
+              gsum.x = fmaf(g, w[m].x, gsum.x); gsum.y = fmaf(g, w[m].y, gsum.y);
+              gsum.z = fmaf(g, w[m].z, gsum.z); gsum.w = fmaf(g, w[m].w, gsum.w);
+              dw[m].x = fmaf(g, hv[j].x, dw[m].x); dw[m].y = fmaf(g, hv[j].y, dw[m].y);
+              dw[m].z = fmaf(g, hv[j].z, dw[m].z); dw[m].w = fmaf(g, hv[j].w, dw[m].w);
+            }
+          }
+          float4 o;
+          o.x = (hv[j].x > 0.f) ? gsum.x * dscale : 0.f; o.y = (hv[j].y > 0.f) ? gsum.y * dscale : 0.f;
+          o.z = (hv[j].z > 0.f) ? gsum.z * dscale : 0.f; o.w = (hv[j].w > 0.f) ? gsum.w * dscale : 0.f;
+          csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
+          if (tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+          *reinterpret_cast<float4*>(pn.C + (int64_t)(b0 + j) * pn.ldc + n) = o;
+        }
+      }
+    }
+  }
+  // reduce the 16 row groups in a fixed order: red[bg][column][m], column = 4 tq + i; slot AMAX holds csum
+  constexpr int RS = AMAX + 1;
+#pragma unroll
+  for (int m = 0; m < AMAX; ++m) {
+    red[(bg * 64 + tq * 4 + 0) * RS + m] = dw[m].x; red[(bg * 64 + tq * 4 + 1) * RS + m] = dw[m].y;
+    red[(bg * 64 + tq * 4 + 2) * RS + m] = dw[m].z; red[(bg * 64 + tq * 4 + 3) * RS + m] = dw[m].w;
+  }
+  red[(bg * 64 + tq * 4 + 0) * RS + AMAX] = csum.x; red[(bg * 64 + tq * 4 + 1) * RS + AMAX] = csum.y;
+  red[(bg * 64 + tq * 4 + 2) * RS + AMAX] = csum.z; red[(bg * 64 + tq * 4 + 3) * RS + AMAX] = csum.w;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * RS; i += 256) {  // one (column, m) sum per thread-iteration
+    const int col = i / RS, m = i - col * RS;
+    const int nn = blockIdx.y * 64 + col;
+    if (nn >= H) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) s += red[(g * 64 + col) * RS + m];
+    if (m < AO) pw.C[(int64_t)m * pw.ldc + nn] = s;
+    else if (m == AMAX && dbias_prev != nullptr) dbias_prev[nn] = s;
+  }
+  if (blockIdx.y == 0 && pw.dbias != nullptr && threadIdx.x < AO) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += gs[b * AMAX + threadIdx.x];
+    pw.dbias[threadIdx.x] = s;
+  }
+}
+
 void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
                      int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st) {
   dim3 grid(nprob, (H + 63) / 64);
   auto smem = [&](int a) { return ((size_t)B * a + 4 * 64 * a) * sizeof(float); };
+  auto smem4 = [&](int a) { return ((size_t)B * a + 16 * 64 * (a + 1)) * sizeof(float); };
   static bool attr = false;
+  static bool no_v4 = false;
   if (!attr) {
     cudaFuncSetAttribute(last_bwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(last_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(last_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(last_bwd_v4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(last_bwd_v4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    no_v4 = getenv("IQL_B200_NO_LASTBWD_V4") != nullptr;
     attr = true;
   }
-  if (amax <= 1) last_bwd_kernel<1><<<grid, 256, smem(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+  const bool v4 = !no_v4 && (H % 4) == 0 && amax <= 8 && smem4(8) <= 200 * 1024;
+  if (v4 && amax <= 1) last_bwd_v4_kernel<1><<<grid, 256, smem4(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+  else if (v4) last_bwd_v4_kernel<8><<<grid, 256, smem4(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+  else if (amax <= 1) last_bwd_kernel<1><<<grid, 256, smem(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else if (amax <= 8) last_bwd_kernel<8><<<grid, 256, smem(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else last_bwd_kernel<24><<<grid, 256, smem(24), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
 }
