@@ -252,12 +252,13 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(const GemmProb* __restric
 }
 
 // Vectorised variant for A_out <= 8 and H % 4 == 0: a thread owns 4 consecutive columns (16-byte loads of H_L,
-// 16-byte stores of G_{L-1}); 256 threads = 16 column quads (64 columns) x 16 row groups.
+// 16-byte stores of G_{L-1}); 256 threads = 64 column quads (256 columns) x 4 row groups, so at H = 256 one CTA
+// covers a whole problem: the loss gradients are staged once and every thread streams 64 rows.
 template <int AMAX>
 __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __restrict__ probs_dgrad,
                                                           const GemmProb* __restrict__ probs_wgrad,
                                                           const GemmProb* __restrict__ probs_prev_wgrad, StepCtx ctx) {
-  extern __shared__ float sm[];  // G tile [B][AMAX], then reduction scratch [16 row groups][64 columns][AMAX + 1]
+  extern __shared__ float sm[];  // G tile [B][AMAX], then reduction scratch [4 row groups][256 columns][AMAX + 1]
   const GemmProb pn = probs_dgrad[blockIdx.x];
   const GemmProb pw = probs_wgrad[blockIdx.x];
   float* dbias_prev = probs_prev_wgrad ? probs_prev_wgrad[blockIdx.x].dbias : nullptr;
@@ -268,8 +269,8 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
     const int b = i / AMAX, m = i - b * AMAX;
     gs[i] = (m < AO) ? pn.A[(int64_t)b * pn.lda + m] : 0.f;
   }
-  const int tq = threadIdx.x & 15, bg = threadIdx.x >> 4;
-  const int n = blockIdx.y * 64 + tq * 4;  // first of this thread's 4 columns
+  const int tq = threadIdx.x & 63, bg = threadIdx.x >> 6;
+  const int n = blockIdx.y * 256 + tq * 4;  // first of this thread's 4 columns
   const bool act = n < H;                  // H % 4 == 0: all four or none
   float4 w[AMAX], dw[AMAX];
 #pragma unroll
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
   const float dscale = (pn.drop_layer >= 0 && sc->drop_threshold != 0u) ? sc->drop_scale : 1.0f;
   const bool tf32 = ctx.tf32 != 0;
   __syncthreads();
-  const int rows_per = (B + 15) / 16;
+  const int rows_per = (B + 3) / 4;
   const int b_lo = bg * rows_per, b_hi = min(B, b_lo + rows_per);
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
   if (act) {
@@ -321,23 +322,23 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
       }
     }
   }
-  // reduce the 16 row groups in a fixed order: red[bg][column][m], column = 4 tq + i; slot AMAX holds csum
+  // reduce the 4 row groups in a fixed order: red[bg][column][m], column = 4 tq + i; slot AMAX holds csum
   constexpr int RS = AMAX + 1;
 #pragma unroll
   for (int m = 0; m < AMAX; ++m) {
-    red[(bg * 64 + tq * 4 + 0) * RS + m] = dw[m].x; red[(bg * 64 + tq * 4 + 1) * RS + m] = dw[m].y;
-    red[(bg * 64 + tq * 4 + 2) * RS + m] = dw[m].z; red[(bg * 64 + tq * 4 + 3) * RS + m] = dw[m].w;
+    red[(bg * 256 + tq * 4 + 0) * RS + m] = dw[m].x; red[(bg * 256 + tq * 4 + 1) * RS + m] = dw[m].y;
+    red[(bg * 256 + tq * 4 + 2) * RS + m] = dw[m].z; red[(bg * 256 + tq * 4 + 3) * RS + m] = dw[m].w;
   }
-  red[(bg * 64 + tq * 4 + 0) * RS + AMAX] = csum.x; red[(bg * 64 + tq * 4 + 1) * RS + AMAX] = csum.y;
-  red[(bg * 64 + tq * 4 + 2) * RS + AMAX] = csum.z; red[(bg * 64 + tq * 4 + 3) * RS + AMAX] = csum.w;
+  red[(bg * 256 + tq * 4 + 0) * RS + AMAX] = csum.x; red[(bg * 256 + tq * 4 + 1) * RS + AMAX] = csum.y;
+  red[(bg * 256 + tq * 4 + 2) * RS + AMAX] = csum.z; red[(bg * 256 + tq * 4 + 3) * RS + AMAX] = csum.w;
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * RS; i += 256) {  // one (column, m) sum per thread-iteration
+  for (int i = threadIdx.x; i < 256 * RS; i += 256) {  // one (column, m) sum per thread-iteration
     const int col = i / RS, m = i - col * RS;
-    const int nn = blockIdx.y * 64 + col;
+    const int nn = blockIdx.y * 256 + col;
     if (nn >= H) continue;
     float s = 0.f;
 #pragma unroll
-    for (int g = 0; g < 16; ++g) s += red[(g * 64 + col) * RS + m];
+    for (int g = 0; g < 4; ++g) s += red[(g * 256 + col) * RS + m];
     if (m < AO) pw.C[(int64_t)m * pw.ldc + nn] = s;
     else if (m == AMAX && dbias_prev != nullptr) dbias_prev[nn] = s;
   }
@@ -352,7 +353,7 @@ void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, c
                      int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st) {
   dim3 grid(nprob, (H + 63) / 64);
   auto smem = [&](int a) { return ((size_t)B * a + 4 * 64 * a) * sizeof(float); };
-  auto smem4 = [&](int a) { return ((size_t)B * a + 16 * 64 * (a + 1)) * sizeof(float); };
+  auto smem4 = [&](int a) { return ((size_t)B * a + 4 * 256 * (a + 1)) * sizeof(float); };
   static bool attr = false;
   static bool no_v4 = false;
   if (!attr) {
@@ -365,8 +366,9 @@ void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, c
     attr = true;
   }
   const bool v4 = !no_v4 && (H % 4) == 0 && amax <= 8 && smem4(8) <= 200 * 1024;
-  if (v4 && amax <= 1) last_bwd_v4_kernel<1><<<grid, 256, smem4(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
-  else if (v4) last_bwd_v4_kernel<8><<<grid, 256, smem4(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+  const dim3 grid4(nprob, (H + 255) / 256);
+  if (v4 && amax <= 1) last_bwd_v4_kernel<1><<<grid4, 256, smem4(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+  else if (v4) last_bwd_v4_kernel<8><<<grid4, 256, smem4(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else if (amax <= 1) last_bwd_kernel<1><<<grid, 256, smem(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else if (amax <= 8) last_bwd_kernel<8><<<grid, 256, smem(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else last_bwd_kernel<24><<<grid, 256, smem(24), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);

@@ -28,7 +28,7 @@ def main(tag="r01"):
                          capture_output=True, text=True).stdout
     open(os.path.join(P, f"{tag}_ncu_full_summary.md"), "w").write(ncu)
     # per-kernel DRAM traffic (dram read + write of one launch) keyed by the bench's kernel labels
-    label_of = {"adam_polyak_kernel": "adam_polyak", "gather_kernel": "gather", "loss_kernel": "loss", "last_bwd_kernel": "last_bwd_wgrad",
+    label_of = {"adam_polyak_kernel": "adam_polyak", "gather_kernel": "gather", "loss_kernel": "loss", "last_bwd_kernel": "last_bwd_wgrad", "last_bwd_v4_kernel": "last_bwd_wgrad",
                 "fused_fwd_kernel": "fused_fwd"}
     traffic, plain = {}, []
     for line in ncu.splitlines()[2:]:
@@ -42,13 +42,13 @@ def main(tag="r01"):
             return float(v) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}.get(u, 1)
 
         tot = mb(cells[2]) + mb(cells[3])
-        if "umma_gemm_kernel<2, 0>" in name:
+        if "umma_gemm_kernel<2, 0" in name:
             traffic.setdefault("first_fwd_fwd", tot)
-        elif "umma_gemm_kernel<2, 1>" in name:
+        elif "umma_gemm_kernel<2, 1" in name:
             traffic.setdefault("hidden_fwd", tot)
-        elif "umma_gemm_kernel<3, 0>" in name:
+        elif "umma_gemm_kernel<3, 0" in name:
             traffic.setdefault("hidden_dgrad", tot)
-        elif "umma_gemm_kernel<0, 0>" in name:
+        elif "umma_gemm_kernel<0, 0" in name:
             plain.append(tot)  # two wgrad launches per step: hidden layer (larger) and input layer
         else:
             for k, lab in label_of.items():
