@@ -421,10 +421,13 @@ def test_philox_dropout_masks_equal_cpu_restatement_and_oracle(math_mode, H, B):
     assert worst < (FP32_TOL if math_mode == "fp32" else TF32_W30_TOL), (worst, where)
 
 
-@pytest.mark.parametrize("B,H,L,A", [(384, 512, 3, 3), (128, 256, 1, 6), (512, 256, 2, 24), (256, 512, 2, 4)])
+@pytest.mark.parametrize("B,H,L,A", [(384, 512, 3, 3), (128, 256, 1, 6), (512, 256, 2, 24), (256, 512, 2, 4),
+                                     (256, 256, 1, 3), (256, 256, 4, 2), (384, 256, 2, 8)])
 def test_tcgen05_path_general_shapes_match_oracle(B, H, L, A):
     """Batch sizes that are multiples of 128, hidden widths that are multiples of 256 (several N tiles and
-    M tiles per problem), one to three hidden layers, wide action spaces: TF32 path vs the numpy oracle."""
+    M tiles per problem), one to four hidden layers, wide action spaces: TF32 path vs the numpy oracle.
+    Hidden width 256 runs the fused forward (CTA pairs when the batch is a multiple of 256, one CTA per 128 rows
+    otherwise; 1 and 3 hidden layers end in TMEM region 0, 2 and 4 in region 1); 512 runs one launch per layer."""
     from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
     from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
     from oracle.philox import philox_indices
