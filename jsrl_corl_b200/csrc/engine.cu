@@ -110,6 +110,10 @@ struct iql_engine {
   std::string err;
   // CUDA graphs of the K-step sequence, keyed by K (Philox sampling mode only)
   std::map<std::tuple<int, int, uintptr_t>, std::pair<cudaGraphExec_t, int64_t>> graphs;
+  // the hidden-layer weight-gradient launches are leaves of the backward: they run on a side stream next to the
+  // dgrad chain so that the partially filled last wave of one persistent kernel is covered by the other
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
   bool use_graphs = true;
 };
 
@@ -257,6 +261,9 @@ extern "C" int iql_create(const iql_config* cfg, iql_engine** out) {
 extern "C" void iql_destroy(iql_engine* e) {
   if (!e) return;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_side) cudaEventDestroy(e->ev_side);
+  if (e->side) cudaStreamDestroy(e->side);
   delete e;
 }
 
@@ -553,6 +560,14 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
         }
     }
   }
+  if (!e->side) {  // optional: without it the backward simply stays on one stream
+    if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      e->side = nullptr;
+    }
+  }
   e->bound = true;
   e->tables_dirty = e->scalars_dirty = e->counters_dirty = e->replay_dirty = true;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);
@@ -664,8 +679,9 @@ extern "C" int iql_load_batch(iql_engine* e, int32_t member, const float* states
 }
 
 // one update step for all members; returns number of launches
-static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t st, StepTimer* tm = nullptr) {
+static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t st_main, StepTimer* tm = nullptr) {
   int launches = 0;
+  cudaStream_t st = st_main;  // the stream run_phase launches on (switched to e->side for the wgrad leaves)
   const bool tf32 = e->cfg.math_mode == IQL_MATH_TF32_TCGEN05;
   const double S_d = e->cfg.n_members;
   if (gather) {
@@ -811,9 +827,32 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   if (tm) tm->mark("loss", 0, S_d * e->cfg.batch_size * 4.0 * (8 + 3 * e->wl.Ald));
   launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, st);
   ++launches;
-  for (size_t i = 0; i < e->bwd_phases.size(); ++i)
-    run_phase(e->bwd_phases[i], i + 1 < e->bwd_phases.size() ? &e->bwd_phases[i + 1] : nullptr,
-              i + 2 < e->bwd_phases.size() ? &e->bwd_phases[i + 2] : nullptr);
+  // per-kernel timing (tm) keeps everything on one stream
+  static const bool no_side = getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
+  const bool two_streams = tf32 && !tm && !no_side && e->side != nullptr;
+  int forks = 0;
+  for (size_t i = 0; i < e->bwd_phases.size(); ++i) {
+    const Phase& ph = e->bwd_phases[i];
+    const Phase* n1 = i + 1 < e->bwd_phases.size() ? &e->bwd_phases[i + 1] : nullptr;
+    const Phase* n2 = i + 2 < e->bwd_phases.size() ? &e->bwd_phases[i + 2] : nullptr;
+    const bool leaf = two_streams && ph.mode == 2 && ph.kind == PH_GENERIC && ph.umma_ok &&
+                      umma_phase_supported(2, B, H) && !skip_next;
+    if (leaf) {
+      // G_l (written by the previous launch) -> side stream.  The previous leaf must be done first: the dgrad that
+      // follows on the main stream overwrites the ping-pong buffer that leaf was reading.
+      if (forks > 0) cudaStreamWaitEvent(st_main, e->ev_side, 0);
+      cudaEventRecord(e->ev_fork, st_main);
+      cudaStreamWaitEvent(e->side, e->ev_fork, 0);
+      st = e->side;
+      run_phase(ph, n1, n2);
+      st = st_main;
+      cudaEventRecord(e->ev_side, e->side);
+      ++forks;
+    } else {
+      run_phase(ph, n1, n2);
+    }
+  }
+  if (forks > 0) cudaStreamWaitEvent(st_main, e->ev_side, 0);  // join before the optimizer
   // Adam: read g, p, m, v + target; write p, m, v + target (+ the TF32 shadow copies in tcgen05 mode)
   if (tm) tm->mark("adam_polyak", 0, S_d * 4.0 * ((7.0 + (ctx.tf32 ? 1 : 0)) * e->layout.param_floats +
                                                   (2.0 + (ctx.tf32 ? 1 : 0)) * e->layout.q_floats));
