@@ -82,6 +82,7 @@ struct iql_engine {
   std::vector<char> h_maps;
   int64_t* d_act_off = nullptr;  // [2][L+1]
   float* d_loss_ring = nullptr;
+  AdamScalars* d_adam_sc = nullptr;  // [S][3], written by the loss kernel, read by the optimizer kernel
   float* d_wshadow = nullptr;    // [S][P]  TF32-rounded params  (tcgen05 mode)
   float* d_tshadow = nullptr;    // [S][PQ] TF32-rounded target
   float* d_wshadow_lo = nullptr; // lo parts (first-layer ranges) for the 3xTF32 input layer
@@ -208,6 +209,7 @@ static void build_layout(iql_engine* e) {
   tab(128 * 2 * nprob);
   tab(sizeof(int64_t) * 2 * (L + 1));
   tab(sizeof(float) * 3 * (int64_t)S * c.max_steps_per_call);
+  tab(sizeof(AdamScalars) * 3 * S);
   if (c.math_mode == IQL_MATH_TF32_TCGEN05) {
     tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
     tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
@@ -475,6 +477,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   e->d_maps = tab(128 * 2 * nprob);
   e->d_act_off = (int64_t*)tab(sizeof(int64_t) * 2 * (L + 1));
   e->d_loss_ring = (float*)tab(sizeof(float) * 3 * (int64_t)S * e->cfg.max_steps_per_call);
+  e->d_adam_sc = (AdamScalars*)tab(sizeof(AdamScalars) * 3 * S);
   if (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) {
     e->d_wshadow = (float*)tab(sizeof(float) * (int64_t)S * e->layout.param_floats);
     e->d_tshadow = (float*)tab(sizeof(float) * (int64_t)S * e->layout.q_floats);
@@ -624,6 +627,7 @@ static StepCtx make_ctx(const iql_engine* e) {
   c.row = e->layout.row;
   c.scalars = e->d_scalars; c.counters = e->d_counters; c.replay = e->d_replay;
   c.loss_ring = e->d_loss_ring;
+  c.adam_sc = e->d_adam_sc;
   c.k_max = e->cfg.max_steps_per_call;
   c.tf32 = (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) && umma_phase_supported(0, e->cfg.batch_size, e->cfg.hidden_dim);
   c.w_shadow = e->d_wshadow;

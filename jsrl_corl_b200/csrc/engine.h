@@ -62,6 +62,13 @@ struct ReplayBinding {
   int64_t size;
 };
 
+// Per (member, optimizer) Adam scalars of the current step: computed once (fp64) by the loss kernel, read by every
+// thread of the optimizer kernel.  Order: q, v, actor.
+struct AdamScalars {
+  float neg_step_size;  // -(lr / (1 - beta1^t))
+  float bc2_sqrt;       // sqrt(1 - beta2^t)
+};
+
 // Context passed by value to every kernel of a step.
 struct StepCtx {
   int k;                         // step offset inside this call (0..K-1)
@@ -82,6 +89,7 @@ struct StepCtx {
   const uint8_t* dropout_masks;  // [S][K][L][B][H] or null
   int64_t* idx_out;              // [S][K][B] or null
   float* loss_ring;              // [S][Kmax][3]
+  AdamScalars* adam_sc;          // [S][3] device
   int k_max;
   int tf32;                      // 1: tcgen05 path; producers round GEMM operands to nearest TF32
   float* w_shadow;               // [S][P]  TF32-rounded copy of params (tcgen05 B operands), tf32 mode only

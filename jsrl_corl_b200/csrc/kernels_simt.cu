@@ -258,6 +258,40 @@ __global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restric
   // per-warp partial sums: [0..3] = value / q1 / q2 / actor loss terms, [4 + a] = d loss / d log_std[a].
   // One shuffle tree per quantity and ONE block barrier; summation order is fixed (rows by lane, warps 0..7).
   __shared__ float red[8][4 + LOSS_MAX_A];
+  if (blockIdx.x >= ctx.n_members) {
+    // Extra CTAs (idle SMs, next to the loss CTAs): the Adam scalars of this step for the optimizer kernel --
+    // torch computes the bias corrections and the step size in Python floats, CosineAnnealingLR in closed form.
+    // 6 threads per member: thread (o, which) takes one fp64 pow, the pair combines through a shuffle.
+    const int idx = (blockIdx.x - ctx.n_members) * 42 + threadIdx.x / 6;
+    const int o = (threadIdx.x % 6) >> 1, which = threadIdx.x & 1;  // o: 0 q, 1 v, 2 actor
+    const bool act = threadIdx.x < 252 && idx < ctx.n_members;
+    double pw = 0.0, lr = 0.0;
+    if (act) {
+      const MemberScalars sc = ctx.scalars[idx];
+      const iql_counters c = ctx.counters[idx];
+      int64_t t;
+      if (o == 0) { lr = sc.qf_lr; t = c.q_step + ctx.k + 1; }
+      else if (o == 1) { lr = sc.vf_lr; t = c.v_step + ctx.k + 1; }
+      else {
+        t = c.actor_step + ctx.k + 1;
+        if (sc.cosine_t_max > 0) {
+          const double e = (double)(c.sched_epoch + ctx.k);
+          lr = sc.lr_eta_min + (sc.actor_lr - sc.lr_eta_min) * (1.0 + cos(M_PI * e / (double)sc.cosine_t_max)) * 0.5;
+        } else {
+          lr = sc.actor_lr;
+        }
+      }
+      pw = pow(which ? sc.adam_beta2_d : sc.adam_beta1_d, (double)t);
+    }
+    const double other = __shfl_xor_sync(0xffffffffu, pw, 1);  // lanes 2j / 2j+1 hold beta1^t / beta2^t
+    if (act && which == 0) {
+      AdamScalars as;
+      as.neg_step_size = (float)(-(lr / (1.0 - pw)));
+      as.bc2_sqrt = (float)sqrt(1.0 - other);
+      ctx.adam_sc[idx * 3 + o] = as;
+    }
+    return;
+  }
   const int m = blockIdx.x;
   const int B = ctx.B, A = ctx.A_dim, RF = ctx.row.row_floats, Ald = wl.Ald;
   float* w = ws + m * ws_member_floats;
@@ -364,7 +398,7 @@ __global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restric
 
 void launch_loss(const StepCtx& ctx, float* ws, int64_t ws_member_floats, const WorkspaceLayout& wl,
                  const float* params, float* grads, cudaStream_t st) {
-  loss_kernel<<<ctx.n_members, 256, 0, st>>>(ctx, ws, ws_member_floats, wl, params, grads);
+  loss_kernel<<<ctx.n_members + (ctx.n_members + 41) / 42, 256, 0, st>>>(ctx, ws, ws_member_floats, wl, params, grads);
 }
 
 // ===========================================================================
@@ -372,65 +406,24 @@ void launch_loss(const StepCtx& ctx, float* ws, int64_t ws_member_floats, const 
 //   torch.optim.Adam defaults (jsrl_utils.py:263-265), soft_update iql.py:72-74,
 //   CosineAnnealingLR iql.py:471 (closed form of the same schedule).
 // ===========================================================================
-struct AdamScalars {
-  float neg_step_size;
-  float bc2_sqrt;
-};
-
-__device__ __forceinline__ AdamScalars adam_scalars(double lr, double b1, double b2, int64_t t) {
-  const double bc1 = 1.0 - pow(b1, (double)t);
-  const double bc2 = 1.0 - pow(b2, (double)t);
-  AdamScalars s;
-  s.neg_step_size = (float)(-(lr / bc1));
-  s.bc2_sqrt = (float)sqrt(bc2);
-  return s;
-}
-
-__global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __restrict__ params,
-                                                          float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                                                          float* __restrict__ target,
-                                                          const float* __restrict__ grads) {
-  __shared__ AdamScalars s_sc[3];
-  const int m = blockIdx.y;
-  const MemberScalars sc = ctx.scalars[m];
-  if (threadIdx.x < 3) {
-    const iql_counters c = ctx.counters[m];
-    double lr;
-    int64_t t;
-    if (threadIdx.x == 0) { lr = sc.qf_lr; t = c.q_step + ctx.k + 1; }
-    else if (threadIdx.x == 1) { lr = sc.vf_lr; t = c.v_step + ctx.k + 1; }
-    else {
-      t = c.actor_step + ctx.k + 1;
-      if (sc.cosine_t_max > 0) {
-        const double e = (double)(c.sched_epoch + ctx.k);
-        lr = sc.lr_eta_min + (sc.actor_lr - sc.lr_eta_min) * (1.0 + cos(M_PI * e / (double)sc.cosine_t_max)) * 0.5;
-      } else {
-        lr = sc.actor_lr;
-      }
-    }
-    s_sc[threadIdx.x] = adam_scalars(lr, sc.adam_beta1_d, sc.adam_beta2_d, t);
-  }
-  __syncthreads();
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= ctx.P) return;
-  const int opt = i < ctx.PQ ? 0 : (i < ctx.v_end ? 1 : 2);
-  const AdamScalars as = s_sc[opt];
+// One float4 of one member: Adam on p / m / v, TF32 shadow copies, Polyak on the target for the Q range.
+__device__ __forceinline__ void adam_quad(const StepCtx& ctx, int m, int64_t i, const float4 g4, float4 p4, float4 m4,
+                                          float4 v4, float4 t4, const AdamScalars as, float adam_w1, float adam_beta2,
+                                          float adam_one_minus_b2, float adam_eps, float tau, float one_minus_tau,
+                                          float* __restrict__ params, float* __restrict__ exp_avg,
+                                          float* __restrict__ exp_avg_sq, float* __restrict__ target) {
   const int64_t off = m * ctx.P + i;
-  const float4 g4 = *reinterpret_cast<const float4*>(grads + off);
-  float4 p4 = *reinterpret_cast<float4*>(params + off);
-  float4 m4 = *reinterpret_cast<float4*>(exp_avg + off);
-  float4 v4 = *reinterpret_cast<float4*>(exp_avg_sq + off);
   const float g[4] = {g4.x, g4.y, g4.z, g4.w};
   float p[4] = {p4.x, p4.y, p4.z, p4.w};
   float mm[4] = {m4.x, m4.y, m4.z, m4.w};
   float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    mm[j] = fmaf(sc.adam_w1, g[j] - mm[j], mm[j]);                       // exp_avg.lerp_(grad, 1-beta1)
-    vv[j] = __fmul_rn(vv[j], sc.adam_beta2);                              // exp_avg_sq.mul_(beta2)
-    vv[j] = fmaf(__fmul_rn(sc.adam_one_minus_b2, g[j]), g[j], vv[j]);     // .addcmul_(g, g, 1-beta2)
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv[j]), as.bc2_sqrt), sc.adam_eps);
-    p[j] = fmaf(as.neg_step_size, __fdiv_rn(mm[j], denom), p[j]);         // addcdiv_
+    mm[j] = fmaf(adam_w1, g[j] - mm[j], mm[j]);                       // exp_avg.lerp_(grad, 1-beta1)
+    vv[j] = __fmul_rn(vv[j], adam_beta2);                              // exp_avg_sq.mul_(beta2)
+    vv[j] = fmaf(__fmul_rn(adam_one_minus_b2, g[j]), g[j], vv[j]);     // .addcmul_(g, g, 1-beta2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv[j]), as.bc2_sqrt), adam_eps);
+    p[j] = fmaf(as.neg_step_size, __fdiv_rn(mm[j], denom), p[j]);      // addcdiv_
   }
   *reinterpret_cast<float4*>(params + off) = make_float4(p[0], p[1], p[2], p[3]);
   bool first_layer = false;
@@ -445,13 +438,12 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
   }
   *reinterpret_cast<float4*>(exp_avg + off) = make_float4(mm[0], mm[1], mm[2], mm[3]);
   *reinterpret_cast<float4*>(exp_avg_sq + off) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-  if (opt == 0) {
+  if (i < ctx.PQ) {
     // soft_update with the post-Adam Q: (1-tau)*target + tau*source, two products and a sum
     const int64_t toff = m * ctx.PQ + i;
-    float4 t4 = *reinterpret_cast<float4*>(target + toff);
     float t[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(sc.one_minus_tau, t[j]), __fmul_rn(sc.tau, p[j]));
+    for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(one_minus_tau, t[j]), __fmul_rn(tau, p[j]));
     *reinterpret_cast<float4*>(target + toff) = make_float4(t[0], t[1], t[2], t[3]);
     if (ctx.tf32) {
       const float4 hi = make_float4(round_tf32(t[0]), round_tf32(t[1]), round_tf32(t[2]), round_tf32(t[3]));
@@ -460,6 +452,43 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
         *reinterpret_cast<float4*>(ctx.t_shadow_lo + toff) =
             make_float4(round_tf32(t[0] - hi.x), round_tf32(t[1] - hi.y), round_tf32(t[2] - hi.z), round_tf32(t[3] - hi.w));
     }
+  }
+}
+
+// grid (ceil(P / 4 / 256 / ADAM_UNROLL), S): a thread owns ADAM_UNROLL float4 groups 256 * 4 floats apart, all of
+// whose loads are issued before the first dependent instruction; no block barrier, no per-block fp64 prologue (the
+// step's Adam scalars come from the loss kernel).
+constexpr int ADAM_UNROLL = 2;
+__global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __restrict__ params,
+                                                          float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                          float* __restrict__ target,
+                                                          const float* __restrict__ grads) {
+  const int m = blockIdx.y;
+  const MemberScalars* sc = ctx.scalars + m;
+  const float adam_w1 = sc->adam_w1, adam_beta2 = sc->adam_beta2, adam_one_minus_b2 = sc->adam_one_minus_b2;
+  const float adam_eps = sc->adam_eps, tau = sc->tau, one_minus_tau = sc->one_minus_tau;
+  const int64_t base = ((int64_t)blockIdx.x * ADAM_UNROLL * 256 + threadIdx.x) * 4;
+  float4 g4[ADAM_UNROLL], p4[ADAM_UNROLL], m4[ADAM_UNROLL], v4[ADAM_UNROLL], t4[ADAM_UNROLL];
+  AdamScalars as[ADAM_UNROLL];
+#pragma unroll
+  for (int u = 0; u < ADAM_UNROLL; ++u) {
+    const int64_t i = base + (int64_t)u * 256 * 4;
+    if (i < ctx.P) {
+      const int64_t off = m * ctx.P + i;
+      g4[u] = *reinterpret_cast<const float4*>(grads + off);
+      p4[u] = *reinterpret_cast<const float4*>(params + off);
+      m4[u] = *reinterpret_cast<const float4*>(exp_avg + off);
+      v4[u] = *reinterpret_cast<const float4*>(exp_avg_sq + off);
+      t4[u] = (i < ctx.PQ) ? *reinterpret_cast<const float4*>(target + m * ctx.PQ + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      as[u] = ctx.adam_sc[m * 3 + (i < ctx.PQ ? 0 : (i < ctx.v_end ? 1 : 2))];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < ADAM_UNROLL; ++u) {
+    const int64_t i = base + (int64_t)u * 256 * 4;
+    if (i < ctx.P)
+      adam_quad(ctx, m, i, g4[u], p4[u], m4[u], v4[u], t4[u], as[u], adam_w1, adam_beta2, adam_one_minus_b2, adam_eps, tau,
+                one_minus_tau, params, exp_avg, exp_avg_sq, target);
   }
 }
 
@@ -497,7 +526,8 @@ void launch_refresh_shadow(const StepCtx& ctx, const float* params, const float*
 
 void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_avg_sq, float* target,
                  const float* grads, cudaStream_t st) {
-  dim3 grid((unsigned)((ctx.P / 4 + 255) / 256), ctx.n_members);
+  const int64_t quads = (ctx.P + 3) / 4;
+  dim3 grid((unsigned)((quads + 256 * ADAM_UNROLL - 1) / (256 * ADAM_UNROLL)), ctx.n_members);
   adam_polyak_kernel<<<grid, 256, 0, st>>>(ctx, params, exp_avg, exp_avg_sq, target, grads);
 }
 
