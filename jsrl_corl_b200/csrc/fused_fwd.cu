@@ -93,7 +93,7 @@ __device__ __forceinline__ void trace_put(const FusedParams& fp, int role, uint3
 }
 
 // Work order: table order (forward-only and critic passes first, the actor pass last).  Handing the actor tiles
-// (policy head, dropout: the longest epilogues) out first made no difference (96 vs 95 us, same box, 64-member ensemble).
+// (policy head, dropout: the longest epilogues) out first measured slower (97 vs 92.5 us, same box, 64-member ensemble).
 __device__ __forceinline__ int unit_prob(const FusedParams& fp, int u) { return u / fp.tiles_m; }
 
 template <bool CTA2>
@@ -365,6 +365,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
         const float* pb = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)g.bias, L));
         const int pa = __shfl_sync(0xffffffffu, g.N, L);
         if (lane < FUSED_POL_MAX) tr->pol_b[lane] = (pol && lane < pa) ? __ldg(pb + lane) : 0.f;
+        if (pol) {  // pull the act_dim x 256 policy weights towards this SM: the epilogue reads them with uniform loads
+          const float* pw = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)g.B, L));
+          const int ldw = __shfl_sync(0xffffffffu, g.ldb, L);
+          for (int idx = lane; idx < pa * (FT_N / 32); idx += 32)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pw + (int64_t)(idx / (FT_N / 32)) * ldw + (idx % (FT_N / 32)) * 32) : "memory");
+        }
         if (lane == L) {
           tr->pol_a = pol ? g.N : 0;
           tr->pol_w = g.B;
