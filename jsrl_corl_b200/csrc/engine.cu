@@ -114,7 +114,7 @@ struct iql_engine {
   // the hidden-layer weight-gradient launches are leaves of the backward: they run on a side stream next to the
   // dgrad chain so that the partially filled last wave of one persistent kernel is covered by the other
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_side = nullptr, ev_fork_g = nullptr, ev_gather = nullptr;
   bool use_graphs = true;
 };
 
@@ -265,6 +265,8 @@ extern "C" void iql_destroy(iql_engine* e) {
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_side) cudaEventDestroy(e->ev_side);
+  if (e->ev_fork_g) cudaEventDestroy(e->ev_fork_g);
+  if (e->ev_gather) cudaEventDestroy(e->ev_gather);
   if (e->side) cudaStreamDestroy(e->side);
   delete e;
 }
@@ -566,7 +568,9 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   if (!e->side) {  // optional: without it the backward simply stays on one stream
     if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_fork_g, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_gather, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       e->side = nullptr;
     }
@@ -683,7 +687,12 @@ extern "C" int iql_load_batch(iql_engine* e, int32_t member, const float* states
 }
 
 // one update step for all members; returns number of launches
-static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t st_main, StepTimer* tm = nullptr) {
+// gather: sample + gather this step's rows first.  gather_next: the NEXT step's gather (ctx.k + 1) runs on the side
+// stream next to this step's optimizer launch -- nothing after the input-layer weight gradient reads the row
+// buffers, the gather is pure latency and the optimizer pure bandwidth -- and the caller passes gather = false for
+// that next step.
+static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t st_main, StepTimer* tm = nullptr,
+                        bool gather_next = false) {
   int launches = 0;
   cudaStream_t st = st_main;  // the stream run_phase launches on (switched to e->side for the wgrad leaves)
   const bool tf32 = e->cfg.math_mode == IQL_MATH_TF32_TCGEN05;
@@ -860,8 +869,19 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   // Adam: read g, p, m, v + target; write p, m, v + target (+ the TF32 shadow copies in tcgen05 mode)
   if (tm) tm->mark("adam_polyak", 0, S_d * 4.0 * ((7.0 + (ctx.tf32 ? 1 : 0)) * e->layout.param_floats +
                                                   (2.0 + (ctx.tf32 ? 1 : 0)) * e->layout.q_floats));
+  const bool fork_gather = gather_next && !tm && e->side != nullptr;
+  if (fork_gather) {
+    StepCtx next = ctx;
+    next.k = ctx.k + 1;
+    cudaEventRecord(e->ev_fork_g, st_main);
+    cudaStreamWaitEvent(e->side, e->ev_fork_g, 0);
+    launch_gather(next, e->d_ws_f, e->wl.member_floats, e->wl.xrow, e->side);
+    cudaEventRecord(e->ev_gather, e->side);
+    ++launches;
+  }
   launch_adam(ctx, e->params, e->exp_avg, e->exp_avg_sq, e->target, e->grads, st);
   ++launches;
+  if (fork_gather) cudaStreamWaitEvent(st_main, e->ev_gather, 0);
   if (tm) tm->finish();
   return launches;
 }
@@ -898,6 +918,8 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
   ctx.dropout_masks = dropout_masks;
   ctx.idx_out = idx_out;
   const bool gather = sample_mode != IQL_SAMPLE_PRELOADED;
+  static const bool no_overlap_gather = getenv("IQL_B200_NO_GATHER_AHEAD") != nullptr || getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
+  const bool overlap_gather = !no_overlap_gather && e->side != nullptr && st != nullptr;
   // the legacy default stream cannot be captured; the facade runs the engine on its own stream
   // Graphs: the K-step Philox loop, and the single preloaded step of the drop-in `train(batch)` path (its ~11
   // launches would otherwise be launch-latency bound).  Keyed by K, negative for the preloaded variant.
@@ -917,7 +939,11 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
     if (it == e->graphs.end()) {
       cudaGraph_t graph = nullptr;
       CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      for (int k = 0; k < k_steps; ++k) { ctx.k = k; launches += enqueue_step(e, ctx, gather, st); }
+      for (int k = 0; k < k_steps; ++k) {
+        ctx.k = k;
+        const bool ahead = gather && overlap_gather && k + 1 < k_steps;  // step k+1's gather rides along step k's optimizer
+        launches += enqueue_step(e, ctx, gather && (k == 0 || !overlap_gather), st, nullptr, ahead);
+      }
       launch_advance(ctx, k_steps, st);
       ++launches;
       cudaError_t cerr = cudaStreamEndCapture(st, &graph);
@@ -930,7 +956,11 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
     CUDA_TRY(e, cudaGraphLaunch(it->second.first, st));
     launches = it->second.second;
   } else {
-    for (int k = 0; k < k_steps; ++k) { ctx.k = k; launches += enqueue_step(e, ctx, gather, st); }
+    for (int k = 0; k < k_steps; ++k) {
+      ctx.k = k;
+      const bool ahead = gather && overlap_gather && k + 1 < k_steps;
+      launches += enqueue_step(e, ctx, gather && (k == 0 || !overlap_gather), st, nullptr, ahead);
+    }
     launch_advance(ctx, k_steps, st);
     ++launches;
   }

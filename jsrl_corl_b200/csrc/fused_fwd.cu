@@ -498,13 +498,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(__uint_as_float(r[j])));
-          uint32_t* const bits = tr->bits[l];
-          if (store && bits != nullptr) {  // 1 bit per element for the dgrad mask (of the ROUNDED value, like the store)
-            uint32_t word = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) word |= (__uint_as_float(r[j]) > 0.f ? 1u : 0u) << j;
-            bits[(int64_t)row * F_CHUNKS + c] = word;
-          }
           if (!last) {  // columns [32 c, +32) of the next layer's operand A, in place; the MMAs of k-block c may go
             tmem_st32(region + (uint32_t)(c * 32), r);
             tmem_st_wait();
@@ -514,6 +507,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               if (CTA2) mbar_arrive_remote(achunk_lead + 8 * c);
               else mbar_arrive(achunk0 + 8 * c);
             }
+          }
+          uint32_t* const bits = tr->bits[l];
+          if (store && bits != nullptr) {  // 1 bit per element for the dgrad mask (of the ROUNDED value, like the store)
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) word |= (__uint_as_float(r[j]) > 0.f ? 1u : 0u) << j;
+            bits[(int64_t)row * F_CHUNKS + c] = word;
           }
           if (store) {
             // every lane holds one full 128-byte row of the chunk: park it (16-byte units XOR-swizzled by the row,
