@@ -712,6 +712,10 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   const bool first_wgrad_ok = first_ok && ((size_t)B * kpad(K0) + 512 * (kpad(K0) + 1)) * 4 <= 200 * 1024;
   const bool out_ok = !no_skinny && A <= 64 && (size_t)(A <= 1 ? 1 : (A <= 8 ? 8 : (A <= 24 ? 24 : 64))) * H * 4 <= 200 * 1024;
   const bool last_ok = !no_skinny && A <= 24 && ((size_t)B * apad(A) + 256 * apad(A)) * 4 <= 200 * 1024;
+  static const bool no_side = getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
+  const bool loss_recomputed = last_ok && last_bwd_recomputes_loss_grads(H, A) && e->bwd_phases.size() >= 2 &&
+                               e->bwd_phases[0].kind == PH_LAST_WGRAD && e->bwd_phases[1].kind == PH_LAST_DGRAD &&
+                               e->bwd_phases[0].count % 4 == 0;
   bool skip_next = false, skip_colsum = false;
   auto run_phase = [&](const Phase& ph, const Phase* next, const Phase* next2) {
     if (skip_next) { skip_next = false; return; }
@@ -775,7 +779,8 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       // fused wgrad + dgrad of the output layer; it also emits db_{L-1} when layer L-1 is a hidden-layer
       // tcgen05 wgrad phase (whose kernel does not produce bias gradients)
       const bool emit_db = next2 && tf32 && next2->umma_ok && umma_phase_supported(2, B, H);
-      launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st);
+      launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st,
+                      loss_recomputed ? e->d_ws_f : nullptr, e->wl.member_floats, &e->wl, e->params);
       skip_next = true;
       skip_colsum = emit_db;
     } else if (ph.kind == PH_FIRST_WGRAD && first_wgrad_ok) {
@@ -837,11 +842,21 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     for (size_t i = 0; i < e->fwd_phases.size(); ++i)
       run_phase(e->fwd_phases[i], i + 1 < e->fwd_phases.size() ? &e->fwd_phases[i + 1] : nullptr, nullptr);
   }
+  // The output-layer backward derives the loss gradients of its rows itself, so loss_kernel (logged losses, log_std
+  // gradient, Adam scalars of the step: all needed by the optimizer launch only) leaves the critical path and
+  // runs on the side stream next to the backward.
+  const bool loss_on_side = loss_recomputed && !tm && !no_side && e->side != nullptr;
   if (tm) tm->mark("loss", 0, S_d * e->cfg.batch_size * 4.0 * (8 + 3 * e->wl.Ald));
-  launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, st);
+  if (loss_on_side) {
+    cudaEventRecord(e->ev_fork, st_main);
+    cudaStreamWaitEvent(e->side, e->ev_fork, 0);
+    launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, e->side);
+    cudaEventRecord(e->ev_side, e->side);
+  } else {
+    launch_loss(ctx, e->d_ws_f, e->wl.member_floats, e->wl, e->params, e->grads, st);
+  }
   ++launches;
   // per-kernel timing (tm) keeps everything on one stream
-  static const bool no_side = getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
   const bool two_streams = tf32 && !tm && !no_side && e->side != nullptr;
   int forks = 0;
   for (size_t i = 0; i < e->bwd_phases.size(); ++i) {
@@ -865,7 +880,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       run_phase(ph, n1, n2);
     }
   }
-  if (forks > 0) cudaStreamWaitEvent(st_main, e->ev_side, 0);  // join before the optimizer
+  if (forks > 0 || loss_on_side) cudaStreamWaitEvent(st_main, e->ev_side, 0);  // join before the optimizer
   // Adam: read g, p, m, v + target; write p, m, v + target (+ the TF32 shadow copies in tcgen05 mode)
   if (tm) tm->mark("adam_polyak", 0, S_d * 4.0 * ((7.0 + (ctx.tf32 ? 1 : 0)) * e->layout.param_floats +
                                                   (2.0 + (ctx.tf32 ? 1 : 0)) * e->layout.q_floats));

@@ -140,8 +140,13 @@ void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float*
 // skinny-layer kernels (kernels_skinny.cu)
 void launch_first_fwd(const GemmProb* probs, int nprob, int B, int H, int kmax, const StepCtx& ctx, cudaStream_t st);
 void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cudaStream_t st);
+// ws / wl / params != null and last_bwd_recomputes_loss_grads(H, amax): the kernel derives the loss gradients of its
+// rows itself (the problem tables hold 4 training nets per member: V, q1, q2, actor) and does not read gy / gpi, so
+// loss_kernel need not precede it.
+bool last_bwd_recomputes_loss_grads(int H, int amax);
 void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
-                     int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st);
+                     int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st, const float* ws = nullptr,
+                     int64_t ws_member_floats = 0, const WorkspaceLayout* wl = nullptr, const float* params = nullptr);
 void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax, cudaStream_t st);
 void launch_act(const StepCtx& ctx, const float* actor_block, int n_members, const int64_t* w_off,
                 const int64_t* b_off, const float* states, int64_t n, float max_action, float* out, cudaStream_t st);

@@ -10,6 +10,9 @@
 //   last_bwd    dW_L = G_L^T H_L, db_L = colsum(G_L),
 //               G_{L-1} = (G_L W_L) * [H_L > 0] * scale            (autograd of the output Linear + ReLU/Dropout)
 //   first_wgrad dW_0 = G_0^T X, db_0 = colsum(G_0)
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "engine.h"
 
@@ -254,10 +257,70 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(const GemmProb* __restric
 // Vectorised variant for A_out <= 8 and H % 4 == 0: a thread owns 4 consecutive columns (16-byte loads of H_L,
 // 16-byte stores of G_{L-1}); 256 threads = 64 column quads (256 columns) x 4 row groups, so at H = 256 one CTA
 // covers a whole problem: the loss gradients are staged once and every thread streams 64 rows.
+// Loss gradients of one batch row for training-net slot t (0 V, 1 q1, 2 q2, 3 actor): the same expressions, in the
+// same order, as loss_kernel (kernels_simt.cu), which keeps producing the logged losses, the log_std gradient and
+// the global gy / gpi copies -- off the critical path, on the side stream -- while this kernel no longer waits
+// for it.  g[a], a < AMAX; entries >= the head width are 0.
+template <int AMAX>
+__device__ __forceinline__ void loss_row_grads(const StepCtx& ctx, const MemberScalars& sc, const float* __restrict__ w,
+                                               const WorkspaceLayout& wl, const float* __restrict__ log_std, int t, int b,
+                                               float* g) {
+  const int B = ctx.B, RF = ctx.row.row_floats;
+  const float* yq = w + wl.yq;
+  const float inv_b = 1.0f / (float)B;
+  const float v = yq[PASS_V * B + b];
+  const float tq = fminf(yq[PASS_TQ1 * B + b], yq[PASS_TQ2 * B + b]);
+  const float adv = tq - v;
+#pragma unroll
+  for (int a = 0; a < AMAX; ++a) g[a] = 0.f;
+  if (t == 0) {  // V (expectile)
+    const float w_neg = fabsf(sc.iql_tau - 1.0f), w_pos = fabsf(sc.iql_tau);
+    const float wt = adv < 0.f ? w_neg : w_pos;
+    g[0] = -((wt * inv_b) * (2.0f * adv));
+  } else if (t <= 2) {  // Q (TD)
+    const float* xr = w + wl.xrow + (int64_t)b * RF;
+    const float next_v = yq[PASS_V_NEXT * B + b];
+    const float q = yq[(t == 1 ? PASS_Q1 : PASS_Q2) * B + b];
+    const float r = xr[ctx.row.off_reward], d = xr[ctx.row.off_done];
+    const float target = r + ((1.0f - d) * sc.discount) * next_v;
+    const float dq = q - target;
+    g[0] = dq * (2.0f * inv_b) * 0.5f;
+  } else {  // policy (AWR)
+    const float* xr = w + wl.xrow + (int64_t)b * RF;
+    const float* zpi = w + wl.zpi;
+    const float e = fminf(expf(sc.beta * adv), 100.0f);
+    const float eb = e * inv_b;
+    const bool gauss = !ctx.deterministic;
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a) {
+      if (a < ctx.A_dim) {
+        const float mu = tanhf(zpi[(int64_t)b * wl.Ald + a]);
+        const float act = xr[ctx.row.off_action + a];
+        float gmu;
+        if (!gauss) {
+          const float diff = mu - act;
+          gmu = eb * (2.0f * diff);
+        } else {
+          const float ls = fminf(fmaxf(log_std[a], -20.0f), 2.0f);
+          const float sd = expf(ls);
+          const float var = sd * sd;
+          const float diff = act - mu;
+          gmu = -eb * diff / var;
+        }
+        g[a] = gmu * (1.0f - mu * mu);
+      }
+    }
+  }
+}
+
+// ws != null: the G tile comes from loss_row_grads (problem index % 4 = training-net slot, the table order of the
+// engine) instead of the gy / gpi arrays loss_kernel writes.
 template <int AMAX>
 __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __restrict__ probs_dgrad,
                                                           const GemmProb* __restrict__ probs_wgrad,
-                                                          const GemmProb* __restrict__ probs_prev_wgrad, StepCtx ctx) {
+                                                          const GemmProb* __restrict__ probs_prev_wgrad, StepCtx ctx,
+                                                          const float* __restrict__ ws, int64_t ws_member_floats,
+                                                          WorkspaceLayout wl, const float* __restrict__ params) {
   extern __shared__ float sm[];  // G tile [B][AMAX], then reduction scratch [4 row groups][256 columns][AMAX + 1]
   const GemmProb pn = probs_dgrad[blockIdx.x];
   const GemmProb pw = probs_wgrad[blockIdx.x];
@@ -265,9 +328,22 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
   const int B = pn.M, H = pn.N, AO = pn.K;
   float* gs = sm;
   float* red = sm + (size_t)B * AMAX;
-  for (int i = threadIdx.x; i < B * AMAX; i += 256) {
-    const int b = i / AMAX, m = i - b * AMAX;
-    gs[i] = (m < AO) ? pn.A[(int64_t)b * pn.lda + m] : 0.f;
+  if (ws != nullptr) {
+    const MemberScalars msc = ctx.scalars[pn.member];
+    const float* wmem = ws + (int64_t)pn.member * ws_member_floats;
+    const float* log_std = params + (int64_t)pn.member * ctx.P + ctx.log_std_off;
+    const int t = blockIdx.x & 3;
+    for (int b = threadIdx.x; b < B; b += 256) {
+      float g[AMAX];
+      loss_row_grads<AMAX>(ctx, msc, wmem, wl, log_std, t, b, g);
+#pragma unroll
+      for (int a = 0; a < AMAX; ++a) gs[b * AMAX + a] = g[a];
+    }
+  } else {
+    for (int i = threadIdx.x; i < B * AMAX; i += 256) {
+      const int b = i / AMAX, m = i - b * AMAX;
+      gs[i] = (m < AO) ? pn.A[(int64_t)b * pn.lda + m] : 0.f;
+    }
   }
   const int tq = threadIdx.x & 63, bg = threadIdx.x >> 6;
   const int n = blockIdx.y * 256 + tq * 4;  // first of this thread's 4 columns
@@ -349,8 +425,13 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
   }
 }
 
+bool last_bwd_recomputes_loss_grads(int H, int amax) {
+  return getenv("IQL_B200_NO_LASTBWD_V4") == nullptr && getenv("IQL_B200_NO_LOSS_OVERLAP") == nullptr && (H % 4) == 0 && amax <= 8;
+}
+
 void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
-                     int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st) {
+                     int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st, const float* ws,
+                     int64_t ws_member_floats, const WorkspaceLayout* wl, const float* params) {
   dim3 grid(nprob, (H + 63) / 64);
   auto smem = [&](int a) { return ((size_t)B * a + 4 * 64 * a) * sizeof(float); };
   auto smem4 = [&](int a) { return ((size_t)B * a + 4 * 256 * (a + 1)) * sizeof(float); };
@@ -367,8 +448,12 @@ void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, c
   }
   const bool v4 = !no_v4 && (H % 4) == 0 && amax <= 8 && smem4(8) <= 200 * 1024;
   const dim3 grid4(nprob, (H + 255) / 256);
-  if (v4 && amax <= 1) last_bwd_v4_kernel<1><<<grid4, 256, smem4(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
-  else if (v4) last_bwd_v4_kernel<8><<<grid4, 256, smem4(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+  WorkspaceLayout wlv;
+  memset(&wlv, 0, sizeof(wlv));
+  if (wl) wlv = *wl;
+  const float* wsp = (wl && nprob % 4 == 0) ? ws : nullptr;  // 4 training nets per member, in table order
+  if (v4 && amax <= 1) last_bwd_v4_kernel<1><<<grid4, 256, smem4(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, wsp, ws_member_floats, wlv, params);
+  else if (v4) last_bwd_v4_kernel<8><<<grid4, 256, smem4(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, wsp, ws_member_floats, wlv, params);
   else if (amax <= 1) last_bwd_kernel<1><<<grid, 256, smem(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else if (amax <= 8) last_bwd_kernel<8><<<grid, 256, smem(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else last_bwd_kernel<24><<<grid, 256, smem(24), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
