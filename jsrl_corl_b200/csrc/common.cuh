@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace iql {
 
@@ -88,5 +90,53 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with launch_pdl may become resident and run its set-up (barrier
+// init, TMEM allocation, reads of the static problem tables) while the preceding kernel of the stream drains; it
+// must call pdl_wait() before it reads anything that kernel wrote -- or writes anything that kernel reads.
+// Without a trigger the successor is released when every CTA of this kernel has exited (it still saves the launch
+// latency and its set-up: +3.5 % on the 64-member step).  pdl_trigger() at the top of a kernel releases the
+// successor as soon as all of this kernel's CTAs are running, so that it fills SMs as they drain; measured per
+// kernel: helps after last_bwd (+1.2 %), neutral in adam, hurts in the persistent tcgen05 kernels (their successors
+// then sit on SMs the stragglers' co-runners could use: -7 % in umma_gemm, -1.4 % in fused_fwd), so only last_bwd
+// calls it.  IQL_B200_NO_PDL switches the launch attribute off.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("IQL_B200_NO_PDL") ? 0 : 1;
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 }  // namespace iql

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
+  pdl_wait();  // everything above overlapped the tail of the previous launch; the gathered rows and weights are read below
   const int nkb_h = FT_N / FT_K;  // 8 k-blocks of a hidden layer (K = 256)
   // pair: rank 0 leads (issues the MMAs, owns full / achunk / elast); work is dealt to pairs, 256 rows per tile
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
@@ -647,24 +648,11 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
   fp.trace = fused_trace_buffer();
   if (!pair) {
     const int grid = fp.units < n_sm ? fp.units : n_sm;
-    fused_fwd_kernel<false><<<grid, F_THREADS, F_SMEM, st>>>(fp, ctx);
+    launch_pdl(fused_fwd_kernel<false>, dim3(grid), dim3(F_THREADS), F_SMEM, st, 1, fp, ctx);
     return;
   }
   const int workers = fp.units < n_sm / 2 ? fp.units : n_sm / 2;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * workers);
-  cfg.blockDim = dim3(F_THREADS);
-  cfg.dynamicSmemBytes = F_SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, fused_fwd_kernel<true>, fp, ctx);
+  launch_pdl(fused_fwd_kernel<true>, dim3(2 * workers), dim3(F_THREADS), F_SMEM, st, 2, fp, ctx);
 }
 
 // measurement hook (tools/fused_trace.py): copies the clock64 stamps of the last fused_fwd launch to the host

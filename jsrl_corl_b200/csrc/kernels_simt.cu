@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
                                                           const float* __restrict__ grads) {
   const int m = blockIdx.y;
   const MemberScalars* sc = ctx.scalars + m;
+  pdl_wait();  // gradients, Adam scalars of the step: written by the launches before this one
   const float adam_w1 = sc->adam_w1, adam_beta2 = sc->adam_beta2, adam_one_minus_b2 = sc->adam_one_minus_b2;
   const float adam_eps = sc->adam_eps, tau = sc->tau, one_minus_tau = sc->one_minus_tau;
   const int64_t base = ((int64_t)blockIdx.x * ADAM_UNROLL * 256 + threadIdx.x) * 4;
@@ -530,7 +531,7 @@ void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_a
                  const float* grads, cudaStream_t st) {
   const int64_t quads = (ctx.P + 3) / 4;
   dim3 grid((unsigned)((quads + 256 * ADAM_UNROLL - 1) / (256 * ADAM_UNROLL)), ctx.n_members);
-  adam_polyak_kernel<<<grid, 256, 0, st>>>(ctx, params, exp_avg, exp_avg_sq, target, grads);
+  launch_pdl(adam_polyak_kernel, grid, dim3(256), 0, st, 1, ctx, params, exp_avg, exp_avg_sq, target, grads);
 }
 
 __global__ void advance_kernel(StepCtx ctx, int K) {

@@ -322,9 +322,11 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
                                                           const float* __restrict__ ws, int64_t ws_member_floats,
                                                           WorkspaceLayout wl, const float* __restrict__ params) {
   extern __shared__ float sm[];  // G tile [B][AMAX], then reduction scratch [4 row groups][256 columns][AMAX + 1]
+  pdl_trigger();
   const GemmProb pn = probs_dgrad[blockIdx.x];
   const GemmProb pw = probs_wgrad[blockIdx.x];
   float* dbias_prev = probs_prev_wgrad ? probs_prev_wgrad[blockIdx.x].dbias : nullptr;
+  pdl_wait();  // the static problem tables are read above; the forward's outputs below
   const int B = pn.M, H = pn.N, AO = pn.K;
   float* gs = sm;
   float* red = sm + (size_t)B * AMAX;
@@ -452,8 +454,12 @@ void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, c
   memset(&wlv, 0, sizeof(wlv));
   if (wl) wlv = *wl;
   const float* wsp = (wl && nprob % 4 == 0) ? ws : nullptr;  // 4 training nets per member, in table order
-  if (v4 && amax <= 1) last_bwd_v4_kernel<1><<<grid4, 256, smem4(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, wsp, ws_member_floats, wlv, params);
-  else if (v4) last_bwd_v4_kernel<8><<<grid4, 256, smem4(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, wsp, ws_member_floats, wlv, params);
+  if (v4 && amax <= 1)
+    launch_pdl(last_bwd_v4_kernel<1>, grid4, dim3(256), smem4(1), st, 1, probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, wsp,
+               ws_member_floats, wlv, params);
+  else if (v4)
+    launch_pdl(last_bwd_v4_kernel<8>, grid4, dim3(256), smem4(8), st, 1, probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, wsp,
+               ws_member_floats, wlv, params);
   else if (amax <= 1) last_bwd_kernel<1><<<grid, 256, smem(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else if (amax <= 8) last_bwd_kernel<8><<<grid, 256, smem(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
   else last_bwd_kernel<24><<<grid, 256, smem(24), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);

@@ -158,6 +158,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
+  pdl_wait();  // set-up above overlaps the previous launch; operands, masks and outputs are touched below
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -730,24 +731,12 @@ static void launch_variant(bool cta2, int workers, const GemmProb* probs, const 
     cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, true, ROWEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     attr_set = true;
   }
-  if (!cta2) {
-    umma_gemm_kernel<EPI, FUSE_OUT, false, ROWEPI><<<workers, N_THREADS, SMEM_BYTES, st>>>(probs, maps, probs_out, cmaps, up, ctx);
-    return;
-  }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * workers);
-  cfg.blockDim = dim3(N_THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, FUSE_OUT, true, ROWEPI>, probs, maps, probs_out, cmaps, up, ctx);
+  if (!cta2)
+    launch_pdl(umma_gemm_kernel<EPI, FUSE_OUT, false, ROWEPI>, dim3(workers), dim3(N_THREADS), SMEM_BYTES, st, 1, probs, maps,
+               probs_out, cmaps, up, ctx);
+  else
+    launch_pdl(umma_gemm_kernel<EPI, FUSE_OUT, true, ROWEPI>, dim3(2 * workers), dim3(N_THREADS), SMEM_BYTES, st, 2, probs, maps,
+               probs_out, cmaps, up, ctx);
 }
 
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
