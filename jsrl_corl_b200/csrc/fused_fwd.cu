@@ -43,6 +43,7 @@ constexpr int F_STAGES = 3;
 // CTA pair: the ring is cut into 16 KB granules; a layer-0 k-block takes two (own rows of X, own half of W0),
 // a hidden-layer k-block one (own half of the W_l k-block): the whole of W_l (8 granules) can be in flight
 constexpr int F_GRAN = 16 * 1024, F_NGRAN = 9, F_MAXBAR = 9;
+constexpr int F_NA = 4, F_NB = F_NGRAN - F_NA;  // pair: granules of the layer-0 ring / of the hidden-layer weight ring
 constexpr int F_EPI_WARPS = 16, F_CGROUPS = 4, F_CHUNKS = FT_N / 32;
 constexpr int F_STG_FLOATS = 32 * 32;  // per-warp staging: one 32 x 32 chunk, rows of 128 B, 128-byte swizzled (TMA store box)
 constexpr int F_RING = F_STAGES * F_STAGE;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, tile_it = 0;
+      uint32_t stage = 0, phase = 0, bphase = 0, tile_it = 0;  // pair: phase = ring A, (stage, bphase) = ring B
       for (int u = worker; u < fp.units; u += n_workers, ++tile_it) {
         const int prob = unit_prob(fp, u);
         const int m0 = (u % fp.tiles_m) * tile_rows + m_off;
@@ -175,23 +176,31 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
         }
         if (CTA2) {
           const uint32_t full_lead = mapa_u32(full0, 0);
-          auto put = [&](const CUtensorMap* map, int c0, int c1) {  // one 16 KB granule of this CTA
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * F_GRAN);  // the peer's granule lands on the same barrier
-            tma_load_2d_cg2(base + stage * F_GRAN, map, full_lead + 8 * stage, c0, c1);
-            if (++stage == F_NGRAN) { stage = 0; phase ^= 1; }
+          // ring A (granules 0..3) holds ONE layer-0 k-block: Xhi, W0hi, Xlo, W0lo (each operand loaded once for the three
+          // 3xTF32 passes); ring B (granules 4..8) streams the hidden-layer weight k-blocks.  Two rings instead of one
+          // FIFO: the layer-0 operands of tile t+1 are requested as soon as the layer-0 MMAs of tile t are done instead
+          // of queueing behind the hidden-layer k-blocks of tile t
+          auto put = [&](uint32_t slot, uint32_t ph, const CUtensorMap* map, int c0, int c1) {  // one 16 KB granule of this CTA
+            mbar_wait(empty0 + 8 * slot, ph ^ 1);
+            if (rank == 0) mbar_expect_tx(full0 + 8 * slot, 2 * F_GRAN);  // the peer's granule lands on the same barrier
+            tma_load_2d_cg2(base + slot * F_GRAN, map, full_lead + 8 * slot, c0, c1);
           };
           for (int l = 0; l < L; ++l) {
             trace_put(fp, 0, tile_it, l, 0);
             if (l == 0) {
               const CUtensorMap* pm = fp.maps[0] + 4 * prob;
-              for (int sj = 0; sj < 3; ++sj)
-                for (int kb = 0; kb < fp.nkb0; ++kb) {
-                  put(pm + (sj == 1 ? 2 : 0), kb * FT_K, m0);               // own 128 rows of Xhi / Xlo
-                  put(pm + (sj == 2 ? 3 : 1), kb * FT_K, (int)rank * 128);  // own half of W0hi / W0lo
-                }
+              for (int kb = 0; kb < fp.nkb0; ++kb) {
+                put(0, phase, pm + 0, kb * FT_K, m0);               // own 128 rows of Xhi
+                put(1, phase, pm + 1, kb * FT_K, (int)rank * 128);  // own half of W0hi
+                put(2, phase, pm + 2, kb * FT_K, m0);               // Xlo
+                put(3, phase, pm + 3, kb * FT_K, (int)rank * 128);  // W0lo
+                phase ^= 1;
+              }
             } else {
-              for (int kb = 0; kb < nkb_h; ++kb) put(fp.maps[l] + 2 * prob + 1, kb * FT_K, (int)rank * 128);
+              for (int kb = 0; kb < nkb_h; ++kb) {
+                put(F_NA + stage, bphase, fp.maps[l] + 2 * prob + 1, kb * FT_K, (int)rank * 128);
+                if (++stage == F_NB) { stage = 0; bphase ^= 1; }
+              }
             }
             trace_put(fp, 0, tile_it, l, 1);
           }
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && rank == 0) {
-      uint32_t stage = 0, phase = 0, ev = 0, tile_it = 0, aev = 0;
+      uint32_t stage = 0, phase = 0, bphase = 0, ev = 0, tile_it = 0, aev = 0;  // pair: phase = ring A, (stage, bphase) = ring B
       // the last layer's accumulator region (L-1)&1 is still being drained by the previous tile's last epilogue
       // when this tile reaches the first layer that writes the same region
       const int l_guard = (L - 1) & 1;
@@ -246,36 +255,39 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           const uint32_t ta = tmem_base + (uint32_t)((l - 1) & 1) * 256u;
           const int nkb = (l == 0) ? 3 * fp.nkb0 : nkb_h;
           if (CTA2) {
-            for (int kb = 0; kb < nkb; ++kb) {
-              if (l == 0) {
-                const uint32_t ga = stage, pa = phase;
-                if (++stage == F_NGRAN) { stage = 0; phase ^= 1; }
-                const uint32_t gb = stage, pb = phase;
-                if (++stage == F_NGRAN) { stage = 0; phase ^= 1; }
-                mbar_wait(full0 + 8 * ga, pa);
-                mbar_wait(full0 + 8 * gb, pb);
-                tc_fence_after();
-                if (kb == 0) trace_put(fp, 1, tile_it, l, 2);
-                const uint64_t adesc0 = make_desc(base + ga * F_GRAN, 1, 1024 >> 4, 2);
-                const uint64_t bdesc0 = make_desc(base + gb * F_GRAN, 1, 1024 >> 4, 2);
-                const int nks = ((kb % fp.nkb0) == fp.nkb0 - 1) ? fp.ks_last0 : FT_K / F_UMMA_K;
+            if (l == 0) {
+              for (int kb = 0; kb < fp.nkb0; ++kb) {
+                const int nks = (kb == fp.nkb0 - 1) ? fp.ks_last0 : FT_K / F_UMMA_K;  // skip all-zero K steps
 #pragma unroll
-                for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
-                  if (ks < nks) umma_tf32_cg2(tacc, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), fp.idesc, (kb | ks) != 0);
-                umma_commit_cg2(empty0 + 8 * ga);
-                umma_commit_cg2(empty0 + 8 * gb);
-              } else {
+                for (int sj = 0; sj < 3; ++sj) {  // Xhi W0hi, Xlo W0hi, Xhi W0lo
+                  const uint32_t ga = (sj == 1) ? 2u : 0u, gb = (sj == 2) ? 3u : 1u;
+                  if (sj == 0) mbar_wait(full0, phase);
+                  mbar_wait(full0 + 8 * (sj + 1), phase);
+                  tc_fence_after();
+                  if (kb == 0 && sj == 0) trace_put(fp, 1, tile_it, l, 2);
+                  const uint64_t adesc0 = make_desc(base + ga * F_GRAN, 1, 1024 >> 4, 2);
+                  const uint64_t bdesc0 = make_desc(base + gb * F_GRAN, 1, 1024 >> 4, 2);
+#pragma unroll
+                  for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
+                    if (ks < nks)
+                      umma_tf32_cg2(tacc, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), fp.idesc, (kb | sj | ks) != 0);
+                }
+                for (uint32_t g = 0; g < (uint32_t)F_NA; ++g) umma_commit_cg2(empty0 + 8 * g);
+                phase ^= 1;
+              }
+            } else {
+              for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(achunk0 + 8 * kb, aev & 1);  // both CTAs have columns [32 kb, +32) of H_l in tensor memory
-                mbar_wait(full0 + 8 * stage, phase);
+                mbar_wait(full0 + 8 * (F_NA + stage), bphase);
                 tc_fence_after();
                 if (kb == 0) trace_put(fp, 1, tile_it, l, 2);
-                const uint64_t bdesc0 = make_desc(base + stage * F_GRAN, 1, 1024 >> 4, 2);
+                const uint64_t bdesc0 = make_desc(base + (F_NA + stage) * F_GRAN, 1, 1024 >> 4, 2);
 #pragma unroll
                 for (int ks = 0; ks < FT_K / F_UMMA_K; ++ks)
                   umma_tf32_ts_cg2(tacc, ta + (uint32_t)(kb * FT_K + ks * F_UMMA_K), bdesc0 + (uint64_t)(ks * 2), fp.idesc,
                                    (kb | ks) != 0);
-                umma_commit_cg2(empty0 + 8 * stage);
-                if (++stage == F_NGRAN) { stage = 0; phase ^= 1; }
+                umma_commit_cg2(empty0 + 8 * (F_NA + stage));
+                if (++stage == F_NB) { stage = 0; bphase ^= 1; }
               }
             }
             if (l > 0) ++aev;

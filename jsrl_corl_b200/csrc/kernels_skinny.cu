@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "engine.h"
 
@@ -471,13 +473,13 @@ void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, c
 //   p: TN problem (A = G_0 [B][H] (K = B rows, M = H), B = X [B][ldx] (N = K0), C = dW_0 [H][K0], dbias = db_0)
 // ---------------------------------------------------------------------------
 template <int KMAX, int NC>
-__global__ void __launch_bounds__(256) first_wgrad_kernel(const GemmProb* __restrict__ probs) {
-  extern __shared__ float sm[];  // X [B][KMAX], then reduction scratch [4][64*NC][KMAX + 1]
+__global__ void __launch_bounds__(256, KMAX <= 24 ? 3 : 1) first_wgrad_kernel(const GemmProb* __restrict__ probs) {
+  extern __shared__ float sm[];  // X [B][KMAX]; afterwards the reduction scratch [4][64*NC][KMAX + 1] in the same bytes
   const GemmProb p = probs[blockIdx.x];
   const int B = p.K, H = p.M, K0 = p.N;
   constexpr int CW = 64 * NC;  // columns per CTA
   float* xs = sm;
-  float* red = sm + (size_t)B * KMAX;
+  float* red = sm;  // aliases xs once the main loop is done
   for (int i = threadIdx.x; i < B * KMAX; i += 256) {
     const int b = i / KMAX, k = i - b * KMAX;
     xs[i] = (k < K0) ? p.B[(int64_t)b * p.ldb + k] : 0.f;
@@ -495,26 +497,37 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const GemmProb* __rest
   __syncthreads();
   const int rows_per = (B + 3) / 4;
   const int b_lo = bg * rows_per, b_hi = min(B, b_lo + rows_per);
-  for (int b = b_lo; b < b_hi; ++b) {
-    float g[NC];
+  // RU rows per trip with all their G loads issued before the first FMA: the loop is bound by the latency of the
+  // (coalesced, 256-byte) G reads, so what matters is how many of them each thread keeps in flight
+  constexpr int RU = 8;
+  for (int b = b_lo; b < b_hi; b += RU) {
+    float g[RU][NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int n = n0 + c * 64;
-      g[c] = (n < H) ? p.A[(int64_t)b * p.lda + n] : 0.f;
-      bsum[c] += g[c];
-    }
-#pragma unroll
-    for (int k4 = 0; k4 < KMAX; k4 += 4) {
-      const float4 x = *reinterpret_cast<const float4*>(&xs[b * KMAX + k4]);
+    for (int r = 0; r < RU; ++r)
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        acc[c][k4] = fmaf(g[c], x.x, acc[c][k4]);
-        acc[c][k4 + 1] = fmaf(g[c], x.y, acc[c][k4 + 1]);
-        acc[c][k4 + 2] = fmaf(g[c], x.z, acc[c][k4 + 2]);
-        acc[c][k4 + 3] = fmaf(g[c], x.w, acc[c][k4 + 3]);
+        const int n = n0 + c * 64;
+        g[r][c] = (b + r < b_hi && n < H) ? __ldg(&p.A[(int64_t)(b + r) * p.lda + n]) : 0.f;
+      }
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      const int br = min(b + r, B - 1);  // rows past b_hi carry g = 0
+#pragma unroll
+      for (int c = 0; c < NC; ++c) bsum[c] += g[r][c];
+#pragma unroll
+      for (int k4 = 0; k4 < KMAX; k4 += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(&xs[br * KMAX + k4]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          acc[c][k4] = fmaf(g[r][c], x.x, acc[c][k4]);
+          acc[c][k4 + 1] = fmaf(g[r][c], x.y, acc[c][k4 + 1]);
+          acc[c][k4 + 2] = fmaf(g[r][c], x.z, acc[c][k4 + 2]);
+          acc[c][k4 + 3] = fmaf(g[r][c], x.w, acc[c][k4 + 3]);
+        }
       }
     }
   }
+  __syncthreads();  // the reduction scratch reuses the X tile
   constexpr int RS = KMAX + 1;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -537,7 +550,7 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const GemmProb* __rest
 }
 
 void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax, cudaStream_t st) {
-  auto smem = [&](int k, int nc) { return ((size_t)B * k + 4 * 64 * nc * (k + 1)) * sizeof(float); };
+  auto smem = [&](int k, int nc) { return std::max((size_t)B * k, (size_t)4 * 64 * nc * (k + 1)) * sizeof(float); };
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(first_wgrad_kernel<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
