@@ -44,14 +44,16 @@ constexpr int F_STAGES = 3;
 // a hidden-layer k-block one (own half of the W_l k-block): the whole of W_l (8 granules) can be in flight
 constexpr int F_GRAN = 16 * 1024, F_NGRAN = 9, F_MAXBAR = 9;
 constexpr int F_NA = 4, F_NB = F_NGRAN - F_NA;  // pair: granules of the layer-0 ring / of the hidden-layer weight ring
-constexpr int F_EPI_WARPS = 16, F_CGROUPS = 4, F_CHUNKS = FT_N / 32;
+// 16 epilogue warps in two groups of 8 (2 per TMEM lane quarter = 2 column groups); group g owns the tiles with
+// tile_it % 2 == g, so the first-layer epilogue of tile t+1 overlaps the last-layer epilogue of tile t
+constexpr int F_EPI_WARPS = 16, F_EGROUPS = 2, F_GROUP_WARPS = F_EPI_WARPS / F_EGROUPS, F_CGROUPS = 2, F_CHUNKS = FT_N / 32;
 constexpr int F_STG_FLOATS = 32 * 32;  // per-warp staging: one 32 x 32 chunk, rows of 128 B, 128-byte swizzled (TMA store box)
 constexpr int F_RING = F_STAGES * F_STAGE;
 constexpr int F_STG_BYTES = F_EPI_WARPS * F_STG_FLOATS * 4;
 // per-tile record written by the prefetch warp one tile ahead: biases of every layer, head weights, scalars
 constexpr int F_REC_FLOATS = FUSED_MAX_LAYERS * FT_N + FT_N + 64;
 constexpr int F_REC_BYTES = F_REC_FLOATS * 4;
-constexpr int F_YPART_BYTES = 2 * F_CGROUPS * FT_M * 4;
+constexpr int F_YPART_BYTES = F_EGROUPS * 2 * F_CGROUPS * FT_M * 4;  // [group][2 buffers][column group][row]
 constexpr int F_SMEM = F_RING + F_STG_BYTES + 2 * F_REC_BYTES + F_YPART_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int F_THREADS = 608;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-17 epilogue, warp 18 per-tile prefetch
 constexpr int FUSED_POL_MAX = 8;
@@ -83,6 +85,7 @@ struct FusedParams {
   const GemmProb* probs_out;                 // output-layer problems (scalar heads of the first fuse_count)
   int L, nprob, tiles_m, units, fuse_count, nkb0;
   int fuse_policy;  // the problems >= fuse_count (actor pass) get their N = act_dim head fused as well
+  int dbg;  // IQL_FUSED_DBG timing probes (results are wrong when set): 1 no sign bits, 2 no activation stores, 4 no staging wait, 8 no head / policy math
   int ks_last0;  // UMMA_K steps that carry data in the last k-block of layer 0 (observation widths <= 24: 3 of 4)
   uint32_t idesc;
   long long* trace;  // IQL_FUSED_TRACE: clock64 stamps of CTA 0, [3 roles][FUSED_TRACE_TILES][FUSED_MAX_LAYERS][4]
@@ -105,11 +108,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   uint8_t* smem = smem_raw + (base - raw);
   float* stg_all = reinterpret_cast<float*>(smem + F_RING);
   float* rec_s = reinterpret_cast<float*>(smem + F_RING + F_STG_BYTES);                        // [2][F_REC_FLOATS]
-  float* ypart_s = reinterpret_cast<float*>(smem + F_RING + F_STG_BYTES + 2 * F_REC_BYTES);    // [2][4][128]
+  float* ypart_s = reinterpret_cast<float*>(smem + F_RING + F_STG_BYTES + 2 * F_REC_BYTES);    // [2 groups][2][2][128]
   constexpr int BAR_OFF = F_RING + F_STG_BYTES + 2 * F_REC_BYTES + F_YPART_BYTES;
   const uint32_t bars = base + BAR_OFF;
-  // full[3] empty[3] tfull[2] elast achunk[8] recfull[2] recempty[2] | tmem slot
-  const uint32_t full0 = bars, empty0 = bars + 8 * F_MAXBAR, tfull0 = bars + 16 * F_MAXBAR, elast = tfull0 + 16;
+  // full[9] empty[9] tfull[2 groups][2] elast achunk[8] recfull[2] recempty[2] | tmem slot
+  const uint32_t full0 = bars, empty0 = bars + 8 * F_MAXBAR, tfull0 = bars + 16 * F_MAXBAR, elast = tfull0 + 32;
   const uint32_t achunk0 = elast + 8, recfull0 = achunk0 + 8 * F_CHUNKS, recempty0 = recfull0 + 16;
   const uint32_t tslot = recempty0 + 16;
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + (tslot - bars));
@@ -121,14 +124,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tfull0, 1);
-    mbar_init(tfull0 + 8, 1);
+    for (int i = 0; i < 2 * F_EGROUPS; ++i) mbar_init(tfull0 + 8 * i, 1);
     // pair: the leader's barriers collect the epilogue warps of both CTAs
-    mbar_init(elast, CTA2 ? 2 * F_EPI_WARPS : F_EPI_WARPS);
+    mbar_init(elast, CTA2 ? 2 * F_GROUP_WARPS : F_GROUP_WARPS);  // the warps of the group that owns the tile
     for (int c = 0; c < F_CHUNKS; ++c) mbar_init(achunk0 + 8 * c, CTA2 ? 8 : 4);  // the lane quarters of chunk c
     for (int b = 0; b < 2; ++b) {
       mbar_init(recfull0 + 8 * b, 32);
-      mbar_init(recempty0 + 8 * b, F_EPI_WARPS);
+      mbar_init(recempty0 + 8 * b, F_GROUP_WARPS);  // record buffer b belongs to epilogue group b
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -185,25 +187,38 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             if (rank == 0) mbar_expect_tx(full0 + 8 * slot, 2 * F_GRAN);  // the peer's granule lands on the same barrier
             tma_load_2d_cg2(base + slot * F_GRAN, map, full_lead + 8 * slot, c0, c1);
           };
-          for (int l = 0; l < L; ++l) {
+          // layer-0 operands of tile `uu`; requested one tile ahead, in the middle of the previous tile's last
+          // hidden layer: ring A is free as soon as that tile's layer-0 MMAs are done, long before ring B has room
+          // for the rest of its k-blocks
+          auto put_l0 = [&](int uu, uint32_t ti) {
+            const CUtensorMap* pm = fp.maps[0] + 4 * unit_prob(fp, uu);
+            const int mm = (uu % fp.tiles_m) * tile_rows + m_off;
+            trace_put(fp, 0, ti, 0, 0);
+            for (int kb = 0; kb < fp.nkb0; ++kb) {
+              put(0, phase, pm + 0, kb * FT_K, mm);                // own 128 rows of Xhi
+              put(1, phase, pm + 1, kb * FT_K, (int)rank * 128);  // own half of W0hi
+              put(2, phase, pm + 2, kb * FT_K, mm);                // Xlo
+              put(3, phase, pm + 3, kb * FT_K, (int)rank * 128);  // W0lo
+              phase ^= 1;
+            }
+            trace_put(fp, 0, ti, 0, 1);
+          };
+          if (tile_it == 0) put_l0(u, 0);
+          const int un = u + n_workers;
+          bool ahead = un >= fp.units;  // nothing to request ahead after the last tile
+          for (int l = 1; l < L; ++l) {
             trace_put(fp, 0, tile_it, l, 0);
-            if (l == 0) {
-              const CUtensorMap* pm = fp.maps[0] + 4 * prob;
-              for (int kb = 0; kb < fp.nkb0; ++kb) {
-                put(0, phase, pm + 0, kb * FT_K, m0);               // own 128 rows of Xhi
-                put(1, phase, pm + 1, kb * FT_K, (int)rank * 128);  // own half of W0hi
-                put(2, phase, pm + 2, kb * FT_K, m0);               // Xlo
-                put(3, phase, pm + 3, kb * FT_K, (int)rank * 128);  // W0lo
-                phase ^= 1;
+            for (int kb = 0; kb < nkb_h; ++kb) {
+              if (l == L - 1 && kb == F_NB && !ahead) {
+                put_l0(un, tile_it + 1);
+                ahead = true;
               }
-            } else {
-              for (int kb = 0; kb < nkb_h; ++kb) {
-                put(F_NA + stage, bphase, fp.maps[l] + 2 * prob + 1, kb * FT_K, (int)rank * 128);
-                if (++stage == F_NB) { stage = 0; bphase ^= 1; }
-              }
+              put(F_NA + stage, bphase, fp.maps[l] + 2 * prob + 1, kb * FT_K, (int)rank * 128);
+              if (++stage == F_NB) { stage = 0; bphase ^= 1; }
             }
             trace_put(fp, 0, tile_it, l, 1);
           }
+          if (!ahead) put_l0(un, tile_it + 1);  // L == 1
           continue;
         }
         for (int l = 0; l < L; ++l) {
@@ -254,6 +269,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           const uint32_t tacc = tmem_base + (uint32_t)(l & 1) * 256u;
           const uint32_t ta = tmem_base + (uint32_t)((l - 1) & 1) * 256u;
           const int nkb = (l == 0) ? 3 * fp.nkb0 : nkb_h;
+          // accumulator-full barriers: a pair per epilogue group, alternating over the group's own events
+          const uint32_t tf_bar = (tile_it & 1) * 2 + (((tile_it >> 1) * (uint32_t)L + (uint32_t)l) & 1);
           if (CTA2) {
             if (l == 0) {
               for (int kb = 0; kb < fp.nkb0; ++kb) {
@@ -291,7 +308,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               }
             }
             if (l > 0) ++aev;
-            umma_commit_cg2(tfull0 + 8 * (ev & 1));
+            umma_commit_cg2(tfull0 + 8 * tf_bar);
             trace_put(fp, 1, tile_it, l, 3);
             continue;
           }
@@ -321,7 +338,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
           }
           if (l > 0) ++aev;  // one completion of every achunk barrier per non-last epilogue
-          umma_commit(tfull0 + 8 * (ev & 1));
+          umma_commit(tfull0 + 8 * tf_bar);
           trace_put(fp, 1, tile_it, l, 3);
         }
       }
@@ -397,17 +414,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int ch = (warp - 2) >> 2;   // column group: chunks ch and ch + 4
-    const int tr_id = threadIdx.x - 64;  // 0..511
+    const int eg = (warp - 2) / F_GROUP_WARPS;         // epilogue group: tiles with tile_it % 2 == eg
+    const int ch = ((warp - 2) % F_GROUP_WARPS) >> 2;  // column group within the group: chunks ch, ch + 2, ch + 4, ch + 6
+    const int tr_id = threadIdx.x - 64 - eg * (F_GROUP_WARPS * 32);  // 0..255 within the group
+    const bool tracer = ((warp - 2) % F_GROUP_WARPS) == 0 && lane == 0;
     float* stg = stg_all + (warp - 2) * F_STG_FLOATS;
     uint32_t ev = 0, tile_it = 0;
     const uint32_t elast_lead = CTA2 ? mapa_u32(elast, 0) : elast;
     const uint32_t achunk_lead = CTA2 ? mapa_u32(achunk0, 0) : achunk0;
     for (int u = worker; u < fp.units; u += n_workers, ++tile_it) {
+      if ((int)(tile_it & 1) != eg) continue;  // the other group's tile
       const int prob = unit_prob(fp, u);
       const int m0 = (u % fp.tiles_m) * tile_rows + m_off;
       const uint32_t b = tile_it & 1;
       const float* rec = rec_s + b * F_REC_FLOATS;
+      ev = (tile_it >> 1) * (uint32_t)L;  // this group's event counter at the tile's first layer
       mbar_wait(recfull0 + 8 * b, (tile_it >> 1) & 1);
       const TileRec* tr = reinterpret_cast<const TileRec*>(rec + FUSED_MAX_LAYERS * FT_N + FT_N);
       const bool store = tr->store != 0;
@@ -421,11 +442,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
         const float drop_scale = tr->drop_scale;
         const float* bs = rec + l * FT_N;
         const float* ws = rec + FUSED_MAX_LAYERS * FT_N;
-        float* ypart = ypart_s + (tile_it & 1) * (F_CGROUPS * FT_M);
-        if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 0);
-        mbar_wait(tfull0 + 8 * (ev & 1), (ev >> 1) & 1);
+        float* ypart = ypart_s + (eg * 2 + ((tile_it >> 1) & 1)) * (F_CGROUPS * FT_M);
+        if (tracer) trace_put(fp, 2, tile_it, l, 0);
+        mbar_wait(tfull0 + 8 * (eg * 2 + (ev & 1)), (ev >> 1) & 1);
         tc_fence_after();
-        if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 1);
+        if (tracer) trace_put(fp, 2, tile_it, l, 1);
         const uint32_t region = tmem_base + (uint32_t)(l & 1) * 256u + ((uint32_t)(q * 32) << 16);
         float yacc = 0.f;
         const int pol_a = last ? tr->pol_a : 0;  // > 0: actor pass, policy head fused
@@ -480,7 +501,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               }
             }
           }
-          if (fuse) {  // FP32 head on the unrounded activations
+          if (fuse && !(fp.dbg & 8)) {  // FP32 head on the unrounded activations
             const float4* wc = reinterpret_cast<const float4*>(ws + c * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -491,22 +512,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               yacc = fmaf(__uint_as_float(r[4 * j + 3]), w4.w, yacc);
             }
           }
-          if (pol_a > 0) {  // act_dim dot products per row; the weight rows are the same for every lane (L1 broadcast)
-            const float* wp = tr->pol_w + c * 32;
+          if (pol_a > 0 && !(fp.dbg & 8)) {
+            // act_dim dot products per row.  Lane i fetches column 32 c + i of every weight row (one coalesced 128-byte
+            // load per action) and the warp passes the values round with shuffles: every lane needs every weight, and
+            // there is no shared memory left to broadcast them from (uniform global loads serialised on the
+            // register budget: 15 us per actor tile)
+            float wreg[FUSED_POL_MAX];
+            const float* wp = tr->pol_w + c * 32 + lane;
             const int ldw = tr->pol_ldw;
 #pragma unroll
-            for (int a = 0; a < FUSED_POL_MAX; ++a) {
-              if (a < pol_a) {
-                const float4* wr = reinterpret_cast<const float4*>(wp + (int64_t)a * ldw);
+            for (int a = 0; a < FUSED_POL_MAX; ++a) wreg[a] = (a < pol_a) ? __ldg(wp + (int64_t)a * ldw) : 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 w4 = __ldg(wr + j);
-                  pacc[a] = fmaf(__uint_as_float(r[4 * j + 0]), w4.x, pacc[a]);
-                  pacc[a] = fmaf(__uint_as_float(r[4 * j + 1]), w4.y, pacc[a]);
-                  pacc[a] = fmaf(__uint_as_float(r[4 * j + 2]), w4.z, pacc[a]);
-                  pacc[a] = fmaf(__uint_as_float(r[4 * j + 3]), w4.w, pacc[a]);
-                }
-              }
+            for (int j = 0; j < 32; ++j) {  // branch-free: the rows past act_dim carry zero weights
+              const float h = __uint_as_float(r[j]);
+#pragma unroll
+              for (int a = 0; a < FUSED_POL_MAX; ++a) pacc[a] = fmaf(h, __shfl_sync(0xffffffffu, wreg[a], j), pacc[a]);
             }
           }
 #pragma unroll
@@ -521,18 +541,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               else mbar_arrive(achunk0 + 8 * c);
             }
           }
-          uint32_t* const bits = tr->bits[l];
-          if (store && bits != nullptr) {  // 1 bit per element for the dgrad mask (of the ROUNDED value, like the store)
-            uint32_t word = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) word |= (__uint_as_float(r[j]) > 0.f ? 1u : 0u) << j;
-            bits[(int64_t)row * F_CHUNKS + c] = word;
-          }
-          if (store) {
+          if (store && !(fp.dbg & 2)) {
             // every lane holds one full 128-byte row of the chunk: park it (16-byte units XOR-swizzled by the row,
             // the layout a SWIZZLE_128B tensor map expects) and let one TMA store write the 32 x 32 box -- no
             // transposition, and no store instruction of this warp waits for the memory system
-            if (lane == 0) bulk_wait_read0();  // the previous box has left the staging tile
+            if (lane == 0 && !(fp.dbg & 4)) bulk_wait_read0();  // the previous box has left the staging tile
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -546,14 +559,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               bulk_commit();
             }
           }
+          uint32_t* const bits = tr->bits[l];
+          if (store && bits != nullptr && !(fp.dbg & 1)) {  // 1 bit per element for the dgrad mask (of the ROUNDED value, like the store)
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) word |= (__uint_as_float(r[j]) > 0.f ? 1u : 0u) << j;
+            bits[(int64_t)row * F_CHUNKS + c] = word;
+          }
         }
-        if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 2);
+        if (tracer) trace_put(fp, 2, tile_it, l, 2);
         if (fuse) {
           ypart[ch * FT_M + q * 32 + lane] = yacc;
-          asm volatile("bar.sync 1, 512;" ::: "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + eg), "r"(F_GROUP_WARPS * 32) : "memory");
           if (tr_id < FT_M)
-            tr->head_out[(int64_t)(m0 + tr_id) * tr->head_ldc] =
-                (((ypart[tr_id] + ypart[FT_M + tr_id]) + ypart[2 * FT_M + tr_id]) + ypart[3 * FT_M + tr_id]) + tr->head_b;
+            tr->head_out[(int64_t)(m0 + tr_id) * tr->head_ldc] = (ypart[tr_id] + ypart[FT_M + tr_id]) + tr->head_b;
         }
         if (pol_a > 0) {
           // the four column groups park their partial sums in their (idle) staging tiles; the warps of group 0
@@ -562,7 +581,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           __syncwarp();
 #pragma unroll
           for (int a = 0; a < FUSED_POL_MAX; ++a) stg[lane * FUSED_POL_MAX + a] = pacc[a];
-          asm volatile("bar.sync 1, 512;" ::: "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + eg), "r"(F_GROUP_WARPS * 32) : "memory");
           if (ch == 0) {
             float* zrow = tr->pol_out + (int64_t)row * tr->pol_ldc;
 #pragma unroll
@@ -576,9 +595,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               }
             }
           }
-          asm volatile("bar.sync 1, 512;" ::: "memory");  // the staging tiles go back to the activation stores
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + eg), "r"(F_GROUP_WARPS * 32) : "memory");  // the staging tiles go back to the activation stores
         }
-        if (warp == 2 && lane == 0) trace_put(fp, 2, tile_it, l, 3);
+        if (tracer) trace_put(fp, 2, tile_it, l, 3);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(recempty0 + 8 * b);  // this warp no longer reads the tile's record
@@ -646,6 +665,10 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
   fp.units = a.nprob * fp.tiles_m;
   fp.fuse_count = a.probs_out ? a.fuse_count : 0;
   fp.fuse_policy = (a.probs_out && a.fuse_policy) ? 1 : 0;
+  {
+    static const int dbg = getenv("IQL_FUSED_DBG") ? atoi(getenv("IQL_FUSED_DBG")) : 0;
+    fp.dbg = dbg;
+  }
   fp.nkb0 = (a.k0_max + FT_K - 1) / FT_K;
   fp.ks_last0 = (a.k0_max - (fp.nkb0 - 1) * FT_K + F_UMMA_K - 1) / F_UMMA_K;
   // c = F32, a = b = TF32, both K-major, N = 256, M = 128 (256 for a CTA pair)
