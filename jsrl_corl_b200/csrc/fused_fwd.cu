@@ -58,7 +58,8 @@ constexpr int F_SMEM = F_RING + F_STG_BYTES + 2 * F_REC_BYTES + F_YPART_BYTES + 
 constexpr int F_THREADS = 608;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-17 epilogue, warp 18 per-tile prefetch
 constexpr int FUSED_POL_MAX = 8;
 constexpr int FUSED_TRACE_TILES = 8;
-constexpr int FUSED_TRACE_WORDS = 3 * FUSED_TRACE_TILES * FUSED_MAX_LAYERS * 4;
+constexpr int FUSED_TRACE_ROLES = 5;  // TMA, MMA, epilogue (layer level), epilogue chunk level x 2
+constexpr int FUSED_TRACE_WORDS = FUSED_TRACE_ROLES * FUSED_TRACE_TILES * FUSED_MAX_LAYERS * 4;
 
 struct TileRec {  // the 64-float tail of a record
   float* C[FUSED_MAX_LAYERS];
@@ -458,6 +459,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           uint32_t r[32];
           tmem_ld32(region + (uint32_t)(c * 32), r);
           tmem_ld_wait();
+          if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 0);
+          if (tracer && c == ch + F_CGROUPS) trace_put(fp, 4, tile_it, l, 0);
           if (last && c + F_CGROUPS >= F_CHUNKS) {  // this warp's last read of the tile: the region may be overwritten
             tc_fence_before();
             __syncwarp();
@@ -531,6 +534,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(__uint_as_float(r[j])));
+          if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 1);
           if (!last) {  // columns [32 c, +32) of the next layer's operand A, in place; the MMAs of k-block c may go
             tmem_st32(region + (uint32_t)(c * 32), r);
             tmem_st_wait();
@@ -541,6 +545,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               else mbar_arrive(achunk0 + 8 * c);
             }
           }
+          if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 2);
           if (store && !(fp.dbg & 2)) {
             // every lane holds one full 128-byte row of the chunk: park it (16-byte units XOR-swizzled by the row,
             // the layout a SWIZZLE_128B tensor map expects) and let one TMA store write the 32 x 32 box -- no
@@ -559,6 +564,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               bulk_commit();
             }
           }
+          if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 3);
           uint32_t* const bits = tr->bits[l];
           if (store && bits != nullptr && !(fp.dbg & 1)) {  // 1 bit per element for the dgrad mask (of the ROUNDED value, like the store)
             uint32_t word = 0;
@@ -566,6 +572,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             for (int j = 0; j < 32; ++j) word |= (__uint_as_float(r[j]) > 0.f ? 1u : 0u) << j;
             bits[(int64_t)row * F_CHUNKS + c] = word;
           }
+          if (tracer && c == ch) trace_put(fp, 4, tile_it, l, 1);
         }
         if (tracer) trace_put(fp, 2, tile_it, l, 2);
         if (fuse) {

@@ -468,23 +468,34 @@ void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, c
 }
 
 // ---------------------------------------------------------------------------
-// first layer weight gradient.  grid (nprob, ceil(H/(64*NC))), 256 threads = 64 column slots x 4 row groups,
+// first layer weight gradient.  grid (nprob, ceil(H/(SLOTS*NC))), NT threads = SLOTS column slots x 4 row groups,
 // NC columns per thread (the X row fetched from shared memory is reused NC times).
 //   p: TN problem (A = G_0 [B][H] (K = B rows, M = H), B = X [B][ldx] (N = K0), C = dW_0 [H][K0], dbias = db_0)
+// Sized so that the whole launch is ONE wave at the reference's shapes (KMAX = 24: 1024 CTAs of 128 threads, 7 per
+// SM): with 512 larger CTAs the second, 15 % full wave doubled the kernel time.
 // ---------------------------------------------------------------------------
-template <int KMAX, int NC>
-__global__ void __launch_bounds__(256, KMAX <= 24 ? 3 : 1) first_wgrad_kernel(const GemmProb* __restrict__ probs) {
-  extern __shared__ float sm[];  // X [B][KMAX]; afterwards the reduction scratch [4][64*NC][KMAX + 1] in the same bytes
+template <int KMAX, int NC, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) first_wgrad_kernel(const GemmProb* __restrict__ probs) {
+  extern __shared__ float sm[];  // X [B][KMAX]; afterwards the reduction scratch [4][SLOTS*NC][KMAX + 1] in the same bytes
   const GemmProb p = probs[blockIdx.x];
   const int B = p.K, H = p.M, K0 = p.N;
-  constexpr int CW = 64 * NC;  // columns per CTA
+  constexpr int SLOTS = NT / 4;
+  constexpr int CW = SLOTS * NC;  // columns per CTA
   float* xs = sm;
   float* red = sm;  // aliases xs once the main loop is done
-  for (int i = threadIdx.x; i < B * KMAX; i += 256) {
-    const int b = i / KMAX, k = i - b * KMAX;
-    xs[i] = (k < K0) ? p.B[(int64_t)b * p.ldb + k] : 0.f;
+  // X rows are 16-byte aligned and ldb is a multiple of 4: float4 loads, columns >= K0 (the next fields of the
+  // replay row) zeroed
+  for (int i = threadIdx.x; i < B * (KMAX / 4); i += NT) {
+    const int b = i / (KMAX / 4), k4 = (i - b * (KMAX / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k4 < K0 && k4 + 4 <= p.ldb) v = __ldg(reinterpret_cast<const float4*>(p.B + (int64_t)b * p.ldb + k4));
+    if (k4 + 0 >= K0) v.x = 0.f;
+    if (k4 + 1 >= K0) v.y = 0.f;
+    if (k4 + 2 >= K0) v.z = 0.f;
+    if (k4 + 3 >= K0) v.w = 0.f;
+    *reinterpret_cast<float4*>(&xs[b * KMAX + k4]) = v;
   }
-  const int tn = threadIdx.x & 63, bg = threadIdx.x >> 6;
+  const int tn = threadIdx.x % SLOTS, bg = threadIdx.x / SLOTS;
   const int n0 = blockIdx.y * CW + tn;
   float acc[NC][KMAX];
   float bsum[NC];
@@ -498,15 +509,15 @@ __global__ void __launch_bounds__(256, KMAX <= 24 ? 3 : 1) first_wgrad_kernel(co
   const int rows_per = (B + 3) / 4;
   const int b_lo = bg * rows_per, b_hi = min(B, b_lo + rows_per);
   // RU rows per trip with all their G loads issued before the first FMA: the loop is bound by the latency of the
-  // (coalesced, 256-byte) G reads, so what matters is how many of them each thread keeps in flight
-  constexpr int RU = 8;
+  // (coalesced) G reads, so what matters is how many of them each thread keeps in flight
+  constexpr int RU = MINB >= 4 ? 4 : 8;
   for (int b = b_lo; b < b_hi; b += RU) {
     float g[RU][NC];
 #pragma unroll
     for (int r = 0; r < RU; ++r)
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const int n = n0 + c * 64;
+        const int n = n0 + c * SLOTS;
         g[r][c] = (b + r < b_hi && n < H) ? __ldg(&p.A[(int64_t)(b + r) * p.lda + n]) : 0.f;
       }
 #pragma unroll
@@ -531,14 +542,14 @@ __global__ void __launch_bounds__(256, KMAX <= 24 ? 3 : 1) first_wgrad_kernel(co
   constexpr int RS = KMAX + 1;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    float* mine = red + (size_t)(bg * CW + c * 64 + tn) * RS;
+    float* mine = red + (size_t)(bg * CW + c * SLOTS + tn) * RS;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) mine[k] = acc[c][k];
     mine[KMAX] = bsum[c];
   }
   __syncthreads();
-  // 256 threads cooperatively finish the CW x (K0 + 1) outputs of this column block (fixed order)
-  for (int i = threadIdx.x; i < CW * RS; i += 256) {
+  // the CTA cooperatively finishes the CW x (K0 + 1) outputs of this column block (fixed order)
+  for (int i = threadIdx.x; i < CW * RS; i += NT) {
     const int c = i / RS, k = i - c * RS;
     const int nn = blockIdx.y * CW + c;
     if (nn >= H) continue;
@@ -550,17 +561,17 @@ __global__ void __launch_bounds__(256, KMAX <= 24 ? 3 : 1) first_wgrad_kernel(co
 }
 
 void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax, cudaStream_t st) {
-  auto smem = [&](int k, int nc) { return std::max((size_t)B * k, (size_t)4 * 64 * nc * (k + 1)) * sizeof(float); };
+  auto smem = [&](int k, int cw) { return std::max((size_t)B * k, (size_t)4 * cw * (k + 1)) * sizeof(float); };
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(first_wgrad_kernel<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(first_wgrad_kernel<40, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(first_wgrad_kernel<72, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(first_wgrad_kernel<24, 2, 128, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(first_wgrad_kernel<40, 2, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(first_wgrad_kernel<72, 1, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  if (kmax <= 24) first_wgrad_kernel<24, 2><<<dim3(nprob, (H + 127) / 128), 256, smem(24, 2), st>>>(probs);
-  else if (kmax <= 40) first_wgrad_kernel<40, 2><<<dim3(nprob, (H + 127) / 128), 256, smem(40, 2), st>>>(probs);
-  else first_wgrad_kernel<72, 1><<<dim3(nprob, (H + 63) / 64), 256, smem(72, 1), st>>>(probs);
+  if (kmax <= 24) first_wgrad_kernel<24, 2, 128, 7><<<dim3(nprob, (H + 63) / 64), 128, smem(24, 64), st>>>(probs);
+  else if (kmax <= 40) first_wgrad_kernel<40, 2, 256, 1><<<dim3(nprob, (H + 127) / 128), 256, smem(40, 128), st>>>(probs);
+  else first_wgrad_kernel<72, 1, 256, 1><<<dim3(nprob, (H + 63) / 64), 256, smem(72, 64), st>>>(probs);
 }
 
 }  // namespace iql

@@ -36,24 +36,26 @@ def main():
     torch.cuda.synchronize()
     ens.engine.profile_step(1)  # eager launches: the last fused launch wrote the trace
     torch.cuda.synchronize()
-    buf = np.zeros(3 * 8 * 4 * 4, dtype=np.int64)
+    buf = np.zeros(5 * 8 * 4 * 4, dtype=np.int64)
     n = _lib.lib().iql_debug_fused_trace(buf.ctypes.data_as(C.c_void_p), buf.size)
     if n <= 0:
         raise SystemExit(f"no trace (rc={n})")
-    t = buf.reshape(3, 8, 4, 4).astype(np.float64)
+    t = buf.reshape(5, 8, 4, 4).astype(np.float64)
     L = w["L"]
     t0 = t[t > 0].min()
     us = lambda x: (x - t0) / 1965.0  # noqa: E731  (SM clock 1965 MHz)
     print("times in us since the first stamp of CTA 0; one line per (tile, layer)")
     print(f"{'tile':>4} {'l':>2} | {'tma first':>9} {'tma last':>9} | {'mma start':>9} {'A ready':>9} {'kb0 full':>9} {'issued':>9} | "
-          f"{'epi start':>9} {'acc full':>9} {'A stored':>9} {'epi end':>9}")
+          f"{'epi start':>9} {'acc full':>9} {'A stored':>9} {'epi end':>9} | first chunk: {'ld done':>8} {'math':>8} {'A st+arr':>8} {'TMA st':>8} {'bits':>8} {'ld 2nd':>8}")
     for ti in range(8):
         for l in range(L):
             p, m, e = t[0, ti, l], t[1, ti, l], t[2, ti, l]
             if m[0] == 0:
                 continue
             print(f"{ti:>4} {l:>2} | {us(p[0]):9.2f} {us(p[1]):9.2f} | {us(m[0]):9.2f} {us(m[1]):9.2f} {us(m[2]):9.2f} {us(m[3]):9.2f} | "
-                  f"{us(e[0]):9.2f} {us(e[1]):9.2f} {us(e[2]):9.2f} {us(e[3]):9.2f}")
+                  f"{us(e[0]):9.2f} {us(e[1]):9.2f} {us(e[2]):9.2f} {us(e[3]):9.2f} |              "
+                  f"{us(t[3, ti, l, 0]):8.2f} {us(t[3, ti, l, 1]):8.2f} {us(t[3, ti, l, 2]):8.2f} {us(t[3, ti, l, 3]):8.2f} "
+                  f"{us(t[4, ti, l, 1]):8.2f} {us(t[4, ti, l, 0]):8.2f}")
 
 
 if __name__ == "__main__":
