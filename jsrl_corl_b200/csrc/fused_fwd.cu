@@ -86,7 +86,7 @@ struct FusedParams {
   const GemmProb* probs_out;                 // output-layer problems (scalar heads of the first fuse_count)
   int L, nprob, tiles_m, units, fuse_count, nkb0;
   int fuse_policy;  // the problems >= fuse_count (actor pass) get their N = act_dim head fused as well
-  int dbg;  // IQL_FUSED_DBG timing probes (results are wrong when set): 1 no sign bits, 2 no activation stores, 4 no staging wait, 8 no head / policy math
+  int dbg;  // IQL_FUSED_DBG timing probes (results are wrong when set): 1 no sign bits, 2 no activation stores, 4 no staging wait, 8 no head / policy math, 16 reversed tile order
   int ks_last0;  // UMMA_K steps that carry data in the last k-block of layer 0 (observation widths <= 24: 3 of 4)
   uint32_t idesc;
   long long* trace;  // IQL_FUSED_TRACE: clock64 stamps of CTA 0, [3 roles][FUSED_TRACE_TILES][FUSED_MAX_LAYERS][4]
@@ -99,7 +99,7 @@ __device__ __forceinline__ void trace_put(const FusedParams& fp, int role, uint3
 
 // Work order: table order (forward-only and critic passes first, the actor pass last).  Handing the actor tiles
 // (policy head, dropout: the longest epilogues) out first measured slower (97 vs 92.5 us, same box, 64-member ensemble).
-__device__ __forceinline__ int unit_prob(const FusedParams& fp, int u) { return u / fp.tiles_m; }
+__device__ __forceinline__ int unit_prob(const FusedParams& fp, int u) { return ((fp.dbg & 16) ? fp.units - 1 - u : u) / fp.tiles_m; }
 
 template <bool CTA2>
 __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp, StepCtx ctx) {
