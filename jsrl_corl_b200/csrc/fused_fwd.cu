@@ -191,27 +191,31 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           // layer-0 operands of tile `uu`; requested one tile ahead, in the middle of the previous tile's last
           // hidden layer: ring A is free as soon as that tile's layer-0 MMAs are done, long before ring B has room
           // for the rest of its k-blocks
-          auto put_l0 = [&](int uu, uint32_t ti) {
+          // ring A holds one k-block at a time, so only the FIRST layer-0 k-block of a tile is requested ahead; the
+          // others (observation widths > 32) follow at the top of the tile itself -- requesting them ahead would wait
+          // for layer-0 MMAs of a tile whose predecessor still lacks hidden-layer k-blocks this thread has yet to send
+          auto put_l0 = [&](int uu, uint32_t ti, int kb_lo, int kb_hi) {
             const CUtensorMap* pm = fp.maps[0] + 4 * unit_prob(fp, uu);
             const int mm = (uu % fp.tiles_m) * tile_rows + m_off;
-            trace_put(fp, 0, ti, 0, 0);
-            for (int kb = 0; kb < fp.nkb0; ++kb) {
+            if (kb_lo == 0) trace_put(fp, 0, ti, 0, 0);
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
               put(0, phase, pm + 0, kb * FT_K, mm);                // own 128 rows of Xhi
               put(1, phase, pm + 1, kb * FT_K, (int)rank * 128);  // own half of W0hi
               put(2, phase, pm + 2, kb * FT_K, mm);                // Xlo
               put(3, phase, pm + 3, kb * FT_K, (int)rank * 128);  // W0lo
               phase ^= 1;
             }
-            trace_put(fp, 0, ti, 0, 1);
+            if (kb_hi == fp.nkb0) trace_put(fp, 0, ti, 0, 1);
           };
-          if (tile_it == 0) put_l0(u, 0);
+          if (tile_it == 0) put_l0(u, 0, 0, 1);
+          if (fp.nkb0 > 1) put_l0(u, tile_it, 1, fp.nkb0);
           const int un = u + n_workers;
           bool ahead = un >= fp.units;  // nothing to request ahead after the last tile
           for (int l = 1; l < L; ++l) {
             trace_put(fp, 0, tile_it, l, 0);
             for (int kb = 0; kb < nkb_h; ++kb) {
               if (l == L - 1 && kb == F_NB && !ahead) {
-                put_l0(un, tile_it + 1);
+                put_l0(un, tile_it + 1, 0, 1);
                 ahead = true;
               }
               put(F_NA + stage, bphase, fp.maps[l] + 2 * prob + 1, kb * FT_K, (int)rank * 128);
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             }
             trace_put(fp, 0, tile_it, l, 1);
           }
-          if (!ahead) put_l0(un, tile_it + 1);  // L == 1
+          if (!ahead) put_l0(un, tile_it + 1, 0, 1);  // L == 1
           continue;
         }
         for (int l = 0; l < L; ++l) {

@@ -100,19 +100,28 @@ void launch_first_fwd(const GemmProb* probs, int nprob, int B, int H, int kmax, 
 }
 
 // ---------------------------------------------------------------------------
-// output layer forward.  grid (nprob, ceil(B/32)), 256 threads = 8 warps, one
-// warp per row (4 rows per warp), lanes stride the hidden dimension.
+// output layer forward.  grid (nprob, ceil(B/ROWS)), 256 threads = 8 warps, one warp per row at a time, lanes stride
+// the hidden dimension.  ROWS rows per CTA amortise the staging of the [N][K] weights in shared memory (with 32
+// rows per CTA the 24 KB weight load of a 24-action head took 10x longer than the dot products).
 // ---------------------------------------------------------------------------
-template <int AMAX>
+template <int AMAX, int ROWS>
 __global__ void __launch_bounds__(256) out_fwd_kernel(const GemmProb* __restrict__ probs) {
   extern __shared__ float wsm[];  // [N][K]
   const GemmProb p = probs[blockIdx.x];
   const int K = p.K, N = p.N;
-  for (int i = threadIdx.x; i < N * K; i += 256) wsm[i] = p.B[(int64_t)(i / K) * p.ldb + (i % K)];
+  if ((K & 3) == 0 && (p.ldb & 3) == 0) {
+    const int k4n = K >> 2;
+    for (int i = threadIdx.x; i < N * k4n; i += 256) {
+      const int n = i / k4n, k4 = i - n * k4n;
+      reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(p.B + (int64_t)n * p.ldb) + k4);
+    }
+  } else {
+    for (int i = threadIdx.x; i < N * K; i += 256) wsm[i] = p.B[(int64_t)(i / K) * p.ldb + (i % K)];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rr = 0; rr < 4; ++rr) {
-    const int row = blockIdx.y * 32 + warp * 4 + rr;
+  for (int rr = warp; rr < ROWS; rr += 8) {
+    const int row = blockIdx.y * ROWS + rr;
     if (row >= p.M) break;
     float acc[AMAX];
 #pragma unroll
@@ -136,21 +145,75 @@ __global__ void __launch_bounds__(256) out_fwd_kernel(const GemmProb* __restrict
   }
 }
 
+// Wide heads (8 < N <= 24, the pen-human policy head): one thread per batch row, the [K][AMAX] weights transposed in
+// shared memory and read back as broadcast 16-byte loads (6 per k for 24 FMAs).  The warp-per-row kernel above spends
+// its time in 8 dependent strided loads and 120 shuffles per row (159 us for 256 members x 256 rows on a B200).
+template <int AMAX>
+__global__ void __launch_bounds__(128) out_fwd_rows_kernel(const GemmProb* __restrict__ probs) {
+  extern __shared__ float wsm[];  // [K][AMAX], columns >= N zero
+  const GemmProb p = probs[blockIdx.x];
+  const int K = p.K, N = p.N;
+  for (int i = threadIdx.x; i < AMAX * K; i += 128) {
+    const int m = i / K, k = i - m * K;  // coalesced along k
+    wsm[k * AMAX + m] = (m < N) ? __ldg(p.B + (int64_t)m * p.ldb + k) : 0.f;
+  }
+  __syncthreads();
+  const int row = blockIdx.y * 128 + threadIdx.x;
+  if (row >= p.M) return;
+  float acc[AMAX];
+#pragma unroll
+  for (int m = 0; m < AMAX; ++m) acc[m] = 0.f;
+  const float4* h4 = reinterpret_cast<const float4*>(p.A + (int64_t)row * p.lda);
+#pragma unroll 4
+  for (int k4 = 0; k4 < (K >> 2); ++k4) {
+    const float4 x = __ldg(h4 + k4);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4* wr = reinterpret_cast<const float4*>(wsm + (4 * k4 + j) * AMAX);
+#pragma unroll
+      for (int m4 = 0; m4 < AMAX / 4; ++m4) {
+        const float4 w = wr[m4];
+        acc[4 * m4 + 0] = fmaf(xs[j], w.x, acc[4 * m4 + 0]);
+        acc[4 * m4 + 1] = fmaf(xs[j], w.y, acc[4 * m4 + 1]);
+        acc[4 * m4 + 2] = fmaf(xs[j], w.z, acc[4 * m4 + 2]);
+        acc[4 * m4 + 3] = fmaf(xs[j], w.w, acc[4 * m4 + 3]);
+      }
+    }
+  }
+  float* out = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+  for (int m = 0; m < AMAX; ++m)
+    if (m < N) out[m] = acc[m] + p.bias[m];
+}
+
 void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cudaStream_t st) {
-  dim3 grid(nprob, (B + 31) / 32);
   const size_t sm = (size_t)amax * H * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(out_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<8, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<24, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<24, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(out_fwd_rows_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  if (amax <= 1) out_fwd_kernel<1><<<grid, 256, sm, st>>>(probs);
-  else if (amax <= 8) out_fwd_kernel<8><<<grid, 256, sm, st>>>(probs);
-  else if (amax <= 24) out_fwd_kernel<24><<<grid, 256, sm, st>>>(probs);
-  else out_fwd_kernel<64><<<grid, 256, sm, st>>>(probs);
+  // few problems (single learner): 32 rows per CTA keep the GPU busy; ensembles: 128 rows per CTA
+  const bool big = (int64_t)nprob * ((B + 127) / 128) >= 296;
+  dim3 grid(nprob, big ? (B + 127) / 128 : (B + 31) / 32);
+  if (amax <= 1) out_fwd_kernel<1, 32><<<dim3(nprob, (B + 31) / 32), 256, sm, st>>>(probs);
+  else if (amax <= 8) {
+    if (big) out_fwd_kernel<8, 128><<<grid, 256, sm, st>>>(probs);
+    else out_fwd_kernel<8, 32><<<grid, 256, sm, st>>>(probs);
+  } else if (amax <= 24) {
+    static const bool no_rows = getenv("IQL_B200_NO_OUT_ROWS") != nullptr;
+    if (big && (H & 3) == 0 && !no_rows)
+      out_fwd_rows_kernel<24><<<dim3(nprob, (B + 127) / 128), 128, (size_t)24 * H * sizeof(float), st>>>(probs);
+    else if (big) out_fwd_kernel<24, 128><<<grid, 256, sm, st>>>(probs);
+    else out_fwd_kernel<24, 32><<<grid, 256, sm, st>>>(probs);
+  } else out_fwd_kernel<64, 128><<<dim3(nprob, (B + 127) / 128), 256, sm, st>>>(probs);
 }
 
 // ---------------------------------------------------------------------------

@@ -454,6 +454,52 @@ def test_tcgen05_path_general_shapes_match_oracle(B, H, L, A):
         assert worst < TF32_W30_TOL, (worst, where)
 
 
+@pytest.mark.parametrize("S_dim,A,dropout", [(45, 24, 0.0), (17, 6, 0.0), (29, 8, 0.0), (45, 24, 0.1)])
+def test_fused_forward_several_tiles_per_cta_pair_match_oracle(S_dim, A, dropout):
+    """32 members x 7 passes = 224 tiles on the 74 CTA pairs of a B200: every pair walks 3-4 tiles, which is what
+    exercises the cross-tile machinery of the fused forward (operands of the next tile requested ahead, the two
+    epilogue groups on alternate tiles, the accumulator hand-over between tiles).  pen shape: three layer-0 k-blocks
+    (observation width 69 > 32) and the policy head in its own kernel; halfcheetah / antmaze: policy head fused.
+    Every member against the FP32 path of the engine, three of them against the numpy oracle."""
+    from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
+    from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
+    from oracle.philox import philox_indices
+
+    members, B, H, L, n_rows, steps = 32, 256, 256, 2, 5000, 2
+    data = synthetic_dataset(n_rows, S_dim, A, 2)
+    rb = ReplayBuffer(S_dim, A, n_rows, "cuda")
+    rb.load_d4rl_dataset(data)
+    seeds = list(range(100, 100 + members))
+    masks = None
+    if dropout > 0:
+        rs = np.random.RandomState(7)
+        masks = torch.from_numpy((rs.uniform(size=(members, steps, L, B, H)) < 1.0 - dropout).astype(np.uint8))
+    out, init = {}, None
+    for mode in ("tf32", "fp32"):
+        ens = IQLEnsemble(members, S_dim, A, H, L, B, deterministic=False, actor_dropout=dropout, math_mode=mode, seeds=seeds,
+                          max_steps_per_call=4, hparams=[dict(cosine_t_max=50)] * members)
+        ens.bind_replay(rb)
+        if init is None:
+            init = {m: {g: {k: v.copy() for k, v in d.items()} for g, d in _cpu_tree(ens.engine.param_views(m, dropout > 0)).items()}
+                    for m in (0, 17, 31)}
+        out[mode] = ens.train_steps(steps, dropout_masks=masks).cpu().numpy()
+        if mode == "tf32":
+            trees = {m: _cpu_tree(ens.engine.param_views(m, dropout > 0)) for m in (0, 17, 31)}
+    assert np.isfinite(out["tf32"]).all()
+    for m in range(members):
+        assert _loss_errors(out["tf32"][m], out["fp32"][m]).max() < TF32_TOL, (m, out["tf32"][m], out["fp32"][m])
+    for m in (0, 17, 31):
+        orc = NumpyIQL(OracleConfig(S_dim, A, H, L, False, dropout, max_steps=50), init[m], np.float32)
+        ref = []
+        for k in range(steps):
+            mk = masks[m, k].numpy().astype(bool) if masks is not None else None
+            lo = orc.train(batch_from(data, philox_indices(seeds[m], k, n_rows, B)), dropout_masks=mk)
+            ref.append([lo["value_loss"], lo["q_loss"], lo["actor_loss"]])
+        assert _loss_errors(out["tf32"][m], np.array(ref)).max() < TF32_TOL, (m, out["tf32"][m], ref)
+        worst, where = tree_max_rel(trees[m], orc.state())
+        assert worst < TF32_W30_TOL, (m, worst, where)
+
+
 def test_facade_batch_size_change_and_partial_load_keep_state():
     """The drop-in trainer sizes its engine from the first batch; a different batch size later migrates the
     whole state (weights, Adam moments, counters).  partial_load_state_dict copies networks only."""
