@@ -779,7 +779,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       // fused wgrad + dgrad of the output layer; it also emits db_{L-1} when layer L-1 is a hidden-layer
       // tcgen05 wgrad phase (whose kernel does not produce bias gradients)
       const bool emit_db = next2 && tf32 && next2->umma_ok && umma_phase_supported(2, B, H);
-      launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st,
+      launches += -1 + launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st,
                       loss_recomputed ? e->d_ws_f : nullptr, e->wl.member_floats, &e->wl, e->params);
       skip_next = true;
       skip_colsum = emit_db;

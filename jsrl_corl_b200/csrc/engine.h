@@ -144,7 +144,7 @@ void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cu
 // rows itself (the problem tables hold 4 training nets per member: V, q1, q2, actor) and does not read gy / gpi, so
 // loss_kernel need not precede it.
 bool last_bwd_recomputes_loss_grads(int H, int amax);
-void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
+int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
                      int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st, const float* ws = nullptr,
                      int64_t ws_member_floats = 0, const WorkspaceLayout* wl = nullptr, const float* params = nullptr);
 void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax, cudaStream_t st);

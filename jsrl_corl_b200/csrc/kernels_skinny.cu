@@ -225,12 +225,15 @@ void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cu
 template <int AMAX>
 __global__ void __launch_bounds__(256) last_bwd_kernel(const GemmProb* __restrict__ probs_dgrad,
                                                        const GemmProb* __restrict__ probs_wgrad,
-                                                       const GemmProb* __restrict__ probs_prev_wgrad, StepCtx ctx) {
+                                                       const GemmProb* __restrict__ probs_prev_wgrad, StepCtx ctx,
+                                                       int sel_n, int sel_off) {
   extern __shared__ float sm[];  // G tile [B][AMAX] then reduction scratch [4][64][AMAX]
-  const GemmProb pn = probs_dgrad[blockIdx.x];
-  const GemmProb pw = probs_wgrad[blockIdx.x];
+  // sel_n > 0: this launch covers sel_n of every 4 problems (the training nets of a member, table order), from sel_off
+  const int pi = sel_n > 0 ? (int)(blockIdx.x / sel_n) * 4 + sel_off + (int)(blockIdx.x % sel_n) : (int)blockIdx.x;
+  const GemmProb pn = probs_dgrad[pi];
+  const GemmProb pw = probs_wgrad[pi];
   // bias gradient of layer L-1 (the wgrad problem of the NEXT backward phase), when that layer is a hidden one
-  float* dbias_prev = probs_prev_wgrad ? probs_prev_wgrad[blockIdx.x].dbias : nullptr;
+  float* dbias_prev = probs_prev_wgrad ? probs_prev_wgrad[pi].dbias : nullptr;
   const int B = pn.M, H = pn.N, AO = pn.K;
   float* gs = sm;
   float* red = sm + (size_t)B * AMAX;
@@ -385,12 +388,14 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
                                                           const GemmProb* __restrict__ probs_wgrad,
                                                           const GemmProb* __restrict__ probs_prev_wgrad, StepCtx ctx,
                                                           const float* __restrict__ ws, int64_t ws_member_floats,
-                                                          WorkspaceLayout wl, const float* __restrict__ params) {
+                                                          WorkspaceLayout wl, const float* __restrict__ params, int sel_n,
+                                                          int sel_off) {
   extern __shared__ float sm[];  // G tile [B][AMAX], then reduction scratch [4 row groups][256 columns][AMAX + 1]
   pdl_trigger();
-  const GemmProb pn = probs_dgrad[blockIdx.x];
-  const GemmProb pw = probs_wgrad[blockIdx.x];
-  float* dbias_prev = probs_prev_wgrad ? probs_prev_wgrad[blockIdx.x].dbias : nullptr;
+  const int pi = sel_n > 0 ? (int)(blockIdx.x / sel_n) * 4 + sel_off + (int)(blockIdx.x % sel_n) : (int)blockIdx.x;
+  const GemmProb pn = probs_dgrad[pi];
+  const GemmProb pw = probs_wgrad[pi];
+  float* dbias_prev = probs_prev_wgrad ? probs_prev_wgrad[pi].dbias : nullptr;
   pdl_wait();  // the static problem tables are read above; the forward's outputs below
   const int B = pn.M, H = pn.N, AO = pn.K;
   float* gs = sm;
@@ -399,7 +404,7 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
     const MemberScalars msc = ctx.scalars[pn.member];
     const float* wmem = ws + (int64_t)pn.member * ws_member_floats;
     const float* log_std = params + (int64_t)pn.member * ctx.P + ctx.log_std_off;
-    const int t = blockIdx.x & 3;
+    const int t = pi & 3;
     for (int b = threadIdx.x; b < B; b += 256) {
       float g[AMAX];
       loss_row_grads<AMAX>(ctx, msc, wmem, wl, log_std, t, b, g);
@@ -496,7 +501,7 @@ bool last_bwd_recomputes_loss_grads(int H, int amax) {
   return getenv("IQL_B200_NO_LASTBWD_V4") == nullptr && getenv("IQL_B200_NO_LOSS_OVERLAP") == nullptr && (H % 4) == 0 && amax <= 8;
 }
 
-void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
+int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
                      int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st, const float* ws,
                      int64_t ws_member_floats, const WorkspaceLayout* wl, const float* params) {
   dim3 grid(nprob, (H + 63) / 64);
@@ -521,13 +526,21 @@ void launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, c
   const float* wsp = (wl && nprob % 4 == 0) ? ws : nullptr;  // 4 training nets per member, in table order
   if (v4 && amax <= 1)
     launch_pdl(last_bwd_v4_kernel<1>, grid4, dim3(256), smem4(1), st, 1, probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, wsp,
-               ws_member_floats, wlv, params);
+               ws_member_floats, wlv, params, 0, 0);
   else if (v4)
     launch_pdl(last_bwd_v4_kernel<8>, grid4, dim3(256), smem4(8), st, 1, probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, wsp,
-               ws_member_floats, wlv, params);
-  else if (amax <= 1) last_bwd_kernel<1><<<grid, 256, smem(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
-  else if (amax <= 8) last_bwd_kernel<8><<<grid, 256, smem(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
-  else last_bwd_kernel<24><<<grid, 256, smem(24), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx);
+               ws_member_floats, wlv, params, 0, 0);
+  else if (amax <= 1) last_bwd_kernel<1><<<grid, 256, smem(1), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, 0, 0);
+  else if (amax <= 8) last_bwd_kernel<8><<<grid, 256, smem(8), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, 0, 0);
+  else if (!no_v4 && (H % 4) == 0 && nprob % 4 == 0 && wl != nullptr && smem4(1) <= 200 * 1024) {
+    // wide policy head (pen: 24 actions): the three scalar-head nets of every member (V, Q1, Q2: problems 0..2 of each
+    // group of 4, table order) take the vectorised kernel, only the actor (problem 3) the generic one
+    launch_pdl(last_bwd_v4_kernel<1>, dim3(nprob / 4 * 3, (H + 255) / 256), dim3(256), smem4(1), st, 1, probs_dgrad, probs_wgrad,
+               probs_prev_wgrad, ctx, (const float*)nullptr, ws_member_floats, wlv, params, 3, 0);
+    last_bwd_kernel<24><<<dim3(nprob / 4, (H + 63) / 64), 256, smem(24), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, 1, 3);
+    return 2;
+  } else last_bwd_kernel<24><<<grid, 256, smem(24), st>>>(probs_dgrad, probs_wgrad, probs_prev_wgrad, ctx, 0, 0);
+  return 1;  // kernels launched
 }
 
 // ---------------------------------------------------------------------------
