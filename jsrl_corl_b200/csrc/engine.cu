@@ -713,7 +713,8 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   const bool out_ok = !no_skinny && A <= 64 && (size_t)(A <= 1 ? 1 : (A <= 8 ? 8 : (A <= 24 ? 24 : 64))) * H * 4 <= 200 * 1024;
   const bool last_ok = !no_skinny && A <= 24 && ((size_t)B * apad(A) + 256 * apad(A)) * 4 <= 200 * 1024;
   static const bool no_side = getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
-  const bool loss_recomputed = last_ok && last_bwd_recomputes_loss_grads(H, A) && e->bwd_phases.size() >= 2 &&
+  const bool loss_recomputed = last_ok && e->bwd_phases.size() >= 2 &&
+                               last_bwd_recomputes_loss_grads(H, A, e->bwd_phases[0].count, B) &&
                                e->bwd_phases[0].kind == PH_LAST_WGRAD && e->bwd_phases[1].kind == PH_LAST_DGRAD &&
                                e->bwd_phases[0].count % 4 == 0;
   bool skip_next = false, skip_colsum = false;

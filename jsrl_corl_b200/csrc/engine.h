@@ -143,7 +143,7 @@ void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cu
 // ws / wl / params != null and last_bwd_recomputes_loss_grads(H, amax): the kernel derives the loss gradients of its
 // rows itself (the problem tables hold 4 training nets per member: V, q1, q2, actor) and does not read gy / gpi, so
 // loss_kernel need not precede it.
-bool last_bwd_recomputes_loss_grads(int H, int amax);
+bool last_bwd_recomputes_loss_grads(int H, int amax, int nprob, int B);
 int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
                      int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st, const float* ws = nullptr,
                      int64_t ws_member_floats = 0, const WorkspaceLayout* wl = nullptr, const float* params = nullptr);

@@ -497,8 +497,14 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
   }
 }
 
-bool last_bwd_recomputes_loss_grads(int H, int amax) {
-  return getenv("IQL_B200_NO_LASTBWD_V4") == nullptr && getenv("IQL_B200_NO_LOSS_OVERLAP") == nullptr && (H % 4) == 0 && amax <= 8;
+// The vectorised kernel covers 256 columns x ALL batch rows per CTA: with few problems and a large batch (stress
+// shape: 4 problems x 4096 rows x 1024 columns = 16 CTAs) it leaves the GPU empty; the generic kernel then has 4x
+// the CTAs (64 columns each) and measured 3x faster.
+static bool last_bwd_v4_fills(int nprob, int B, int H) { return !(B >= 2048 && (int64_t)nprob * ((H + 255) / 256) < 64); }
+
+bool last_bwd_recomputes_loss_grads(int H, int amax, int nprob, int B) {
+  return getenv("IQL_B200_NO_LASTBWD_V4") == nullptr && getenv("IQL_B200_NO_LOSS_OVERLAP") == nullptr && (H % 4) == 0 && amax <= 8 &&
+         last_bwd_v4_fills(nprob, B, H);
 }
 
 int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
@@ -518,7 +524,7 @@ int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, co
     no_v4 = getenv("IQL_B200_NO_LASTBWD_V4") != nullptr;
     attr = true;
   }
-  const bool v4 = !no_v4 && (H % 4) == 0 && amax <= 8 && smem4(8) <= 200 * 1024;
+  const bool v4 = !no_v4 && (H % 4) == 0 && amax <= 8 && smem4(8) <= 200 * 1024 && last_bwd_v4_fills(nprob, B, H);
   const dim3 grid4(nprob, (H + 255) / 256);
   WorkspaceLayout wlv;
   memset(&wlv, 0, sizeof(wlv));
