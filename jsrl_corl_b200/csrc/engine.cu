@@ -69,6 +69,10 @@ struct iql_engine {
   int64_t w_off[4][16], b_off[4][16];
   int w_ld[4][16];
   int64_t log_std_off = 0;
+  // output-layer backward split by batch rows (few problems, large batch): lb_splits > 1, split problem tables at
+  // h_probs[lb_first ...] ordered [dgrad | wgrad | prev wgrad][split][member][net]
+  int lb_splits = 1;
+  int64_t lb_first = 0;
   // bound device memory
   float *params = nullptr, *exp_avg = nullptr, *exp_avg_sq = nullptr, *target = nullptr, *grads = nullptr;
   char* ws = nullptr;
@@ -190,6 +194,20 @@ static void build_layout(iql_engine* e) {
   wl.gy = region(3 * B);
   wl.gpi = region(B * wl.Ald);
   wl.gh = region((int64_t)4 * 2 * B * H);
+  // row split of the output-layer backward: enough CTAs to fill the GPU when there are few problems and many rows
+  e->lb_splits = 1;
+  wl.lb_scratch = 0;
+  wl.lb_stride = 0;
+  if (B >= 2048 && c.action_dim <= 24 && (H % 4) == 0 && getenv("IQL_B200_NO_LASTBWD_SPLIT") == nullptr) {
+    const int64_t ctas = (int64_t)4 * c.n_members * ((H + 255) / 256);
+    int sp = 1;
+    while (ctas * sp < 148 && sp * 2 <= B / 256 && B % (sp * 2) == 0 && sp < 32) sp *= 2;
+    if (sp > 1) {
+      e->lb_splits = sp;
+      wl.lb_stride = round_up((int64_t)std::max(c.action_dim, 1) * H + 32 + H, 32);  // dW partial, db partial, db_{L-1} partial
+      wl.lb_scratch = region((int64_t)4 * sp * wl.lb_stride);
+    }
+  }
   wl.xhi = wl.xlo = wl.bits = 0;
   if (c.math_mode == IQL_MATH_TF32_TCGEN05) {
     wl.xhi = region(B * e->layout.row.row_floats);
@@ -199,7 +217,7 @@ static void build_layout(iql_engine* e) {
   wl.member_floats = w;
 
   const int S = c.n_members;
-  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L);
+  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L) + (e->lb_splits > 1 ? (int64_t)12 * S * e->lb_splits : 0);
   int64_t tb = 0;
   auto tab = [&](int64_t bytes) { int64_t o = tb; tb = round_up(tb + bytes, 256); return o; };
   tab(sizeof(MemberScalars) * S);
@@ -455,6 +473,38 @@ static void build_problems(iql_engine* e) {
     px.count = (int)e->h_probs.size() - px.first;
     e->bwd_phases.push_back(px);
   }
+  // row-split copies of the output-layer backward problems: every split is a problem of its own over B / splits rows
+  // whose weight / bias gradient partials go to the scratch region; lb_reduce_kernel adds them up in split order
+  e->lb_first = (int64_t)e->h_probs.size();
+  if (e->lb_splits > 1 && e->bwd_phases.size() >= 3) {
+    const int sp = e->lb_splits, Bs = B / sp;
+    const Phase pw0 = e->bwd_phases[0], pn0 = e->bwd_phases[1], pv0 = e->bwd_phases[2];
+    for (int which = 0; which < 3; ++which)
+      for (int s_ = 0; s_ < sp; ++s_)
+        for (int m = 0; m < S; ++m)
+          for (int t = 0; t < 4; ++t) {
+            const int i = m * 4 + t;
+            float* scr = wsm(m) + wl.lb_scratch + ((int64_t)t * sp + s_) * wl.lb_stride;
+            GemmProb p;
+            if (which == 0) {  // dgrad: rows [s Bs, (s + 1) Bs)
+              p = e->h_probs[pn0.first + i];
+              p.A += (int64_t)s_ * Bs * p.lda;
+              p.C += (int64_t)s_ * Bs * p.ldc;
+              p.mask += (int64_t)s_ * Bs * p.ldmask;
+              p.M = Bs;
+            } else if (which == 1) {  // wgrad: partial dW_L [A][H], partial db_L
+              p = e->h_probs[pw0.first + i];
+              p.C = scr;
+              p.ldc = H;
+              p.dbias = scr + (int64_t)std::max(c.action_dim, 1) * H;
+              p.K = Bs;
+            } else {  // wgrad of the layer below: only its bias gradient (column sums of the G this kernel produces)
+              p = e->h_probs[pv0.first + i];
+              p.dbias = scr + (int64_t)std::max(c.action_dim, 1) * H + 32;
+            }
+            e->h_probs.push_back(p);
+          }
+  }
 }
 
 extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, float* exp_avg_sq, float* target,
@@ -469,7 +519,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   e->params = params; e->exp_avg = exp_avg; e->exp_avg_sq = exp_avg_sq; e->target = target; e->grads = grads;
   e->ws = (char*)workspace; e->ws_bytes = workspace_bytes;
   const int S = e->cfg.n_members, L = e->cfg.n_hidden;
-  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L);
+  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L) + (e->lb_splits > 1 ? (int64_t)12 * S * e->lb_splits : 0);
   int64_t tb = 0;
   auto tab = [&](int64_t bytes) { char* o = e->ws + tb; tb = round_up(tb + bytes, 256); return o; };
   e->d_scalars = (MemberScalars*)tab(sizeof(MemberScalars) * S);
@@ -780,6 +830,13 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       // fused wgrad + dgrad of the output layer; it also emits db_{L-1} when layer L-1 is a hidden-layer
       // tcgen05 wgrad phase (whose kernel does not produce bias gradients)
       const bool emit_db = next2 && tf32 && next2->umma_ok && umma_phase_supported(2, B, H);
+      if (e->lb_splits > 1 && e->bwd_phases.size() >= 3 && ph.first == e->bwd_phases[0].first) {
+        const int sp = e->lb_splits, n = ph.count * sp;
+        const GemmProb* t0 = e->d_probs + e->lb_first;
+        launches += launch_last_bwd(t0, t0 + n, emit_db ? t0 + 2 * n : nullptr, n, B / sp, H, A, ctx, st, nullptr,
+                                    e->wl.member_floats, &e->wl, e->params);
+        launch_lb_reduce(t0 + n, emit_db ? t0 + 2 * n : nullptr, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, sp, H, st);
+      } else
       launches += -1 + launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st,
                       loss_recomputed ? e->d_ws_f : nullptr, e->wl.member_floats, &e->wl, e->params);
       skip_next = true;

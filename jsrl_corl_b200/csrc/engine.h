@@ -118,6 +118,7 @@ struct WorkspaceLayout {
   int64_t gh;        // [4][2][B][H]  ping-pong activation gradients of the 4 trainable nets
   int64_t xhi, xlo;  // [B][ROW] each: TF32 hi / lo split of the gathered rows (tcgen05 mode)
   int64_t bits;      // [4][L-1][B][H/32] uint32: ReLU sign bits of H_1..H_{L-1} of the 4 training passes (tcgen05 mode)
+  int64_t lb_scratch, lb_stride;  // [4][splits][lb_stride]: row-split partials of the output-layer backward (0: unused)
   int64_t member_floats;
   int Ald;
 };
@@ -144,6 +145,10 @@ void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cu
 // rows itself (the problem tables hold 4 training nets per member: V, q1, q2, actor) and does not read gy / gpi, so
 // loss_kernel need not precede it.
 bool last_bwd_recomputes_loss_grads(int H, int amax, int nprob, int B);
+// row-split output-layer backward: dW_L, db_L (and db_{L-1}) of problem i = sum over s of the partials the split
+// problems [s * nprob + i] wrote, added in split order
+void launch_lb_reduce(const GemmProb* pw_split, const GemmProb* prev_split, const GemmProb* pw, const GemmProb* prev, int nprob,
+                      int splits, int H, cudaStream_t st);
 int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
                      int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st, const float* ws = nullptr,
                      int64_t ws_member_floats = 0, const WorkspaceLayout* wl = nullptr, const float* params = nullptr);

@@ -422,12 +422,13 @@ def test_philox_dropout_masks_equal_cpu_restatement_and_oracle(math_mode, H, B):
 
 
 @pytest.mark.parametrize("B,H,L,A", [(384, 512, 3, 3), (128, 256, 1, 6), (512, 256, 2, 24), (256, 512, 2, 4),
-                                     (256, 256, 1, 3), (256, 256, 4, 2), (384, 256, 2, 8)])
+                                     (256, 256, 1, 3), (256, 256, 4, 2), (384, 256, 2, 8), (2048, 256, 2, 3), (2048, 512, 2, 24)])
 def test_tcgen05_path_general_shapes_match_oracle(B, H, L, A):
     """Batch sizes that are multiples of 128, hidden widths that are multiples of 256 (several N tiles and
     M tiles per problem), one to four hidden layers, wide action spaces: TF32 path vs the numpy oracle.
     Hidden width 256 runs the fused forward (CTA pairs when the batch is a multiple of 256, one CTA per 128 rows
-    otherwise; 1 and 3 hidden layers end in TMEM region 0, 2 and 4 in region 1); 512 runs one launch per layer."""
+    otherwise; 1 and 3 hidden layers end in TMEM region 0, 2 and 4 in region 1); 512 runs one launch per layer.
+    Batch 2048 with 2 members: the output-layer backward is split by batch rows (8 splits) and reduced in split order."""
     from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
     from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
     from oracle.philox import philox_indices
@@ -498,6 +499,56 @@ def test_fused_forward_several_tiles_per_cta_pair_match_oracle(S_dim, A, dropout
         assert _loss_errors(out["tf32"][m], np.array(ref)).max() < TF32_TOL, (m, out["tf32"][m], ref)
         worst, where = tree_max_rel(trees[m], orc.state())
         assert worst < TF32_W30_TOL, (m, worst, where)
+
+
+def test_row_split_output_layer_backward(monkeypatch):
+    """Batch 2048, one member: the output-layer backward runs as 16 row splits + a fixed-order reduction.  FP32
+    path: gradients of one step against the fp64 oracle (the bar of test_gradients_single_step_against_oracle).
+    Both paths: against the same step with the split switched off -- only the summation order of dW_L, db_L and
+    db_{L-1} changes, everything downstream of the (identical) activation gradients is bit-identical."""
+    from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
+    from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
+    from oracle.philox import philox_indices
+    import oracle.iql_numpy as onp
+
+    S_dim, A, H, L, B, n_rows = 11, 3, 256, 2, 2048, 6000
+    data = synthetic_dataset(n_rows, S_dim, A, 3)
+    rb = ReplayBuffer(S_dim, A, n_rows, "cuda")
+    rb.load_d4rl_dataset(data)
+
+    def one_step(math_mode):
+        ens = IQLEnsemble(1, S_dim, A, H, L, B, deterministic=False, math_mode=math_mode, seeds=[9], max_steps_per_call=2,
+                          hparams=[dict(cosine_t_max=50)])
+        ens.bind_replay(rb)
+        init = {g: {k: v.copy() for k, v in d.items()} for g, d in _cpu_tree(ens.engine.param_views(0)).items()}
+        losses = ens.train_steps(1).cpu().numpy()[0, 0]
+        gv = _cpu_tree(ens.engine.grad_views(0))
+        return init, losses, {**gv["qf"], **gv["vf"], **gv["actor"]}
+
+    for math_mode in ("fp32", "tf32"):
+        monkeypatch.delenv("IQL_B200_NO_LASTBWD_SPLIT", raising=False)
+        init, losses, grads = one_step(math_mode)
+        monkeypatch.setenv("IQL_B200_NO_LASTBWD_SPLIT", "1")
+        _, losses0, grads0 = one_step(math_mode)
+        assert np.array_equal(losses, losses0)  # the forward and the losses do not depend on the split
+        for k in grads:
+            assert rel_err(grads[k], grads0[k]) < 1e-5, (math_mode, k, rel_err(grads[k], grads0[k]))
+        if math_mode == "fp32":
+            orc = NumpyIQL(OracleConfig(S_dim, A, H, L, False, 0.0, max_steps=50), init, np.float64)
+            ref_grads = {}
+
+            class Spy(onp._Adam):
+                def step(self, gr):
+                    ref_grads.update(gr)
+                    super().step(gr)
+
+            for o in (orc.q_opt, orc.v_opt, orc.a_opt):
+                o.__class__ = Spy
+            lo = orc.train(batch_from(data, philox_indices(9, 0, n_rows, B)))
+            ref = np.array([lo["value_loss"], lo["q_loss"], lo["actor_loss"]])
+            assert _loss_errors(losses, ref).max() < 1e-5
+            for k, rg in ref_grads.items():
+                assert rel_err(grads[k], rg) < 2e-5, (k, rel_err(grads[k], rg))
 
 
 def test_facade_batch_size_change_and_partial_load_keep_state():
