@@ -198,10 +198,11 @@ static void build_layout(iql_engine* e) {
   e->lb_splits = 1;
   wl.lb_scratch = 0;
   wl.lb_stride = 0;
-  if (B >= 2048 && c.action_dim <= 24 && (H % 4) == 0 && getenv("IQL_B200_NO_LASTBWD_SPLIT") == nullptr) {
+  // (stress shape: 4 problems x 4096 rows; single learners: 4 problems x 256 rows, 8 splits of 32 rows)
+  if ((B >= 2048 || c.n_members <= 4) && c.action_dim <= 24 && (H % 4) == 0 && getenv("IQL_B200_NO_LASTBWD_SPLIT") == nullptr) {
     const int64_t ctas = (int64_t)4 * c.n_members * ((H + 255) / 256);
     int sp = 1;
-    while (ctas * sp < 148 && sp * 2 <= B / 256 && B % (sp * 2) == 0 && sp < 32) sp *= 2;
+    while (ctas * sp < 148 && B / (sp * 2) >= 32 && B % (sp * 2) == 0 && sp < 32) sp *= 2;
     if (sp > 1) {
       e->lb_splits = sp;
       wl.lb_stride = round_up((int64_t)std::max(c.action_dim, 1) * H + 32 + H, 32);  // dW partial, db partial, db_{L-1} partial
@@ -492,6 +493,7 @@ static void build_problems(iql_engine* e) {
               p.C += (int64_t)s_ * Bs * p.ldc;
               p.mask += (int64_t)s_ * Bs * p.ldmask;
               p.M = Bs;
+              p.row0 = s_ * Bs;
             } else if (which == 1) {  // wgrad: partial dW_L [A][H], partial db_L
               p = e->h_probs[pw0.first + i];
               p.C = scr;
@@ -764,7 +766,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   const bool last_ok = !no_skinny && A <= 24 && ((size_t)B * apad(A) + 256 * apad(A)) * 4 <= 200 * 1024;
   static const bool no_side = getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
   const bool loss_recomputed = last_ok && e->bwd_phases.size() >= 2 &&
-                               last_bwd_recomputes_loss_grads(H, A, e->bwd_phases[0].count, B) &&
+                               last_bwd_recomputes_loss_grads(H, A, e->bwd_phases[0].count * e->lb_splits, B / e->lb_splits) &&
                                e->bwd_phases[0].kind == PH_LAST_WGRAD && e->bwd_phases[1].kind == PH_LAST_DGRAD &&
                                e->bwd_phases[0].count % 4 == 0;
   bool skip_next = false, skip_colsum = false;
@@ -833,8 +835,8 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       if (e->lb_splits > 1 && e->bwd_phases.size() >= 3 && ph.first == e->bwd_phases[0].first) {
         const int sp = e->lb_splits, n = ph.count * sp;
         const GemmProb* t0 = e->d_probs + e->lb_first;
-        launches += launch_last_bwd(t0, t0 + n, emit_db ? t0 + 2 * n : nullptr, n, B / sp, H, A, ctx, st, nullptr,
-                                    e->wl.member_floats, &e->wl, e->params);
+        launches += launch_last_bwd(t0, t0 + n, emit_db ? t0 + 2 * n : nullptr, n, B / sp, H, A, ctx, st,
+                                    loss_recomputed ? e->d_ws_f : nullptr, e->wl.member_floats, &e->wl, e->params);
         launch_lb_reduce(t0 + n, emit_db ? t0 + 2 * n : nullptr, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, sp, H, st);
       } else
       launches += -1 + launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st,

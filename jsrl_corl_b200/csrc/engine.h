@@ -33,6 +33,7 @@ struct GemmProb {
   int member;
   int drop_layer;      // >= 0: hidden-layer index whose dropout applies (actor only)
   int no_store;        // 1: C is consumed only by a fused follow-up (forward-only passes), skip the store
+  int row0;            // row-split output-layer backward: first batch row of this split (A, C, mask already point at it)
   // ReLU sign bits of a hidden activation, [rows][N / 32] words, bit j of word (r, c) = H[r][32 c + j] > 0:
   // written by the fused forward for the layers a tcgen05 dgrad phase masks with, read by that dgrad phase
   uint32_t* bits;

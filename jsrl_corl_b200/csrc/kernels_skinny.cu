@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
     const int t = pi & 3;
     for (int b = threadIdx.x; b < B; b += 256) {
       float g[AMAX];
-      loss_row_grads<AMAX>(ctx, msc, wmem, wl, log_std, t, b, g);
+      loss_row_grads<AMAX>(ctx, msc, wmem, wl, log_std, t, b + pn.row0, g);
 #pragma unroll
       for (int a = 0; a < AMAX; ++a) gs[b * AMAX + a] = g[a];
     }
