@@ -73,6 +73,10 @@ struct iql_engine {
   // h_probs[lb_first ...] ordered [dgrad | wgrad | prev wgrad][split][member][net]
   int lb_splits = 1;
   int64_t lb_first = 0;
+  // input-layer weight gradient (tcgen05 path) split along the batch (K) dimension: fw_splits > 1, split problems in
+  // fw_phase ([split][member][net]); partial dW_0 / db_0 in the scratch region, reduced by lb_reduce_kernel
+  int fw_splits = 1;
+  Phase fw_phase;
   // bound device memory
   float *params = nullptr, *exp_avg = nullptr, *exp_avg_sq = nullptr, *target = nullptr, *grads = nullptr;
   char* ws = nullptr;
@@ -209,6 +213,20 @@ static void build_layout(iql_engine* e) {
       wl.lb_scratch = region((int64_t)4 * sp * wl.lb_stride);
     }
   }
+  e->fw_splits = 1;
+  wl.fw_scratch = 0;
+  wl.fw_stride = 0;
+  if (B >= 2048 && c.math_mode == IQL_MATH_TF32_TCGEN05 && getenv("IQL_B200_NO_FIRST_WGRAD_SPLIT") == nullptr) {
+    const int64_t tiles = (int64_t)4 * c.n_members * ((H + 127) / 128);
+    int sp = 1;
+    while (tiles * sp < 148 && B / (sp * 2) >= 256 && B % (sp * 2) == 0 && sp < 16) sp *= 2;
+    if (sp > 1) {
+      e->fw_splits = sp;
+      const int64_t ldmax = round_up(c.state_dim + c.action_dim, 4);
+      wl.fw_stride = round_up((int64_t)H * ldmax + H, 32);  // dW_0 partial [H][ld], db_0 partial [H]
+      wl.fw_scratch = region((int64_t)4 * sp * wl.fw_stride);
+    }
+  }
   wl.xhi = wl.xlo = wl.bits = 0;
   if (c.math_mode == IQL_MATH_TF32_TCGEN05) {
     wl.xhi = region(B * e->layout.row.row_floats);
@@ -218,7 +236,8 @@ static void build_layout(iql_engine* e) {
   wl.member_floats = w;
 
   const int S = c.n_members;
-  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L) + (e->lb_splits > 1 ? (int64_t)12 * S * e->lb_splits : 0);
+  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L) + (e->lb_splits > 1 ? (int64_t)12 * S * e->lb_splits : 0) +
+                        (e->fw_splits > 1 ? (int64_t)4 * S * e->fw_splits : 0);
   int64_t tb = 0;
   auto tab = [&](int64_t bytes) { int64_t o = tb; tb = round_up(tb + bytes, 256); return o; };
   tab(sizeof(MemberScalars) * S);
@@ -496,8 +515,7 @@ static void build_problems(iql_engine* e) {
               p.row0 = s_ * Bs;
             } else if (which == 1) {  // wgrad: partial dW_L [A][H], partial db_L
               p = e->h_probs[pw0.first + i];
-              p.C = scr;
-              p.ldc = H;
+              p.C = scr;  // ldc stays that of dW_L (= H)
               p.dbias = scr + (int64_t)std::max(c.action_dim, 1) * H;
               p.K = Bs;
             } else {  // wgrad of the layer below: only its bias gradient (column sums of the G this kernel produces)
@@ -506,6 +524,31 @@ static void build_problems(iql_engine* e) {
             }
             e->h_probs.push_back(p);
           }
+  }
+  // K-split copies of the input-layer weight-gradient problems (G_0 and X rows [s Bs, (s + 1) Bs))
+  e->fw_phase = Phase();
+  if (e->fw_splits > 1 && !e->bwd_phases.empty() && e->bwd_phases.back().kind == PH_FIRST_WGRAD) {
+    const int sp = e->fw_splits, Bs = B / sp;
+    const Phase p0 = e->bwd_phases.back();
+    Phase pf = p0;
+    pf.first = (int)e->h_probs.size();
+    pf.K = Bs;
+    for (int s_ = 0; s_ < sp; ++s_)
+      for (int m = 0; m < S; ++m)
+        for (int t = 0; t < 4; ++t) {
+          GemmProb p = e->h_probs[p0.first + m * 4 + t];
+          float* scr = wsm(m) + wl.fw_scratch + ((int64_t)t * sp + s_) * wl.fw_stride;
+          p.A += (int64_t)s_ * Bs * p.lda;
+          p.B += (int64_t)s_ * Bs * p.ldb;
+          p.K = Bs;
+          p.C = scr;  // same ldc as dW_0
+          p.dbias = p.dbias ? scr + (int64_t)p.M * p.ldc : nullptr;
+          e->h_probs.push_back(p);
+        }
+    pf.count = (int)e->h_probs.size() - pf.first;
+    e->fw_phase = pf;
+  } else {
+    e->fw_splits = 1;
   }
 }
 
@@ -521,7 +564,8 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   e->params = params; e->exp_avg = exp_avg; e->exp_avg_sq = exp_avg_sq; e->target = target; e->grads = grads;
   e->ws = (char*)workspace; e->ws_bytes = workspace_bytes;
   const int S = e->cfg.n_members, L = e->cfg.n_hidden;
-  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L) + (e->lb_splits > 1 ? (int64_t)12 * S * e->lb_splits : 0);
+  const int64_t nprob = (int64_t)S * ((L + 1) * N_PASS + 4 * (L + 1) + 4 * L) + (e->lb_splits > 1 ? (int64_t)12 * S * e->lb_splits : 0) +
+                        (e->fw_splits > 1 ? (int64_t)4 * S * e->fw_splits : 0);
   int64_t tb = 0;
   auto tab = [&](int64_t bytes) { char* o = e->ws + tb; tb = round_up(tb + bytes, 256); return o; };
   e->d_scalars = (MemberScalars*)tab(sizeof(MemberScalars) * S);
@@ -564,6 +608,13 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
       ph.rowepi = (hidden_dgrad || (ph.mode == 2 && ph.kind == PH_GENERIC && tc_mode && getenv("IQL_B200_ROWEPI_WGRAD"))) &&
                   getenv("IQL_B200_NO_ROWEPI") == nullptr;
     }
+  if (e->fw_splits > 1) {
+    Phase& pf = e->fw_phase;
+    pf.maxK = 0;
+    for (int i = 0; i < pf.count; ++i) pf.maxK = std::max(pf.maxK, e->h_probs[pf.first + i].K);
+    pf.cta2 = pf.umma_ok && umma_cta2(pf.mode, pf.count, pf.maxM, pf.maxN, pf.maxK);
+    pf.rowepi = false;
+  }
   if ((int64_t)e->h_probs.size() != nprob) return fail(e, IQL_ERR_STATE, "internal: problem count mismatch");
   e->h_maps.assign((size_t)128 * 2 * nprob, 0);
   if (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) {
@@ -597,6 +648,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
         return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (3xTF32 input layer)");
     }
     for (const Phase& ph : e->bwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward phase)");
+    if (e->fw_splits > 1 && encode(e->fw_phase)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (split input-layer wgrad)");
     e->h_maps_c.assign((size_t)128 * nprob, 0);
     for (const Phase& ph : e->bwd_phases)
       if (ph.rowepi)
@@ -837,7 +889,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
         const GemmProb* t0 = e->d_probs + e->lb_first;
         launches += launch_last_bwd(t0, t0 + n, emit_db ? t0 + 2 * n : nullptr, n, B / sp, H, A, ctx, st,
                                     loss_recomputed ? e->d_ws_f : nullptr, e->wl.member_floats, &e->wl, e->params);
-        launch_lb_reduce(t0 + n, emit_db ? t0 + 2 * n : nullptr, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, sp, H, st);
+        launch_lb_reduce(t0 + n, emit_db ? t0 + 2 * n : nullptr, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, sp, st);
       } else
       launches += -1 + launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st,
                       loss_recomputed ? e->d_ws_f : nullptr, e->wl.member_floats, &e->wl, e->params);
@@ -925,6 +977,14 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     const Phase* n2 = i + 2 < e->bwd_phases.size() ? &e->bwd_phases[i + 2] : nullptr;
     const bool leaf = two_streams && ph.mode == 2 && ph.kind == PH_GENERIC && ph.umma_ok &&
                       umma_phase_supported(2, B, H) && !skip_next;
+    if (ph.kind == PH_FIRST_WGRAD && e->fw_splits > 1 && tf32 && ph.umma_ok && umma_phase_supported(2, B, H) && !skip_next) {
+      // few problems x a long batch: the tcgen05 kernel runs the K-split copies (enough tiles to fill the GPU), then the
+      // partial dW_0 / db_0 are added up in split order
+      run_phase(e->fw_phase, nullptr, nullptr);  // batch > 256: the phase also runs colsum_kernel (partial db_0)
+      launch_lb_reduce(e->d_probs + e->fw_phase.first, nullptr, e->d_probs + ph.first, nullptr, ph.count, e->fw_splits, st);
+      ++launches;
+      continue;
+    }
     if (leaf) {
       // G_l (written by the previous launch) -> side stream.  The previous leaf must be done first: the dgrad that
       // follows on the main stream overwrites the ping-pong buffer that leaf was reading.

@@ -120,6 +120,7 @@ struct WorkspaceLayout {
   int64_t xhi, xlo;  // [B][ROW] each: TF32 hi / lo split of the gathered rows (tcgen05 mode)
   int64_t bits;      // [4][L-1][B][H/32] uint32: ReLU sign bits of H_1..H_{L-1} of the 4 training passes (tcgen05 mode)
   int64_t lb_scratch, lb_stride;  // [4][splits][lb_stride]: row-split partials of the output-layer backward (0: unused)
+  int64_t fw_scratch, fw_stride;  // [4][splits][fw_stride]: K-split partials of the input-layer weight gradient (0: unused)
   int64_t member_floats;
   int Ald;
 };
@@ -148,8 +149,10 @@ void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cu
 bool last_bwd_recomputes_loss_grads(int H, int amax, int nprob, int B);
 // row-split output-layer backward: dW_L, db_L (and db_{L-1}) of problem i = sum over s of the partials the split
 // problems [s * nprob + i] wrote, added in split order
+// (rows = M of the wgrad problem, N valid columns per row, both tables with the leading dimension of dW; also used
+// for the K-split input-layer weight gradient)
 void launch_lb_reduce(const GemmProb* pw_split, const GemmProb* prev_split, const GemmProb* pw, const GemmProb* prev, int nprob,
-                      int splits, int H, cudaStream_t st);
+                      int splits, cudaStream_t st);
 int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, const GemmProb* probs_prev_wgrad,
                      int nprob, int B, int H, int amax, const StepCtx& ctx, cudaStream_t st, const float* ws = nullptr,
                      int64_t ws_member_floats = 0, const WorkspaceLayout* wl = nullptr, const float* params = nullptr);

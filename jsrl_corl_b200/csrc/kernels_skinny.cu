@@ -551,18 +551,18 @@ int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, co
 
 __global__ void __launch_bounds__(256) lb_reduce_kernel(const GemmProb* __restrict__ pw_split, const GemmProb* __restrict__ prev_split,
                                                         const GemmProb* __restrict__ pw, const GemmProb* __restrict__ prev, int nprob,
-                                                        int splits, int H) {
+                                                        int splits) {
   const int i = blockIdx.x;
   const GemmProb o = pw[i];
-  const int AO = o.M;
-  const int n_dw = AO * H, n_all = n_dw + AO + (prev ? H : 0);
+  const int R = o.M, W = o.N, ld = o.ldc;  // dW is [R][W] with leading dimension ld in the output and in every partial
+  const int n_dw = R * W, n_all = n_dw + R + (prev ? W : 0);
   for (int e = blockIdx.y * 256 + threadIdx.x; e < n_all; e += gridDim.y * 256) {
     float s = 0.f;
     if (e < n_dw) {
-      const int a = e / H, n = e - a * H;
-      for (int k = 0; k < splits; ++k) s += pw_split[k * nprob + i].C[(int64_t)a * H + n];
-      o.C[(int64_t)a * o.ldc + n] = s;
-    } else if (e < n_dw + AO) {
+      const int a = e / W, n = e - a * W;
+      for (int k = 0; k < splits; ++k) s += pw_split[k * nprob + i].C[(int64_t)a * ld + n];
+      o.C[(int64_t)a * ld + n] = s;
+    } else if (e < n_dw + R) {
       if (o.dbias != nullptr) {
         for (int k = 0; k < splits; ++k) s += pw_split[k * nprob + i].dbias[e - n_dw];
         o.dbias[e - n_dw] = s;
@@ -570,16 +570,16 @@ __global__ void __launch_bounds__(256) lb_reduce_kernel(const GemmProb* __restri
     } else {
       float* dst = prev[i].dbias;
       if (dst != nullptr) {
-        for (int k = 0; k < splits; ++k) s += prev_split[k * nprob + i].dbias[e - n_dw - AO];
-        dst[e - n_dw - AO] = s;
+        for (int k = 0; k < splits; ++k) s += prev_split[k * nprob + i].dbias[e - n_dw - R];
+        dst[e - n_dw - R] = s;
       }
     }
   }
 }
 
 void launch_lb_reduce(const GemmProb* pw_split, const GemmProb* prev_split, const GemmProb* pw, const GemmProb* prev, int nprob,
-                      int splits, int H, cudaStream_t st) {
-  lb_reduce_kernel<<<dim3(nprob, 8), 256, 0, st>>>(pw_split, prev_split, pw, prev, nprob, splits, H);
+                      int splits, cudaStream_t st) {
+  lb_reduce_kernel<<<dim3(nprob, 8), 256, 0, st>>>(pw_split, prev_split, pw, prev, nprob, splits);
 }
 
 // ---------------------------------------------------------------------------
