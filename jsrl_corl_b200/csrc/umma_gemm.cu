@@ -542,7 +542,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
 }
 
 // bias gradient of the wgrad phases: dbias[m] = sum_k A[k][m]  (A = G, [K = batch rows][M] row-major).
-// 1024 threads = 32 columns x 32 row groups: coalesced 128-byte row segments, 8 independent loads in flight per
+// 1024 threads = 32 columns x 32 row groups: coalesced 128-byte row segments, 16 / 8 independent loads in flight per
 // thread, fixed summation order.  (256 threads with 4 loads in flight walked 512 rows per thread at batch 4096:
 // 75 us of pure load latency per launch on the stress shape.)
 __global__ void __launch_bounds__(1024) colsum_kernel(const GemmProb* __restrict__ probs) {
@@ -554,6 +554,13 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const GemmProb* __restrict
   if (m < p.M && p.dbias != nullptr) {
     const float* col = p.A + m;
     int k = g;
+    for (; k + 15 * 32 < p.K; k += 16 * 32) {
+      float a[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = col[(int64_t)(k + 32 * j) * p.lda];
+      s += (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) +
+           (((a[8] + a[9]) + (a[10] + a[11])) + ((a[12] + a[13]) + (a[14] + a[15])));
+    }
     for (; k + 7 * 32 < p.K; k += 8 * 32) {
       float a[8];
 #pragma unroll
