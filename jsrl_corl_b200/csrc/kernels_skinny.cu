@@ -100,12 +100,12 @@ void launch_first_fwd(const GemmProb* probs, int nprob, int B, int H, int kmax, 
 }
 
 // ---------------------------------------------------------------------------
-// output layer forward.  grid (nprob, ceil(B/ROWS)), 256 threads = 8 warps, one warp per row at a time, lanes stride
-// the hidden dimension.  ROWS rows per CTA amortise the staging of the [N][K] weights in shared memory (with 32
-// rows per CTA the 24 KB weight load of a 24-action head took 10x longer than the dot products).
+// output layer forward.  grid (nprob, ceil(B/rows)), 256 threads = 8 warps, one warp per row at a time, lanes stride
+// the hidden dimension.  `rows` per CTA is chosen by the launcher so that the launch is a whole number of waves
+// (the stress shape ran 896 CTAs on 740 resident slots: 1.21 waves, i.e. twice the time of one).
 // ---------------------------------------------------------------------------
-template <int AMAX, int ROWS>
-__global__ void __launch_bounds__(256) out_fwd_kernel(const GemmProb* __restrict__ probs) {
+template <int AMAX>
+__global__ void __launch_bounds__(256) out_fwd_kernel(const GemmProb* __restrict__ probs, int rows) {
   extern __shared__ float wsm[];  // [N][K]
   const GemmProb p = probs[blockIdx.x];
   const int K = p.K, N = p.N;
@@ -120,18 +120,35 @@ __global__ void __launch_bounds__(256) out_fwd_kernel(const GemmProb* __restrict
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rr = warp; rr < ROWS; rr += 8) {
-    const int row = blockIdx.y * ROWS + rr;
+  for (int rr = warp; rr < rows; rr += 8) {
+    const int row = blockIdx.y * rows + rr;
     if (row >= p.M) break;
     float acc[AMAX];
 #pragma unroll
     for (int m = 0; m < AMAX; ++m) acc[m] = 0.f;
     const float* h = p.A + (int64_t)row * p.lda;
-    for (int k = lane; k < K; k += 32) {
-      const float x = h[k];
+    if (((K | p.lda) & 3) == 0) {  // 16-byte loads of the row and of the weights
+      const float4* h4 = reinterpret_cast<const float4*>(h);
+      for (int k4 = lane; k4 < (K >> 2); k4 += 32) {
+        const float4 x = h4[k4];
 #pragma unroll
-      for (int m = 0; m < AMAX; ++m)
-        if (m < N) acc[m] = fmaf(x, wsm[m * K + k], acc[m]);
+        for (int m = 0; m < AMAX; ++m) {
+          if (m < N) {
+            const float4 w = *reinterpret_cast<const float4*>(&wsm[m * K + 4 * k4]);
+            acc[m] = fmaf(x.x, w.x, acc[m]);
+            acc[m] = fmaf(x.y, w.y, acc[m]);
+            acc[m] = fmaf(x.z, w.z, acc[m]);
+            acc[m] = fmaf(x.w, w.w, acc[m]);
+          }
+        }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        const float x = h[k];
+#pragma unroll
+        for (int m = 0; m < AMAX; ++m)
+          if (m < N) acc[m] = fmaf(x, wsm[m * K + k], acc[m]);
+      }
     }
 #pragma unroll
     for (int m = 0; m < AMAX; ++m) {
@@ -187,33 +204,47 @@ __global__ void __launch_bounds__(128) out_fwd_rows_kernel(const GemmProb* __res
     if (m < N) out[m] = acc[m] + p.bias[m];
 }
 
+// rows per CTA: the multiple of 8 that minimises (waves of resident CTAs) x (rows + the weight staging, ~8 rows' worth)
+template <int AMAX>
+static void launch_out_fwd_t(const GemmProb* probs, int nprob, int B, size_t sm, cudaStream_t st) {
+  static int per_sm = 0, n_sm = 0;
+  static size_t sm_of = 0;
+  if (!per_sm || sm_of != sm) {
+    sm_of = sm;
+    cudaFuncSetAttribute(out_fwd_kernel<AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, out_fwd_kernel<AMAX>, 256, sm) != cudaSuccess || per_sm <= 0) per_sm = 1;
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const int64_t slots = (int64_t)per_sm * n_sm;
+  int best = 32;
+  int64_t best_cost = -1;
+  for (int rows = 8; rows <= ((B + 7) / 8) * 8; rows += 8) {
+    const int64_t ctas = (int64_t)nprob * ((B + rows - 1) / rows);
+    const int64_t cost = ((ctas + slots - 1) / slots) * (rows + 8);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rows; }
+  }
+  out_fwd_kernel<AMAX><<<dim3(nprob, (B + best - 1) / best), 256, sm, st>>>(probs, best);
+}
+
 void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cudaStream_t st) {
   const size_t sm = (size_t)amax * H * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(out_fwd_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_kernel<8, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_kernel<24, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_kernel<24, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(out_fwd_rows_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
-  // few problems (single learner): 32 rows per CTA keep the GPU busy; ensembles: 128 rows per CTA
-  const bool big = (int64_t)nprob * ((B + 127) / 128) >= 296;
-  dim3 grid(nprob, big ? (B + 127) / 128 : (B + 31) / 32);
-  if (amax <= 1) out_fwd_kernel<1, 32><<<dim3(nprob, (B + 31) / 32), 256, sm, st>>>(probs);
-  else if (amax <= 8) {
-    if (big) out_fwd_kernel<8, 128><<<grid, 256, sm, st>>>(probs);
-    else out_fwd_kernel<8, 32><<<grid, 256, sm, st>>>(probs);
-  } else if (amax <= 24) {
+  if (amax <= 1) launch_out_fwd_t<1>(probs, nprob, B, sm, st);
+  else if (amax <= 8) launch_out_fwd_t<8>(probs, nprob, B, sm, st);
+  else if (amax <= 24) {
     static const bool no_rows = getenv("IQL_B200_NO_OUT_ROWS") != nullptr;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(out_fwd_rows_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    const bool big = (int64_t)nprob * ((B + 127) / 128) >= 296;
     if (big && (H & 3) == 0 && !no_rows)
       out_fwd_rows_kernel<24><<<dim3(nprob, (B + 127) / 128), 128, (size_t)24 * H * sizeof(float), st>>>(probs);
-    else if (big) out_fwd_kernel<24, 128><<<grid, 256, sm, st>>>(probs);
-    else out_fwd_kernel<24, 32><<<grid, 256, sm, st>>>(probs);
-  } else out_fwd_kernel<64, 128><<<dim3(nprob, (B + 127) / 128), 256, sm, st>>>(probs);
+    else launch_out_fwd_t<24>(probs, nprob, B, sm, st);
+  } else launch_out_fwd_t<64>(probs, nprob, B, sm, st);
 }
 
 // ---------------------------------------------------------------------------
