@@ -12,9 +12,10 @@ Default workload = BASELINE.json configs[2]: halfcheetah-medium-replay shape
 per GPU (weak scaling); members never exchange data -- the only collective is
 the NCCL all-gather of the per-step loss scalars.
 
-`--impl reference` times the reference's CPU implementation of the same path
-(the numpy port under oracle/, since /root/reference does not travel to the GPU
-box) on the host cores, one member, a bounded number of steps.
+`--impl reference` times the UNMODIFIED reference classes (offline/iql.py, staged under
+oracle/_ref by __graft_entry__.build()) on the host cores -- one member, all threads and one
+thread, 1M-row buffer, a bounded number of steps -- and the same code with device="cuda"
+(`torch_eager_b200`: what a user of the reference gets on this GPU today).
 """
 import argparse
 import json
@@ -110,6 +111,20 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+TF32_NOMINAL_TFLOPS = 1125.0  # B200 dense TF32 = half of the 2.25 PFLOP/s bf16 figure
+
+
+def pinned_tf32_peak(torch, device):
+    """The TF32 denominator is PINNED: profiles/tf32_peak.json (one measurement of cuBLAS TF32 8192^3 on this pool's
+    B200, committed with its method and clocks).  Only when that file is absent is it measured live."""
+    path = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["tf32_tflops_sustained"]), "pinned: profiles/tf32_peak.json (" + d.get("how", "") + ")"
+    return measure_tf32_peak(torch, device), "cuBLAS TF32 8192^3 measured live (profiles/tf32_peak.json missing)"
+
+
 def measure_tf32_peak(torch, device):
     """cuBLAS TF32 8192^3 GEMM, sustained for ~1.5 s, same method as MEASURED_PEAKS.json uses for bf16
     (the file has no TF32 entry).  Library call used as a yardstick only."""
@@ -135,15 +150,117 @@ def measure_tf32_peak(torch, device):
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the reference algorithm on the host cores (numpy port of the oracle)
+# Reference arm: the UNMODIFIED reference classes (algorithms/offline/iql.py, staged under oracle/_ref by
+# __graft_entry__.build()) on the host cores -- and, as "what users get today", on the GPU in stock eager mode.
+# Falls back to the numpy port of the oracle (kind "port") only when the staged files are missing.
 # ---------------------------------------------------------------------------
-def cpu_reference_steps_per_sec(w, steps, warmup, n_rows=200_000):
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def build_reference_trainer(w, device, n_rows, seed=0):
+    """ReplayBuffer + ImplicitQLearning of the unmodified reference (offline/iql.py:125-184, 397-537) on `device`,
+    built the way offline/iql.py:564-621 builds them (class-default Adam, TwinQ -> V -> policy order)."""
+    import contextlib
+    import io
+
+    import torch
+
+    from jsrl_corl_b200.synthetic import synthetic_dataset
+    from oracle.ref_loader import load_reference_iql
+
+    ref = load_reference_iql("offline")
+    data = synthetic_dataset(n_rows, w["S"], w["A"], 0, antmaze_rewards=w["antmaze"])
+    rb = ref.ReplayBuffer(w["S"], w["A"], n_rows, device)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rb.load_d4rl_dataset(data)
+    torch.manual_seed(seed)
+    q = ref.TwinQ(w["S"], w["A"], hidden_dim=w["H"], n_hidden=w["L"]).to(device)
+    v = ref.ValueFunction(w["S"], hidden_dim=w["H"], n_hidden=w["L"]).to(device)
+    pol = ref.DeterministicPolicy if w["det"] else ref.GaussianPolicy
+    actor = pol(w["S"], w["A"], 1.0, hidden_dim=w["H"], n_hidden=w["L"],
+                dropout=w["dropout"] if w["dropout"] > 0 else None).to(device)
+    trainer = ref.ImplicitQLearning(
+        max_action=1.0, actor=actor, actor_optimizer=torch.optim.Adam(actor.parameters(), lr=3e-4),
+        q_network=q, q_optimizer=torch.optim.Adam(q.parameters(), lr=3e-4), v_network=v,
+        v_optimizer=torch.optim.Adam(v.parameters(), lr=3e-4), iql_tau=w["iql_tau"], beta=w["beta"],
+        max_steps=1_000_000, discount=0.99, tau=w["tau"], device=device)
+    return rb, trainer
+
+
+def time_reference_loop(rb, trainer, B, device, steps, warmup, sync=None):
+    """The reference's hot loop, verbatim (offline/iql.py:631-635): sample -> .to(device) -> train."""
+    def one():
+        batch = rb.sample(B)
+        batch = [b.to(device) for b in batch]
+        return trainer.train(batch)
+
+    for _ in range(warmup):
+        one()
+    if sync:
+        sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    if sync:
+        sync()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt
+
+
+def reference_available():
+    try:
+        from oracle.ref_loader import reference_available as ra
+        return ra()
+    except Exception:
+        return False
+
+
+def cpu_reference_measurements(w, steps_all, steps_one, warmup, n_rows=N_ROWS):
+    """steps/s of ONE member through the unmodified reference on the host: all cores, then one thread."""
+    import torch
+
+    cores = os.cpu_count() or 1
+    rb, trainer = build_reference_trainer(w, "cpu", n_rows)
+    prev = torch.get_num_threads()
+    torch.set_num_threads(cores)  # torchrun pins OMP_NUM_THREADS=1 in the workers' environment; undo that for this arm
+    sps_all, dt_all = time_reference_loop(rb, trainer, w["B"], "cpu", steps_all, warmup)
+    used = torch.get_num_threads()
+    torch.set_num_threads(1)
+    sps_one, dt_one = time_reference_loop(rb, trainer, w["B"], "cpu", steps_one, min(warmup, 5))
+    torch.set_num_threads(prev)
+    return {"all": sps_all, "dt_all": dt_all, "one": sps_one, "dt_one": dt_one, "cores": used, "nproc": cores}
+
+
+def torch_eager_b200(w, steps=300, warmup=30, n_rows=N_ROWS):
+    """The unmodified reference with device="cuda": what a user of the reference gets on this B200 today."""
+    import torch
+
+    if not torch.cuda.is_available() or not reference_available():
+        return None
+    dev = "cuda"
+    rb, trainer = build_reference_trainer(w, dev, n_rows)
+    sps, dt = time_reference_loop(rb, trainer, w["B"], dev, steps, warmup, sync=torch.cuda.synchronize)
+    del rb, trainer
+    torch.cuda.empty_cache()
+    return {"value": sps, "unit": "steps/s", "members": 1, "steps": steps,
+            "what": "unmodified reference offline/iql.py classes, device='cuda', stock eager torch, sample()+train() loop"}
+
+
+def cpu_port_steps_per_sec(w, steps, warmup, n_rows=200_000):
+    """Fallback when the staged reference files are absent: the numpy port under oracle/ (kind "port")."""
     import numpy as np
 
     from jsrl_corl_b200.ensemble import reference_init
     from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
 
-    # all host threads (torchrun pins OMP_NUM_THREADS=1 in the workers' environment; undo that for this arm)
     cores = os.cpu_count() or 1
     try:
         from threadpoolctl import threadpool_info, threadpool_limits
@@ -175,21 +292,56 @@ def cpu_reference_steps_per_sec(w, steps, warmup, n_rows=200_000):
     return steps / dt, dt, cores
 
 
+def cpu_baseline_block(w, cpu_steps):
+    """The `cpu_baseline` object of the JSON line (rank 0, N = 1): a bounded sample of the workload's member-step."""
+    if reference_available():
+        big = w["H"] > 256 or w["B"] > 256
+        m = cpu_reference_measurements(w, max(20, cpu_steps // (40 if big else 1)), max(10, cpu_steps // (120 if big else 4)), 3 if big else 20)
+        return {"value": m["all"], "unit": "steps/s", "cores": m["cores"], "kind": "reference",
+                "one_thread": m["one"], "nproc": m["nproc"], "cpu_model": cpu_model(),
+                "one_member_per_core_derived": m["one"] * m["nproc"],
+                "sample": f"unmodified reference offline/iql.py (staged oracle/_ref), ONE member, {N_ROWS}-row buffer, sample()+train(): "
+                          f"{m['dt_all']:.1f} s on {m['cores']} threads, {m['dt_one']:.1f} s on 1 thread"}
+    sps, dt, cores = cpu_port_steps_per_sec(w, cpu_steps, 5)
+    return {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": f"{cpu_steps} sample+train steps of ONE member, numpy port of the reference update (staged reference "
+                      f"files missing), {dt:.1f} s"}
+
+
 def run_reference_arm(args, w, rank):
     if rank != 0:
         return
-    inner = args.inner if args.inner else 250  # ~1 s of CPU work per bench step
+    big = w["H"] > 256 or w["B"] > 256
+    inner = args.inner if args.inner else (2 if big else 100)  # reference steps per bench step (bounded sample)
     steps_total = max(1, args.steps) * inner
-    sps, dt, cores = cpu_reference_steps_per_sec(w, steps_total, max(3, args.warmup))
+    warm = max(3, args.warmup) * (1 if big else 5)
+    if reference_available():
+        m = cpu_reference_measurements(w, steps_total, max(10, steps_total // 4), warm)
+        sps, dt, cores, kind = m["all"], m["dt_all"], m["cores"], "reference"
+        extra = {"one_thread": m["one"], "nproc": m["nproc"], "cpu_model": cpu_model(),
+                 "one_member_per_core_derived": m["one"] * m["nproc"]}
+        sample = (f"{steps_total} sample()+train() steps of ONE member through the unmodified reference offline/iql.py "
+                  f"(staged oracle/_ref), {N_ROWS}-row buffer, {dt:.1f} s on {cores} threads; 1 thread: {m['one']:.1f} steps/s")
+        eager = None
+        if not args.no_eager:
+            try:
+                eager = torch_eager_b200(w, steps=30 if big else 300, warmup=5 if big else 30)
+            except Exception as ex:  # the CPU arm must not fail because the GPU leg did
+                eager = {"error": repr(ex)[:200]}
+    else:
+        sps, dt, cores = cpu_port_steps_per_sec(w, steps_total, warm)
+        kind, extra, eager = "port", {}, None
+        sample = f"{steps_total} sample+train steps of ONE member (numpy port: staged reference files missing), 200k-row buffer, {dt:.1f} s"
     line = {
         "impl": "reference", "metric": "iql_gradient_steps_per_sec_summed_over_seeds", "value": sps, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "members": 1, "inner_steps_per_bench_step": inner,
-                   "batch": w["B"], "hidden": f'{w["L"]}x{w["H"]}', "obs": w["S"], "act": w["A"]},
-        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps_total} sample+train steps of ONE member (numpy port of the reference update, "
-                                   f"200k-row buffer), {dt:.1f} s"},
+                   "batch": w["B"], "hidden": f'{w["L"]}x{w["H"]}', "obs": w["S"], "act": w["A"], "buffer_rows": N_ROWS,
+                   "same_shape_and_buffer_as_ours": kind == "reference",
+                   "note": "the reference trains ONE member per process (ray_trainer.py:20-24); our arm sums 64+ members"},
+        "cpu_baseline": dict({"value": sps, "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample}, **extra),
+        "torch_eager_b200": eager,
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,7 +365,8 @@ def run_ours(args, w, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     S_local = w["members"]
-    inner = args.inner if args.inner else (50 if w["H"] <= 256 and w["B"] <= 256 else 4)
+    # one bench step = `inner` updates per member in ONE engine call; sized so that the default 20 timed steps last >= 2 s
+    inner = args.inner if args.inner else ((320 if w["members"] >= 32 else 1000) if w["H"] <= 256 and w["B"] <= 256 else 16)
     first_member = rank * S_local  # weak scaling: every GPU trains its own block of members
     seeds = list(range(first_member, first_member + S_local))
     hp = [dict(beta=w["beta"], iql_tau=w["iql_tau"], tau=w["tau"], cosine_t_max=1_000_000) for _ in seeds]
@@ -268,11 +421,12 @@ def run_ours(args, w, rank, world, local_rank):
     value = total_steps / (ms * 1e-3)
 
     # ---- e2e: the same work through the public API with HOST inputs -------------
-    # every bench step copies that step's sample indices (the reference draws them on the host,
-    # iql.py:172) from pinned host memory and reads the loss scalars back.
-    # every call: host-drawn indices (pinned) -> H2D into the engine's staging buffer -> K fused steps -> losses D2H
+    # every bench step DRAWS that step's sample indices on the host inside the timed loop (the reference draws them per
+    # step with numpy, iql.py:172), copies them from pinned host memory into the engine's staging buffer, runs the K
+    # fused steps and reads the loss scalars back.  The draw for call i+1 overlaps the GPU work of call i.
     rs = np.random.RandomState(rank)
-    idx_host = [torch.from_numpy(rs.randint(0, N_ROWS, size=(S_local, inner, w["B"]))).pin_memory() for _ in range(2)]
+    idx_host = [torch.empty(S_local, inner, w["B"], dtype=torch.int64).pin_memory() for _ in range(2)]
+    idx_host[0].numpy()[...] = rs.randint(0, N_ROWS, size=(S_local, inner, w["B"]))
     loss_host = torch.empty(S_local, inner, 3, dtype=torch.float32).pin_memory()
     state = {"i": 0}
 
@@ -281,12 +435,13 @@ def run_ours(args, w, rank, world, local_rank):
         state["i"] += 1
         out = eng.train_steps(inner, mode="indices", indices=idx_host[cur], out=losses)
         loss_host.copy_(out, non_blocking=True)
+        idx_host[cur ^ 1].numpy()[...] = rs.randint(0, N_ROWS, size=(S_local, inner, w["B"]))  # next call's indices
         torch.cuda.current_stream(device).synchronize()  # the caller consumes the log dict every call
 
     for _ in range(3):
         e2e_step()
     sync_all()
-    e2e_steps = max(2, args.steps // 2)
+    e2e_steps = max(2, args.steps)
     e0.record()
     for _ in range(e2e_steps):
         e2e_step()
@@ -299,12 +454,17 @@ def run_ours(args, w, rank, world, local_rank):
         ms_e2e = float(t.item())
     e2e_value = world * S_local * inner * e2e_steps / (ms_e2e * 1e-3)
 
+    # ---- drop-in loop (S = 1): the reference's own hot loop, verbatim, on the facade classes ----------------
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_dropin:
+        dropin = dropin_loop_rate(w, device, rb)
+
     # per-kernel CUDA-event timing of the step (events on the engine's launch stream), after the timed region
     kernels = eng.profile_step(reps=5) if rank == 0 else []
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        tf32_peak = measure_tf32_peak(torch, device) if args.math == "tf32" else 148 * 128 * 2 * 1.965e9 / 1e12
+        tf32_peak, tf32_src = pinned_tf32_peak(torch, device) if args.math == "tf32" else (148 * 128 * 2 * 1.965e9 / 1e12, "fp32 FMA nominal")
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         fl = flops_per_step(w)
         achieved_tflops = (S_local * inner * args.steps * fl) / (ms * 1e-3) / 1e12  # per GPU, whole step
@@ -329,19 +489,25 @@ def run_ours(args, w, rank, world, local_rank):
                     "kernel": dom["kernel"], "kernel_us": dom["us"], "kernel_share_of_step": round(dom["us"] / step_us, 3),
                     "algorithmic_bytes_per_launch": dk["bytes"], "algorithmic_flops_per_launch": dk["flops"],
                     "peak_source": (f"HBM {peak_src} (MEASURED_PEAKS.json)" if dom["bound"] == "hbm" else
-                                    "cuBLAS TF32 8192^3 measured live (MEASURED_PEAKS.json has no TF32 entry)"),
+                                    tf32_src),
                     "how": "CUDA events on the engine's launch stream around every kernel of the step, 5 reps, "
                            "after the timed region (iql_profile_step)"}
         step_view = {"step_us_sum_of_kernels": round(step_us, 1),
                      "whole_step_tflops": round(achieved_tflops, 2), "tf32_peak_tflops": round(tf32_peak, 1),
+                     "tf32_peak_source": tf32_src, "tf32_nominal_tflops": TF32_NOMINAL_TFLOPS,
+                     "whole_step_frac_of_nominal_tf32": round(achieved_tflops / TF32_NOMINAL_TFLOPS, 4),
                      "whole_step_frac_of_tensor_peak": round(achieved_tflops / tf32_peak, 4),
                      "whole_step_hbm_gbs": round(sum(kq["bytes"] for kq in kernels) / (step_us * 1e-6) / 1e9, 1) if step_us else None,
                      "hbm_peak_gbs": hbm_peak, "bf16_peak_tflops": peaks.get("bf16_tflops"), "peak_source": peak_src}
         cpu = None
         if not args.no_cpu_baseline:
-            sps, dt, cores = cpu_reference_steps_per_sec(w, args.cpu_steps, 5)
-            cpu = {"value": sps, "unit": "steps/s", "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_steps} sample+train steps of ONE member, numpy port of the reference update, {dt:.1f} s"}
+            cpu = cpu_baseline_block(w, args.cpu_steps)
+        eager = None
+        if world == 1 and not args.no_eager:
+            try:
+                eager = torch_eager_b200(w, steps=30 if (w["H"] > 256 or w["B"] > 256) else 300, warmup=5 if w["H"] > 256 else 30)
+            except Exception as ex:
+                eager = {"error": repr(ex)[:200]}
         line = {
             "metric": "iql_gradient_steps_per_sec_summed_over_seeds", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -355,7 +521,10 @@ def run_ours(args, w, rank, world, local_rank):
                        "math_mode": args.math, "parallelism": f"members sharded x{world}, no update-path collective"},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": idx_host[0].numel() * 8,
                     "d2h_bytes_per_step": loss_host.numel() * 4,
-                    "note": "host-drawn int64 sample indices in (pinned memory), loss scalars out, one sync per bench step"},
+                    "note": "int64 sample indices drawn on the host INSIDE the timed loop (numpy), copied from pinned memory, "
+                            "loss scalars read back, one sync per bench step"},
+            "e2e_dropin": dropin,
+            "torch_eager_b200": eager,
             "gpu_launches": launches,
             "roofline": roof,
             "step_roofline": step_view,
@@ -371,6 +540,39 @@ def run_ours(args, w, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def dropin_loop_rate(w, device, rb, steps=3000, warmup=300):
+    """`batch = rb.sample(B); trainer.train(batch)` (offline/iql.py:631-635) on the drop-in classes, one learner."""
+    import numpy as np
+    import torch
+
+    from jsrl_corl_b200 import iql as facade
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    q = facade.TwinQ(w["S"], w["A"], w["H"], w["L"])
+    v = facade.ValueFunction(w["S"], w["H"], w["L"])
+    pol = facade.DeterministicPolicy if w["det"] else facade.GaussianPolicy
+    actor = pol(w["S"], w["A"], 1.0, w["H"], w["L"], dropout=w["dropout"])
+    trainer = facade.ImplicitQLearning(1.0, actor, torch.optim.Adam(actor.parameters(), lr=3e-4), q,
+                                       torch.optim.Adam(q.parameters(), lr=3e-4), v, torch.optim.Adam(v.parameters(), lr=3e-4),
+                                       iql_tau=w["iql_tau"], beta=w["beta"], max_steps=1_000_000, discount=0.99, tau=w["tau"],
+                                       device=str(device))
+    if w["H"] > 256 or w["B"] > 256:
+        steps, warmup = 200, 20
+    for _ in range(warmup):
+        trainer.train(rb.sample(w["B"]))
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        log = trainer.train(rb.sample(w["B"]))
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    assert all(np.isfinite(x) for x in log.values())
+    return {"value": steps / dt, "unit": "steps/s", "members": 1, "steps": steps,
+            "what": "ReplayBuffer.sample() + ImplicitQLearning.train(batch) per step through the drop-in classes "
+                    "(numpy index stream, host-visible log dict every step), wall clock"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -381,8 +583,10 @@ def main():
     ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--inner", type=int, default=0, help="updates per engine call (0 = workload default)")
     ap.add_argument("--members", type=int, default=0, help="override members per GPU")
-    ap.add_argument("--cpu-steps", type=int, default=3000)
+    ap.add_argument("--cpu-steps", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the stock-torch-on-GPU leg (torch_eager_b200)")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the S=1 drop-in loop leg (e2e_dropin)")
     ap.add_argument("--fast-init", action="store_true")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

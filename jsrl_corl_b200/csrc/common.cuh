@@ -105,6 +105,17 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: true the first time this call site
+// runs on the current device (engines on several GPUs of one process each need their own call).
+static inline bool first_use_on_device(bool* seen /* [64], zero-initialised */) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 static inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) v = getenv("IQL_B200_NO_PDL") ? 0 : 1;

@@ -654,11 +654,10 @@ bool fused_fwd_pair(int batch) {
 bool fused_fwd_policy_head(int act_dim) { return act_dim >= 1 && act_dim <= FUSED_POL_MAX && getenv("IQL_B200_NO_FUSED_POLICY") == nullptr; }
 
 void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
     cudaFuncSetAttribute(fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
-    attr_set = true;
   }
   const bool pair = a.pair != 0;
   const int tile_rows = pair ? 2 * FT_M : FT_M;

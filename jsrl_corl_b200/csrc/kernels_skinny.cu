@@ -209,9 +209,10 @@ template <int AMAX>
 static void launch_out_fwd_t(const GemmProb* probs, int nprob, int B, size_t sm, cudaStream_t st) {
   static int per_sm = 0, n_sm = 0;
   static size_t sm_of = 0;
+  static bool attr[64] = {};
+  if (first_use_on_device(attr)) cudaFuncSetAttribute(out_fwd_kernel<AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (!per_sm || sm_of != sm) {
     sm_of = sm;
-    cudaFuncSetAttribute(out_fwd_kernel<AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -235,11 +236,9 @@ void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cu
   else if (amax <= 8) launch_out_fwd_t<8>(probs, nprob, B, sm, st);
   else if (amax <= 24) {
     static const bool no_rows = getenv("IQL_B200_NO_OUT_ROWS") != nullptr;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (first_use_on_device(attr))
       cudaFuncSetAttribute(out_fwd_rows_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
-    }
     const bool big = (int64_t)nprob * ((B + 127) / 128) >= 296;
     if (big && (H & 3) == 0 && !no_rows)
       out_fwd_rows_kernel<24><<<dim3(nprob, (B + 127) / 128), 128, (size_t)24 * H * sizeof(float), st>>>(probs);
@@ -544,16 +543,15 @@ int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, co
   dim3 grid(nprob, (H + 63) / 64);
   auto smem = [&](int a) { return ((size_t)B * a + 4 * 64 * a) * sizeof(float); };
   auto smem4 = [&](int a) { return ((size_t)B * a + 4 * 256 * (a + 1)) * sizeof(float); };
-  static bool attr = false;
+  static bool attr[64] = {};
   static bool no_v4 = false;
-  if (!attr) {
+  if (first_use_on_device(attr)) {
     cudaFuncSetAttribute(last_bwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(last_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(last_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(last_bwd_v4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(last_bwd_v4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     no_v4 = getenv("IQL_B200_NO_LASTBWD_V4") != nullptr;
-    attr = true;
   }
   const bool v4 = !no_v4 && (H % 4) == 0 && amax <= 8 && smem4(8) <= 200 * 1024 && last_bwd_v4_fills(nprob, B, H);
   const dim3 grid4(nprob, (H + 255) / 256);
@@ -708,12 +706,11 @@ __global__ void __launch_bounds__(NT, MINB) first_wgrad_kernel(const GemmProb* _
 
 void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax, cudaStream_t st) {
   auto smem = [&](int k, int cw) { return std::max((size_t)B * k, (size_t)4 * cw * (k + 1)) * sizeof(float); };
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (first_use_on_device(attr)) {
     cudaFuncSetAttribute(first_wgrad_kernel<24, 2, 128, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(first_wgrad_kernel<40, 2, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(first_wgrad_kernel<72, 1, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
   }
   if (kmax <= 24) first_wgrad_kernel<24, 2, 128, 7><<<dim3(nprob, (H + 63) / 64), 128, smem(24, 64), st>>>(probs);
   else if (kmax <= 40) first_wgrad_kernel<40, 2, 256, 1><<<dim3(nprob, (H + 127) / 128), 256, smem(40, 128), st>>>(probs);

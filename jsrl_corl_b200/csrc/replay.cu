@@ -57,8 +57,7 @@ __global__ void replay_pack_kernel(float* __restrict__ rows, iql_row_layout lay,
 
 __global__ void replay_insert_kernel(float* __restrict__ rows, int RF, int64_t pointer,
                                      const float* __restrict__ staged) {
-  int c = threadIdx.x;
-  if (c < RF) rows[pointer * RF + c] = staged[c];
+  for (int c = threadIdx.x; c < RF; c += blockDim.x) rows[pointer * RF + c] = staged[c];  // any row width
 }
 
 // ---- sample: Philox (or given) indices + vectorised row gather ------------
@@ -117,6 +116,7 @@ extern "C" int iql_replay_insert(float* rows, const iql_row_layout* lay, int64_t
                                  void* stream) {
   if (!layout_ok(lay) || !rows || !staged_row || pointer < 0) return IQL_ERR_INVALID;
   int threads = (lay->row_floats + 31) / 32 * 32;
+  if (threads > 256) threads = 256;  // wide rows (2 S + A > ~250 floats) loop inside the kernel
   replay_insert_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(rows, lay->row_floats, pointer, staged_row);
   return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
 }

@@ -740,11 +740,10 @@ bool umma_can_fuse_out(int act_dim) { (void)act_dim; return getenv("IQL_B200_NO_
 template <int EPI, bool FUSE_OUT, bool ROWEPI>
 static void launch_variant(bool cta2, int workers, const GemmProb* probs, const CUtensorMap* maps, const GemmProb* probs_out,
                            const CUtensorMap* cmaps, const UmmaParams& up, const StepCtx& ctx, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, false, ROWEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<EPI, FUSE_OUT, true, ROWEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    attr_set = true;
   }
   if (!cta2)
     launch_pdl(umma_gemm_kernel<EPI, FUSE_OUT, false, ROWEPI>, dim3(workers), dim3(N_THREADS), SMEM_BYTES, st, 1, probs, maps,

@@ -8,6 +8,7 @@ inside ``libiql_b200.so``.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Dict, List, Optional
 
@@ -86,9 +87,13 @@ class EnsembleEngine:
             self.workspace = torch.zeros(self.layout.workspace_bytes, dtype=torch.uint8, device=self.device)
             # dedicated stream: CUDA-graph capture is not allowed on the legacy default stream
             self.stream = torch.cuda.Stream(device=self.device)
-        _lib.check(self._L.iql_bind_state(self._h, self.params.data_ptr(), self.exp_avg.data_ptr(),
-                                          self.exp_avg_sq.data_ptr(), self.target.data_ptr(), self.grads.data_ptr(),
-                                          self.workspace.data_ptr(), self.workspace.numel()), self._h, "iql_bind_state")
+            # inside the guard: the engine creates its side stream / events on the CURRENT device and sets
+            # per-device kernel attributes (engines on cuda:N while the process sits on cuda:0 must work)
+            _lib.check(self._L.iql_bind_state(self._h, self.params.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), self.target.data_ptr(), self.grads.data_ptr(),
+                                              self.workspace.data_ptr(), self.workspace.numel()), self._h, "iql_bind_state")
+        self.act_calls = 0
+        self._act_in = self._act_out = self._act_in_dev = None
         self._hparams = [self._default_hparams(m) for m in range(n_members)]
         self._replay_refs: Dict[int, torch.Tensor] = {}
         self._idx_stage: Dict[int, torch.Tensor] = {}
@@ -193,8 +198,9 @@ class EnsembleEngine:
 
     def sync_target(self, member: int):
         """q_target <- qf (copy.deepcopy(self.qf), iql.py:464,584,598)."""
-        cur = torch.cuda.current_stream(self.device)
-        _lib.check(self._L.iql_sync_target(self._h, member, cur.cuda_stream), self._h)
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            _lib.check(self._L.iql_sync_target(self._h, member, cur.cuda_stream), self._h)
 
     # ------------------------------------------------------------------
     def bind_replay(self, member: int, rows: torch.Tensor, size: int):
@@ -217,12 +223,9 @@ class EnsembleEngine:
             raise RuntimeError("Actions shape missmatch")  # iql.py:530
         if r.numel() != B or d.numel() != B:
             raise ValueError("rewards / dones must have batch_size elements")
-        st = self._enter()
-        try:
+        with self._on_stream() as st:
             _lib.check(self._L.iql_load_batch(self._h, member, s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr(),
                                               d.data_ptr(), st.cuda_stream), self._h)
-        finally:
-            self._exit()
         self._keep = (s, a, r, s2, d)
 
     def train_on_batch(self, batch, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -238,14 +241,11 @@ class EnsembleEngine:
             raise ValueError("rewards / dones must have batch_size elements")
         if out is None:
             out = torch.empty(self.n_members, 1, 3, dtype=torch.float32, device=self.device)
-        st = self._enter()
-        try:
+        with self._on_stream() as st:
             _lib.check(self._L.iql_load_batch(self._h, 0, s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr(),
                                               d.data_ptr(), st.cuda_stream), self._h, "iql_load_batch")
             _lib.check(self._L.iql_train_steps(self._h, 1, _lib.SAMPLE_PRELOADED, None, None, out.data_ptr(), None,
                                                st.cuda_stream), self._h, "iql_train_steps")
-        finally:
-            self._exit()
         self._keep = (s, a, r, s2, d)
         return out
 
@@ -254,12 +254,18 @@ class EnsembleEngine:
             return t
         return t.to(device=self.device, dtype=torch.float32).contiguous()
 
-    def _enter(self) -> torch.cuda.Stream:
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
-        return self.stream
-
-    def _exit(self):
-        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+    @contextlib.contextmanager
+    def _on_stream(self):
+        """Every C-ABI call that launches runs inside this: the engine's device is made current (the engine may
+        live on cuda:N while the process's current device is another) and the engine stream is ordered after / before
+        the caller's current stream on that device."""
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            self.stream.wait_stream(cur)
+            try:
+                yield self.stream
+            finally:
+                cur.wait_stream(self.stream)
 
     def train_steps(self, k_steps: int, mode: str = "philox", indices: Optional[torch.Tensor] = None,
                     dropout_masks: Optional[torch.Tensor] = None, return_indices: bool = False,
@@ -282,9 +288,10 @@ class EnsembleEngine:
             src = indices.reshape(-1)
             if src.dtype != torch.int64:
                 src = src.to(torch.int64)
-            self.stream.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(self.stream):
-                stage.copy_(src, non_blocking=True)
+            with torch.cuda.device(self.device):
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self.stream):
+                    stage.copy_(src, non_blocking=True)
             indices = stage
             idx_ptr = stage.data_ptr()
         mask_ptr = None
@@ -296,13 +303,10 @@ class EnsembleEngine:
         if out is None:
             out = torch.empty(S, k_steps, 3, dtype=torch.float32, device=self.device)
         idx_out = torch.empty(S, k_steps, B, dtype=torch.int64, device=self.device) if return_indices else None
-        st = self._enter()
-        try:
+        with self._on_stream() as st:
             _lib.check(self._L.iql_train_steps(self._h, k_steps, smode, idx_ptr, mask_ptr, out.data_ptr(),
                                                idx_out.data_ptr() if idx_out is not None else None, st.cuda_stream),
                        self._h, "iql_train_steps")
-        finally:
-            self._exit()
         # keep argument tensors alive until the stream has consumed them
         self._keep2 = (indices, dropout_masks)
         return (out, idx_out) if return_indices else out
@@ -316,12 +320,9 @@ class EnsembleEngine:
         fl = (C.c_double * cap)()
         by = (C.c_double * cap)()
         labels = C.create_string_buffer(32 * cap)
-        st = self._enter()
-        try:
+        with self._on_stream() as st:
             _lib.check(self._L.iql_profile_step(self._h, reps, cap, C.byref(n), ms, fl, by, labels, st.cuda_stream),
                        self._h, "iql_profile_step")
-        finally:
-            self._exit()
         out = []
         for i in range(n.value):
             out.append({"label": labels.raw[32 * i:32 * (i + 1)].split(b"\0")[0].decode(), "ms": float(ms[i]),
@@ -342,10 +343,31 @@ class EnsembleEngine:
             states = self._dense(states).view(-1, self.state_dim)
             n = states.shape[0]
             out = torch.empty(n, self.action_dim, dtype=torch.float32, device=self.device)
-        st = self._enter()
-        try:
+        with self._on_stream() as st:
             _lib.check(self._L.iql_act(self._h, member, states.data_ptr(), n, float(max_action),
                                        out.data_ptr(), st.cuda_stream), self._h, "iql_act")
-        finally:
-            self._exit()
+        self.act_calls += 1
         return out
+
+    def act_host(self, member: int, state: np.ndarray, max_action: float = 1.0) -> np.ndarray:
+        """One env step of ``policy.act`` (iql.py:371-379, 403-413) through the engine's act kernel: the observation
+        goes host -> device from a pinned staging row, the kernel reads the policy weights straight from the
+        parameter arena, the action comes back through a pinned row; everything is queued on the engine stream and
+        one stream synchronize ends the call.  Returns the flat numpy action (scaled and clamped by max_action)."""
+        if self._act_in is None:
+            self._act_in = torch.empty(self.state_dim, dtype=torch.float32).pin_memory()
+            self._act_out = torch.empty(self.action_dim, dtype=torch.float32).pin_memory()
+            self._act_in_dev = torch.empty(self.state_dim, dtype=torch.float32, device=self.device)
+            self._act_out_dev = torch.empty(self.action_dim, dtype=torch.float32, device=self.device)
+        self._act_in.numpy()[:] = np.asarray(state, dtype=np.float32).reshape(-1)
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            self.stream.wait_stream(cur)  # parameter writes queued by the caller (checkpoint loads) come first
+            with torch.cuda.stream(self.stream):
+                self._act_in_dev.copy_(self._act_in, non_blocking=True)
+                _lib.check(self._L.iql_act(self._h, member, self._act_in_dev.data_ptr(), 1, float(max_action),
+                                           self._act_out_dev.data_ptr(), self.stream.cuda_stream), self._h, "iql_act")
+                self._act_out.copy_(self._act_out_dev, non_blocking=True)
+            self.stream.synchronize()
+        self.act_calls += 1
+        return self._act_out.numpy().copy()

@@ -234,8 +234,16 @@ class ReplayBuffer:
         self._rewards = self._rows[:, lay.off_reward:lay.off_reward + 1]
         self._next_states = self._rows[:, lay.off_next_state:lay.off_next_state + state_dim]
         self._dones = self._rows[:, lay.off_done:lay.off_done + 1]
-        self._stage = torch.zeros(lay.row_floats, dtype=torch.float32, device=self._device)
-        self._stage_host = torch.zeros(lay.row_floats, dtype=torch.float32).pin_memory()
+        # add_transition: two pinned staging rows used alternately, each guarded by an event recorded after its
+        # host->device copy, so an insert never waits for the whole stream (only, rarely, for its own slot)
+        self._stage = [torch.zeros(lay.row_floats, dtype=torch.float32, device=self._device) for _ in range(2)]
+        self._stage_host = [torch.zeros(lay.row_floats, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._stage_ev = [None, None]
+        self._stage_i = 0
+        # sample: ring of pinned index rows (numpy stream -> pinned -> device, non-blocking)
+        self._idx_ring: List[Tuple[torch.Tensor, torch.Tensor, Optional[torch.cuda.Event]]] = []
+        self._idx_i = 0
+        self._last_indices = None
 
     @property
     def rows(self) -> torch.Tensor:
@@ -264,8 +272,9 @@ class ReplayBuffer:
         d = self._to_tensor(data["terminals"]).reshape(-1).contiguous()
         if s.shape[1] != self._state_dim or a.shape[1] != self._action_dim:
             raise ValueError("dataset dims do not match the buffer")
-        _lib.check(self._L.iql_replay_pack(self._rows.data_ptr(), C.byref(self._lay), 0, n, s.data_ptr(), a.data_ptr(),
-                                           r.data_ptr(), s2.data_ptr(), d.data_ptr(), self._stream()), None, "iql_replay_pack")
+        with torch.cuda.device(self._device):
+            _lib.check(self._L.iql_replay_pack(self._rows.data_ptr(), C.byref(self._lay), 0, n, s.data_ptr(), a.data_ptr(),
+                                               r.data_ptr(), s2.data_ptr(), d.data_ptr(), self._stream()), None, "iql_replay_pack")
         torch.cuda.current_stream(self._device).synchronize()  # inputs are temporaries
         self._size += n
         self._pointer = min(self._size, n)
@@ -274,42 +283,71 @@ class ReplayBuffer:
     def _high(self) -> int:
         return min(self._size, self._pointer) if self._offline_semantics else self._size
 
+    def _idx_slot(self, B: int):
+        """Next (pinned host row, device row) pair of the index ring; waits only if its previous copy is still queued."""
+        if not self._idx_ring or self._idx_ring[0][0].numel() != B:
+            self._idx_ring = [(torch.empty(B, dtype=torch.int64).pin_memory(),
+                               torch.empty(B, dtype=torch.int64, device=self._device), None) for _ in range(4)]
+            self._idx_i = 0
+        i = self._idx_i
+        self._idx_i = (i + 1) % len(self._idx_ring)
+        host, dev, ev = self._idx_ring[i]
+        if ev is not None:
+            ev.synchronize()
+        return i, host, dev
+
     def sample(self, batch_size: int) -> TensorBatch:
         B = int(batch_size)
         dev = self._device
-        f32 = dict(dtype=torch.float32, device=dev)
-        out = [torch.empty((B, self._state_dim), **f32), torch.empty((B, self._action_dim), **f32),
-               torch.empty((B, 1), **f32), torch.empty((B, self._state_dim), **f32), torch.empty((B, 1), **f32)]
+        S, A = self._state_dim, self._action_dim
+        # one allocation per call (fresh tensors, like the reference), carved into the five dense outputs
+        flat = torch.empty(B * (2 * S + A + 2), dtype=torch.float32, device=dev)
+        o = [0, B * S, B * (S + A), B * (S + A + 1), B * (2 * S + A + 1), B * (2 * S + A + 2)]
+        out = [flat[o[0]:o[1]].view(B, S), flat[o[1]:o[2]].view(B, A), flat[o[2]:o[3]].view(B, 1),
+               flat[o[3]:o[4]].view(B, S), flat[o[4]:o[5]].view(B, 1)]
         high = self._high()
-        if self._sampler == "numpy":
-            idx_host = np.random.randint(0, high, size=B)  # raises ValueError on an empty buffer, like the reference
-            idx = torch.from_numpy(idx_host).to(dev, non_blocking=False)
-            idx_ptr, seed, step = idx.data_ptr(), 0, 0
-        else:
-            if high <= 0:
-                raise ValueError("low >= high")
-            idx, idx_ptr, seed, step = None, None, self._seed, self._sample_calls
-        self._sample_calls += 1
-        _lib.check(self._L.iql_replay_sample(self._rows.data_ptr(), C.byref(self._lay), high, B, idx_ptr, seed, step,
-                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
-                                             out[3].data_ptr(), out[4].data_ptr(), None, self._stream()),
-                   None, "iql_replay_sample")
-        self._last_indices = idx
+        with torch.cuda.device(dev):
+            if self._sampler == "numpy":
+                idx_host = np.random.randint(0, high, size=B)  # raises ValueError on an empty buffer, like the reference
+                slot, pin, idx = self._idx_slot(B)
+                pin.numpy()[:] = idx_host
+                idx.copy_(pin, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                self._idx_ring[slot] = (pin, idx, ev)
+                idx_ptr, seed, step = idx.data_ptr(), 0, 0
+            else:
+                if high <= 0:
+                    raise ValueError("low >= high")
+                idx, idx_ptr, seed, step = None, None, self._seed, self._sample_calls
+            self._sample_calls += 1
+            _lib.check(self._L.iql_replay_sample(self._rows.data_ptr(), C.byref(self._lay), high, B, idx_ptr, seed, step,
+                                                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                                 out[3].data_ptr(), out[4].data_ptr(), None, self._stream()),
+                       None, "iql_replay_sample")
+        self._last_indices = idx  # device row of the ring: valid until 3 more sample() calls
         return out
 
     def add_transition(self, state: np.ndarray, action: np.ndarray, reward: float, next_state: np.ndarray, done: bool):
         lay = self._lay
-        h = self._stage_host
-        torch.cuda.current_stream(self._device).synchronize()  # the pinned stage may still be in flight
-        h.zero_()
-        h[lay.off_state:lay.off_state + self._state_dim] = torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(-1))
-        h[lay.off_action:lay.off_action + self._action_dim] = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(-1))
+        i = self._stage_i
+        self._stage_i = i ^ 1
+        if self._stage_ev[i] is not None:
+            self._stage_ev[i].synchronize()  # this slot's previous host->device copy (two inserts ago) has run
+        h = self._stage_host[i].numpy()
+        h[:] = 0.0
+        h[lay.off_state:lay.off_state + self._state_dim] = np.asarray(state, dtype=np.float32).reshape(-1)
+        h[lay.off_action:lay.off_action + self._action_dim] = np.asarray(action, dtype=np.float32).reshape(-1)
         h[lay.off_reward] = float(reward)
-        h[lay.off_next_state:lay.off_next_state + self._state_dim] = torch.as_tensor(np.asarray(next_state, dtype=np.float32).reshape(-1))
+        h[lay.off_next_state:lay.off_next_state + self._state_dim] = np.asarray(next_state, dtype=np.float32).reshape(-1)
         h[lay.off_done] = float(done)
-        self._stage.copy_(h, non_blocking=True)
-        _lib.check(self._L.iql_replay_insert(self._rows.data_ptr(), C.byref(lay), self._pointer, self._stage.data_ptr(),
-                                             self._stream()), None, "iql_replay_insert")
+        with torch.cuda.device(self._device):
+            self._stage[i].copy_(self._stage_host[i], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self._device))
+            self._stage_ev[i] = ev
+            _lib.check(self._L.iql_replay_insert(self._rows.data_ptr(), C.byref(lay), self._pointer, self._stage[i].data_ptr(),
+                                                 self._stream()), None, "iql_replay_insert")
         self._pointer = (self._pointer + 1) % self._buffer_size
         self._size = min(self._size + 1, self._buffer_size)
 
@@ -366,6 +404,32 @@ class _PolicyBase(nn.Module):
         self.state_dim, self.act_dim = state_dim, act_dim
         self.hidden_dim, self.n_hidden = hidden_dim, n_hidden
         self.max_action = max_action
+        self._engine_ref = None  # (EnsembleEngine, member) once the parameters alias an engine arena
+
+    def _engine_act(self, state: np.ndarray) -> Optional[np.ndarray]:
+        """clamp(max_action * tanh(MLP(s))) from the engine's fused act kernel (reads the arena the parameters
+        alias) instead of 2 n_hidden + 3 stock torch launches; None when the module is not engine-backed."""
+        ref = self._engine_ref
+        if ref is None:
+            return None
+        eng, member = ref
+        p = self.net.net[0].weight
+        if p.device != eng.device or p.data_ptr() < eng.params.data_ptr() or \
+                p.data_ptr() >= eng.params.data_ptr() + eng.params.numel() * 4:
+            return None  # parameters were re-pointed (module moved / re-initialised): stock torch path
+        return eng.act_host(member, state, float(self.max_action))
+
+    def __deepcopy__(self, memo):
+        ref, self._engine_ref = self._engine_ref, None  # a copy owns its parameters, not the arena
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                setattr(new, k, copy.deepcopy(v, memo))
+        finally:
+            self._engine_ref = ref
+        return new
 
     def _clip(self, action: torch.Tensor) -> np.ndarray:
         scaled = torch.clamp(self.max_action * action, -self.max_action, self.max_action)
@@ -384,6 +448,10 @@ class GaussianPolicy(_PolicyBase):
 
     @torch.no_grad()
     def act(self, state: np.ndarray, device: str = "cpu"):
+        if not self.training:  # eval mode: the mean action, one fused kernel on the engine
+            a = self._engine_act(state)
+            if a is not None:
+                return a
         obs = torch.tensor(state.reshape(1, -1), device=device, dtype=torch.float32)
         dist = self(obs)
         return self._clip(dist.sample() if self.training else dist.mean)
@@ -399,6 +467,10 @@ class DeterministicPolicy(_PolicyBase):
 
     @torch.no_grad()
     def act(self, state: np.ndarray, device: str = "cpu"):
+        if not (self.training and self.net.has_dropout_modules and self.net.dropout_p > 0.0):
+            a = self._engine_act(state)  # no active dropout: the deterministic action, one fused kernel
+            if a is not None:
+                return a
         obs = torch.tensor(state.reshape(1, -1), device=device, dtype=torch.float32)
         return self._clip(self(obs))
 
@@ -473,6 +545,7 @@ class ImplicitQLearning:
         self._steps = {"v": 0, "q": 0, "actor": 0}
         self._step_tensors: Dict[str, torch.Tensor] = {}
         self._published = False
+        self._moment_cache = None
         self._loss_buf: Optional[torch.Tensor] = None
         S, A, H, L = self.qf.state_dim, self.qf.action_dim, self.qf.hidden_dim, self.qf.n_hidden
         if (self.vf.state_dim, self.vf.hidden_dim, self.vf.n_hidden) != (S, H, L) or \
@@ -530,6 +603,7 @@ class ImplicitQLearning:
                 view.copy_(p.data)
                 p.data = view
         self._engine = eng
+        self.actor._engine_ref = (eng, 0)
         self._pushed = None
         self._published = False
         self._push_counters()
@@ -550,7 +624,10 @@ class ImplicitQLearning:
         ``optimizer.state_dict()`` has the stock Adam layout (step/exp_avg/exp_avg_sq)."""
         eng = self._engine
         drop_keys = self.actor.net.has_dropout_modules
-        m_views, v_views = eng.moment_views(0, drop_keys)
+        if getattr(self, "_moment_cache", None) is None or self._moment_cache[0] is not eng:
+            self._moment_cache = (eng,) + tuple(eng.moment_views(0, drop_keys))  # one set of view objects per engine
+        _, m_views, v_views = self._moment_cache
+        attached = 0
         for grp, mod in self._modules().items():
             opt = self._optimizers()[grp]
             steps = self._steps[{"qf": "q", "vf": "v", "actor": "actor"}[grp]]
@@ -565,7 +642,10 @@ class ImplicitQLearning:
                 st = opt.state.get(p)
                 if st is None or st.get("exp_avg") is not m_views[grp][name] or st.get("step") is not step_t:
                     opt.state[p] = {"step": step_t, "exp_avg": m_views[grp][name], "exp_avg_sq": v_views[grp][name]}
-        self._published = len(self._step_tensors) == 3  # every optimizer has stepped at least once
+            attached += 1
+        # true only when all three optimizers really hold arena views (a checkpoint with empty optimizer state
+        # loaded into a stepped trainer resets this through load_state_dict)
+        self._published = attached == 3
 
     def _push_hparams(self):
         gq, gv, ga = _adam_group(self.q_optimizer), _adam_group(self.v_optimizer), _adam_group(self.actor_optimizer)
@@ -691,6 +771,7 @@ class ImplicitQLearning:
             self.actor_lr_schedule.load_state_dict(state_dict["actor_lr_schedule"])
         self._total_it = state_dict["total_it"]
         self._pushed = None
+        self._published = False
         if self._engine is not None:
             self._push_counters()
             self._publish_optimizer_state()

@@ -227,6 +227,9 @@ def learner_or_guide_action(state, step, env, learner, guide, config, device, ev
     return action, use_learner, horizon
 
 
+_actors_built = 0
+
+
 def make_actor(config, state_dim, action_dim, max_action, device=None, max_steps=None, **engine_kw):
     """Build Q / V / policy networks, their three Adam optimizers and the trainer exactly as the
     reference does (jsrl_utils.py:219-282: class-default 2x256 networks, TwinQ -> V -> policy
@@ -240,6 +243,11 @@ def make_actor(config, state_dim, action_dim, max_action, device=None, max_steps
     v_optimizer = torch.optim.Adam(v_network.parameters(), lr=config.vf_lr)
     q_optimizer = torch.optim.Adam(q_network.parameters(), lr=config.qf_lr)
     actor_optimizer = torch.optim.Adam(actor.parameters(), lr=config.actor_lr)
+    # the Philox dropout key follows the run's seed (the reference's masks follow torch.manual_seed(config.seed));
+    # every trainer built for a run (guide, learner) gets a distinct stream via the construction counter
+    global _actors_built
+    engine_kw.setdefault("seed", (int(getattr(config, "seed", 0)) << 8) + (_actors_built & 0xFF))
+    _actors_built += 1
     return ImplicitQLearning(max_action=max_action, actor=actor, actor_optimizer=actor_optimizer,
                              q_network=q_network, q_optimizer=q_optimizer, v_network=v_network,
                              v_optimizer=v_optimizer, discount=config.discount, tau=config.tau, device=device,

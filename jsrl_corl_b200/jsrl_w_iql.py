@@ -158,6 +158,11 @@ def train_loop(config, env, eval_env, replay_buffer: Optional[ReplayBuffer], sta
                     config.curriculum_stage = np.nan
                 scores, success, config.mean_horizon_reached, config.eval_mean_agent_type = eval_actor(eval_env, actor, guide, config)
                 score = float(scores.mean())
+                # reference jsrl_w_iql.py:573-592: with normalize_reward the curriculum callback and the log see the
+                # D4RL-normalised score (an affine rescale changes when `best - tol * best` is reached)
+                norm_fn = getattr(eval_env, "get_normalized_score", None) if config.normalize_reward else None
+                if norm_fn is not None:
+                    score = float(norm_fn(score))  # the callback sees this value; the log 100x it (reference :587)
                 eval_log = {}
                 if is_env_with_goal:
                     eval_successes.append(success)
@@ -166,7 +171,10 @@ def train_loop(config, env, eval_env, replay_buffer: Optional[ReplayBuffer], sta
                 if t >= config.offline_iterations:
                     config = jsrl.horizon_update_callback(config, score)
                     eval_log = jsrl.add_jsrl_metrics(eval_log, config)
-                eval_log["eval/score"] = score
+                if norm_fn is not None:
+                    eval_log["eval/d4rl_normalized_score"] = score * 100.0
+                else:
+                    eval_log["eval/score"] = score
                 if config.checkpoints_path is not None:
                     torch.save(trainer.state_dict(), os.path.join(config.checkpoints_path, f"checkpoint_{t}.pt"))
                 log(eval_log, trainer.total_it)

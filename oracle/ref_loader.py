@@ -15,10 +15,21 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("JSRL_REFERENCE_ROOT", "/root/reference")
+# build-time copy of the two reference files (oracle/make_ref.py, called by __graft_entry__.build()): git-ignored,
+# but it travels to the GPU box with the repo snapshot so that bench.py's reference arm can time the UNMODIFIED
+# reference classes there.  Only bench.py's `--impl reference` / `cpu_baseline` legs and CPU tests use it.
+LOCAL_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _ref_path(variant: str) -> str:
+    live = os.path.join(REFERENCE_ROOT, "algorithms", variant, "iql.py")
+    if os.path.isfile(live):
+        return live
+    return os.path.join(LOCAL_REF, f"{variant}_iql.py")
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "algorithms", "finetune", "iql.py"))
+    return os.path.isfile(_ref_path("finetune")) and os.path.isfile(_ref_path("offline"))
 
 
 def _stub(name, **attrs):
@@ -62,9 +73,9 @@ def load_reference_iql(variant: str = "finetune"):
     if variant in _CACHE:
         return _CACHE[variant]
     if not reference_available():
-        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
+        raise FileNotFoundError(f"reference iql.py not found under {REFERENCE_ROOT} or {LOCAL_REF}")
     _install_stubs()
-    path = os.path.join(REFERENCE_ROOT, "algorithms", variant, "iql.py")
+    path = _ref_path(variant)
     spec = importlib.util.spec_from_file_location(f"_ref_{variant}_iql", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

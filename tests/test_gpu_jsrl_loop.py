@@ -72,3 +72,132 @@ def test_jsrl_offline_to_online_loop(tmp_path):
     assert sd["total_it"] == 300 and sd["actor_lr_schedule"] == {}
     episodes = [d for d in online if "train/episode_length" in d]
     assert len(episodes) == 260 // PointEnv.T and all(d["train/episode_length"] == PointEnv.T for d in episodes)
+
+
+def _make_trainer(det, dropout=0.0, S=5, A=3, device="cuda"):
+    from jsrl_corl_b200 import iql as facade
+
+    torch.manual_seed(3)
+    q, v = facade.TwinQ(S, A), facade.ValueFunction(S)
+    actor = (facade.DeterministicPolicy if det else facade.GaussianPolicy)(S, A, 0.8, dropout=dropout)
+    return facade.ImplicitQLearning(0.8, actor, torch.optim.Adam(actor.parameters(), lr=3e-4), q,
+                                    torch.optim.Adam(q.parameters(), lr=3e-4), v, torch.optim.Adam(v.parameters(), lr=3e-4),
+                                    device=device, max_steps=100)
+
+
+def _batch(S=5, A=3, B=32, device="cuda"):
+    g = torch.Generator().manual_seed(0)
+    return [torch.randn(B, S, generator=g).to(device), torch.rand(B, A, generator=g).to(device) * 2 - 1,
+            torch.randn(B, 1, generator=g).to(device), torch.randn(B, S, generator=g).to(device), torch.zeros(B, 1, device=device)]
+
+
+@pytest.mark.parametrize("det", [True, False])
+def test_policy_act_runs_on_the_engine_kernel(det):
+    """once the module aliases the engine arena, ``act`` (iql.py:371-379, 403-413) is the fused
+    act kernel -- same numbers as the stock torch forward on the same (updated) parameters."""
+    trainer = _make_trainer(det)
+    for _ in range(3):
+        trainer.train(_batch())
+    actor, eng = trainer.actor, trainer._engine
+    actor.eval()
+    state = np.linspace(-1, 1, 5).astype(np.float32)
+    calls0 = eng.act_calls
+    a = actor.act(state, "cuda")
+    assert eng.act_calls == calls0 + 1 and a.shape == (3,) and a.dtype == np.float32
+    with torch.no_grad():
+        out = actor(torch.tensor(state.reshape(1, -1), device="cuda"))
+        mean = out if det else out.mean
+        want = torch.clamp(0.8 * mean, -0.8, 0.8).cpu().numpy().flatten()
+    np.testing.assert_allclose(a, want, rtol=0, atol=2e-6)
+    actor.train()
+    if not det:  # training mode keeps dist.sample(): stock torch path
+        calls1 = eng.act_calls
+        actor.act(state, "cuda")
+        assert eng.act_calls == calls1
+    import copy
+    clone = copy.deepcopy(actor).eval()  # a copy owns its parameters: no engine behind it
+    assert clone._engine_ref is None
+    np.testing.assert_allclose(clone.act(state, "cuda"), want, rtol=0, atol=2e-6)
+
+
+def test_jsrl_loop_issues_act_kernel_launches():
+    from jsrl_corl_b200 import ReplayBuffer
+    from jsrl_corl_b200.jsrl_utils import JsrlTrainConfig
+    from jsrl_corl_b200.jsrl_w_iql import train_loop
+    from jsrl_corl_b200.engine import EnsembleEngine
+
+    cfg = JsrlTrainConfig(device="cuda", env="Point-v0", seed=0, eval_freq=40, n_episodes=1, offline_iterations=40,
+                          online_iterations=40, batch_size=32, n_curriculum_stages=2, rolling_mean_n=1, tolerance=0.5,
+                          horizon_fn="time_step", online_buffer_size=100, iql_deterministic=True)
+    rng = np.random.RandomState(1)
+    n = 200
+    data = {"observations": rng.uniform(-1, 1, (n, 3)).astype(np.float32), "actions": rng.uniform(-1, 1, (n, 2)).astype(np.float32),
+            "rewards": rng.uniform(-1, 0, n).astype(np.float32), "next_observations": rng.uniform(-1, 1, (n, 3)).astype(np.float32),
+            "terminals": np.zeros(n, bool)}
+    rb = ReplayBuffer(3, 2, n, "cuda")
+    rb.load_d4rl_dataset(data)
+    count = {"n": 0}
+    orig = EnsembleEngine.act_host
+
+    def counting(self, *a, **k):
+        count["n"] += 1
+        return orig(self, *a, **k)
+
+    EnsembleEngine.act_host = counting
+    try:
+        train_loop(cfg, PointEnv(0), PointEnv(1), rb, 3, 2, 1.0, max_steps=PointEnv.T)
+    finally:
+        EnsembleEngine.act_host = orig
+    # guide-only probe (1 episode) + two evaluations (1 episode each) + guide steps of the online phase: every one of
+    # them an engine act-kernel launch (learner steps with deterministic policies too)
+    assert count["n"] >= 3 * PointEnv.T
+
+
+def test_engine_on_a_non_current_device():
+    """device='cuda:N' while the process's current device is another one."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    torch.cuda.set_device(0)
+    trainer = _make_trainer(True, device="cuda:1")
+    logs = [trainer.train(_batch(device="cuda:1")) for _ in range(3)]
+    assert torch.cuda.current_device() == 0 and all(np.isfinite(v) for d in logs for v in d.values())
+    ref = _make_trainer(True, device="cuda:0")
+    logs0 = [ref.train(_batch(device="cuda:0")) for _ in range(3)]
+    for a, b in zip(logs, logs0):
+        for k in a:
+            assert a[k] == b[k]  # same kernels, same inputs: bit-identical across devices
+
+
+def test_wide_row_insert_and_unsynchronised_inserts():
+    from jsrl_corl_b200 import ReplayBuffer
+
+    S, A = 600, 8  # row_floats > 1024: the insert kernel loops over the row
+    rb = ReplayBuffer(S, A, 16, "cuda")
+    rng = np.random.RandomState(0)
+    rows = []
+    for i in range(20):  # wraps the ring; consecutive inserts reuse the two pinned staging rows
+        s, a, s2 = rng.randn(S).astype(np.float32), rng.randn(A).astype(np.float32), rng.randn(S).astype(np.float32)
+        rb.add_transition(s, a, float(i), s2, i % 3 == 0)
+        rows.append((s, a, float(i), s2, float(i % 3 == 0)))
+    torch.cuda.synchronize()
+    assert rb._size == 16 and rb._pointer == 4
+    for slot in range(16):
+        s, a, r, s2, d = rows[slot + 16] if slot < 4 else rows[slot]
+        np.testing.assert_array_equal(rb._states[slot].cpu().numpy(), s)
+        np.testing.assert_array_equal(rb._actions[slot].cpu().numpy(), a)
+        np.testing.assert_array_equal(rb._next_states[slot].cpu().numpy(), s2)
+        assert float(rb._rewards[slot]) == r and float(rb._dones[slot]) == d
+
+
+def test_optimizer_state_republished_after_loading_an_empty_checkpoint():
+    """a step-0 checkpoint loaded into a stepped trainer must not leave `_published` stale."""
+    fresh = _make_trainer(False)
+    sd0 = fresh.state_dict()
+    trainer = _make_trainer(False)
+    for _ in range(2):
+        trainer.train(_batch())
+    trainer.load_state_dict(sd0)
+    assert trainer.q_optimizer.state_dict()["state"] == {}
+    trainer.train(_batch())
+    st = trainer.q_optimizer.state_dict()["state"]
+    assert len(st) == 12 and float(st[0]["step"]) == 1.0 and st[0]["exp_avg"].abs().sum() > 0
