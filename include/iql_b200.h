@@ -137,6 +137,20 @@ int iql_bind_state(iql_engine* e, float* params, float* exp_avg, float* exp_avg_
                    float* target, float* grads, void* workspace, size_t workspace_bytes);
 int iql_set_hparams(iql_engine* e, int32_t member, const iql_hparams* hp);
 int iql_set_counters(iql_engine* e, int32_t member, const iql_counters* c);
+
+/* Engine options (no counterpart in the reference: they select between equivalent B200 code paths and exist for
+ * tests and measurements).  IQL_OPT_STEP_PATH must be set before iql_bind_state. */
+#define IQL_OPT_STEP_PATH 1  /* 0 auto (default; = 1 today), 1 one kernel per phase + adam_polyak, 2 chained backward + fused optimizer (bind fails where unsupported) */
+#define IQL_OPT_KEEP_GRADS 2 /* != 0: the chained backward also stores the hidden / input weight gradients to `grads` */
+int iql_set_option(iql_engine* e, int32_t key, int64_t value);
+/* Which code path serves this handle (after iql_bind_state).  IQL_INFO_TENSOR_CORE_PATH == 0 under
+ * IQL_MATH_TF32_TCGEN05 means the shape is outside the tcgen05 kernels (batch % 128, hidden % 256) and the FP32
+ * CUDA-core kernels run instead: callers that require tensor cores must check it -- the Python facade raises when
+ * math_mode="tf32" was asked for with strict=True. */
+#define IQL_INFO_TENSOR_CORE_PATH 1
+#define IQL_INFO_FUSED_FORWARD 2
+#define IQL_INFO_CHAINED_BACKWARD 3
+int iql_get_info(const iql_engine* e, int32_t key, int64_t* out);
 int iql_get_counters(iql_engine* e, int32_t member, iql_counters* out, void* stream);
 /* replaces: copy.deepcopy(self.qf) iql.py:464,584,598 (q_target <- qf) */
 int iql_sync_target(iql_engine* e, int32_t member, void* stream);
@@ -207,6 +221,8 @@ int64_t iql_last_launch_count(const iql_engine* e);
  * stamps of the last launch, [3 roles][8 tiles][4 layers][4 stamps] int64, to the host.  Returns the number of
  * words written, < 0 when tracing is off or `max_words` is too small. */
 int iql_debug_fused_trace(long long* out, int32_t max_words);
+/* IQL_CHAIN_TRACE=1: globaltimer stamps of CTA pair 0 of the last bwd_chain launch (tools/chain_trace.py) */
+int iql_debug_chain_trace(long long* out, int32_t max_words);
 
 #ifdef __cplusplus
 }

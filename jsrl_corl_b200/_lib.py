@@ -18,6 +18,9 @@ MATH_FP32_SIMT, MATH_TF32_TCGEN05 = 0, 1
 SAMPLE_PHILOX, SAMPLE_INDICES, SAMPLE_PRELOADED = 0, 1, 2
 NET_Q1, NET_Q2, NET_V, NET_ACTOR = 0, 1, 2, 3
 KIND_WEIGHT, KIND_BIAS, KIND_LOG_STD = 0, 1, 2
+OPT_STEP_PATH, OPT_KEEP_GRADS = 1, 2
+INFO_TENSOR_CORE_PATH, INFO_FUSED_FORWARD, INFO_CHAINED_BACKWARD = 1, 2, 3
+STEP_PATHS = {"auto": 0, "phases": 1, "chain": 2}
 
 
 class Config(C.Structure):
@@ -86,6 +89,8 @@ SYMBOLS = {
     "iql_bind_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_size_t]),
     "iql_set_hparams": (C.c_int, [_P, C.c_int32, C.POINTER(HParams)]),
     "iql_set_counters": (C.c_int, [_P, C.c_int32, C.POINTER(Counters)]),
+    "iql_set_option": (C.c_int, [_P, C.c_int32, C.c_int64]),
+    "iql_get_info": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64)]),
     "iql_get_counters": (C.c_int, [_P, C.c_int32, C.POINTER(Counters), _P]),
     "iql_sync_target": (C.c_int, [_P, C.c_int32, _P]),
     "iql_replay_row_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(RowLayout)]),
@@ -100,6 +105,7 @@ SYMBOLS = {
     "iql_act": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_float, _P, _P]),
     "iql_last_launch_count": (C.c_int64, [_P]),
     "iql_debug_fused_trace": (C.c_int, [_P, C.c_int32]),
+    "iql_debug_chain_trace": (C.c_int, [_P, C.c_int32]),
     "iql_profile_step": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P, _P]),
     "iql_selftest_umma_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32,
                                           _P, C.c_int32, _P, C.c_size_t, _P]),

@@ -101,6 +101,13 @@ struct iql_engine {
   std::vector<char> h_maps_c;
   char* d_maps_store = nullptr;  // [L][S * N_PASS] CUtensorMap: activation outputs of the fused forward (TMA stores)
   std::vector<char> h_maps_store;
+  // chained backward + optimizer (bwd_chain.cu): phase list, CTA-pair tensor maps, small-parameter ranges
+  bool chain = false;
+  int step_path = 0;             // iql_set_option(IQL_OPT_STEP_PATH): 0 auto, 1 per-phase kernels, 2 chained backward (required)
+  int keep_grads = 0;            // iql_set_option(IQL_OPT_KEEP_GRADS): the chained backward also stores the weight gradients
+  BwdChainArgs chain_args;
+  char* d_maps_chain = nullptr;
+  std::vector<char> h_maps_chain;
   bool split_first = false;      // input layer runs as 3xTF32 tcgen05 GEMM
   bool fused_fwd = false;        // whole forward (hidden layers + scalar heads) runs as one fused tcgen05 launch
   bool fused_pair = false;       // ... on CTA pairs (cta_group::2), one pair per 256 batch rows
@@ -256,6 +263,7 @@ static void build_layout(iql_engine* e) {
     tab((int64_t)128 * 4 * S * N_PASS);
     tab((int64_t)128 * L * S * N_PASS);
     tab((int64_t)128 * nprob);
+    tab((int64_t)128 * 2 * 4 * S * (2 * L));  // chain maps: <= 2L - 1 phases x 4 S tasks x (A, B)
   }
   e->tables_bytes = tb;
   e->layout.workspace_bytes = tb + (int64_t)S * wl.member_floats * (int64_t)sizeof(float);
@@ -346,6 +354,34 @@ extern "C" int iql_set_hparams(iql_engine* e, int32_t member, const iql_hparams*
   s.seed = hp->seed;
   e->scalars_dirty = true;
   return IQL_OK;
+}
+
+extern "C" int iql_set_option(iql_engine* e, int32_t key, int64_t value) {
+  if (!e) return IQL_ERR_INVALID;
+  if (key == IQL_OPT_STEP_PATH) {
+    if (value < 0 || value > 2) return fail(e, IQL_ERR_INVALID, "iql_set_option: IQL_OPT_STEP_PATH must be 0 (auto), 1 (per-phase kernels) or 2 (chained backward)");
+    if (e->bound && e->step_path != (int)value) return fail(e, IQL_ERR_STATE, "iql_set_option: IQL_OPT_STEP_PATH must be set before iql_bind_state");
+    e->step_path = (int)value;
+    return IQL_OK;
+  }
+  if (key == IQL_OPT_KEEP_GRADS) {
+    e->keep_grads = value != 0;
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);  // the flag is baked into captured launches
+    e->graphs.clear();
+    return IQL_OK;
+  }
+  return fail(e, IQL_ERR_INVALID, "iql_set_option: unknown key");
+}
+
+extern "C" int iql_get_info(const iql_engine* e, int32_t key, int64_t* out) {
+  if (!e || !out) return IQL_ERR_INVALID;
+  const bool tc = e->cfg.math_mode == IQL_MATH_TF32_TCGEN05 && umma_phase_supported(0, e->cfg.batch_size, e->cfg.hidden_dim);
+  switch (key) {
+    case IQL_INFO_TENSOR_CORE_PATH: *out = tc ? 1 : 0; return IQL_OK;   // 0: the FP32 CUDA-core kernels run this shape
+    case IQL_INFO_FUSED_FORWARD: *out = e->bound && e->fused_fwd ? 1 : 0; return IQL_OK;
+    case IQL_INFO_CHAINED_BACKWARD: *out = e->bound && e->chain ? 1 : 0; return IQL_OK;
+    default: return IQL_ERR_INVALID;
+  }
 }
 
 extern "C" int iql_set_counters(iql_engine* e, int32_t member, const iql_counters* c) {
@@ -584,6 +620,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
     e->d_maps_first = tab((int64_t)128 * 4 * S * N_PASS);
     e->d_maps_store = tab((int64_t)128 * L * S * N_PASS);
     e->d_maps_c = tab((int64_t)128 * nprob);
+    e->d_maps_chain = tab((int64_t)128 * 2 * 4 * S * (2 * L));
   }
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
@@ -669,6 +706,66 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
         }
     }
   }
+  // ---- chained backward + optimizer: phase list and CTA-pair maps ----
+  e->chain = false;
+  e->h_maps_chain.clear();
+  // opt-in (IQL_OPT_STEP_PATH = 2): measured on the 64-member ensemble the chained backward streams the optimizer state
+  // at 72 % of the HBM peak against 99 % for adam_polyak_kernel and ends up 10 % behind the per-phase kernels
+  // (DESIGN.md section 8); "auto" therefore keeps one kernel per phase
+  if (tc_mode && e->step_path == 2 && e->fw_splits == 1 &&
+      bwd_chain_supported(e->cfg.batch_size, e->cfg.hidden_dim, e->cfg.n_hidden, e->fused_fwd)) {
+    const int L = e->cfg.n_hidden, ntask = 4 * S;
+    BwdChainArgs& ca = e->chain_args;
+    memset(&ca, 0, sizeof(ca));
+    e->h_maps_chain.assign((size_t)128 * 2 * ntask * (2 * L), 0);
+    int np = 0;
+    bool ok = (int)e->bwd_phases.size() == 2 * L + 1;
+    auto add_phase = [&](int kind, const Phase& ph, int tile_n, int k, int wait) {
+      if (!ok) return;
+      if (ph.count != ntask) { ok = false; return; }
+      ca.kind[np] = kind; ca.prob_first[np] = ph.first; ca.map_first[np] = 2 * ntask * np;
+      ca.tile_n[np] = tile_n; ca.k[np] = k; ca.wait_dgrads[np] = wait;
+      if (umma_encode_maps(kind == 0 ? 1 : 2, e->h_probs.data() + ph.first, ph.count, tile_n,
+                           e->h_maps_chain.data() + (size_t)128 * ca.map_first[np], true)) ok = false;
+      ++np;
+    };
+    for (int l = L - 1; l >= 1 && ok; --l) {
+      const Phase& pw = e->bwd_phases[2 * (L - l)];      // dW_l = dZ_l^T H_l
+      const Phase& px = e->bwd_phases[2 * (L - l) + 1];  // dZ_{l-1} = (dZ_l W_l) * [H_l > 0]
+      if (!px.rowepi || px.mode != 1 || pw.mode != 2) { ok = false; break; }
+      add_phase(0, px, 256, e->cfg.hidden_dim, L - 1 - l);
+      add_phase(1, pw, 256, e->cfg.batch_size, L - 1 - l);
+    }
+    if (ok) {
+      const Phase& p0 = e->bwd_phases[2 * L];
+      add_phase(1, p0, bwd_chain_wgrad0_tile_n(p0.maxN), e->cfg.batch_size, L - 1);
+    }
+    if (ok) {
+      ca.n_phases = np;
+      ca.n_tasks = ntask;
+      // parameters no phase covers: everything of a net except the weights of layers 0..L-1; adjacent tensors merge
+      const int slot_net[4] = {IQL_NET_V, IQL_NET_Q1, IQL_NET_Q2, IQL_NET_ACTOR};
+      for (int t = 0; t < 4 && ok; ++t) {
+        int n = 0;
+        for (size_t i = 0; i < e->tensors.size(); ++i) {
+          const iql_tensor_info& ti = e->tensors[i];
+          if (ti.net != slot_net[t]) continue;
+          if (ti.kind == IQL_KIND_WEIGHT && ti.layer < L) continue;
+          const int64_t lo = ti.offset;
+          const int64_t hi = (i + 1 < e->tensors.size()) ? e->tensors[i + 1].offset : e->layout.param_floats;
+          if (n > 0 && ca.seg_hi[t][n - 1] == lo) ca.seg_hi[t][n - 1] = hi;
+          else if (n < FUSED_MAX_LAYERS + 2) { ca.seg_lo[t][n] = lo; ca.seg_hi[t][n] = hi; ++n; }
+          else ok = false;
+        }
+        ca.n_seg[t] = n;
+      }
+    }
+    e->chain = ok;
+    if (!ok) e->h_maps_chain.clear();
+  }
+  if (e->step_path == 2 && !e->chain)
+    return fail(e, IQL_ERR_INVALID, "iql_bind_state: IQL_OPT_STEP_PATH = chained backward, but this shape / math mode does not support it "
+                                    "(needs tf32, hidden 256, batch 256, 2..4 hidden layers)");
   if (!e->side) {  // optional: without it the backward simply stays on one stream
     if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -697,6 +794,8 @@ static int flush_tables(iql_engine* e, cudaStream_t st) {
       CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_c, e->h_maps_c.data(), e->h_maps_c.size(), cudaMemcpyHostToDevice, st));
     if (!e->h_maps_store.empty())
       CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_store, e->h_maps_store.data(), e->h_maps_store.size(), cudaMemcpyHostToDevice, st));
+    if (!e->h_maps_chain.empty())
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_chain, e->h_maps_chain.data(), e->h_maps_chain.size(), cudaMemcpyHostToDevice, st));
     std::vector<int64_t> off(2 * (L + 1));
     for (int l = 0; l <= L; ++l) {
       off[l] = e->w_off[IQL_NET_ACTOR][l];
@@ -971,7 +1070,12 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   // per-kernel timing (tm) keeps everything on one stream
   const bool two_streams = tf32 && !tm && !no_side && e->side != nullptr;
   int forks = 0;
+  // chained backward: the output-layer backward (phases 0, 1) runs as before, everything after it -- hidden dgrad /
+  // wgrad chain, input-layer wgrad, Adam + Polyak -- is ONE launch on CTA pairs
+  const bool chain = e->chain && tf32 && last_ok && e->bwd_phases.size() >= 3 && e->bwd_phases[0].kind == PH_LAST_WGRAD &&
+                     e->bwd_phases[1].kind == PH_LAST_DGRAD;
   for (size_t i = 0; i < e->bwd_phases.size(); ++i) {
+    if (chain && i >= 2) break;
     const Phase& ph = e->bwd_phases[i];
     const Phase* n1 = i + 1 < e->bwd_phases.size() ? &e->bwd_phases[i + 1] : nullptr;
     const Phase* n2 = i + 2 < e->bwd_phases.size() ? &e->bwd_phases[i + 2] : nullptr;
@@ -1004,7 +1108,9 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   // Adam: read g, p, m, v + target; write p, m, v + target (+ the TF32 shadow copies in tcgen05 mode)
   if (tm) tm->mark("adam_polyak", 0, S_d * 4.0 * ((7.0 + (ctx.tf32 ? 1 : 0)) * e->layout.param_floats +
                                                   (2.0 + (ctx.tf32 ? 1 : 0)) * e->layout.q_floats));
-  const bool fork_gather = gather_next && !tm && e->side != nullptr;
+  // (chained backward: its input-layer weight-gradient phase still reads the gathered rows, so the next step's gather
+  // cannot run beside it; the caller then gathers at the top of every step)
+  const bool fork_gather = gather_next && !tm && e->side != nullptr && !chain;
   if (fork_gather) {
     StepCtx next = ctx;
     next.k = ctx.k + 1;
@@ -1014,7 +1120,32 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     cudaEventRecord(e->ev_gather, e->side);
     ++launches;
   }
-  launch_adam(ctx, e->params, e->exp_avg, e->exp_avg_sq, e->target, e->grads, st);
+  if (chain) {
+    if (tm) {
+      double fl = 0, by = 0;
+      for (size_t i = 2; i < e->bwd_phases.size(); ++i) {
+        const Phase& q = e->bwd_phases[i];
+        for (int j = 0; j < q.count; ++j) {
+          const GemmProb& g = e->h_probs[q.first + j];
+          fl += 2.0 * g.M * g.N * g.K;
+          by += 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (q.mode == 1 ? (double)g.M * g.N : 0.0));
+        }
+      }
+      by += S_d * 4.0 * ((6.0 + 1.0) * e->layout.param_floats + 3.0 * e->layout.q_floats);  // p, m, v in and out + shadows
+      tm->label.back() = "bwd_chain";
+      tm->flops.back() = fl;
+      tm->bytes.back() = by;
+    }
+    BwdChainArgs ca = e->chain_args;
+    ca.probs = e->d_probs;
+    ca.maps = e->d_maps_chain;
+    ca.cmaps = e->d_maps_c;
+    ca.keep_grads = e->keep_grads;
+    ca.params = e->params; ca.exp_avg = e->exp_avg; ca.exp_avg_sq = e->exp_avg_sq; ca.target = e->target; ca.grads = e->grads;
+    launch_bwd_chain(ca, ctx, st);
+  } else {
+    launch_adam(ctx, e->params, e->exp_avg, e->exp_avg_sq, e->target, e->grads, st);
+  }
   ++launches;
   if (fork_gather) cudaStreamWaitEvent(st_main, e->ev_gather, 0);
   if (tm) tm->finish();
@@ -1054,7 +1185,8 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
   ctx.idx_out = idx_out;
   const bool gather = sample_mode != IQL_SAMPLE_PRELOADED;
   static const bool no_overlap_gather = getenv("IQL_B200_NO_GATHER_AHEAD") != nullptr || getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
-  const bool overlap_gather = !no_overlap_gather && e->side != nullptr && st != nullptr;
+  // (not with the chained backward: its last phase still reads the gathered rows, see enqueue_step)
+  const bool overlap_gather = !no_overlap_gather && e->side != nullptr && st != nullptr && !e->chain;
   // the legacy default stream cannot be captured; the facade runs the engine on its own stream
   // Graphs: the K-step Philox loop, and the single preloaded step of the drop-in `train(batch)` path (its ~11
   // launches would otherwise be launch-latency bound).  Keyed by K, negative for the preloaded variant.

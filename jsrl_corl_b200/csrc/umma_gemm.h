@@ -46,6 +46,25 @@ bool fused_fwd_supported(int batch, int hidden, int n_hidden, int k0);
 bool fused_fwd_pair(int batch);
 bool fused_fwd_policy_head(int act_dim);  // the actor's output layer fits the fused epilogue  // whether the fused forward runs on CTA pairs for this batch size
 void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st);
+// Chained backward + optimizer (bwd_chain.cu): one CTA pair per (member, trainable net) runs the hidden-layer dgrad /
+// wgrad phases back to back and applies Adam + Polyak in the wgrad epilogues.  Hidden width 256, batch 256,
+// 2..FUSED_MAX_LAYERS hidden layers, fused forward on (it writes the ReLU sign bits the dgrad phases mask with).
+struct BwdChainArgs {
+  const GemmProb* probs;  // the engine's device problem table (base)
+  const void* maps;       // chain tensor maps, CTA-pair boxes: per phase 2 per task (A, B)
+  const void* cmaps;      // store maps of the backward outputs, indexed by absolute problem index
+  int n_phases, n_tasks, keep_grads;
+  int kind[2 * FUSED_MAX_LAYERS];         // 0 dgrad, 1 wgrad + optimizer
+  int prob_first[2 * FUSED_MAX_LAYERS];   // first problem of the phase (task i uses prob_first + i)
+  int map_first[2 * FUSED_MAX_LAYERS];    // first map of the phase inside `maps` (in maps)
+  int tile_n[2 * FUSED_MAX_LAYERS], k[2 * FUSED_MAX_LAYERS], wait_dgrads[2 * FUSED_MAX_LAYERS];
+  int n_seg[4];
+  long long seg_lo[4][FUSED_MAX_LAYERS + 2], seg_hi[4][FUSED_MAX_LAYERS + 2];
+  float *params, *exp_avg, *exp_avg_sq, *target, *grads;
+};
+bool bwd_chain_supported(int batch, int hidden, int n_hidden, bool fused_fwd);
+int bwd_chain_wgrad0_tile_n(int k0);
+void launch_bwd_chain(const BwdChainArgs& a, const StepCtx& ctx, cudaStream_t st);
 // bias gradients of a wgrad phase: dbias[m] = sum_k A[k][m]
 void launch_colsum(const GemmProb* probs, int nprob, int maxM, cudaStream_t st);
 }  // namespace iql

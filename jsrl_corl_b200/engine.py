@@ -56,7 +56,7 @@ class EnsembleEngine:
 
     def __init__(self, n_members: int, state_dim: int, action_dim: int, hidden_dim: int = 256, n_hidden: int = 2,
                  batch_size: int = 256, deterministic: bool = False, math_mode: str = "tf32",
-                 device="cuda", max_steps_per_call: int = 256):
+                 device="cuda", max_steps_per_call: int = 256, step_path: str = "auto", strict_tf32: bool = False):
         self.device = _lib.require_cuda(device)
         self._L = _lib.lib()
         if math_mode not in MATH_MODES:
@@ -69,6 +69,10 @@ class EnsembleEngine:
                      MATH_MODES[math_mode], max_steps_per_call)
         self._h = C.c_void_p()
         _lib.check(self._L.iql_create(C.byref(cfg), C.byref(self._h)), None, "iql_create")
+        if step_path not in _lib.STEP_PATHS:
+            raise ValueError(f"step_path must be one of {sorted(_lib.STEP_PATHS)}")
+        _lib.check(self._L.iql_set_option(self._h, _lib.OPT_STEP_PATH, _lib.STEP_PATHS[step_path]), self._h, "iql_set_option")
+        self.step_path = step_path
         self.layout = Layout()
         _lib.check(self._L.iql_get_layout(self._h, C.byref(self.layout)), self._h)
         self.tensors = []
@@ -92,6 +96,14 @@ class EnsembleEngine:
             _lib.check(self._L.iql_bind_state(self._h, self.params.data_ptr(), self.exp_avg.data_ptr(),
                                               self.exp_avg_sq.data_ptr(), self.target.data_ptr(), self.grads.data_ptr(),
                                               self.workspace.data_ptr(), self.workspace.numel()), self._h, "iql_bind_state")
+        # which kernels serve this shape: math_mode="tf32" outside the tcgen05 shapes (batch % 128, hidden % 256) runs the
+        # FP32 CUDA-core kernels -- reported here, and refused when the caller insists on tensor cores
+        self.paths = {"tensor_cores": bool(self.info(_lib.INFO_TENSOR_CORE_PATH)),
+                      "fused_forward": bool(self.info(_lib.INFO_FUSED_FORWARD)),
+                      "chained_backward": bool(self.info(_lib.INFO_CHAINED_BACKWARD))}
+        if math_mode == "tf32" and strict_tf32 and not self.paths["tensor_cores"]:
+            raise ValueError(f"math_mode='tf32' with strict_tf32: batch {batch_size} / hidden {hidden_dim} is outside the tcgen05 "
+                             "kernels (batch % 128 == 0 and hidden % 256 == 0 required); the FP32 kernels would run")
         self.act_calls = 0
         self._act_in = self._act_out = self._act_in_dev = None
         self._hparams = [self._default_hparams(m) for m in range(n_members)]
@@ -112,6 +124,15 @@ class EnsembleEngine:
         return HParams(beta=3.0, iql_tau=0.7, discount=0.99, tau=0.005, vf_lr=3e-4, qf_lr=3e-4, actor_lr=3e-4,
                        actor_dropout=0.0, adam_beta1=0.9, adam_beta2=0.999, adam_eps=1e-8, lr_eta_min=0.0,
                        cosine_t_max=1000000, seed=m)
+
+    def info(self, key: int) -> int:
+        out = C.c_int64(0)
+        _lib.check(self._L.iql_get_info(self._h, key, C.byref(out)), self._h, "iql_get_info")
+        return int(out.value)
+
+    def keep_grads(self, on: bool = True):
+        """The chained backward consumes weight gradients in its epilogue; with this on it also stores them to `grads`."""
+        _lib.check(self._L.iql_set_option(self._h, _lib.OPT_KEEP_GRADS, int(bool(on))), self._h, "iql_set_option")
 
     def set_hparams(self, member: int, **kw):
         hp = self._hparams[member]

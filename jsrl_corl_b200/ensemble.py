@@ -45,9 +45,9 @@ class IQLEnsemble:
                  batch_size: int = 256, deterministic: bool = False, actor_dropout: float = 0.0,
                  math_mode: str = "tf32", device="cuda", max_steps_per_call: int = 256,
                  seeds: Optional[Sequence[int]] = None, hparams: Optional[Sequence[Dict[str, Any]]] = None,
-                 init: bool = True):
+                 init: bool = True, step_path: str = "auto"):
         self.engine = EnsembleEngine(n_members, state_dim, action_dim, hidden_dim, n_hidden, batch_size,
-                                     deterministic, math_mode, device, max_steps_per_call)
+                                     deterministic, math_mode, device, max_steps_per_call, step_path=step_path)
         self.n_members = n_members
         self.actor_dropout = actor_dropout
         self.seeds = list(seeds) if seeds is not None else list(range(n_members))

@@ -525,7 +525,7 @@ class ImplicitQLearning:
                  q_network: nn.Module, q_optimizer: torch.optim.Optimizer, v_network: nn.Module,
                  v_optimizer: torch.optim.Optimizer, iql_tau: float = 0.7, beta: float = 3.0,
                  max_steps: Optional[int] = 1000000, discount: float = 0.99, tau: float = 0.005,
-                 device: str = "cpu", *, math_mode: str = "tf32", seed: int = 0):
+                 device: str = "cpu", *, math_mode: str = "tf32", seed: int = 0, step_path: str = "auto"):
         self.device = _lib.require_cuda(device)
         if not isinstance(q_network, TwinQ) or not isinstance(v_network, ValueFunction) or \
                 not isinstance(actor, (GaussianPolicy, DeterministicPolicy)):
@@ -538,7 +538,7 @@ class ImplicitQLearning:
         self.v_optimizer, self.q_optimizer, self.actor_optimizer = v_optimizer, q_optimizer, actor_optimizer
         self.actor_lr_schedule = CosineAnnealingLR(self.actor_optimizer, max_steps) if max_steps is not None else None
         self.iql_tau, self.beta, self.discount, self.tau = iql_tau, beta, discount, tau
-        self._math_mode, self._seed = math_mode, int(seed)
+        self._math_mode, self._seed, self._step_path = math_mode, int(seed), step_path
         self._engine: Optional[EnsembleEngine] = None
         self._pushed = None
         self._total_it = 0
@@ -582,7 +582,7 @@ class ImplicitQLearning:
             self._pull_counters()
             self._publish_optimizer_state()
         eng = EnsembleEngine(1, S, A, H, L, batch_size, isinstance(self.actor, DeterministicPolicy),
-                             self._math_mode, self.device, max_steps_per_call=64)
+                             self._math_mode, self.device, max_steps_per_call=64, step_path=self._step_path)
         drop_keys = self.actor.net.has_dropout_modules
         views = eng.param_views(0, drop_keys)
         m_views, v_views = eng.moment_views(0, drop_keys)

@@ -34,11 +34,12 @@ def _cpu_tree(views):
     return {g: {k: v.detach().cpu().numpy() for k, v in d.items()} for g, d in views.items()}
 
 
-def _make_engine(g, math_mode, n_members=1, max_k=64):
+def _make_engine(g, math_mode, n_members=1, max_k=64, step_path="auto"):
     from jsrl_corl_b200 import EnsembleEngine, ReplayBuffer
 
     m = g.meta
-    eng = EnsembleEngine(n_members, m["S"], m["A"], m["H"], m["L"], m["B"], bool(m["det"]), math_mode, "cuda", max_k)
+    eng = EnsembleEngine(n_members, m["S"], m["A"], m["H"], m["L"], m["B"], bool(m["det"]), math_mode, "cuda", max_k,
+                         step_path=step_path)
     rb = ReplayBuffer(m["S"], m["A"], m["n_rows"], "cuda")
     rb.load_d4rl_dataset(g.dataset())
     init = g.init_tree()
@@ -165,12 +166,14 @@ def test_update_matches_reference_short_horizon_fp32(name, steps):
     assert worst < FP32_TOL, (worst, where)
 
 
-@pytest.mark.parametrize("variant", ["default", "cta_pairs", "per_layer_forward_cta_pairs", "per_layer_forward",
-                                     "fused_single_cta"])
+@pytest.mark.parametrize("variant", ["default", "chained_backward", "cta_pairs", "per_layer_forward_cta_pairs",
+                                     "per_layer_forward", "fused_single_cta"])
 @pytest.mark.parametrize("name,steps", CASES)
 def test_update_matches_reference_short_horizon_tf32(name, steps, variant, monkeypatch):
     """default: fused forward on CTA pairs (hidden layers chained through tensor memory, policy head in the last
-    epilogue) + single-CTA backward GEMMs.
+    epilogue) + single-CTA backward GEMMs + adam_polyak.
+    chained_backward (step_path="chain", hidden 256 / batch 256 shapes): bwd_chain.cu -- the dgrad / wgrad phases of a
+    (member, net) on one CTA pair, Adam + Polyak in the wgrad epilogues, no gradient arena round trip.
     cta_pairs: every eligible per-layer tcgen05 phase (dgrad with the bias gradient exchanged through DSMEM,
     wgrad) on CTA pairs (cta_group::2).  per_layer_forward: one launch per layer (3xTF32 input layer, hidden
     forward with the fused heads) instead of the fused forward, with and without CTA pairs."""
@@ -182,7 +185,13 @@ def test_update_matches_reference_short_horizon_tf32(name, steps, variant, monke
         monkeypatch.setenv("IQL_B200_NO_FUSED_PAIR", "1")
         monkeypatch.setenv("IQL_B200_NO_FUSED_POLICY", "1")
     g = Golden(name)
-    eng, _ = _make_engine(g, "tf32")
+    chain = variant == "chained_backward"
+    if chain and not (g.meta["H"] == 256 and g.meta["B"] == 256):
+        with pytest.raises(ValueError, match="chained backward"):  # unsupported shape: refused, never silently replaced
+            _make_engine(g, "tf32", step_path="chain")
+        return
+    eng, _ = _make_engine(g, "tf32", step_path="chain" if chain else "auto")
+    assert eng.paths["chained_backward"] == chain and eng.paths["tensor_cores"] == (g.meta["H"] % 256 == 0 and g.meta["B"] % 128 == 0)
     losses = _run_indices(eng, g, steps)[0]
     err = _loss_errors(losses, g.losses[:steps].astype(np.float64))
     # the actor loss carries exp(beta * adv): its sensitivity to a perturbation of adv scales with beta
@@ -702,3 +711,50 @@ def test_full_size_properties_64_members_1m_rows():
     split = make(seeds)
     ls = np.concatenate([split.train_steps(2).cpu().numpy(), split.train_steps(4).cpu().numpy()], axis=1)
     assert np.array_equal(ls, losses)
+
+
+# ---------------------------------------------------------------------------
+# chained backward + optimizer in the wgrad epilogue (bwd_chain.cu)
+# ---------------------------------------------------------------------------
+def test_chained_backward_gradients_and_state_against_per_phase_path():
+    """One step on two engines from the same state: the weight gradients the chain keeps (IQL_OPT_KEEP_GRADS) equal the
+    per-phase kernels' bit for bit (same GEMM tiles, same operands); parameters / moments / target agree to the
+    approximate-sqrt / reciprocal tolerance of its optimizer epilogue; 25 fused steps stay within the TF32 bars."""
+    g = Golden("antmaze_3x256")  # 3 hidden layers: two dgrad -> wgrad hand-overs per task
+    a, _ = _make_engine(g, "tf32")
+    b, _ = _make_engine(g, "tf32", step_path="chain")
+    b.keep_grads(True)
+    la = _run_indices(a, g, 1)[0]
+    lb = _run_indices(b, g, 1)[0]
+    np.testing.assert_array_equal(la, lb)  # same forward, same loss kernel
+    ga, gb = _cpu_tree(a.grad_views(0)), _cpu_tree(b.grad_views(0))
+    for grp in ga:
+        for k in ga[grp]:
+            np.testing.assert_array_equal(ga[grp][k], gb[grp][k], err_msg=f"{grp}/{k}")
+    pa, pb = _cpu_tree(a.param_views(0)), _cpu_tree(b.param_views(0))
+    for grp in pa:
+        for k in pa[grp]:
+            # one Adam step moves a weight by ~lr = 3e-4; the two optimizers may differ by a few ulp of that step
+            np.testing.assert_allclose(pa[grp][k], pb[grp][k], rtol=0, atol=3e-4 * 1e-5, err_msg=f"{grp}/{k}")
+    ta, tb = a.target_views(0), b.target_views(0)
+    for k in ta:
+        np.testing.assert_allclose(ta[k].cpu().numpy(), tb[k].cpu().numpy(), rtol=0, atol=3e-4 * 1e-5)
+    ma, va = a.moment_views(0)
+    mb, vb = b.moment_views(0)
+    for grp in ma:
+        for k in ma[grp]:
+            np.testing.assert_allclose(ma[grp][k].cpu().numpy(), mb[grp][k].cpu().numpy(), rtol=1e-6, atol=1e-12)
+            np.testing.assert_allclose(va[grp][k].cpu().numpy(), vb[grp][k].cpu().numpy(), rtol=1e-6, atol=1e-20)
+
+
+def test_chained_backward_ensemble_k_fusion_and_launch_count():
+    """8 members x K = 6 in one call == six calls of one step (bit-identical), and 5 launches per step + 1."""
+    g = Golden("halfcheetah_2x256")
+    one, _ = _make_engine(g, "tf32", n_members=8, step_path="chain")
+    six, _ = _make_engine(g, "tf32", n_members=8, step_path="chain")
+    l6 = six.train_steps(6).cpu().numpy()
+    assert six.last_launch_count() == 6 * 5 + 1  # gather, fused forward, loss, output-layer backward, chain (+ advance)
+    l1 = np.concatenate([one.train_steps(1).cpu().numpy() for _ in range(6)], axis=1)
+    np.testing.assert_array_equal(l1, l6)
+    assert torch.equal(one.params, six.params) and torch.equal(one.exp_avg_sq, six.exp_avg_sq) and torch.equal(one.target, six.target)
+    assert not np.array_equal(l6[0], l6[1])  # members have their own Philox streams
