@@ -162,6 +162,16 @@ int iql_replay_row_layout(int32_t state_dim, int32_t action_dim, iql_row_layout*
 int iql_replay_pack(float* rows, const iql_row_layout* lay, int64_t first_row, int64_t n,
                     const float* states, const float* actions, const float* rewards,
                     const float* next_states, const float* dones, void* stream);
+/* replaces: the dataset preprocessing in front of load_d4rl_dataset -- compute_mean_std / normalize_states
+ * (iql.py:77-84; jsrl_w_iql.py:349-360) and the arithmetic of modify_reward (iql.py:286-297) -- fused with the pack:
+ * normalize != 0 computes mean[S] and std[S] = sqrt(var) + eps of `states` with numpy's row-order fp32 summation
+ * (bit-exact against states.mean(0) / states.std(0)), writes them to mean_out / std_out (device) and stores
+ * (x - mean) / std for states and next_states; rewards are stored as (r / reward_div) * reward_mul - reward_sub
+ * (pass 1, 1, 0 for none).  All inputs are dense device arrays as for iql_replay_pack. */
+int iql_replay_ingest(float* rows, const iql_row_layout* lay, int64_t first_row, int64_t n, const float* states,
+                      const float* actions, const float* rewards, const float* next_states, const float* dones,
+                      int32_t normalize, float eps, float* mean_out, float* std_out, float reward_div, float reward_mul,
+                      float reward_sub, void* stream);
 /* replaces: ReplayBuffer.add_transition iql.py:180-196 (one fused row insert;
  * `staged_row` is a device row in packed layout) */
 int iql_replay_insert(float* rows, const iql_row_layout* lay, int64_t pointer,

@@ -95,6 +95,8 @@ SYMBOLS = {
     "iql_sync_target": (C.c_int, [_P, C.c_int32, _P]),
     "iql_replay_row_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(RowLayout)]),
     "iql_replay_pack": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "iql_replay_ingest": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, C.c_float,
+                                    _P, _P, C.c_float, C.c_float, C.c_float, _P]),
     "iql_replay_insert": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, _P, _P]),
     "iql_replay_sample": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, C.c_int64, _P, C.c_uint64, C.c_uint64,
                                     _P, _P, _P, _P, _P, _P, _P]),

@@ -55,6 +55,71 @@ __global__ void replay_pack_kernel(float* __restrict__ rows, iql_row_layout lay,
   }
 }
 
+// ---- dataset ingest: column statistics with numpy's summation order, then normalise + rescale + pack ----------
+// numpy reduces a C-contiguous [n][S] float32 array along axis 0 row by row -- one running fp32 sum per column, no
+// pairwise blocking -- so `states.mean(0)` / `states.std(0)` (compute_mean_std, finetune/iql.py:77-80) are reproduced
+// bit for bit by ONE thread per column that walks the rows in order; 8 loads are in flight per thread and the adds are
+// applied in row order.  mode 0: sum of x -> mean = sum / n.  mode 1: sum of (x - mean)^2 -> std = sqrt(sum / n) + eps.
+__global__ void colstat_kernel(const float* __restrict__ x, int64_t n, int S, int mode, const float* __restrict__ mean_in,
+                               float eps, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= S) return;
+  const float mu = mode ? mean_in[c] : 0.f;
+  float acc = 0.f;
+  int64_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = x[(i + j) * S + c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (mode) { const float d = __fsub_rn(v[j], mu); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+      else acc = __fadd_rn(acc, v[j]);
+    }
+  }
+  for (; i < n; ++i) {
+    const float v = x[i * S + c];
+    if (mode) { const float d = __fsub_rn(v, mu); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+    else acc = __fadd_rn(acc, v);
+  }
+  const float q = __fdiv_rn(acc, (float)n);
+  out[c] = mode ? __fadd_rn(__fsqrt_rn(q), eps) : q;
+}
+
+// pack with the reference's preprocessing applied on the way: states and next states (x - mean) / std
+// (normalize_states, finetune/iql.py:83-84), rewards (r / div) * mul - sub (modify_reward, :286-297: locomotion
+// div = max_ret - min_ret, mul = max_episode_steps; antmaze sub = 1), each operation rounded like numpy's float32 ops
+__global__ void replay_ingest_kernel(float* __restrict__ rows, iql_row_layout lay, int64_t first_row, int64_t n,
+                                     const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ r,
+                                     const float* __restrict__ s2, const float* __restrict__ d,
+                                     const float* __restrict__ mean, const float* __restrict__ stdv, float rdiv, float rmul,
+                                     float rsub, int scale_reward) {
+  const int RF = lay.row_floats, S = lay.state_dim, A = lay.action_dim;
+  const int64_t total = n * RF;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / RF;
+    const int c = (int)(i - row * RF);
+    float v = 0.f;
+    if (c < S) {
+      v = s[row * S + c];
+      if (mean) v = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+    } else if (c < S + A) {
+      v = a[row * A + (c - S)];
+    } else if (c >= lay.off_next_state && c < lay.off_next_state + S) {
+      const int k = c - lay.off_next_state;
+      v = s2[row * S + k];
+      if (mean) v = __fdiv_rn(__fsub_rn(v, mean[k]), stdv[k]);
+    } else if (c == lay.off_reward) {
+      v = r[row];
+      if (scale_reward) v = __fmul_rn(__fdiv_rn(v, rdiv), rmul);
+      if (rsub != 0.f) v = __fsub_rn(v, rsub);
+    } else if (c == lay.off_done) {
+      v = d[row];
+    }
+    rows[(first_row + row) * RF + c] = v;
+  }
+}
+
 __global__ void replay_insert_kernel(float* __restrict__ rows, int RF, int64_t pointer,
                                      const float* __restrict__ staged) {
   for (int c = threadIdx.x; c < RF; c += blockDim.x) rows[pointer * RF + c] = staged[c];  // any row width
@@ -109,6 +174,28 @@ extern "C" int iql_replay_pack(float* rows, const iql_row_layout* lay, int64_t f
   int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   replay_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, *lay, first_row, n, states, actions, rewards,
                                                                next_states, dones);
+  return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
+}
+
+extern "C" int iql_replay_ingest(float* rows, const iql_row_layout* lay, int64_t first_row, int64_t n, const float* states,
+                                 const float* actions, const float* rewards, const float* next_states, const float* dones,
+                                 int32_t normalize, float eps, float* mean_out, float* std_out, float reward_div,
+                                 float reward_mul, float reward_sub, void* stream) {
+  if (!layout_ok(lay) || !rows || n < 0 || first_row < 0) return IQL_ERR_INVALID;
+  if (n == 0) return IQL_OK;
+  if (!states || !actions || !rewards || !next_states || !dones) return IQL_ERR_INVALID;
+  if (normalize && (!mean_out || !std_out)) return IQL_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = lay->state_dim;
+  if (normalize) {
+    colstat_kernel<<<(S + 31) / 32, 32, 0, st>>>(states, n, S, 0, nullptr, 0.f, mean_out);
+    colstat_kernel<<<(S + 31) / 32, 32, 0, st>>>(states, n, S, 1, mean_out, eps, std_out);
+  }
+  const int64_t total = n * lay->row_floats;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  replay_ingest_kernel<<<blocks, 256, 0, st>>>(rows, *lay, first_row, n, states, actions, rewards, next_states, dones,
+                                                normalize ? mean_out : nullptr, normalize ? std_out : nullptr, reward_div,
+                                                reward_mul, reward_sub, (reward_div != 1.0f || reward_mul != 1.0f) ? 1 : 0);
   return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
 }
 

@@ -280,6 +280,45 @@ class ReplayBuffer:
         self._pointer = min(self._size, n)
         print(f"Dataset size: {n}")
 
+    def ingest_d4rl_dataset(self, data: Dict[str, np.ndarray], normalize: bool = True, eps: float = 1e-3,
+                            reward_mod: Optional[Dict[str, float]] = None, reward_shift: float = 0.0):
+        """The reference's preprocessing + load in one device pass (jsrl_w_iql.py:344-368): state mean / std with
+        numpy's summation order (bit-exact against ``compute_mean_std``, iql.py:77-80), ``normalize_states`` of
+        observations and next observations, the reward rescaling of ``modify_reward`` (``reward_mod`` = its return
+        value for locomotion tasks; ``reward_shift=1`` for antmaze), then the pack.  ``data`` is NOT modified.
+        Returns ``(state_mean, state_std)`` as numpy arrays (``(0, 1)`` when ``normalize`` is off), which the caller
+        hands to ``wrap_env`` exactly as with the reference functions."""
+        if self._size != 0:
+            raise ValueError("Trying to load data into non-empty replay buffer")
+        n = data["observations"].shape[0]
+        if n > self._buffer_size:
+            raise ValueError("Replay buffer is smaller than the dataset you are trying to load!")
+        s = self._to_tensor(data["observations"]).contiguous()
+        a = self._to_tensor(data["actions"]).contiguous()
+        r = self._to_tensor(data["rewards"]).reshape(-1).contiguous()
+        s2 = self._to_tensor(data["next_observations"]).contiguous()
+        d = self._to_tensor(data["terminals"]).reshape(-1).contiguous()
+        if s.shape[1] != self._state_dim or a.shape[1] != self._action_dim:
+            raise ValueError("dataset dims do not match the buffer")
+        mean = torch.zeros(self._state_dim, dtype=torch.float32, device=self._device)
+        std = torch.ones(self._state_dim, dtype=torch.float32, device=self._device)
+        rdiv = rmul = 1.0
+        if reward_mod:
+            rdiv = float(np.float32(reward_mod["max_ret"] - reward_mod["min_ret"]))
+            rmul = float(reward_mod["max_episode_steps"])
+        with torch.cuda.device(self._device):
+            _lib.check(self._L.iql_replay_ingest(self._rows.data_ptr(), C.byref(self._lay), 0, n, s.data_ptr(), a.data_ptr(),
+                                                 r.data_ptr(), s2.data_ptr(), d.data_ptr(), int(bool(normalize)), float(eps),
+                                                 mean.data_ptr(), std.data_ptr(), rdiv, rmul, float(reward_shift),
+                                                 self._stream()), None, "iql_replay_ingest")
+        torch.cuda.current_stream(self._device).synchronize()
+        self._size += n
+        self._pointer = min(self._size, n)
+        print(f"Dataset size: {n}")
+        if not normalize:
+            return 0, 1
+        return mean.cpu().numpy(), std.cpu().numpy()
+
     def _high(self) -> int:
         return min(self._size, self._pointer) if self._offline_semantics else self._size
 

@@ -85,6 +85,26 @@ def jsrl_online_actor(config, env, trainer, state_dim, action_dim, max_action, h
     return trainer, guide, config
 
 
+def make_offline_buffer(config, dataset: Dict[str, np.ndarray], state_dim: int, action_dim: int, max_episode_steps: int = 1000):
+    """Dataset -> device replay buffer the way the reference driver does it (jsrl_w_iql.py:344-368), with the
+    arithmetic on the GPU: ``return_reward_range`` (host scan, as in the reference) gives the locomotion reward range,
+    ``ReplayBuffer.ingest_d4rl_dataset`` computes the state statistics, normalises, rescales rewards and packs.
+    Returns (replay_buffer, state_mean, state_std, reward_mod_dict); wrap the envs with the statistics as before."""
+    from .iql import return_reward_range
+
+    reward_mod, shift = {}, 0.0
+    if config.normalize_reward:
+        if any(s in config.env for s in ("halfcheetah", "hopper", "walker2d")):
+            lo, hi = return_reward_range(dataset, max_episode_steps)
+            reward_mod = {"max_ret": hi, "min_ret": lo, "max_episode_steps": max_episode_steps}
+        elif "antmaze" in config.env:
+            shift = 1.0
+    rb = ReplayBuffer(state_dim, action_dim, config.buffer_size, config.device)
+    mean, std = rb.ingest_d4rl_dataset(dataset, normalize=bool(config.normalize), eps=1e-3, reward_mod=reward_mod or None,
+                                       reward_shift=shift)
+    return rb, mean, std, reward_mod
+
+
 def train_loop(config, env, eval_env, replay_buffer: Optional[ReplayBuffer], state_dim: int, action_dim: int,
                max_action: float, max_steps: int, log: Optional[Callable[[Dict, int], None]] = None,
                reward_mod_dict: Optional[Dict] = None, heuristics=None, is_env_with_goal: bool = False):

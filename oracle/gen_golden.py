@@ -219,8 +219,72 @@ def resume_golden():
     print(f"resume: checkpoint {os.path.getsize(path) / 1e6:.2f} MB, final losses {losses[-1]}")
 
 
+def late_snapshot(name, S, A, H, L, det, B, at, *, n_rows=10000, beta=3.0, iql_tau=0.7, tau=0.005, discount=0.99, lr=3e-4,
+                  seed=0, idx_seed=1, antmaze=False, max_steps=None):
+    """Teacher-forcing fixture for the LATE trajectory (nothing tight between step 40 and 1000): the full
+    reference state after `at` free-running steps -- weights, target network, Adam moments, step counts, schedule epoch
+    -- then ONE more reference step from it: its batch indices, its three losses and the post-step weights / target
+    (every 16th element: enough to pin an independent one-step computation, 1/16 of the bytes).  At at = 999 with
+    T_max = 1000 this is the large-step-count / bias-correction ~ 1 / cosine-LR ~ 0 regime."""
+    ref = load_reference_iql("finetune")
+    max_steps = at + 1 if max_steps is None else max_steps
+    torch.manual_seed(seed)
+    q, v = ref.TwinQ(S, A, H, L), ref.ValueFunction(S, H, L)
+    actor = (ref.DeterministicPolicy if det else ref.GaussianPolicy)(S, A, 1.0, H, L)
+    vo, qo, ao = (torch.optim.Adam(m.parameters(), lr=lr) for m in (v, q, actor))
+    tr = ref.ImplicitQLearning(1.0, actor, ao, q, qo, v, vo, iql_tau=iql_tau, beta=beta, max_steps=max_steps, discount=discount,
+                               tau=tau, device="cpu")
+    data = synthetic_dataset(n_rows, S, A, 0, antmaze_rewards=antmaze)
+    rb = ref.ReplayBuffer(S, A, n_rows, "cpu")
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        rb.load_d4rl_dataset(data)
+    np.random.seed(idx_seed)
+    losses = []
+    for _ in range(at):
+        log = tr.train(rb.sample(B))
+        losses.append([log["value_loss"], log["q_loss"], log["actor_loss"]])
+    meta = dict(S=S, A=A, H=H, L=L, det=int(det), B=B, steps=at + 1, n_rows=n_rows, beta=beta, iql_tau=iql_tau, tau=tau,
+                discount=discount, lr=lr, dropout=0.0, seed=seed, idx_seed=idx_seed, antmaze=int(antmaze), max_steps=max_steps)
+    out = {"meta_keys": np.array(list(meta.keys())), "meta_vals": np.array([float(x) for x in meta.values()], dtype=np.float64)}
+    pre = f"step{at}"
+    out.update(flat_state(q, v, actor, pre))
+    out.update({f"{pre}/q_target/{k}": x.numpy().copy() for k, x in tr.q_target.state_dict().items()})
+    for grp, mod, opt in (("qf", q, qo), ("vf", v, vo), ("actor", actor, ao)):
+        out.update(flat_opt(opt, mod, grp, f"{pre}/opt"))
+    out[f"{pre}/actor_lr"] = np.float64(ao.param_groups[0]["lr"])
+    out[f"{pre}/sched_epoch"] = np.int64(tr.actor_lr_schedule.last_epoch)
+    state = np.random.get_state()
+    batch = rb.sample(B)
+    np.random.set_state(state)
+    idx = np.random.randint(0, rb._size, size=B)
+    log = tr.train(batch)
+    losses.append([log["value_loss"], log["q_loss"], log["actor_loss"]])
+    out["next_indices"] = idx.astype(np.int64)
+    out["losses"] = np.array(losses, dtype=np.float32)
+    out["indices_sha256"] = np.array(hashlib.sha256(idx.astype(np.int64).tobytes()).hexdigest())
+    post = f"step{at + 1}"
+    for k, a in flat_state(q, v, actor, post).items():
+        out[k + "@16"] = a.reshape(-1)[::16].copy()
+    for k, x in tr.q_target.state_dict().items():
+        out[f"{post}/q_target/{k}@16"] = x.numpy().reshape(-1)[::16].copy()
+    out[f"{post}/actor_lr"] = np.float64(ao.param_groups[0]["lr"])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  losses at step {at + 1}: {losses[-1]}  actor lr {ao.param_groups[0]['lr']:.3e}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--pen-only" in sys.argv:
+        torch.set_num_threads(8)
+        run_reference("pen_2x256_dropout", 45, 24, 256, 2, False, 256, 6, {6}, dropout=0.1, iql_tau=0.8, store_indices=False, lean=True)
+        return
+    if "--late-only" in sys.argv:
+        torch.set_num_threads(8)
+        late_snapshot("hopper_late_999", 11, 3, 256, 2, True, 256, 999, tau=0.001)
+        late_snapshot("antmaze_late_999", 29, 8, 256, 3, False, 256, 999, beta=10.0, iql_tau=0.9, antmaze=True)
+        return
     resume_golden()
     torch.set_num_threads(8)
     sampler_golden()
@@ -229,12 +293,17 @@ def main():
     run_reference("small_det", 5, 2, 32, 1, True, 16, 20, {1, 20})
     # dropout actor (pen-like, small) with injected masks
     run_reference("small_dropout", 45, 24, 64, 2, False, 32, 12, {1, 12}, dropout=0.1, iql_tau=0.8)
+    # BASELINE configs[3] at full shape: pen-human (obs 45, act 24), dropout actor p = 0.1, injected masks
+    run_reference("pen_2x256_dropout", 45, 24, 256, 2, False, 256, 6, {6}, dropout=0.1, iql_tau=0.8, store_indices=False, lean=True)
     # antmaze shape, 3 hidden layers, beta 10
     run_reference("antmaze_3x256", 29, 8, 256, 3, False, 256, 30, {30}, beta=10.0, iql_tau=0.9, antmaze=True, store_indices=False, lean=True)
     # halfcheetah shape, Gaussian, full width
     run_reference("halfcheetah_2x256", 17, 6, 256, 2, False, 256, 30, {30}, store_indices=False, lean=True)
     # config 1: hopper-medium, deterministic, polyak 0.001, 1000 steps with fp64 noise floor
     run_reference("hopper_1000", 11, 3, 256, 2, True, 256, 1000, {1000}, tau=0.001, with_fp64=True, store_indices=False, lean=True)
+    # late-trajectory teacher-forcing snapshots (same runs as hopper_1000 / a 1000-step antmaze 3x256 beta 10 run)
+    late_snapshot("hopper_late_999", 11, 3, 256, 2, True, 256, 999, tau=0.001)
+    late_snapshot("antmaze_late_999", 29, 8, 256, 3, False, 256, 999, beta=10.0, iql_tau=0.9, antmaze=True)
 
 
 if __name__ == "__main__":

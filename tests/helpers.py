@@ -121,3 +121,40 @@ def network_errors_vs_floor(g, state, step_prefix):
             floor += (float(g.z[f"noise/{grp}/{k}"]) ** 2) * float(np.sum(ref ** 2))
         out[grp] = (np.sqrt(num / den), np.sqrt(floor / den))
     return out
+
+
+class LateSnapshot(Golden):
+    """tests/golden/*_late_<at>.npz (oracle/gen_golden.py::late_snapshot): the full reference state after `at` steps,
+    the batch indices / losses of step at + 1 and every 16th element of the post-step weights and target."""
+
+    def __init__(self, name):
+        super().__init__(name)
+        self.at = self.meta["steps"] - 1
+        self.pre = f"step{self.at}"
+        self.next_indices = self.z["next_indices"].astype(np.int64)
+        self.next_losses = self.losses[-1].astype(np.float64)
+
+    def post_sampled(self):
+        """{"qf"/"vf"/"actor"/"q_target": {name: values[::16]}} after step at + 1."""
+        out, pre = {}, f"step{self.at + 1}/"
+        for key in self.z.files:
+            if key.startswith(pre) and key.endswith("@16"):
+                grp, name = key[len(pre):-3].split("/", 1)
+                out.setdefault(grp, {})[name] = self.z[key]
+        return out
+
+    def load_into_oracle(self, dtype=np.float32):
+        from oracle.iql_numpy import NumpyIQL
+
+        tree = self.tree(self.pre)
+        orc = NumpyIQL(self.oracle_config(), tree, dtype)
+        opt = self.opt(self.pre)
+        for grp, o in (("qf", orc.q_opt), ("vf", orc.v_opt), ("actor", orc.a_opt)):
+            o.step_count = self.at
+            for name, (m, v) in opt[grp].items():
+                o.exp_avg[name][...] = m
+                o.exp_avg_sq[name][...] = v
+        orc.sched_epoch = int(self.z[f"{self.pre}/sched_epoch"])
+        orc.a_opt.lr = float(self.z[f"{self.pre}/actor_lr"])
+        orc.total_it = self.at
+        return orc

@@ -95,3 +95,23 @@ def test_oracle_against_live_reference():
         lo = orc.train(batch)
         for k in lr:
             assert abs(lr[k] - lo[k]) <= 2e-5 * abs(lr[k]) + 1e-8
+
+
+@pytest.mark.parametrize("name", ["hopper_late_999", "antmaze_late_999"])
+def test_oracle_one_step_from_late_reference_snapshot(name):
+    """Late-trajectory regime (Adam step 1000, bias corrections ~ 1, cosine LR ~ 0, saturated exp(beta adv) clamp for
+    antmaze): ONE oracle step from the reference's own state at step 999 reproduces the reference's step 1000."""
+    from helpers import LateSnapshot
+
+    g = LateSnapshot(name)
+    orc = g.load_into_oracle(np.float32)
+    lo = orc.train(batch_from(g.dataset(), g.next_indices))
+    got = np.array([lo["value_loss"], lo["q_loss"], lo["actor_loss"]])
+    np.testing.assert_allclose(got, g.next_losses, rtol=1e-5)
+    post = g.post_sampled()
+    state = orc.state()
+    for grp, d in post.items():
+        for k, want in d.items():
+            have = np.asarray(state[grp][k]).reshape(-1)[::16]
+            np.testing.assert_allclose(have, want, rtol=1e-5, atol=1e-7, err_msg=f"{grp}/{k}")
+    assert abs(orc.a_opt.lr - float(g.z[f"step{g.at + 1}/actor_lr"])) < 1e-15
