@@ -40,7 +40,8 @@ WORKLOADS = {
     "antmaze_jsrl": dict(S=29, A=8, H=256, L=3, B=256, det=False, dropout=0.0, members=1, beta=10.0, iql_tau=0.9,
                          tau=0.005, antmaze=True, desc="BASELINE configs[1]: antmaze-umaze shape, 3x256, single learner"),
     "pen_sweep256": dict(S=45, A=24, H=256, L=2, B=256, det=False, dropout=0.1, members=256, beta=3.0, iql_tau=0.8,
-                         tau=0.005, antmaze=False, desc="BASELINE configs[3]: pen-human shape, dropout actor, 256-member sweep"),
+                         tau=0.005, antmaze=False, scaling="strong",
+                         desc="BASELINE configs[3]: pen-human shape, dropout actor, 256-member sweep SPLIT over the GPUs"),
     "stress_4x1024": dict(S=11, A=3, H=1024, L=4, B=4096, det=True, dropout=0.0, members=1, beta=3.0, iql_tau=0.7,
                           tau=0.005, antmaze=False, desc="BASELINE configs[4]: batch 4096, 4x1024 MLPs, hopper shape"),
 }
@@ -361,7 +362,7 @@ def run_reference_arm(args, w, rank):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
-def run_ours(args, w, rank, world, local_rank):
+def run_ours(args, w, rank, world, local_rank, collect=None):
     import numpy as np
     import torch
 
@@ -374,9 +375,15 @@ def run_ours(args, w, rank, world, local_rank):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
-    S_local = w["members"]
+    scaling = w.get("scaling", "weak")
+    if scaling == "strong":  # a fixed member count split over the ranks (pen sweep: 256 -> 128 / 64 / 32 per GPU)
+        if w["members"] % world:
+            raise SystemExit(f"{w['members']} members do not split over {world} GPUs")
+        S_local = w["members"] // world
+    else:
+        S_local = w["members"]
     # one bench step = `inner` updates per member in ONE engine call; sized so that the default 20 timed steps last >= 2 s
-    inner = args.inner if args.inner else ((320 if w["members"] >= 32 else 1000) if w["H"] <= 256 and w["B"] <= 256 else 16)
+    inner = args.inner if args.inner else ((320 if w["members"] >= 32 else 1000) if w["H"] <= 256 and w["B"] <= 256 else 100)
     first_member = rank * S_local  # weak scaling: every GPU trains its own block of members
     seeds = list(range(first_member, first_member + S_local))
     hp = [dict(beta=w["beta"], iql_tau=w["iql_tau"], tau=w["tau"], cosine_t_max=1_000_000) for _ in seeds]
@@ -522,7 +529,7 @@ def run_ours(args, w, rank, world, local_rank):
         line = {
             "metric": "iql_gradient_steps_per_sec_summed_over_seeds", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "desc": w["desc"], "members_per_gpu": S_local, "members_total": world * S_local,
                        "inner_steps_per_bench_step": inner, "batch": w["B"], "hidden": f'{w["L"]}x{w["H"]}', "obs": w["S"],
                        "act": w["A"], "buffer_rows": N_ROWS, "sampler": "philox in-kernel",
@@ -546,7 +553,12 @@ def run_ours(args, w, rank, world, local_rank):
             "flop_per_member_step": fl,
             "last_losses_member0": [float(x) for x in final[0, -1]],
         }
-        print(json.dumps(line), flush=True)
+        if collect is not None:
+            collect.append(line)
+        else:
+            print(json.dumps(line), flush=True)
+    del ens, eng, rb
+    torch.cuda.empty_cache()
     if world > 1:
         dist.destroy_process_group()
 
@@ -599,6 +611,8 @@ def main():
     ap.add_argument("--no-eager", action="store_true", help="skip the stock-torch-on-GPU leg (torch_eager_b200)")
     ap.add_argument("--no-dropin", action="store_true", help="skip the S=1 drop-in loop leg (e2e_dropin)")
     ap.add_argument("--fast-init", action="store_true")
+    ap.add_argument("--all-configs", action="store_true",
+                    help="N = 1: run every BASELINE.json workload back to back and print ONE line with the table")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.members:
@@ -608,6 +622,31 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, w, rank)
+        return
+    if args.all_configs:
+        if world != 1:
+            raise SystemExit("--all-configs is a single-GPU summary")
+        rows = []
+        for name in ("hopper_single", "antmaze_jsrl", "halfcheetah_ens64", "hopper_ens64", "pen_sweep256", "stress_4x1024"):
+            args.workload = name
+            args.inner = 0
+            got = []
+            run_ours(args, dict(WORKLOADS[name]), 0, 1, local_rank, collect=got)
+            ln = got[0]
+            rows.append({"workload": name, "desc": ln["config"]["desc"], "members": ln["config"]["members_total"],
+                         "steps_per_s": round(ln["value"], 1), "e2e_steps_per_s": round(ln["e2e"]["value"], 1),
+                         "e2e_dropin_steps_per_s": (round(ln["e2e_dropin"]["value"], 1) if ln.get("e2e_dropin") else None),
+                         "torch_eager_b200_steps_per_s": (round(ln["torch_eager_b200"]["value"], 1) if ln.get("torch_eager_b200") and "value" in ln["torch_eager_b200"] else None),
+                         "cpu_reference_steps_per_s": (round(ln["cpu_baseline"]["value"], 1) if ln.get("cpu_baseline") else None),
+                         "whole_step_tflops": ln["step_roofline"]["whole_step_tflops"],
+                         "frac_of_tf32_peak": ln["step_roofline"]["whole_step_frac_of_tensor_peak"],
+                         "hbm_gbs": ln["step_roofline"]["whole_step_hbm_gbs"],
+                         "dominant_kernel": ln["roofline"]["kernel"] if ln.get("roofline") else None,
+                         "dominant_frac": ln["roofline"]["frac"] if ln.get("roofline") else None,
+                         "launches_per_step": round(ln["gpu_launches"] / (ln["steps"] * ln["config"]["inner_steps_per_bench_step"]), 2),
+                         "clocks": ln["clocks"]})
+        print(json.dumps({"all_configs": rows, "n_gpus": 1, "tf32_peak_tflops": got[0]["step_roofline"]["tf32_peak_tflops"],
+                          "hbm_peak_gbs": got[0]["step_roofline"]["hbm_peak_gbs"]}), flush=True)
         return
     if world == 1 and args.gpus > 1:
         print(json.dumps({"error": f"--gpus {args.gpus} must be launched with torch.distributed.run (one rank per GPU)"}))

@@ -280,6 +280,14 @@ class EnsembleEngine:
         """Every C-ABI call that launches runs inside this: the engine's device is made current (the engine may
         live on cuda:N while the process's current device is another) and the engine stream is ordered after / before
         the caller's current stream on that device."""
+        if torch.cuda.current_device() == self.device.index:  # common case: no device switch needed
+            cur = torch.cuda.current_stream(self.device)
+            self.stream.wait_stream(cur)
+            try:
+                yield self.stream
+            finally:
+                cur.wait_stream(self.stream)
+            return
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
             self.stream.wait_stream(cur)

@@ -351,7 +351,7 @@ class ReplayBuffer:
                 slot, pin, idx = self._idx_slot(B)
                 pin.numpy()[:] = idx_host
                 idx.copy_(pin, non_blocking=True)
-                ev = torch.cuda.Event()
+                ev = self._idx_ring[slot][2] or torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
                 self._idx_ring[slot] = (pin, idx, ev)
                 idx_ptr, seed, step = idx.data_ptr(), 0, 0
@@ -687,9 +687,14 @@ class ImplicitQLearning:
         self._published = attached == 3
 
     def _push_hparams(self):
-        gq, gv, ga = _adam_group(self.q_optimizer), _adam_group(self.v_optimizer), _adam_group(self.actor_optimizer)
+        groups = getattr(self, "_adam_groups", None)
+        if groups is None or groups[0] is not self.q_optimizer.param_groups[0]:
+            # validated once per optimizer object: the param-group dicts are stable, later calls only read them
+            gq, gv, ga = _adam_group(self.q_optimizer), _adam_group(self.v_optimizer), _adam_group(self.actor_optimizer)
+            self._adam_groups = (gq, gv, ga)
+        gq, gv, ga = self._adam_groups
         for g in (gv, ga):
-            if tuple(g["betas"]) != tuple(gq["betas"]) or g["eps"] != gq["eps"]:
+            if g["betas"] != gq["betas"] or g["eps"] != gq["eps"]:
                 raise NotImplementedError("the three Adam optimizers must share betas and eps")
         sched = self.actor_lr_schedule
         if sched is not None:
