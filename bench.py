@@ -307,7 +307,8 @@ def cpu_baseline_block(w, cpu_steps):
     """The `cpu_baseline` object of the JSON line (rank 0, N = 1): a bounded sample of the workload's member-step."""
     if reference_available():
         big = w["H"] > 256 or w["B"] > 256
-        m = cpu_reference_measurements(w, max(20, cpu_steps // (40 if big else 1)), max(10, cpu_steps // (120 if big else 4)), 3 if big else 20)
+        m = (cpu_reference_measurements(w, 12, 3, 2) if big else
+             cpu_reference_measurements(w, max(20, cpu_steps), max(10, cpu_steps // 4), 20))
         return {"value": m["all"], "unit": "steps/s", "cores": m["cores"], "kind": "reference",
                 "one_thread": m["one"], "nproc": m["nproc"], "cpu_model": cpu_model(),
                 "one_member_per_core_derived": m["one"] * m["nproc"],
