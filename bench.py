@@ -519,7 +519,7 @@ def run_ours(args, w, rank, world, local_rank, collect=None):
                      "whole_step_hbm_gbs": round(sum(kq["bytes"] for kq in kernels) / (step_us * 1e-6) / 1e9, 1) if step_us else None,
                      "hbm_peak_gbs": hbm_peak, "bf16_peak_tflops": peaks.get("bf16_tflops"), "peak_source": peak_src}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
             cpu = cpu_baseline_block(w, args.cpu_steps)
         eager = None
         if world == 1 and not args.no_eager:

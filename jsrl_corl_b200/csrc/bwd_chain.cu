@@ -494,7 +494,7 @@ static long long* chain_trace_buffer() {  // allocated once (at bind time, never
   static bool tried = false;
   if (!tried) {
     tried = true;
-    if (getenv("IQL_CHAIN_TRACE") && cudaMalloc(&buf, sizeof(long long) * C_TRACE_WORDS) == cudaSuccess)
+    if (dbg_getenv("IQL_CHAIN_TRACE") && cudaMalloc(&buf, sizeof(long long) * C_TRACE_WORDS) == cudaSuccess)
       cudaMemset(buf, 0, sizeof(long long) * C_TRACE_WORDS);
     else
       buf = nullptr;
@@ -545,7 +545,7 @@ void launch_bwd_chain(const BwdChainArgs& a, const StepCtx& ctx, cudaStream_t st
   cp.n_dgrad = dg;
   cp.trace = chain_trace_buffer();
   {
-    static const int dbg = getenv("IQL_CHAIN_DBG") ? atoi(getenv("IQL_CHAIN_DBG")) : 0;
+    static const int dbg = dbg_getenv("IQL_CHAIN_DBG") ? atoi(dbg_getenv("IQL_CHAIN_DBG")) : 0;
     cp.dbg = dbg;
   }
   for (int s = 0; s < 4; ++s) {

@@ -91,6 +91,15 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Every IQL_* environment switch of the library (path selection for A/B measurements, probes, traces: INTEGRATION.md
+// section 4) is a DEBUG facility behind one master flag: without IQL_B200_DEBUG=1 in the environment none of them is
+// read, so none of them is API.  Supported, documented selection goes through iql_set_option().
+static inline const char* dbg_getenv(const char* name) {
+  static int on = -1;
+  if (on < 0) on = getenv("IQL_B200_DEBUG") ? 1 : 0;
+  return on ? getenv(name) : nullptr;
+}
+
 // ---------------------------------------------------------------------------
 // Programmatic dependent launch: a kernel launched with launch_pdl may become resident and run its set-up (barrier
 // init, TMEM allocation, reads of the static problem tables) while the preceding kernel of the stream drains; it
@@ -118,7 +127,7 @@ static inline bool first_use_on_device(bool* seen /* [64], zero-initialised */) 
 
 static inline bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) v = getenv("IQL_B200_NO_PDL") ? 0 : 1;
+  if (v < 0) v = dbg_getenv("IQL_B200_NO_PDL") ? 0 : 1;
   return v != 0;
 }
 

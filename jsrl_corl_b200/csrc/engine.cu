@@ -210,7 +210,7 @@ static void build_layout(iql_engine* e) {
   wl.lb_scratch = 0;
   wl.lb_stride = 0;
   // (stress shape: 4 problems x 4096 rows; single learners: 4 problems x 256 rows, 8 splits of 32 rows)
-  if ((B >= 2048 || c.n_members <= 4) && c.action_dim <= 24 && (H % 4) == 0 && getenv("IQL_B200_NO_LASTBWD_SPLIT") == nullptr) {
+  if ((B >= 2048 || c.n_members <= 4) && c.action_dim <= 24 && (H % 4) == 0 && dbg_getenv("IQL_B200_NO_LASTBWD_SPLIT") == nullptr) {
     const int64_t ctas = (int64_t)4 * c.n_members * ((H + 255) / 256);
     int sp = 1;
     while (ctas * sp < 148 && B / (sp * 2) >= 32 && B % (sp * 2) == 0 && sp < 32) sp *= 2;
@@ -223,7 +223,7 @@ static void build_layout(iql_engine* e) {
   e->fw_splits = 1;
   wl.fw_scratch = 0;
   wl.fw_stride = 0;
-  if (B >= 2048 && c.math_mode == IQL_MATH_TF32_TCGEN05 && getenv("IQL_B200_NO_FIRST_WGRAD_SPLIT") == nullptr) {
+  if (B >= 2048 && c.math_mode == IQL_MATH_TF32_TCGEN05 && dbg_getenv("IQL_B200_NO_FIRST_WGRAD_SPLIT") == nullptr) {
     const int64_t tiles = (int64_t)4 * c.n_members * ((H + 127) / 128);
     int sp = 1;
     while (tiles * sp < 148 && B / (sp * 2) >= 256 && B % (sp * 2) == 0 && sp < 16) sp *= 2;
@@ -300,7 +300,7 @@ extern "C" int iql_create(const iql_config* cfg, iql_engine** out) {
   def.adam_beta1 = 0.9; def.adam_beta2 = 0.999; def.adam_eps = 1e-8;
   def.cosine_t_max = 1000000;
   for (int m = 0; m < S; ++m) { def.seed = (uint64_t)m; iql_set_hparams(e, m, &def); }
-  const char* g = getenv("IQL_B200_GRAPHS");
+  const char* g = dbg_getenv("IQL_B200_GRAPHS");
   if (g && g[0] == '0') e->use_graphs = false;
   *out = e;
   return IQL_OK;
@@ -626,7 +626,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   build_problems(e);
   const bool tc_mode = e->cfg.math_mode == IQL_MATH_TF32_TCGEN05 && umma_phase_supported(0, e->cfg.batch_size, e->cfg.hidden_dim);
   // 3xTF32 input layer, and on top of it the fused forward (all hidden layers of a tile chained through TMEM)
-  e->split_first = tc_mode && getenv("IQL_B200_NO_SPLIT_FIRST") == nullptr;
+  e->split_first = tc_mode && dbg_getenv("IQL_B200_NO_SPLIT_FIRST") == nullptr;
   e->fused_fwd = e->split_first && umma_can_fuse_out(e->cfg.action_dim) &&
                  fused_fwd_supported(e->cfg.batch_size, e->cfg.hidden_dim, e->cfg.n_hidden, e->cfg.state_dim + e->cfg.action_dim);
   e->fused_pair = e->fused_fwd && fused_fwd_pair(e->cfg.batch_size);
@@ -642,8 +642,8 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
       // (the same epilogue on the weight-gradient phase measured 46.4 vs 44.2 us: it stays on the transposing one)
       const bool hidden_dgrad = tc_mode && ph.umma_ok && ph.kind == PH_GENERIC && (ph.maxN % 32) == 0 && ph.mode == 1 &&
                                 e->fused_fwd;
-      ph.rowepi = (hidden_dgrad || (ph.mode == 2 && ph.kind == PH_GENERIC && tc_mode && getenv("IQL_B200_ROWEPI_WGRAD"))) &&
-                  getenv("IQL_B200_NO_ROWEPI") == nullptr;
+      ph.rowepi = (hidden_dgrad || (ph.mode == 2 && ph.kind == PH_GENERIC && tc_mode && dbg_getenv("IQL_B200_ROWEPI_WGRAD"))) &&
+                  dbg_getenv("IQL_B200_NO_ROWEPI") == nullptr;
     }
   if (e->fw_splits > 1) {
     Phase& pf = e->fw_phase;
@@ -908,14 +908,14 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   const iql_config& c = e->cfg;
   const int B = c.batch_size, H = c.hidden_dim, A = c.action_dim, K0 = c.state_dim + c.action_dim;
   // the skinny-layer kernels keep one operand in shared memory; fall back to the generic GEMM when it does not fit
-  static const bool no_skinny = getenv("IQL_B200_NO_SKINNY") != nullptr;
+  static const bool no_skinny = dbg_getenv("IQL_B200_NO_SKINNY") != nullptr;
   auto kpad = [](int k) { return k <= 24 ? 24 : (k <= 40 ? 40 : 72); };
   auto apad = [](int a) { return a <= 1 ? 1 : (a <= 8 ? 8 : 24); };
   const bool first_ok = !no_skinny && K0 <= 72;
   const bool first_wgrad_ok = first_ok && ((size_t)B * kpad(K0) + 512 * (kpad(K0) + 1)) * 4 <= 200 * 1024;
   const bool out_ok = !no_skinny && A <= 64 && (size_t)(A <= 1 ? 1 : (A <= 8 ? 8 : (A <= 24 ? 24 : 64))) * H * 4 <= 200 * 1024;
   const bool last_ok = !no_skinny && A <= 24 && ((size_t)B * apad(A) + 256 * apad(A)) * 4 <= 200 * 1024;
-  static const bool no_side = getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
+  static const bool no_side = dbg_getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
   const bool loss_recomputed = last_ok && e->bwd_phases.size() >= 2 &&
                                last_bwd_recomputes_loss_grads(H, A, e->bwd_phases[0].count * e->lb_splits, B / e->lb_splits) &&
                                e->bwd_phases[0].kind == PH_LAST_WGRAD && e->bwd_phases[1].kind == PH_LAST_DGRAD &&
@@ -1184,7 +1184,7 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
   ctx.dropout_masks = dropout_masks;
   ctx.idx_out = idx_out;
   const bool gather = sample_mode != IQL_SAMPLE_PRELOADED;
-  static const bool no_overlap_gather = getenv("IQL_B200_NO_GATHER_AHEAD") != nullptr || getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
+  static const bool no_overlap_gather = dbg_getenv("IQL_B200_NO_GATHER_AHEAD") != nullptr || dbg_getenv("IQL_B200_NO_SIDE_STREAM") != nullptr;
   // (not with the chained backward: its last phase still reads the gathered rows, see enqueue_step)
   const bool overlap_gather = !no_overlap_gather && e->side != nullptr && st != nullptr && !e->chain;
   // the legacy default stream cannot be captured; the facade runs the engine on its own stream

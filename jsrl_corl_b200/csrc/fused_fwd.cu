@@ -632,7 +632,7 @@ static long long* fused_trace_buffer() {  // allocated once when IQL_FUSED_TRACE
   static bool tried = false;
   if (!tried) {
     tried = true;
-    if (getenv("IQL_FUSED_TRACE") && cudaMalloc(&buf, sizeof(long long) * FUSED_TRACE_WORDS) == cudaSuccess)
+    if (dbg_getenv("IQL_FUSED_TRACE") && cudaMalloc(&buf, sizeof(long long) * FUSED_TRACE_WORDS) == cudaSuccess)
       cudaMemset(buf, 0, sizeof(long long) * FUSED_TRACE_WORDS);
     else
       buf = nullptr;
@@ -642,16 +642,16 @@ static long long* fused_trace_buffer() {  // allocated once when IQL_FUSED_TRACE
 
 bool fused_fwd_supported(int batch, int hidden, int n_hidden, int k0) {
   fused_trace_buffer();  // allocated here (state binding), never inside a stream capture
-  return getenv("IQL_B200_NO_FUSED_FWD") == nullptr && umma_phase_supported(0, batch, hidden) && hidden == FT_N &&
+  return dbg_getenv("IQL_B200_NO_FUSED_FWD") == nullptr && umma_phase_supported(0, batch, hidden) && hidden == FT_N &&
          n_hidden >= 1 && n_hidden <= FUSED_MAX_LAYERS && k0 >= 1;
 }
 
 // CTA pairs: one pair per 256 batch rows of a problem, each CTA staging half of every weight k-block
 bool fused_fwd_pair(int batch) {
-  return getenv("IQL_B200_NO_FUSED_PAIR") == nullptr && getenv("IQL_B200_NO_CTA2") == nullptr && batch % (2 * FT_M) == 0;
+  return dbg_getenv("IQL_B200_NO_FUSED_PAIR") == nullptr && dbg_getenv("IQL_B200_NO_CTA2") == nullptr && batch % (2 * FT_M) == 0;
 }
 
-bool fused_fwd_policy_head(int act_dim) { return act_dim >= 1 && act_dim <= FUSED_POL_MAX && getenv("IQL_B200_NO_FUSED_POLICY") == nullptr; }
+bool fused_fwd_policy_head(int act_dim) { return act_dim >= 1 && act_dim <= FUSED_POL_MAX && dbg_getenv("IQL_B200_NO_FUSED_POLICY") == nullptr; }
 
 void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st) {
   static bool attr_set[64] = {};
@@ -676,7 +676,7 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
   fp.fuse_count = a.probs_out ? a.fuse_count : 0;
   fp.fuse_policy = (a.probs_out && a.fuse_policy) ? 1 : 0;
   {
-    static const int dbg = getenv("IQL_FUSED_DBG") ? atoi(getenv("IQL_FUSED_DBG")) : 0;
+    static const int dbg = dbg_getenv("IQL_FUSED_DBG") ? atoi(dbg_getenv("IQL_FUSED_DBG")) : 0;
     fp.dbg = dbg;
   }
   fp.nkb0 = (a.k0_max + FT_K - 1) / FT_K;

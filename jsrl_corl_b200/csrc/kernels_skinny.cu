@@ -235,7 +235,7 @@ void launch_out_fwd(const GemmProb* probs, int nprob, int B, int H, int amax, cu
   if (amax <= 1) launch_out_fwd_t<1>(probs, nprob, B, sm, st);
   else if (amax <= 8) launch_out_fwd_t<8>(probs, nprob, B, sm, st);
   else if (amax <= 24) {
-    static const bool no_rows = getenv("IQL_B200_NO_OUT_ROWS") != nullptr;
+    static const bool no_rows = dbg_getenv("IQL_B200_NO_OUT_ROWS") != nullptr;
     static bool attr[64] = {};
     if (first_use_on_device(attr))
       cudaFuncSetAttribute(out_fwd_rows_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
 static bool last_bwd_v4_fills(int nprob, int B, int H) { return !(B >= 2048 && (int64_t)nprob * ((H + 255) / 256) < 64); }
 
 bool last_bwd_recomputes_loss_grads(int H, int amax, int nprob, int B) {
-  return getenv("IQL_B200_NO_LASTBWD_V4") == nullptr && getenv("IQL_B200_NO_LOSS_OVERLAP") == nullptr && (H % 4) == 0 && amax <= 8 &&
+  return dbg_getenv("IQL_B200_NO_LASTBWD_V4") == nullptr && dbg_getenv("IQL_B200_NO_LOSS_OVERLAP") == nullptr && (H % 4) == 0 && amax <= 8 &&
          last_bwd_v4_fills(nprob, B, H);
 }
 
@@ -551,7 +551,7 @@ int launch_last_bwd(const GemmProb* probs_dgrad, const GemmProb* probs_wgrad, co
     cudaFuncSetAttribute(last_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(last_bwd_v4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(last_bwd_v4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    no_v4 = getenv("IQL_B200_NO_LASTBWD_V4") != nullptr;
+    no_v4 = dbg_getenv("IQL_B200_NO_LASTBWD_V4") != nullptr;
   }
   const bool v4 = !no_v4 && (H % 4) == 0 && amax <= 8 && smem4(8) <= 200 * 1024 && last_bwd_v4_fills(nprob, B, H);
   const dim3 grid4(nprob, (H + 255) / 256);

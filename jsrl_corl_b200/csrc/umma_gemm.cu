@@ -598,14 +598,14 @@ static EncodeTiledFn get_encode() {
 }
 
 static uint32_t env_u32(const char* name, uint32_t dflt) {
-  const char* s = getenv(name);
+  const char* s = dbg_getenv(name);
   return s ? (uint32_t)strtoul(s, nullptr, 0) : dflt;
 }
 
 bool umma_phase_supported(int mode, int batch, int hidden) {
   (void)mode;  // every tcgen05 phase has M in {batch, hidden}: both must be multiples of the 256-row tile
   static int disabled = -1;
-  if (disabled < 0) disabled = getenv("IQL_B200_NO_UMMA") ? 1 : 0;
+  if (disabled < 0) disabled = dbg_getenv("IQL_B200_NO_UMMA") ? 1 : 0;
   return !disabled && batch >= 128 && batch % 128 == 0 && hidden >= 256 && hidden % 256 == 0;
 }
 
@@ -658,7 +658,7 @@ int umma_tile_n(int maxN) {
 bool umma_dgrad_writes_dbias(int batch);
 
 bool umma_cta2_ok(int maxM, int maxN) {
-  return getenv("IQL_B200_NO_CTA2") == nullptr && maxM > 0 && (maxM % (2 * TILE_M)) == 0 && maxN >= TILE_N &&
+  return dbg_getenv("IQL_B200_NO_CTA2") == nullptr && maxM > 0 && (maxM % (2 * TILE_M)) == 0 && maxN >= TILE_N &&
          (maxN % TILE_N) == 0;
 }
 
@@ -668,7 +668,7 @@ bool umma_cta2_ok(int maxM, int maxN) {
 // change, and the coupling of the two epilogues costs ~8 %.
 bool umma_cta2(int mode, int nprob, int maxM, int maxN, int maxK) {
   if (!umma_cta2_ok(maxM, maxN)) return false;
-  if (getenv("IQL_B200_FORCE_CTA2")) return true;  // tests: run every eligible phase on pairs
+  if (dbg_getenv("IQL_B200_FORCE_CTA2")) return true;  // tests: run every eligible phase on pairs
   if (mode == 1) return umma_dgrad_writes_dbias(maxM) && nprob * (maxN / TILE_N) <= 74;
   return maxK >= 512;
 }
@@ -735,7 +735,7 @@ int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob
 
 bool umma_dgrad_writes_dbias(int batch) { return (batch + TILE_M - 1) / TILE_M <= 2; }
 
-bool umma_can_fuse_out(int act_dim) { (void)act_dim; return getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
+bool umma_can_fuse_out(int act_dim) { (void)act_dim; return dbg_getenv("IQL_B200_NO_FUSE_OUT") == nullptr; }
 
 template <int EPI, bool FUSE_OUT, bool ROWEPI>
 static void launch_variant(bool cta2, int workers, const GemmProb* probs, const CUtensorMap* maps, const GemmProb* probs_out,

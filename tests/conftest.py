@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# The library reads its IQL_* environment switches (path selection for A/B tests) only under this master debug flag.
+os.environ.setdefault("IQL_B200_DEBUG", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -25,3 +28,4 @@ def _built_library():
 
         os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "oracle", "philox_ref.c")])
+

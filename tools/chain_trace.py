@@ -1,5 +1,6 @@
 """IQL_CHAIN_TRACE=1 python tools/chain_trace.py [members]: where the time of a bwd_chain task goes (CTA pair 0)."""
 import ctypes as C, os, sys
+os.environ["IQL_B200_DEBUG"] = "1"
 os.environ["IQL_CHAIN_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("IQL_B200_DEBUG", "1")
 os.environ.setdefault("IQL_FUSED_TRACE", "1")
 
 import bench  # noqa: E402

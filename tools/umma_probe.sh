@@ -3,6 +3,7 @@
 # default workload with parts of the tcgen05 kernel switched off, to see which resource bounds each phase.
 #   1 = no global stores in the epilogue, 2 = operands of 4 problems only (L2 hits), 4 = no epilogue at all,
 #   8 = no MMAs (TMA only), 16 = no TMA (MMA only), 32 = no tensor-map prefetch
+export IQL_B200_DEBUG=1  # the IQL_* switches below are debug facilities behind this master flag
 mkdir -p gpurun_out
 for pair in 0 1; do
   for dbg in 0 32 4 36 12 20 6 14; do
