@@ -281,7 +281,7 @@ class EnsembleEngine:
         live on cuda:N while the process's current device is another) and the engine stream is ordered after / before
         the caller's current stream on that device."""
         if torch.cuda.current_device() == self.device.index:  # common case: no device switch needed
-            cur = torch.cuda.current_stream(self.device)
+            cur = torch.cuda.current_stream()
             self.stream.wait_stream(cur)
             try:
                 yield self.stream
