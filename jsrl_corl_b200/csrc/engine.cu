@@ -921,6 +921,10 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
                                e->bwd_phases[0].kind == PH_LAST_WGRAD && e->bwd_phases[1].kind == PH_LAST_DGRAD &&
                                e->bwd_phases[0].count % 4 == 0;
   bool skip_next = false, skip_colsum = false;
+  // the reduction of the row-split output-layer backward (single learners) only feeds the optimizer: it leaves the
+  // critical path last_bwd -> dgrad -> ... through the side stream (8 us of a 57 us single-learner step)
+  const bool lb_side = tf32 && !tm && !no_side && e->side != nullptr;
+  bool lb_on_side = false;
   auto run_phase = [&](const Phase& ph, const Phase* next, const Phase* next2) {
     if (skip_next) { skip_next = false; return; }
     const GemmProb* pp = e->d_probs + ph.first;
@@ -988,7 +992,15 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
         const GemmProb* t0 = e->d_probs + e->lb_first;
         launches += launch_last_bwd(t0, t0 + n, emit_db ? t0 + 2 * n : nullptr, n, B / sp, H, A, ctx, st,
                                     loss_recomputed ? e->d_ws_f : nullptr, e->wl.member_floats, &e->wl, e->params);
-        launch_lb_reduce(t0 + n, emit_db ? t0 + 2 * n : nullptr, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, sp, st);
+        if (lb_side) {
+          cudaEventRecord(e->ev_fork, st_main);
+          cudaStreamWaitEvent(e->side, e->ev_fork, 0);
+          launch_lb_reduce(t0 + n, emit_db ? t0 + 2 * n : nullptr, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, sp, e->side);
+          cudaEventRecord(e->ev_side, e->side);
+          lb_on_side = true;
+        } else {
+          launch_lb_reduce(t0 + n, emit_db ? t0 + 2 * n : nullptr, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, sp, st);
+        }
       } else
       launches += -1 + launch_last_bwd(e->d_probs + next->first, pp, emit_db ? e->d_probs + next2->first : nullptr, ph.count, B, H, A, ctx, st,
                       loss_recomputed ? e->d_ws_f : nullptr, e->wl.member_floats, &e->wl, e->params);
@@ -1104,7 +1116,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       run_phase(ph, n1, n2);
     }
   }
-  if (forks > 0 || loss_on_side) cudaStreamWaitEvent(st_main, e->ev_side, 0);  // join before the optimizer
+  if (forks > 0 || loss_on_side || lb_on_side) cudaStreamWaitEvent(st_main, e->ev_side, 0);  // join before the optimizer
   // Adam: read g, p, m, v + target; write p, m, v + target (+ the TF32 shadow copies in tcgen05 mode)
   if (tm) tm->mark("adam_polyak", 0, S_d * 4.0 * ((7.0 + (ctx.tf32 ? 1 : 0)) * e->layout.param_floats +
                                                   (2.0 + (ctx.tf32 ? 1 : 0)) * e->layout.q_floats));
