@@ -162,3 +162,50 @@ def test_train_config_fields_match_reference_dataclasses():
     assert list(pol.state_dict().keys()) == list(ref_pol.state_dict().keys())
     ref_fin = load_reference_iql("finetune").GaussianPolicy(4, 2, 1.0, 16, 2, dropout=0.0)
     assert list(J.GaussianPolicy(4, 2, 1.0, 16, 2, dropout=0.0).state_dict().keys()) == list(ref_fin.state_dict().keys())
+
+
+def test_options_and_path_info_without_a_gpu():
+    """iql_set_option / iql_get_info (include/iql_b200.h): argument checking and the pre-bind answers; the step path must
+    be chosen before the state is bound, unknown keys are refused, the tensor-core answer follows the shape rule."""
+    L = _lib.lib()
+
+    def handle(batch, hidden, math):
+        h = C.c_void_p()
+        cfg = _lib.Config(1, 17, 6, hidden, 2, batch, 0, math, 4)
+        _lib.check(L.iql_create(C.byref(cfg), C.byref(h)), None, "iql_create")
+        return h
+
+    h = handle(256, 256, _lib.MATH_TF32_TCGEN05)
+    try:
+        out = C.c_int64(-1)
+        assert L.iql_get_info(h, _lib.INFO_TENSOR_CORE_PATH, C.byref(out)) == _lib.IQL_OK and out.value == 1
+        assert L.iql_get_info(h, _lib.INFO_CHAINED_BACKWARD, C.byref(out)) == _lib.IQL_OK and out.value == 0  # not bound yet
+        assert L.iql_get_info(h, 99, C.byref(out)) == _lib.IQL_ERR_INVALID
+        assert L.iql_get_info(h, _lib.INFO_FUSED_FORWARD, None) == _lib.IQL_ERR_INVALID
+        for v in (0, 1, 2):
+            assert L.iql_set_option(h, _lib.OPT_STEP_PATH, v) == _lib.IQL_OK
+        assert L.iql_set_option(h, _lib.OPT_STEP_PATH, 3) == _lib.IQL_ERR_INVALID
+        assert b"IQL_OPT_STEP_PATH" in L.iql_last_error(h)
+        assert L.iql_set_option(h, 77, 1) == _lib.IQL_ERR_INVALID
+        assert L.iql_set_option(h, _lib.OPT_KEEP_GRADS, 1) == _lib.IQL_OK
+    finally:
+        L.iql_destroy(h)
+    for batch, hidden, math, want in ((100, 256, _lib.MATH_TF32_TCGEN05, 0), (256, 64, _lib.MATH_TF32_TCGEN05, 0),
+                                      (256, 256, _lib.MATH_FP32_SIMT, 0), (4096, 1024, _lib.MATH_TF32_TCGEN05, 1)):
+        h = handle(batch, hidden, math)
+        try:
+            out = C.c_int64(-1)
+            assert L.iql_get_info(h, _lib.INFO_TENSOR_CORE_PATH, C.byref(out)) == _lib.IQL_OK and out.value == want, (batch, hidden)
+        finally:
+            L.iql_destroy(h)
+
+
+def test_replay_ingest_rejects_bad_arguments():
+    L = _lib.lib()
+    lay = _lib.RowLayout()
+    assert L.iql_replay_row_layout(11, 3, C.byref(lay)) == _lib.IQL_OK
+    assert L.iql_replay_ingest(None, C.byref(lay), 0, 4, None, None, None, None, None, 1, 1e-3, None, None, 1.0, 1.0, 0.0, None) == _lib.IQL_ERR_INVALID
+    bad = _lib.RowLayout()
+    assert L.iql_replay_ingest(1, C.byref(bad), 0, 4, 1, 1, 1, 1, 1, 0, 1e-3, None, None, 1.0, 1.0, 0.0, None) == _lib.IQL_ERR_INVALID
+    # n == 0 is a no-op that succeeds (an empty dataset), before any pointer is dereferenced
+    assert L.iql_replay_ingest(1, C.byref(lay), 0, 0, None, None, None, None, None, 0, 1e-3, None, None, 1.0, 1.0, 0.0, None) == _lib.IQL_OK
