@@ -32,7 +32,7 @@ __device__ __forceinline__ void adam_quad(const StepCtx& ctx, int m, int64_t i, 
     const float4 hi = make_float4(round_tf32(p[0]), round_tf32(p[1]), round_tf32(p[2]), round_tf32(p[3]));
     *reinterpret_cast<float4*>(ctx.w_shadow + off) = hi;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) first_layer |= (i >= ctx.first_w_begin[r] && i < ctx.first_w_end[r]);
+    for (int r = 0; r < 5; ++r) first_layer |= (i >= ctx.first_w_begin[r] && i < ctx.first_w_end[r]);
     if (first_layer)
       *reinterpret_cast<float4*>(ctx.w_shadow_lo + off) =
           make_float4(round_tf32(p[0] - hi.x), round_tf32(p[1] - hi.y), round_tf32(p[2] - hi.z), round_tf32(p[3] - hi.w));

@@ -470,7 +470,8 @@ bwd_chain_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           const float4 m4 = *reinterpret_cast<const float4*>(exp_avg + mo + i);
           const float4 v4 = *reinterpret_cast<const float4*>(exp_avg_sq + mo + i);
           const float4 t4 = is_q ? *reinterpret_cast<const float4*>(target + to + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          adam_quad_fast(ctx, member, i, g4, p4, m4, v4, t4, as.neg_step_size, inv_bc2, a_w1, a_b2, a_1mb2, a_eps, tau, omt, false,
+          const bool lo_too = i >= ctx.first_w_begin[4] && i < ctx.first_w_end[4];  // policy head run as a two-pass tcgen05 GEMM
+          adam_quad_fast(ctx, member, i, g4, p4, m4, v4, t4, as.neg_step_size, inv_bc2, a_w1, a_b2, a_1mb2, a_eps, tau, omt, lo_too,
                          params, exp_avg, exp_avg_sq, target);
         }
       }

@@ -108,6 +108,11 @@ struct iql_engine {
   BwdChainArgs chain_args;
   char* d_maps_chain = nullptr;
   std::vector<char> h_maps_chain;
+  // policy heads wider than the fused forward's epilogue handles (8 < act_dim <= 32): z = H_L Wp^T + b as a two-pass
+  // tcgen05 GEMM (H_L is stored TF32-exact, Wp = hi + lo) instead of the FP32 SIMT kernel
+  bool pol_umma = false;
+  char* d_maps_pol = nullptr;
+  std::vector<char> h_maps_pol;
   bool split_first = false;      // input layer runs as 3xTF32 tcgen05 GEMM
   bool fused_fwd = false;        // whole forward (hidden layers + scalar heads) runs as one fused tcgen05 launch
   bool fused_pair = false;       // ... on CTA pairs (cta_group::2), one pair per 256 batch rows
@@ -264,6 +269,7 @@ static void build_layout(iql_engine* e) {
     tab((int64_t)128 * L * S * N_PASS);
     tab((int64_t)128 * nprob);
     tab((int64_t)128 * 2 * 4 * S * (2 * L));  // chain maps: <= 2L - 1 phases x 4 S tasks x (A, B)
+    tab((int64_t)128 * 4 * S);                // policy-head maps: H_L, Wp hi, H_L, Wp lo
   }
   e->tables_bytes = tb;
   e->layout.workspace_bytes = tb + (int64_t)S * wl.member_floats * (int64_t)sizeof(float);
@@ -621,6 +627,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
     e->d_maps_store = tab((int64_t)128 * L * S * N_PASS);
     e->d_maps_c = tab((int64_t)128 * nprob);
     e->d_maps_chain = tab((int64_t)128 * 2 * 4 * S * (2 * L));
+    e->d_maps_pol = tab((int64_t)128 * 4 * S);
   }
   e->d_ws_f = (float*)(e->ws + e->tables_bytes);
   build_problems(e);
@@ -705,6 +712,29 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
             return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (fused forward outputs)");
         }
     }
+  }
+  // ---- wide policy head on the tensor cores (two-pass: H_L Wp_hi + H_L Wp_lo) ----
+  e->pol_umma = false;
+  e->h_maps_pol.clear();
+  if (tc_mode && e->fused_fwd && !fused_fwd_policy_head(e->cfg.action_dim) && e->cfg.action_dim <= 32 &&
+      dbg_getenv("IQL_B200_NO_POL_UMMA") == nullptr) {
+    const int L = e->cfg.n_hidden;
+    const Phase& pout = e->fwd_phases[L];
+    const int n_scalar = (N_PASS - 1) * S;
+    std::vector<GemmProb> hi(e->h_probs.begin() + pout.first + n_scalar, e->h_probs.begin() + pout.first + pout.count), lo = hi;
+    const int64_t P = e->layout.param_floats;
+    for (size_t i = 0; i < hi.size(); ++i) {
+      const int m = hi[i].member;
+      const int64_t w_off = hi[i].B - (e->params + (int64_t)m * P);
+      hi[i].B = e->d_wshadow + (int64_t)m * P + w_off;
+      lo[i].B = e->d_wshadow_lo + (int64_t)m * P + w_off;
+    }
+    e->h_maps_pol.assign((size_t)128 * 4 * hi.size(), 0);
+    if ((int)hi.size() == S &&
+        umma_encode_maps_split(hi.data(), lo.data(), (int)hi.size(), umma_tile_n(e->cfg.action_dim), e->h_maps_pol.data(), false) == 0)
+      e->pol_umma = true;
+    else
+      e->h_maps_pol.clear();
   }
   // ---- chained backward + optimizer: phase list and CTA-pair maps ----
   e->chain = false;
@@ -796,6 +826,8 @@ static int flush_tables(iql_engine* e, cudaStream_t st) {
       CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_store, e->h_maps_store.data(), e->h_maps_store.size(), cudaMemcpyHostToDevice, st));
     if (!e->h_maps_chain.empty())
       CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_chain, e->h_maps_chain.data(), e->h_maps_chain.size(), cudaMemcpyHostToDevice, st));
+    if (!e->h_maps_pol.empty())
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_maps_pol, e->h_maps_pol.data(), e->h_maps_pol.size(), cudaMemcpyHostToDevice, st));
     std::vector<int64_t> off(2 * (L + 1));
     for (int l = 0; l <= L; ++l) {
       off[l] = e->w_off[IQL_NET_ACTOR][l];
@@ -845,6 +877,9 @@ static StepCtx make_ctx(const iql_engine* e) {
     c.first_w_begin[n] = e->split_first ? e->w_off[n][0] : 0;
     c.first_w_end[n] = e->split_first ? e->w_off[n][0] + (int64_t)e->cfg.hidden_dim * e->w_ld[n][0] : 0;
   }
+  const int Lh = e->cfg.n_hidden;
+  c.first_w_begin[4] = e->pol_umma ? e->w_off[IQL_NET_ACTOR][Lh] : 0;
+  c.first_w_end[4] = e->pol_umma ? e->w_off[IQL_NET_ACTOR][Lh] + (int64_t)e->cfg.action_dim * e->w_ld[IQL_NET_ACTOR][Lh] : 0;
   c.xrow_off_ = e->wl.xrow;
   c.xhi_off = (c.tf32 && e->split_first) ? e->wl.xhi : 0;
   c.xlo_off = (c.tf32 && e->split_first) ? e->wl.xlo : 0;
@@ -1057,7 +1092,9 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       }
       tm->mark("policy_head", fl, by);
     }
-    if (out_ok) launch_out_fwd(pa, pout.count - n_scalar, B, H, A, st);
+    if (e->pol_umma)
+      launch_umma_gemm(0, pa, e->d_maps_pol, nullptr, EPI_LINEAR, pout.count - n_scalar, B, A, ctx, st, 2, 0, false, H);
+    else if (out_ok) launch_out_fwd(pa, pout.count - n_scalar, B, H, A, st);
     else launch_simt_gemm(0, pa, pout.count - n_scalar, B, A, ctx, st);
     ++launches;
     }

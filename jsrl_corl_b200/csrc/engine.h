@@ -99,7 +99,9 @@ struct StepCtx {
   // runs on the tensor cores at FP32 accuracy.  lo parts of the first-layer weights / of the gathered rows:
   float* w_shadow_lo;            // [S][P]  (only the first-layer weight ranges are maintained)
   float* t_shadow_lo;            // [S][PQ]
-  int64_t first_w_begin[4], first_w_end[4];  // first-layer weight ranges of q1, q2, v, actor inside a member block
+  // ranges inside a member block whose TF32 lo parts are maintained next to the hi shadow: the first-layer weights of
+  // q1, q2, v, actor (3xTF32 input layer) and [4] the policy-head weights when the head runs as a two-pass tcgen05 GEMM
+  int64_t first_w_begin[5], first_w_end[5];
   int64_t xrow_off_;             // per-member workspace offset of the gathered rows
   int64_t xhi_off, xlo_off;      // per-member workspace offsets of the hi / lo copies of the gathered rows (0 = off)
 };

@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(256) refresh_shadow_kernel(StepCtx ctx, const 
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   bool first_layer = false;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) first_layer |= (i >= ctx.first_w_begin[r] && i < ctx.first_w_end[r]);
+  for (int r = 0; r < 5; ++r) first_layer |= (i >= ctx.first_w_begin[r] && i < ctx.first_w_end[r]);
   if (i < ctx.P) {
     const float4 v = *reinterpret_cast<const float4*>(params + m * ctx.P + i);
     const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));

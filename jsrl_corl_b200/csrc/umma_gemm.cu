@@ -754,14 +754,19 @@ static void launch_variant(bool cta2, int workers, const GemmProb* probs, const 
 }
 
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
-                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3, int fuse_count, bool cta2,
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, int split3, int fuse_count, bool cta2,
                       int maxK, const void* cmaps) {
   const int tile_n = umma_tile_n(maxN);
   UmmaParams up = make_params(mode, tile_n, cta2);
   up.tiles_m = (maxM + up.tile_m - 1) / up.tile_m;
   up.tiles_n = (maxN + tile_n - 1) / tile_n;
   up.total_tiles = nprob * up.tiles_m * up.tiles_n;
-  if (split3) {  // passes: Xhi Whi, Xlo Whi, Xhi Wlo
+  if (split3 == 2) {  // A is TF32-exact already (a stored activation): passes A Whi, A Wlo
+    up.n_split = 2;
+    up.maps_per_prob = 4;
+    up.a_sel[0] = 0; up.b_sel[0] = 1;
+    up.a_sel[1] = 2; up.b_sel[1] = 3;
+  } else if (split3) {  // passes: Xhi Whi, Xlo Whi, Xhi Wlo
     up.n_split = 3;
     up.maps_per_prob = 4;
     up.a_sel[0] = 0; up.b_sel[0] = 1;

@@ -23,9 +23,11 @@ bool umma_can_fuse_out(int act_dim);
 bool umma_dgrad_writes_dbias(int batch);
 // cmaps != null (EPI_NONE / EPI_DRELU): umma_encode_store_map maps of the outputs, 1 per problem: row-layout
 // epilogue with TMA stores; EPI_DRELU then masks with GemmProb::bits instead of the FP32 activation.
-// split3: 3xTF32 input layer; `maps` then holds 4 maps per problem (umma_encode_maps_split).
+// split3 = 1: 3xTF32 input layer; `maps` then holds 4 maps per problem (umma_encode_maps_split): Xhi, Whi, Xlo, Wlo.
+// split3 = 2: two passes A Whi + A Wlo for an A operand that is TF32-exact already (maps: A, Whi, A, Wlo): FP32-accurate
+// output heads on the tensor cores.
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
-                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, bool split3 = false, int fuse_count = 0,
+                      int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, int split3 = 0, int fuse_count = 0,
                       bool cta2 = false, int maxK = 0, const void* cmaps = nullptr);
 int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out, bool cta2);
 // Fused forward (fused_fwd.cu): all hidden layers + scalar heads of every (member, pass) in one launch, hidden
