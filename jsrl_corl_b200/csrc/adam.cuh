@@ -7,6 +7,16 @@
 
 namespace iql {
 
+// bias_hidden scheme (engine.h): magnitude + / - half a TF32 ulp on the bit pattern; exact and reversible
+__device__ __forceinline__ float tf32_bias(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+__device__ __forceinline__ float tf32_unbias(float x) { return __uint_as_float(__float_as_uint(x) - 0x1000u); }
+__device__ __forceinline__ bool in_hidden_weights(const StepCtx& ctx, int64_t i) {
+  bool h = false;
+  if (ctx.bias_hidden)
+    for (int r = 0; r < ctx.n_hid; ++r) h |= (i >= ctx.hid_begin[r] && i < ctx.hid_end[r]);
+  return h;
+}
+
 // One float4 of one member: Adam on p / m / v, TF32 shadow copies, Polyak on the target for the Q range.
 __device__ __forceinline__ void adam_quad(const StepCtx& ctx, int m, int64_t i, const float4 g4, float4 p4, float4 m4,
                                           float4 v4, float4 t4, const AdamScalars as, float adam_w1, float adam_beta2,
@@ -15,7 +25,12 @@ __device__ __forceinline__ void adam_quad(const StepCtx& ctx, int m, int64_t i, 
                                           float* __restrict__ exp_avg_sq, float* __restrict__ target) {
   const int64_t off = m * ctx.P + i;
   const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+  const bool hidden = in_hidden_weights(ctx, i);
   float p[4] = {p4.x, p4.y, p4.z, p4.w};
+  if (hidden) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = tf32_unbias(p[j]);
+  }
   float mm[4] = {m4.x, m4.y, m4.z, m4.w};
   float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
@@ -26,9 +41,12 @@ __device__ __forceinline__ void adam_quad(const StepCtx& ctx, int m, int64_t i, 
     const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv[j]), as.bc2_sqrt), adam_eps);
     p[j] = fmaf(as.neg_step_size, __fdiv_rn(mm[j], denom), p[j]);      // addcdiv_
   }
-  *reinterpret_cast<float4*>(params + off) = make_float4(p[0], p[1], p[2], p[3]);
+  if (hidden && !ctx.unbias_out)
+    *reinterpret_cast<float4*>(params + off) = make_float4(tf32_bias(p[0]), tf32_bias(p[1]), tf32_bias(p[2]), tf32_bias(p[3]));
+  else
+    *reinterpret_cast<float4*>(params + off) = make_float4(p[0], p[1], p[2], p[3]);
   bool first_layer = false;
-  if (ctx.tf32) {
+  if (ctx.tf32 && !hidden) {
     const float4 hi = make_float4(round_tf32(p[0]), round_tf32(p[1]), round_tf32(p[2]), round_tf32(p[3]));
     *reinterpret_cast<float4*>(ctx.w_shadow + off) = hi;
 #pragma unroll
@@ -44,9 +62,12 @@ __device__ __forceinline__ void adam_quad(const StepCtx& ctx, int m, int64_t i, 
     const int64_t toff = m * ctx.PQ + i;
     float t[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(one_minus_tau, t[j]), __fmul_rn(tau, p[j]));
-    *reinterpret_cast<float4*>(target + toff) = make_float4(t[0], t[1], t[2], t[3]);
-    if (ctx.tf32) {
+    for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(one_minus_tau, hidden ? tf32_unbias(t[j]) : t[j]), __fmul_rn(tau, p[j]));
+    if (hidden && !ctx.unbias_out)
+      *reinterpret_cast<float4*>(target + toff) = make_float4(tf32_bias(t[0]), tf32_bias(t[1]), tf32_bias(t[2]), tf32_bias(t[3]));
+    else
+      *reinterpret_cast<float4*>(target + toff) = make_float4(t[0], t[1], t[2], t[3]);
+    if (ctx.tf32 && !hidden) {
       const float4 hi = make_float4(round_tf32(t[0]), round_tf32(t[1]), round_tf32(t[2]), round_tf32(t[3]));
       *reinterpret_cast<float4*>(ctx.t_shadow + toff) = hi;
       if (first_layer)
@@ -80,7 +101,12 @@ __device__ __forceinline__ void adam_quad_fast(const StepCtx& ctx, int m, int64_
                                                float* __restrict__ target) {
   const int64_t off = m * ctx.P + i;
   const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+  const bool hidden = in_hidden_weights(ctx, i);
   float p[4] = {p4.x, p4.y, p4.z, p4.w};
+  if (hidden) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = tf32_unbias(p[j]);
+  }
   float mm[4] = {m4.x, m4.y, m4.z, m4.w};
   float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
@@ -93,9 +119,12 @@ __device__ __forceinline__ void adam_quad_fast(const StepCtx& ctx, int m, int64_
   // master weights, moments and the target are next read one step later, after ~1 GB of other traffic: streaming
   // stores (evict-first) keep them from displacing the operands the pair is about to reload from L2; the TF32 shadow
   // copies are what the next forward reads first and keep the default policy
-  __stcs(reinterpret_cast<float4*>(params + off), make_float4(p[0], p[1], p[2], p[3]));
+  if (hidden && !ctx.unbias_out)  // read next by this pair's TMA loads (dgrad of the next step, forward): default policy
+    *reinterpret_cast<float4*>(params + off) = make_float4(tf32_bias(p[0]), tf32_bias(p[1]), tf32_bias(p[2]), tf32_bias(p[3]));
+  else
+    __stcs(reinterpret_cast<float4*>(params + off), make_float4(p[0], p[1], p[2], p[3]));
   const float4 hi = make_float4(round_tf32(p[0]), round_tf32(p[1]), round_tf32(p[2]), round_tf32(p[3]));
-  *reinterpret_cast<float4*>(ctx.w_shadow + off) = hi;
+  if (!hidden) *reinterpret_cast<float4*>(ctx.w_shadow + off) = hi;
   if (first_layer)
     *reinterpret_cast<float4*>(ctx.w_shadow_lo + off) =
         make_float4(round_tf32(p[0] - hi.x), round_tf32(p[1] - hi.y), round_tf32(p[2] - hi.z), round_tf32(p[3] - hi.w));
@@ -105,10 +134,13 @@ __device__ __forceinline__ void adam_quad_fast(const StepCtx& ctx, int m, int64_
     const int64_t toff = m * ctx.PQ + i;
     float t[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(one_minus_tau, t[j]), __fmul_rn(tau, p[j]));
-    __stcs(reinterpret_cast<float4*>(target + toff), make_float4(t[0], t[1], t[2], t[3]));
+    for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(one_minus_tau, hidden ? tf32_unbias(t[j]) : t[j]), __fmul_rn(tau, p[j]));
+    if (hidden && !ctx.unbias_out)
+      *reinterpret_cast<float4*>(target + toff) = make_float4(tf32_bias(t[0]), tf32_bias(t[1]), tf32_bias(t[2]), tf32_bias(t[3]));
+    else
+      __stcs(reinterpret_cast<float4*>(target + toff), make_float4(t[0], t[1], t[2], t[3]));
     const float4 th = make_float4(round_tf32(t[0]), round_tf32(t[1]), round_tf32(t[2]), round_tf32(t[3]));
-    *reinterpret_cast<float4*>(ctx.t_shadow + toff) = th;
+    if (!hidden) *reinterpret_cast<float4*>(ctx.t_shadow + toff) = th;
     if (first_layer)
       *reinterpret_cast<float4*>(ctx.t_shadow_lo + toff) =
           make_float4(round_tf32(t[0] - th.x), round_tf32(t[1] - th.y), round_tf32(t[2] - th.z), round_tf32(t[3] - th.w));

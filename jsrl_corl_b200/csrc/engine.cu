@@ -113,6 +113,7 @@ struct iql_engine {
   bool pol_umma = false;
   char* d_maps_pol = nullptr;
   std::vector<char> h_maps_pol;
+  bool bias_hidden = false;      // hidden-layer weights carry the TF32 rounding bias in place during a call (engine.h), no shadow
   bool split_first = false;      // input layer runs as 3xTF32 tcgen05 GEMM
   bool fused_fwd = false;        // whole forward (hidden layers + scalar heads) runs as one fused tcgen05 launch
   bool fused_pair = false;       // ... on CTA pairs (cta_group::2), one pair per 256 batch rows
@@ -411,6 +412,10 @@ static void build_problems(iql_engine* e) {
   const WorkspaceLayout& wl = e->wl;
   const int64_t P = e->layout.param_floats, PQ = e->layout.q_floats;
   const bool use_shadow = c.math_mode == IQL_MATH_TF32_TCGEN05 && umma_phase_supported(0, B, H);
+  // hidden-layer weights as tcgen05 operands: read from the arenas themselves (biased in place during a call) instead of
+  // from a TF32-rounded shadow copy
+  e->bias_hidden = use_shadow && L >= 2 && L <= 4 && dbg_getenv("IQL_B200_NO_BIASED_WEIGHTS") == nullptr;
+  const bool hid_shadow = use_shadow && !e->bias_hidden;
   e->h_probs.clear();
   e->fwd_phases.clear();
   e->bwd_phases.clear();
@@ -445,7 +450,7 @@ static void build_problems(iql_engine* e) {
         if (l == 0) { p.A = wsm(m) + wl.xrow + pd.in_off; p.lda = ROW; p.K = pd.k0; }
         else { p.A = actp(m, f, l - 1); p.lda = H; p.K = H; }
         p.B = blk + e->w_off[pd.net][l];
-        if (use_shadow && l >= 1 && l < L)  // hidden-layer weights feed tcgen05: use the TF32-rounded copy
+        if (hid_shadow && l >= 1 && l < L)  // hidden-layer weights feed tcgen05: the TF32-rounded copy (or, bias_hidden, the arena itself)
           p.B = (pd.tgt ? e->d_tshadow + (int64_t)m * PQ : e->d_wshadow + (int64_t)m * P) + e->w_off[pd.net][l];
         p.ldb = e->w_ld[pd.net][l];
         p.bias = blk + e->b_off[pd.net][l];
@@ -518,7 +523,7 @@ static void build_problems(iql_engine* e) {
           if (t == 3) { p.A = wsm(m) + wl.gpi; p.lda = wl.Ald; p.K = c.action_dim; }
           else { p.A = wsm(m) + wl.gy + (int64_t)t * B; p.lda = 1; p.K = 1; }
         } else { p.A = ghp(m, t, (L - 1 - l) & 1); p.lda = H; p.K = H; }
-        p.B = ((use_shadow && l < L) ? e->d_wshadow : e->params) + (int64_t)m * P + e->w_off[net][l];
+        p.B = ((hid_shadow && l < L) ? e->d_wshadow : e->params) + (int64_t)m * P + e->w_off[net][l];
         p.ldb = e->w_ld[net][l];
         p.C = ghp(m, t, (L - l) & 1);
         p.ldc = H;
@@ -877,6 +882,15 @@ static StepCtx make_ctx(const iql_engine* e) {
     c.first_w_begin[n] = e->split_first ? e->w_off[n][0] : 0;
     c.first_w_end[n] = e->split_first ? e->w_off[n][0] + (int64_t)e->cfg.hidden_dim * e->w_ld[n][0] : 0;
   }
+  c.bias_hidden = (c.tf32 && e->bias_hidden) ? 1 : 0;
+  c.n_hid = 0;
+  if (c.bias_hidden)
+    for (int n = 0; n < 4; ++n)
+      for (int l = 1; l < e->cfg.n_hidden; ++l) {
+        c.hid_begin[c.n_hid] = e->w_off[n][l];
+        c.hid_end[c.n_hid] = e->w_off[n][l] + (int64_t)e->cfg.hidden_dim * e->w_ld[n][l];
+        ++c.n_hid;
+      }
   const int Lh = e->cfg.n_hidden;
   c.first_w_begin[4] = e->pol_umma ? e->w_off[IQL_NET_ACTOR][Lh] : 0;
   c.first_w_end[4] = e->pol_umma ? e->w_off[IQL_NET_ACTOR][Lh] + (int64_t)e->cfg.action_dim * e->w_ld[IQL_NET_ACTOR][Lh] : 0;
@@ -1169,6 +1183,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     cudaEventRecord(e->ev_gather, e->side);
     ++launches;
   }
+  ctx.unbias_out = (ctx.k == ctx.K - 1) ? 1 : 0;  // the call's last optimizer launch leaves plain fp32 in the arenas
   if (chain) {
     if (tm) {
       double fl = 0, by = 0;
@@ -1361,10 +1376,10 @@ extern "C" int iql_profile_step(iql_engine* e, int32_t reps, int32_t max_slots, 
   if (rc != IQL_OK) return rc;
   StepCtx ctx = make_ctx(e);
   ctx.K = 1;
-  if (ctx.tf32) launch_refresh_shadow(ctx, e->params, e->target, st);
   std::vector<double> acc;
   StepTimer last;
   for (int r = 0; r < reps; ++r) {
+    if (ctx.tf32) launch_refresh_shadow(ctx, e->params, e->target, st);  // every rep is a call of its own (K = 1)
     StepTimer tm;
     tm.st = st;
     ctx.k = 0;

@@ -102,6 +102,16 @@ struct StepCtx {
   // ranges inside a member block whose TF32 lo parts are maintained next to the hi shadow: the first-layer weights of
   // q1, q2, v, actor (3xTF32 input layer) and [4] the policy-head weights when the head runs as a two-pass tcgen05 GEMM
   int64_t first_w_begin[5], first_w_end[5];
+  // Hidden-layer weights (W_l, 1 <= l < L, and their target copies) need no TF32 shadow: during an engine call they are
+  // kept in the parameter / target arenas themselves with half a TF32 ulp added to the magnitude (bit pattern + 0x1000),
+  // so that the tensor cores' truncation of the fp32 operand IS round-to-nearest of the true weight.  The call's first
+  // kernel adds the bias in place, the optimizer removes it from what it reads and re-adds it to what it writes, and the
+  // optimizer launch of the call's LAST step writes the true values (unbias_out): outside a call the arenas always hold
+  // plain fp32.  Saves the 1.5 MB per member-step of shadow writes.
+  int bias_hidden;               // 1: scheme active (tcgen05 path)
+  int unbias_out;                // 1: this optimizer launch is the last of the call
+  int n_hid;
+  int64_t hid_begin[4 * 3], hid_end[4 * 3];  // hidden weight ranges inside a member block (4 nets x (L - 1) layers)
   int64_t xrow_off_;             // per-member workspace offset of the gathered rows
   int64_t xhi_off, xlo_off;      // per-member workspace offsets of the hi / lo copies of the gathered rows (0 = off)
 };
@@ -139,7 +149,7 @@ void launch_loss(const StepCtx& ctx, float* ws, int64_t ws_member_floats, const 
 void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_avg_sq, float* target,
                  const float* grads, cudaStream_t st);
 void launch_advance(const StepCtx& ctx, int K, cudaStream_t st);
-void launch_refresh_shadow(const StepCtx& ctx, const float* params, const float* target, cudaStream_t st);
+void launch_refresh_shadow(const StepCtx& ctx, float* params, float* target, cudaStream_t st);
 void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float* s, const float* a, const float* r,
                        const float* s2, const float* d, cudaStream_t st);
 // skinny-layer kernels (kernels_skinny.cu)

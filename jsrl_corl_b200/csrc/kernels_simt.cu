@@ -449,32 +449,40 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
 
 // TF32-rounded operand copies of params / target, rebuilt at the start of every engine call so that weights
 // written from outside (checkpoint loads, parameter surgery through the torch views) are always picked up.
-__global__ void __launch_bounds__(256) refresh_shadow_kernel(StepCtx ctx, const float* __restrict__ params,
-                                                             const float* __restrict__ target) {
+__global__ void __launch_bounds__(256) refresh_shadow_kernel(StepCtx ctx, float* __restrict__ params, float* __restrict__ target) {
   const int m = blockIdx.y;
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   bool first_layer = false;
 #pragma unroll
   for (int r = 0; r < 5; ++r) first_layer |= (i >= ctx.first_w_begin[r] && i < ctx.first_w_end[r]);
+  const bool hidden = in_hidden_weights(ctx, i);  // these enter the call biased in place and have no shadow (engine.h)
   if (i < ctx.P) {
     const float4 v = *reinterpret_cast<const float4*>(params + m * ctx.P + i);
-    const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-    *reinterpret_cast<float4*>(ctx.w_shadow + m * ctx.P + i) = hi;
-    if (first_layer)
-      *reinterpret_cast<float4*>(ctx.w_shadow_lo + m * ctx.P + i) =
-          make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+    if (hidden) {
+      *reinterpret_cast<float4*>(params + m * ctx.P + i) = make_float4(tf32_bias(v.x), tf32_bias(v.y), tf32_bias(v.z), tf32_bias(v.w));
+    } else {
+      const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      *reinterpret_cast<float4*>(ctx.w_shadow + m * ctx.P + i) = hi;
+      if (first_layer)
+        *reinterpret_cast<float4*>(ctx.w_shadow_lo + m * ctx.P + i) =
+            make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+    }
   }
   if (i < ctx.PQ) {
     const float4 v = *reinterpret_cast<const float4*>(target + m * ctx.PQ + i);
-    const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-    *reinterpret_cast<float4*>(ctx.t_shadow + m * ctx.PQ + i) = hi;
-    if (first_layer)
-      *reinterpret_cast<float4*>(ctx.t_shadow_lo + m * ctx.PQ + i) =
-          make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+    if (hidden) {
+      *reinterpret_cast<float4*>(target + m * ctx.PQ + i) = make_float4(tf32_bias(v.x), tf32_bias(v.y), tf32_bias(v.z), tf32_bias(v.w));
+    } else {
+      const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      *reinterpret_cast<float4*>(ctx.t_shadow + m * ctx.PQ + i) = hi;
+      if (first_layer)
+        *reinterpret_cast<float4*>(ctx.t_shadow_lo + m * ctx.PQ + i) =
+            make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+    }
   }
 }
 
-void launch_refresh_shadow(const StepCtx& ctx, const float* params, const float* target, cudaStream_t st) {
+void launch_refresh_shadow(const StepCtx& ctx, float* params, float* target, cudaStream_t st) {
   dim3 grid((unsigned)((ctx.P / 4 + 255) / 256), ctx.n_members);
   refresh_shadow_kernel<<<grid, 256, 0, st>>>(ctx, params, target);
 }
