@@ -186,6 +186,14 @@ int iql_replay_sample(const float* rows, const iql_row_layout* lay, int64_t size
                       float* states, float* actions, float* rewards, float* next_states,
                       float* dones, int64_t* idx_out, void* stream);
 
+/* ReplayBuffer.sample iql.py:171-178 for a HOST caller: `host_indices` [batch] int64 in host memory (the
+ * np.random.randint draw of iql.py:172), each in [0, size).  The indices travel in the kernel parameters (256 per
+ * launch): no staging buffer, no host->device copy, and the caller may reuse `host_indices` as soon as the call
+ * returns.  Outputs as for iql_replay_sample. */
+int iql_replay_sample_host(const float* rows, const iql_row_layout* lay, int64_t size, int64_t batch,
+                           const int64_t* host_indices, float* states, float* actions, float* rewards,
+                           float* next_states, float* dones, void* stream);
+
 /* ---- the update ----------------------------------------------------------- */
 /* Attach member's replay rows (several members may share one buffer). */
 int iql_bind_replay(iql_engine* e, int32_t member, const float* rows, int64_t capacity, int64_t size);
@@ -204,6 +212,16 @@ int iql_load_batch(iql_engine* e, int32_t member, const float* states, const flo
 int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mode, const int64_t* indices,
                     const uint8_t* dropout_masks, float* out_losses, int64_t* idx_out,
                     void* stream);
+/* replaces: ONE iteration of the reference's training loop as a host caller sees it --
+ * `batch = replay_buffer.sample(B); log_dict = trainer.train(batch)` (offline/iql.py:631-635, finetune/iql.py:542-563),
+ * whose log_dict holds the three losses as host floats every step.
+ * host_indices: [S][B] int64 in HOST memory (e.g. numpy's np.random.randint stream, iql.py:172), or NULL to consume the
+ * batch staged by iql_load_batch.  host_losses: [S][3] floats in HOST memory.  One CUDA-graph launch on `stream`
+ * (a non-default stream); the loss kernel writes its scalars into pinned host memory and the call returns as soon as
+ * they have landed, while the step's backward / optimizer launches are still in flight -- work the caller enqueues on
+ * `caller_stream` (may equal `stream`) afterwards is ordered behind the whole step. */
+int iql_train_host_step(iql_engine* e, const int64_t* host_indices, float* host_losses, void* stream,
+                        void* caller_stream);
 /* replaces: actor(obs).mean / DeterministicPolicy.forward as used by
  * GaussianPolicy.act / DeterministicPolicy.act iql.py:371-379,403-413 in eval
  * mode: out[n,A] = clamp(max_action * tanh(MLP(states[n,S]))).  member = -1 evaluates every member's

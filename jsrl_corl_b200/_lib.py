@@ -100,10 +100,12 @@ SYMBOLS = {
     "iql_replay_insert": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, _P, _P]),
     "iql_replay_sample": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, C.c_int64, _P, C.c_uint64, C.c_uint64,
                                     _P, _P, _P, _P, _P, _P, _P]),
+    "iql_replay_sample_host": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "iql_bind_replay": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_int64]),
     "iql_set_replay_size": (C.c_int, [_P, C.c_int32, C.c_int64]),
     "iql_load_batch": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "iql_train_steps": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "iql_train_host_step": (C.c_int, [_P, _P, _P, _P, _P]),
     "iql_act": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_float, _P, _P]),
     "iql_last_launch_count": (C.c_int64, [_P]),
     "iql_debug_fused_trace": (C.c_int, [_P, C.c_int32]),

@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <map>
 #include <tuple>
 #include <string>
@@ -137,6 +139,10 @@ struct iql_engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_side = nullptr, ev_fork_g = nullptr, ev_gather = nullptr;
   bool use_graphs = true;
+  // host-step path (iql_train_host_step): pinned, device-mapped host block = [S][B] int64 indices | [S][4] floats
+  // (losses + flag word, written by the loss kernel); events ordering the engine stream against the caller's stream
+  char* h_mail = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 static int fail(iql_engine* e, int code, const std::string& msg) {
@@ -321,6 +327,9 @@ extern "C" void iql_destroy(iql_engine* e) {
   if (e->ev_fork_g) cudaEventDestroy(e->ev_fork_g);
   if (e->ev_gather) cudaEventDestroy(e->ev_gather);
   if (e->side) cudaStreamDestroy(e->side);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->h_mail) cudaFreeHost(e->h_mail);
   delete e;
 }
 
@@ -1308,6 +1317,119 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
                                   cudaMemcpyDeviceToDevice, st));
   }
   e->last_launches = launches;
+  return IQL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Host-driven single step: the reference's loop `batch = rb.sample(B); log = trainer.train(batch)`
+// (algorithms/offline/iql.py:631-635, finetune/iql.py:542-563) returns the three losses to the host every step.
+// One call = one CUDA graph launch (TF32 operand refresh, gather of the host-drawn indices read straight from
+// pinned memory, the whole step, counter advance).  The loss kernel stores its scalars into device-mapped pinned
+// memory and raises a flag word; this function spins on that word and returns as soon as the losses of the step are on
+// the host -- while the step's backward and optimizer launches are still running, so the caller's host work for the
+// next step (index draw, Python) overlaps them.  Everything the caller enqueues afterwards is stream-ordered behind
+// the step (ev_out), exactly as after iql_train_steps.
+// ---------------------------------------------------------------------------
+extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, float* host_losses, void* stream,
+                                   void* caller_stream) {
+  if (!e) return IQL_ERR_INVALID;
+  if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_train_host_step: state not bound");
+  if (!host_losses) return fail(e, IQL_ERR_INVALID, "iql_train_host_step: host_losses is null");
+  cudaStream_t st = (cudaStream_t)stream, cur = (cudaStream_t)caller_stream;
+  if (!st) return fail(e, IQL_ERR_INVALID, "iql_train_host_step: needs a non-default stream (graph capture)");
+  const int S = e->cfg.n_members, B = e->cfg.batch_size;
+  const bool gather = host_indices != nullptr;
+  for (int m = 0; m < S; ++m) {
+    if (gather && !e->h_replay[m].rows) return fail(e, IQL_ERR_STATE, "iql_train_host_step: replay buffer not bound");
+    if (!gather && !e->preloaded[m]) return fail(e, IQL_ERR_STATE, "iql_train_host_step: no batch staged (call iql_load_batch)");
+  }
+  const size_t idx_bytes = sizeof(int64_t) * (size_t)S * B;
+  if (!e->h_mail) {
+    if (cudaHostAlloc((void**)&e->h_mail, idx_bytes + sizeof(float) * 4 * S, cudaHostAllocMapped) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(e, IQL_ERR_CUDA, "iql_train_host_step: pinned mailbox / event allocation failed");
+    }
+    memset(e->h_mail, 0, idx_bytes + sizeof(float) * 4 * S);
+  }
+  int64_t* mail_idx = (int64_t*)e->h_mail;
+  float* mail = (float*)(e->h_mail + idx_bytes);
+  if (gather)
+    for (int m = 0; m < S; ++m) {
+      const int64_t cap = e->h_replay[m].capacity;
+      for (int b = 0; b < B; ++b) {
+        const int64_t i = host_indices[(size_t)m * B + b];
+        if (i < 0 || i >= cap) return fail(e, IQL_ERR_INVALID, "iql_train_host_step: index outside the bound replay buffer");
+        mail_idx[(size_t)m * B + b] = i;
+      }
+    }
+  for (int m = 0; m < S; ++m) reinterpret_cast<volatile uint32_t*>(mail)[m * 4 + 3] = 0u;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  if (cur != st) {  // the step reads what the caller's stream wrote (inserted rows, loaded weights, a staged batch)
+    CUDA_TRY(e, cudaEventRecord(e->ev_in, cur));
+    CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_in, 0));
+  }
+  int rc = flush_tables(e, st);
+  if (rc != IQL_OK) return rc;
+  const auto graph_key = std::make_tuple(gather ? 101 : 102, 1, (uintptr_t)0);
+  auto it = e->graphs.find(graph_key);
+  if (it == e->graphs.end()) {
+    StepCtx ctx = make_ctx(e);
+    ctx.K = 1;
+    ctx.k = 0;
+    ctx.indices = gather ? mail_idx : nullptr;  // unified addressing: the pinned block is device-visible at its host address
+    ctx.host_mail = mail;
+    cudaGraph_t graph = nullptr;
+    int64_t launches = 0;
+    CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    if (ctx.tf32) { launch_refresh_shadow(ctx, e->params, e->target, st); ++launches; }
+    launches += enqueue_step(e, ctx, gather, st, nullptr, false);
+    launch_advance(ctx, 1, st);
+    ++launches;
+    cudaError_t cerr = cudaStreamEndCapture(st, &graph);
+    if (cerr != cudaSuccess) return fail(e, IQL_ERR_CUDA, std::string("iql_train_host_step: graph capture: ") + cudaGetErrorString(cerr));
+    cudaGraphExec_t exec = nullptr;
+    CUDA_TRY(e, cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = e->graphs.emplace(graph_key, std::make_pair(exec, launches)).first;
+  }
+  CUDA_TRY(e, cudaGraphLaunch(it->second.first, st));
+  e->last_launches = it->second.second;
+  if (cur != st) {
+    CUDA_TRY(e, cudaEventRecord(e->ev_out, st));
+    CUDA_TRY(e, cudaStreamWaitEvent(cur, e->ev_out, 0));
+  }
+  for (int m = 0; m < S; ++m) {
+    iql_counters& c = e->h_counters[m];
+    c.v_step += 1; c.q_step += 1; c.actor_step += 1; c.total_it += 1; c.sample_step += 1;
+    if (e->h_hparams[m].cosine_t_max > 0) c.sched_epoch += 1;
+    e->preloaded[m] = 0;
+  }
+  // wait for the flag words (bounded: a failed launch never raises them)
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int m = 0; m < S; ++m) {
+    volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(mail) + m * 4 + 3;
+    uint32_t spins = 0;
+    while (*flag == 0u) {
+      if ((++spins & 0x3FFFu) == 0u) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) {
+          if (*flag == 0u) return fail(e, IQL_ERR_CUDA, "iql_train_host_step: the step finished without reporting its losses");
+          break;
+        }
+        if (q != cudaErrorNotReady) return fail(e, IQL_ERR_CUDA, std::string("iql_train_host_step: ") + cudaGetErrorString(q));
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20))
+          return fail(e, IQL_ERR_CUDA, "iql_train_host_step: timed out waiting for the losses");
+      }
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  for (int m = 0; m < S; ++m)
+    for (int j = 0; j < 3; ++j) host_losses[m * 3 + j] = reinterpret_cast<volatile float*>(mail)[m * 4 + j];
   return IQL_OK;
 }
 

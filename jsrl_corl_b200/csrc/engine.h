@@ -90,6 +90,9 @@ struct StepCtx {
   const uint8_t* dropout_masks;  // [S][K][L][B][H] or null
   int64_t* idx_out;              // [S][K][B] or null
   float* loss_ring;              // [S][Kmax][3]
+  // host-step path (iql_train_host_step): pinned, device-mapped host memory [S][4] -- the loss kernel stores the three
+  // losses of member m at [m][0..2], fences at system scope and then sets the word [m][3] to 1; null otherwise
+  float* host_mail;
   AdamScalars* adam_sc;          // [S][3] device
   int k_max;
   int tf32;                      // 1: tcgen05 path; producers round GEMM operands to nearest TF32

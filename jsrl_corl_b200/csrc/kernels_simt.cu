@@ -390,6 +390,12 @@ __global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restric
     out[0] = red[0][0] * inv_b;
     out[1] = (red[0][1] * inv_b + red[0][2] * inv_b) * 0.5f;
     out[2] = red[0][3] * inv_b;
+    if (ctx.host_mail) {  // the host is spinning on the flag word: losses first, system-scope fence, then the flag
+      volatile float* mail = ctx.host_mail + (int64_t)m * 4;
+      mail[0] = out[0]; mail[1] = out[1]; mail[2] = out[2];
+      __threadfence_system();
+      *reinterpret_cast<volatile uint32_t*>(mail + 3) = 1u;
+    }
   }
   if (gauss && j < min(A, LOSS_MAX_A)) {
     const float lsr = log_std[j];

@@ -156,6 +156,35 @@ __global__ void replay_sample_kernel(const float* __restrict__ rows, iql_row_lay
   }
 }
 
+// Host-drawn indices passed BY VALUE in the kernel parameters (up to 256 per launch): the reference draws its
+// indices with numpy on the host every step (iql.py:172); this way they reach the gather without a staging buffer,
+// a host->device copy or anything the next sample() call could overwrite while this launch is still queued.
+struct IdxPack { int64_t v[256]; };
+__global__ void __launch_bounds__(256) replay_sample_byval_kernel(const float* __restrict__ rows, iql_row_layout lay, int b0, int nb,
+                                                                  const __grid_constant__ IdxPack idx,
+                                                                  float* __restrict__ so, float* __restrict__ ao,
+                                                                  float* __restrict__ ro, float* __restrict__ s2o,
+                                                                  float* __restrict__ dout) {
+  const int RF = lay.row_floats, S = lay.state_dim, A = lay.action_dim;
+  const int Q = RF >> 2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * Q) return;
+  const int bl = t / Q, q = t - bl * Q;
+  const int64_t b = b0 + bl;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(rows + idx.v[bl] * RF) + q);
+  const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = q * 4 + j;
+    const float x = vals[j];
+    if (c < S) so[b * S + c] = x;
+    else if (c < S + A) ao[b * A + (c - S)] = x;
+    else if (c >= lay.off_next_state && c < lay.off_next_state + S) s2o[b * S + (c - lay.off_next_state)] = x;
+    else if (c == lay.off_reward) ro[b] = x;
+    else if (c == lay.off_done) dout[b] = x;
+  }
+}
+
 }  // namespace iql
 
 using namespace iql;
@@ -220,5 +249,27 @@ extern "C" int iql_replay_sample(const float* rows, const iql_row_layout* lay, i
   int blocks = (int)((threads + 255) / 256);
   replay_sample_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, *lay, size, batch, indices, seed, step, states,
                                                                  actions, rewards, next_states, dones, idx_out);
+  return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
+}
+
+extern "C" int iql_replay_sample_host(const float* rows, const iql_row_layout* lay, int64_t size, int64_t batch,
+                                      const int64_t* host_indices, float* states, float* actions, float* rewards,
+                                      float* next_states, float* dones, void* stream) {
+  if (!layout_ok(lay) || !rows || batch < 0 || size <= 0) return IQL_ERR_INVALID;
+  if (batch == 0) return IQL_OK;
+  if (!host_indices || !states || !actions || !rewards || !next_states || !dones) return IQL_ERR_INVALID;
+  const int Q = lay->row_floats >> 2;
+  IdxPack pack;
+  for (int64_t b0 = 0; b0 < batch; b0 += 256) {
+    const int nb = (int)(batch - b0 < 256 ? batch - b0 : 256);
+    for (int i = 0; i < nb; ++i) {
+      const int64_t v = host_indices[b0 + i];
+      if (v < 0 || v >= size) return IQL_ERR_INVALID;
+      pack.v[i] = v;
+    }
+    for (int i = nb; i < 256; ++i) pack.v[i] = 0;
+    replay_sample_byval_kernel<<<(nb * Q + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, *lay, (int)b0, nb, pack, states, actions,
+                                                                                        rewards, next_states, dones);
+  }
   return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
 }

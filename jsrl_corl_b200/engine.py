@@ -109,6 +109,7 @@ class EnsembleEngine:
         self._hparams = [self._default_hparams(m) for m in range(n_members)]
         self._replay_refs: Dict[int, torch.Tensor] = {}
         self._idx_stage: Dict[int, torch.Tensor] = {}
+        self._host_losses = None
 
     # ------------------------------------------------------------------
     def __del__(self):
@@ -269,6 +270,45 @@ class EnsembleEngine:
                                                st.cuda_stream), self._h, "iql_train_steps")
         self._keep = (s, a, r, s2, d)
         return out
+
+    def host_step(self, batch=None, host_indices: Optional[int] = None) -> List[float]:
+        """One update step for a host-driven loop (`iql_train_host_step`): `host_indices` is the ADDRESS of S x B int64
+        indices in host memory (rows of the bound replay buffers), or `batch` the five dense tensors of an externally
+        built batch (S = 1).  One CUDA-graph launch; returns the step's [S * 3] losses as Python floats as soon as the
+        loss kernel has written them to pinned host memory -- the backward / optimizer launches of the step are still
+        running then, stream-ordered before anything the caller enqueues next."""
+        if self._host_losses is None:
+            self._host_losses = np.zeros(3 * self.n_members, dtype=np.float32)
+            self._host_losses_ptr = self._host_losses.ctypes.data
+            self._stream_raw = self.stream.cuda_stream
+        switch = torch.cuda.current_device() != self.device.index
+        if switch:
+            guard = torch.cuda.device(self.device)
+            guard.__enter__()
+        try:
+            cur = torch._C._cuda_getCurrentRawStream(self.device.index)
+            if host_indices is None:
+                s, a, r, s2, d = [self._dense(b) for b in batch]
+                B = self.batch_size
+                if s.shape != (B, self.state_dim) or s2.shape != (B, self.state_dim):
+                    raise ValueError(f"states must be [{B}, {self.state_dim}]")
+                if a.shape != (B, self.action_dim):
+                    raise RuntimeError("Actions shape missmatch")  # iql.py:530
+                if r.numel() != B or d.numel() != B:
+                    raise ValueError("rewards / dones must have batch_size elements")
+                # staged on the caller's stream: the previous step made it wait for the engine stream (ev_out), and
+                # iql_train_host_step orders the engine stream behind it again (ev_in)
+                rc = self._L.iql_load_batch(self._h, 0, s.data_ptr(), a.data_ptr(), r.data_ptr(), s2.data_ptr(), d.data_ptr(), cur)
+                if rc:
+                    _lib.check(rc, self._h, "iql_load_batch")
+                self._keep = (s, a, r, s2, d)
+            rc = self._L.iql_train_host_step(self._h, host_indices, self._host_losses_ptr, self._stream_raw, cur)
+            if rc:
+                _lib.check(rc, self._h, "iql_train_host_step")
+        finally:
+            if switch:
+                guard.__exit__(None, None, None)
+        return self._host_losses.tolist()
 
     def _dense(self, t: torch.Tensor) -> torch.Tensor:
         if t.device == self.device and t.dtype == torch.float32 and t.is_contiguous():

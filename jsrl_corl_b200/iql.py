@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import copy
 import math
+import weakref
 import os
 import random
 import uuid
@@ -201,6 +202,37 @@ def is_goal_reached(reward: float, info: Dict) -> bool:
 # ---------------------------------------------------------------------------
 # replay buffer (iql.py:122-196) on packed device rows
 # ---------------------------------------------------------------------------
+_N_SLOTS = 4
+# id(observations tensor) -> slot, for the cached output tensors of every live buffer: `ImplicitQLearning.train(batch)`
+# recognises a batch that came straight out of `ReplayBuffer.sample` (same tensor objects, untouched since) and lets the
+# engine gather the rows itself from the host-drawn indices instead of re-packing the five dense tensors
+_SAMPLED: "weakref.WeakValueDictionary[int, _SampleSlot]" = weakref.WeakValueDictionary()
+
+
+class _SampleSlot:
+    """One set of output tensors of ``ReplayBuffer.sample`` + the host indices that filled it."""
+    __slots__ = ("rb", "B", "out", "ptrs", "ver", "idx_host", "high", "__weakref__")
+
+    def __init__(self, rb: "ReplayBuffer", B: int):
+        S, A = rb._state_dim, rb._action_dim
+        # one allocation carved into the five dense outputs
+        flat = torch.empty(B * (2 * S + A + 2), dtype=torch.float32, device=rb._device)
+        s, a, r, s2, d = flat.split((B * S, B * A, B, B * S, B))
+        self.rb, self.B = weakref.ref(rb), B
+        self.out = [s.view(B, S), a.view(B, A), r.view(B, 1), s2.view(B, S), d.view(B, 1)]
+        self.ptrs = tuple(t.data_ptr() for t in self.out)
+        self.ver = None
+        self.idx_host = None
+        self.high = 0
+
+    def untouched(self, batch) -> bool:
+        """`batch` is exactly this slot's tensors and nobody has written to them in place since the gather."""
+        o, v = self.out, self.ver
+        return (batch[0] is o[0] and batch[1] is o[1] and batch[2] is o[2] and batch[3] is o[3] and batch[4] is o[4]
+                and v is not None and o[0]._version == v[0] and o[1]._version == v[1] and o[2]._version == v[2]
+                and o[3]._version == v[3] and o[4]._version == v[4])
+
+
 class ReplayBuffer:
     """Same API as the reference buffer; storage is ONE device tensor of packed
     transition rows ``[buffer_size, row_floats]`` (include/iql_b200.h
@@ -214,7 +246,7 @@ class ReplayBuffer:
     (``high=min(_size, _pointer)``)."""
 
     def __init__(self, state_dim: int, action_dim: int, buffer_size: int, device: str = "cpu",
-                 sampler: str = "numpy", seed: int = 0, offline_semantics: bool = False):
+                 sampler: str = "numpy", seed: int = 0, offline_semantics: bool = False, fresh_outputs: bool = False):
         self._device = _lib.require_cuda(device)
         self._L = _lib.lib()
         if sampler not in ("numpy", "philox"):
@@ -240,11 +272,13 @@ class ReplayBuffer:
         self._stage_host = [torch.zeros(lay.row_floats, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._stage_ev = [None, None]
         self._stage_i = 0
-        # sample: ring of pinned index rows (numpy stream -> pinned -> device, non-blocking)
-        self._idx_ring: List[Tuple[torch.Tensor, torch.Tensor, Optional[torch.cuda.Event]]] = []
-        self._idx_i = 0
-        self._last_indices = None
+        # sample: ring of cached output tensor sets; `fresh_outputs=True` allocates new tensors every call instead
+        self._fresh_outputs = bool(fresh_outputs)
+        self._slots: List["_SampleSlot"] = []
+        self._slot_i = 0
+        self._last_indices = None  # host int64 array of the last sample() call (numpy sampler)
         self._lay_ref = C.byref(self._lay)
+        self._rows_ptr = self._rows.data_ptr()
 
     @property
     def rows(self) -> torch.Tensor:
@@ -324,27 +358,25 @@ class ReplayBuffer:
     def _high(self) -> int:
         return min(self._size, self._pointer) if self._offline_semantics else self._size
 
-    def _idx_slot(self, B: int):
-        """Next (pinned host row, device row) pair of the index ring; waits only if its previous copy is still queued."""
-        if not self._idx_ring or self._idx_ring[0][0].numel() != B:
-            self._idx_ring = [(torch.empty(B, dtype=torch.int64).pin_memory(),
-                               torch.empty(B, dtype=torch.int64, device=self._device), None) for _ in range(4)]
-            self._idx_i = 0
-        i = self._idx_i
-        self._idx_i = (i + 1) % len(self._idx_ring)
-        host, dev, ev = self._idx_ring[i]
-        if ev is not None:
-            ev.synchronize()
-        return i, host, dev
+    def _out_slot(self, B: int) -> "_SampleSlot":
+        """Next set of cached output tensors (ring of ``_N_SLOTS``; a batch returned by ``sample`` is overwritten by the
+        ``_N_SLOTS``-th call after it -- construct the buffer with ``fresh_outputs=True`` for the reference's
+        one-allocation-per-call behaviour)."""
+        ring = self._slots
+        if not ring or ring[0].B != B:
+            for sl in ring:
+                _SAMPLED.pop(id(sl.out[0]), None)
+            ring = self._slots = [_SampleSlot(self, B) for _ in range(_N_SLOTS)]
+            for sl in ring:
+                _SAMPLED[id(sl.out[0])] = sl
+            self._slot_i = 0
+        sl = ring[self._slot_i]
+        self._slot_i = (self._slot_i + 1) % _N_SLOTS
+        return sl
 
     def sample(self, batch_size: int) -> TensorBatch:
         B = int(batch_size)
         dev = self._device
-        S, A = self._state_dim, self._action_dim
-        # one allocation per call (fresh tensors, like the reference), carved into the five dense outputs
-        flat = torch.empty(B * (2 * S + A + 2), dtype=torch.float32, device=dev)
-        s, a, r, s2, d = flat.split((B * S, B * A, B, B * S, B))
-        out = [s.view(B, S), a.view(B, A), r.view(B, 1), s2.view(B, S), d.view(B, 1)]
         high = self._high()
         switch = torch.cuda.current_device() != dev.index
         if switch:
@@ -353,27 +385,33 @@ class ReplayBuffer:
         try:
             if self._sampler == "numpy":
                 idx_host = np.random.randint(0, high, size=B)  # raises ValueError on an empty buffer, like the reference
-                slot, pin, idx = self._idx_slot(B)
-                pin.numpy()[:] = idx_host
-                idx.copy_(pin, non_blocking=True)
-                ev = self._idx_ring[slot][2] or torch.cuda.Event()
-                ev.record()  # torch's current stream on the (now current) device
-                self._idx_ring[slot] = (pin, idx, ev)
-                idx_ptr, seed, step = idx.data_ptr(), 0, 0
+                if self._fresh_outputs:
+                    sl = _SampleSlot(self, B)
+                else:
+                    sl = self._out_slot(B)
+                # the indices ride in the kernel parameters: no staging buffer, no host->device copy
+                rc = self._L.iql_replay_sample_host(self._rows_ptr, self._lay_ref, high, B, idx_host.__array_interface__["data"][0],
+                                                    *sl.ptrs, self._stream())
+                if rc:
+                    _lib.check(rc, None, "iql_replay_sample_host")
+                sl.idx_host, sl.high = idx_host, high
+                self._last_indices = idx_host
             else:
                 if high <= 0:
                     raise ValueError("low >= high")
-                idx, idx_ptr, seed, step = None, None, self._seed, self._sample_calls
+                sl = _SampleSlot(self, B) if self._fresh_outputs else self._out_slot(B)
+                sl.idx_host = None
+                rc = self._L.iql_replay_sample(self._rows_ptr, self._lay_ref, high, B, None, self._seed, self._sample_calls,
+                                               *sl.ptrs, None, self._stream())
+                if rc:
+                    _lib.check(rc, None, "iql_replay_sample")
             self._sample_calls += 1
-            _lib.check(self._L.iql_replay_sample(self._rows.data_ptr(), self._lay_ref, high, B, idx_ptr, seed, step,
-                                                 flat.data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
-                                                 out[3].data_ptr(), out[4].data_ptr(), None, self._stream()),
-                       None, "iql_replay_sample")
         finally:
             if switch:
                 ctx.__exit__(None, None, None)
-        self._last_indices = idx  # device row of the ring: valid until 3 more sample() calls
-        return out
+        out = sl.out
+        sl.ver = (out[0]._version, out[1]._version, out[2]._version, out[3]._version, out[4]._version)
+        return list(out)
 
     def add_transition(self, state: np.ndarray, action: np.ndarray, reward: float, next_state: np.ndarray, done: bool):
         lay = self._lay
@@ -591,6 +629,9 @@ class ImplicitQLearning:
         self._total_it = 0
         self._steps = {"v": 0, "q": 0, "actor": 0}
         self._step_tensors: Dict[str, torch.Tensor] = {}
+        self._step_views: Dict[str, np.ndarray] = {}
+        self._bound_rows: Optional[torch.Tensor] = None
+        self._path_counts = [0, 0]  # train() calls served by [engine-side gather of sample()'s indices, staged dense batch]
         self._published = False
         self._moment_cache = None
         self._loss_buf: Optional[torch.Tensor] = None
@@ -650,6 +691,7 @@ class ImplicitQLearning:
                 view.copy_(p.data)
                 p.data = view
         self._engine = eng
+        self._bound_rows = None
         self.actor._engine_ref = (eng, 0)
         self._pushed = None
         self._published = False
@@ -684,6 +726,7 @@ class ImplicitQLearning:
             # update, so `optimizer.state_dict()` is current even when called directly on the optimizer
             step_t = self._step_tensors.setdefault(grp, torch.tensor(0.0))
             step_t.fill_(float(steps))
+            self._step_views[grp] = step_t.numpy()  # shares memory: train() updates the count without a torch op
             for name in m_views[grp]:
                 p = mod.get_parameter(name)
                 st = opt.state.get(p)
@@ -746,19 +789,32 @@ class ImplicitQLearning:
             raise RuntimeError("Actions shape missmatch")
         eng = self._ensure_engine(int(observations.shape[0]))
         self._push_hparams()
-        if self._loss_buf is None or self._loss_buf.device != eng.device:
-            self._loss_buf = torch.empty(1, 1, 3, dtype=torch.float32, device=eng.device)
-        losses = eng.train_on_batch((observations, actions, rewards, next_observations, dones), out=self._loss_buf)
+        slot = _SAMPLED.get(id(observations))
+        if slot is not None and slot.idx_host is not None and slot.untouched(batch):
+            # the batch is what ReplayBuffer.sample just returned: the engine gathers the same rows itself from the
+            # host-drawn indices (identical values, no re-pack of the five dense tensors)
+            rb = slot.rb()
+            if self._bound_rows is not rb._rows:
+                eng.bind_replay(0, rb._rows, max(rb._size, 1))
+                self._bound_rows = rb._rows
+            v_loss, q_loss, a_loss = eng.host_step(host_indices=slot.idx_host.__array_interface__["data"][0])
+            self._path_counts[0] += 1
+        else:
+            v_loss, q_loss, a_loss = eng.host_step(batch=(observations, actions, rewards, next_observations, dones))
+            self._path_counts[1] += 1
         self._total_it += 1
-        for k in self._steps:
-            self._steps[k] += 1
+        st = self._steps
+        st["v"] += 1
+        st["q"] += 1
+        st["actor"] += 1
         if self._published:
-            for grp, key in (("qf", "q"), ("vf", "v"), ("actor", "actor")):
-                self._step_tensors[grp].fill_(float(self._steps[key]))
+            sv = self._step_views
+            sv["qf"][...] = st["q"]
+            sv["vf"][...] = st["v"]
+            sv["actor"][...] = st["actor"]
         else:
             self._publish_optimizer_state()
         self._advance_schedule(1)
-        v_loss, q_loss, a_loss = losses.view(3).tolist()  # one D2H sync (the reference does three .item())
         return {"value_loss": v_loss, "q_loss": q_loss, "actor_loss": a_loss}
 
     # ---- checkpoints (iql.py:565-606) --------------------------------------

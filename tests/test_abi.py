@@ -209,3 +209,27 @@ def test_replay_ingest_rejects_bad_arguments():
     assert L.iql_replay_ingest(1, C.byref(bad), 0, 4, 1, 1, 1, 1, 1, 0, 1e-3, None, None, 1.0, 1.0, 0.0, None) == _lib.IQL_ERR_INVALID
     # n == 0 is a no-op that succeeds (an empty dataset), before any pointer is dereferenced
     assert L.iql_replay_ingest(1, C.byref(lay), 0, 0, None, None, None, None, None, 0, 1e-3, None, None, 1.0, 1.0, 0.0, None) == _lib.IQL_OK
+
+
+def test_host_step_and_host_sample_reject_bad_arguments():
+    """iql_train_host_step / iql_replay_sample_host (the per-step host loop of offline/iql.py:631-635) check their
+    arguments before touching the GPU."""
+    L = _lib.lib()
+    out = (C.c_float * 3)()
+    assert L.iql_train_host_step(None, None, out, None, None) == _lib.IQL_ERR_INVALID
+    cfg = _lib.Config(1, 11, 3, 256, 2, 256, 1, _lib.MATH_FP32_SIMT, 4)
+    h = C.c_void_p()
+    assert L.iql_create(C.byref(cfg), C.byref(h)) == _lib.IQL_OK
+    try:
+        assert L.iql_train_host_step(h, None, out, 1, 1) == _lib.IQL_ERR_STATE  # nothing bound yet
+        assert b"not bound" in L.iql_last_error(h)
+    finally:
+        L.iql_destroy(h)
+    lay = _lib.RowLayout()
+    assert L.iql_replay_row_layout(11, 3, C.byref(lay)) == _lib.IQL_OK
+    idx = (C.c_int64 * 4)(0, 1, 2, 3)
+    assert L.iql_replay_sample_host(None, C.byref(lay), 10, 4, idx, 1, 1, 1, 1, 1, None) == _lib.IQL_ERR_INVALID
+    assert L.iql_replay_sample_host(1, C.byref(lay), 0, 4, idx, 1, 1, 1, 1, 1, None) == _lib.IQL_ERR_INVALID  # empty buffer
+    assert L.iql_replay_sample_host(1, C.byref(lay), 10, 4, None, 1, 1, 1, 1, 1, None) == _lib.IQL_ERR_INVALID
+    assert L.iql_replay_sample_host(1, C.byref(lay), 3, 4, idx, 1, 1, 1, 1, 1, None) == _lib.IQL_ERR_INVALID  # index 3 >= size 3
+    assert L.iql_replay_sample_host(1, C.byref(lay), 10, 0, None, None, None, None, None, None, None) == _lib.IQL_OK

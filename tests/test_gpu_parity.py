@@ -80,7 +80,7 @@ def test_replay_sample_reference_stream_bit_exact(tag):
     np.random.seed(42)
     for j in range(2):
         batch = rb.sample(B)
-        assert np.array_equal(rb._last_indices.cpu().numpy(), z[f"{tag}/indices"][j])
+        assert np.array_equal(np.asarray(rb._last_indices), z[f"{tag}/indices"][j])
         for nm, t in zip(("s", "a", "r", "s2", "d"), batch):
             ref = z[f"{tag}/batch{j}/{nm}"]
             assert tuple(t.shape) == ref.shape
@@ -566,6 +566,110 @@ def test_row_split_output_layer_backward(monkeypatch):
             assert _loss_errors(losses, ref).max() < 1e-5
             for k, rg in ref_grads.items():
                 assert rel_err(grads[k], rg) < 2e-5, (k, rel_err(grads[k], rg))
+
+
+def test_host_step_paths_agree_and_sample_output_cache():
+    """`train(rb.sample(B))` lets the engine gather the rows from sample()'s host-drawn indices; a batch the caller built
+    or touched is staged from its five dense tensors.  Both are the same step, bit for bit; an in-place edit of a sampled
+    tensor is seen (tensor version counters); `fresh_outputs=True` returns new tensors every call."""
+    import jsrl_corl_b200 as J
+
+    g = Golden("small_gauss")
+    m = g.meta
+    B = m["B"]
+    tr_a, rb = _facade_trainer(g, "fp32")
+    tr_b, _ = _facade_trainer(g, "fp32")
+    tr_c, _ = _facade_trainer(g, "fp32")
+    rb_fresh = J.ReplayBuffer(m["S"], m["A"], m["n_rows"], "cuda", fresh_outputs=True)
+    rb_fresh.load_d4rl_dataset(g.dataset())
+    np.random.seed(5)
+    seen = []
+    for t in range(6):
+        st = np.random.get_state()
+        batch = rb.sample(B)
+        la = tr_a.train(batch)
+        lb = tr_b.train([x.clone() for x in batch])
+        np.random.set_state(st)
+        fb = rb_fresh.sample(B)
+        assert all(torch.equal(x, y) for x, y in zip(fb, batch))
+        assert fb[0].data_ptr() not in [k[0].data_ptr() for k in seen]  # new tensors every call
+        seen.append(fb)  # (kept alive: a recycled allocation must not fake a repeat)
+        lc = tr_c.train(fb)
+        assert la == lb == lc, (t, la, lb, lc)
+    assert tr_a._path_counts == [6, 0] and tr_b._path_counts == [0, 6] and tr_c._path_counts == [0, 6]
+    # the cached outputs come round again after _N_SLOTS calls
+    from jsrl_corl_b200.iql import _N_SLOTS
+    first = rb.sample(B)
+    for _ in range(_N_SLOTS - 1):
+        assert rb.sample(B)[0] is not first[0]
+    assert rb.sample(B)[0] is first[0]
+    # an in-place edit of a sampled tensor is honoured (reward scaling by the caller)
+    batch = rb.sample(B)
+    ref = [x.clone() for x in batch]
+    batch[2].mul_(3.0)
+    ref[2].mul_(3.0)
+    assert tr_a.train(batch) == tr_b.train(ref)
+    assert tr_a._path_counts == [6, 1]
+    for k, v in tr_a.qf.state_dict().items():
+        assert torch.equal(v, tr_b.qf.state_dict()[k])
+    # bounds are checked on the host before anything is launched
+    L = J._lib.lib()
+    bad = np.array([0, m["n_rows"] + 7], dtype=np.int64)
+    sl = rb._slots[0]
+    assert L.iql_replay_sample_host(rb._rows.data_ptr(), rb._lay_ref, m["n_rows"], 2, bad.ctypes.data, *sl.ptrs, None) == J._lib.IQL_ERR_INVALID
+    with pytest.raises(ValueError, match="outside the bound replay buffer"):
+        J._lib.check(L.iql_train_host_step(tr_a._engine._h, np.full(B, 10 ** 9, np.int64).ctypes.data,
+                                           np.zeros(3, np.float32).ctypes.data, tr_a._engine.stream.cuda_stream, None),
+                     tr_a._engine._h)
+
+
+def test_host_step_tf32_matches_k_step_call_and_large_batch_sample():
+    """The host-step graph (refresh, gather from pinned indices, step, advance) against `train_steps(mode="indices")`
+    on the tensor-core path; `iql_replay_sample_host` with a batch that needs several launches."""
+    import jsrl_corl_b200 as J
+    from jsrl_corl_b200.synthetic import synthetic_dataset
+
+    S, A, B, n = 17, 6, 256, 5000
+    data = synthetic_dataset(n, S, A, 2)
+
+    def make():
+        torch.manual_seed(1)
+        q, v, actor = J.TwinQ(S, A), J.ValueFunction(S), J.GaussianPolicy(S, A, 1.0)
+        opts = [torch.optim.Adam(mod.parameters(), lr=3e-4) for mod in (actor, q, v)]
+        return J.ImplicitQLearning(1.0, actor, opts[0], q, opts[1], v, opts[2], device="cuda", math_mode="tf32")
+
+    rb = J.ReplayBuffer(S, A, n, "cuda")
+    rb.load_d4rl_dataset(data)
+    tr = make()
+    np.random.seed(9)
+    logs, idx = [], []
+    for _ in range(8):
+        logs.append(tr.train(rb.sample(B)))
+        idx.append(np.asarray(rb._last_indices).copy())
+    assert tr._path_counts == [8, 0]
+    tr2 = make()
+    tr2.train(rb.sample(B))  # builds the engine; then rewind to the initial state
+    tr3 = make()
+    eng = tr2._engine
+    with torch.no_grad():
+        for mod2, mod3 in ((tr2.qf, tr3.qf), (tr2.vf, tr3.vf), (tr2.actor, tr3.actor), (tr2.q_target, tr3.q_target)):
+            for (k, p2), (_, p3) in zip(mod2.state_dict().items(), mod3.state_dict().items()):
+                p2.copy_(p3)
+    eng.exp_avg.zero_(); eng.exp_avg_sq.zero_()
+    eng.set_counters(0, v_step=0, q_step=0, actor_step=0, sched_epoch=0, total_it=0)
+    eng.bind_replay(0, rb.rows, n)
+    ii = torch.from_numpy(np.stack(idx)).cuda().view(1, 8, B)
+    losses = eng.train_steps(8, mode="indices", indices=ii).cpu().numpy()[0]
+    got = np.array([[l["value_loss"], l["q_loss"], l["actor_loss"]] for l in logs], dtype=np.float32)
+    assert np.array_equal(got, losses), np.abs(got - losses).max()
+    for k, p in tr.qf.state_dict().items():
+        assert torch.equal(p, tr2.qf.state_dict()[k]), k
+    # 600 rows = three by-value launches
+    np.random.seed(1)
+    big = rb.sample(600)
+    ii = np.asarray(rb._last_indices)
+    assert np.array_equal(big[0].cpu().numpy(), data["observations"][ii]) and np.array_equal(big[3].cpu().numpy(), data["next_observations"][ii])
+    assert np.array_equal(big[2].cpu().numpy()[:, 0], data["rewards"][ii]) and np.array_equal(big[1].cpu().numpy(), data["actions"][ii])
 
 
 def test_facade_batch_size_change_and_partial_load_keep_state():

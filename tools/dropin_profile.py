@@ -24,7 +24,7 @@ eng = tr._engine
 torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 b = rb.sample(B)
 e0.record()
-for _ in range(500): eng.train_on_batch(b, out=tr._loss_buf)
+for _ in range(500): eng.train_on_batch(b)
 e1.record(); torch.cuda.synchronize()
 print(f"GPU time of load_batch + 1 step (back to back, no sync): {e0.elapsed_time(e1) / 500 * 1e3:.1f} us")
 pr = cProfile.Profile(); pr.enable()
