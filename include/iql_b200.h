@@ -222,6 +222,9 @@ int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mode, const i
  * `caller_stream` (may equal `stream`) afterwards is ordered behind the whole step. */
 int iql_train_host_step(iql_engine* e, const int64_t* host_indices, float* host_losses, void* stream,
                         void* caller_stream);
+/* host_losses == NULL above returns right after the launch; this collects the losses of that step (spins on the
+ * flag words, bounded; `stream` as above).  Lets the caller do its per-step host bookkeeping while the GPU works. */
+int iql_host_step_wait(iql_engine* e, float* host_losses, void* stream);
 /* replaces: actor(obs).mean / DeterministicPolicy.forward as used by
  * GaussianPolicy.act / DeterministicPolicy.act iql.py:371-379,403-413 in eval
  * mode: out[n,A] = clamp(max_action * tanh(MLP(states[n,S]))).  member = -1 evaluates every member's

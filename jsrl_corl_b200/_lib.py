@@ -106,6 +106,7 @@ SYMBOLS = {
     "iql_load_batch": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "iql_train_steps": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "iql_train_host_step": (C.c_int, [_P, _P, _P, _P, _P]),
+    "iql_host_step_wait": (C.c_int, [_P, _P, _P]),
     "iql_act": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_float, _P, _P]),
     "iql_last_launch_count": (C.c_int64, [_P]),
     "iql_debug_fused_trace": (C.c_int, [_P, C.c_int32]),

@@ -1218,6 +1218,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
     launch_bwd_chain(ca, ctx, st);
   } else {
     launch_adam(ctx, e->params, e->exp_avg, e->exp_avg_sq, e->target, e->grads, st);
+    if (ctx.advance_k > 0) ctx.advance_k = -1;  // consumed: the optimizer launch advanced the counters
   }
   ++launches;
   if (fork_gather) cudaStreamWaitEvent(st_main, e->ev_gather, 0);
@@ -1281,11 +1282,11 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
       CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       for (int k = 0; k < k_steps; ++k) {
         ctx.k = k;
+        if (k == k_steps - 1) ctx.advance_k = k_steps;
         const bool ahead = gather && overlap_gather && k + 1 < k_steps;  // step k+1's gather rides along step k's optimizer
         launches += enqueue_step(e, ctx, gather && (k == 0 || !overlap_gather), st, nullptr, ahead);
       }
-      launch_advance(ctx, k_steps, st);
-      ++launches;
+      if (ctx.advance_k != -1) { launch_advance(ctx, k_steps, st); ++launches; }
       cudaError_t cerr = cudaStreamEndCapture(st, &graph);
       if (cerr != cudaSuccess) return fail(e, IQL_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(cerr));
       cudaGraphExec_t exec = nullptr;
@@ -1298,11 +1299,11 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
   } else {
     for (int k = 0; k < k_steps; ++k) {
       ctx.k = k;
+      if (k == k_steps - 1) ctx.advance_k = k_steps;
       const bool ahead = gather && overlap_gather && k + 1 < k_steps;
       launches += enqueue_step(e, ctx, gather && (k == 0 || !overlap_gather), st, nullptr, ahead);
     }
-    launch_advance(ctx, k_steps, st);
-    ++launches;
+    if (ctx.advance_k != -1) { launch_advance(ctx, k_steps, st); ++launches; }
   }
   CUDA_TRY(e, cudaGetLastError());
   for (int m = 0; m < S; ++m) {
@@ -1330,11 +1331,11 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
 // next step (index draw, Python) overlaps them.  Everything the caller enqueues afterwards is stream-ordered behind
 // the step (ev_out), exactly as after iql_train_steps.
 // ---------------------------------------------------------------------------
+extern "C" int iql_host_step_wait(iql_engine* e, float* host_losses, void* stream);
 extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, float* host_losses, void* stream,
                                    void* caller_stream) {
   if (!e) return IQL_ERR_INVALID;
   if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_train_host_step: state not bound");
-  if (!host_losses) return fail(e, IQL_ERR_INVALID, "iql_train_host_step: host_losses is null");
   cudaStream_t st = (cudaStream_t)stream, cur = (cudaStream_t)caller_stream;
   if (!st) return fail(e, IQL_ERR_INVALID, "iql_train_host_step: needs a non-default stream (graph capture)");
   const int S = e->cfg.n_members, B = e->cfg.batch_size;
@@ -1383,10 +1384,23 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
     cudaGraph_t graph = nullptr;
     int64_t launches = 0;
     CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    if (ctx.tf32) { launch_refresh_shadow(ctx, e->params, e->target, st); ++launches; }
-    launches += enqueue_step(e, ctx, gather, st, nullptr, false);
-    launch_advance(ctx, 1, st);
-    ++launches;
+    // the TF32 operand refresh and the gather are independent: side by side, joined in front of the forward
+    const bool fork_refresh = ctx.tf32 && gather && e->side != nullptr;
+    if (fork_refresh) {
+      cudaEventRecord(e->ev_fork_g, st);
+      cudaStreamWaitEvent(e->side, e->ev_fork_g, 0);
+      launch_refresh_shadow(ctx, e->params, e->target, e->side);
+      cudaEventRecord(e->ev_gather, e->side);
+      launch_gather(ctx, e->d_ws_f, e->wl.member_floats, e->wl.xrow, st);
+      cudaStreamWaitEvent(st, e->ev_gather, 0);
+      launches += 2;
+    } else if (ctx.tf32) {
+      launch_refresh_shadow(ctx, e->params, e->target, st);
+      ++launches;
+    }
+    ctx.advance_k = 1;
+    launches += enqueue_step(e, ctx, gather && !fork_refresh, st, nullptr, false);
+    if (ctx.advance_k != -1) { launch_advance(ctx, 1, st); ++launches; }
     cudaError_t cerr = cudaStreamEndCapture(st, &graph);
     if (cerr != cudaSuccess) return fail(e, IQL_ERR_CUDA, std::string("iql_train_host_step: graph capture: ") + cudaGetErrorString(cerr));
     cudaGraphExec_t exec = nullptr;
@@ -1406,6 +1420,16 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
     if (e->h_hparams[m].cosine_t_max > 0) c.sched_epoch += 1;
     e->preloaded[m] = 0;
   }
+  if (!host_losses) return IQL_OK;  // the caller collects the losses with iql_host_step_wait
+  return iql_host_step_wait(e, host_losses, stream);
+}
+
+extern "C" int iql_host_step_wait(iql_engine* e, float* host_losses, void* stream) {
+  if (!e || !host_losses) return IQL_ERR_INVALID;
+  if (!e->h_mail) return fail(e, IQL_ERR_STATE, "iql_host_step_wait: no host step in flight");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = e->cfg.n_members, B = e->cfg.batch_size;
+  float* mail = (float*)(e->h_mail + sizeof(int64_t) * (size_t)S * B);
   // wait for the flag words (bounded: a failed launch never raises them)
   const auto t0 = std::chrono::steady_clock::now();
   for (int m = 0; m < S; ++m) {

@@ -93,6 +93,11 @@ struct StepCtx {
   // host-step path (iql_train_host_step): pinned, device-mapped host memory [S][4] -- the loss kernel stores the three
   // losses of member m at [m][0..2], fences at system scope and then sets the word [m][3] to 1; null otherwise
   float* host_mail;
+  // > 0 on the call's LAST optimizer launch (adam_polyak_kernel): it also advances the members' counters by this many
+  // steps, which saves the separate advance_kernel launch -- every reader of the counters (gather, forward dropout,
+  // loss kernel) precedes that launch, and nothing after it in the call reads them.  enqueue_step sets it to -1 once
+  // consumed so that the caller knows not to launch advance_kernel.
+  int advance_k;
   AdamScalars* adam_sc;          // [S][3] device
   int k_max;
   int tf32;                      // 1: tcgen05 path; producers round GEMM operands to nearest TF32

@@ -426,6 +426,16 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
   const int m = blockIdx.y;
   const MemberScalars* sc = ctx.scalars + m;
   pdl_wait();  // gradients, Adam scalars of the step: written by the launches before this one
+  if (ctx.advance_k > 0 && blockIdx.x == 0 && threadIdx.x == 0) {  // advance_kernel's work, folded into the call's last launch
+    iql_counters c = ctx.counters[m];
+    c.v_step += ctx.advance_k;
+    c.q_step += ctx.advance_k;
+    c.actor_step += ctx.advance_k;
+    c.total_it += ctx.advance_k;
+    c.sample_step += ctx.advance_k;
+    if (sc->cosine_t_max > 0) c.sched_epoch += ctx.advance_k;
+    ctx.counters[m] = c;
+  }
   const float adam_w1 = sc->adam_w1, adam_beta2 = sc->adam_beta2, adam_one_minus_b2 = sc->adam_one_minus_b2;
   const float adam_eps = sc->adam_eps, tau = sc->tau, one_minus_tau = sc->one_minus_tau;
   const int64_t base = ((int64_t)blockIdx.x * ADAM_UNROLL * 256 + threadIdx.x) * 4;

@@ -77,7 +77,7 @@ struct UmmaParams {
   int k_max;  // largest K of the phase: every problem runs ceil(k_max / 32) k-blocks (TMA zero-fills beyond its own K)
   // IQL_UMMA_DBG, profiling experiments only (tools/umma_probe.sh; the results of the step are WRONG):
   // 1 no global stores, 2 operands of 4 problems only (L2 hits), 4 no epilogue, 8 no MMAs, 16 no TMA loads,
-  // 32 no tensor-map prefetch
+  // 32 no tensor-map prefetch, 64 no loads of the A operand
   int dbg;
 };
 
@@ -165,7 +165,8 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const int b_rows = CTA2 ? (tile_n >> 1) : tile_n;  // pair: this CTA stages half of the B tile
-      const uint32_t tx_bytes = (uint32_t)(CTA2 ? 2 : 1) * (uint32_t)(STAGE_A_BYTES + b_rows * TILE_K * 4);
+      const bool skip_a = (up.dbg & 64) != 0;  // probe: what the phase would cost if its A operand needed no load
+      const uint32_t tx_bytes = (uint32_t)(CTA2 ? 2 : 1) * (uint32_t)((skip_a ? 0 : STAGE_A_BYTES) + b_rows * TILE_K * 4);
       const uint32_t full0_lead = CTA2 ? mapa_u32(full0, 0) : full0;
       for (int u = worker; u < up.units; u += n_workers)
       for (int j = 0; j < up.tiles_per_unit; ++j) {
@@ -200,14 +201,16 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
           if (CTA2) {  // the leader arms its barrier for the loads of both CTAs; the peer's bytes land on it too
             const uint32_t fb = full0_lead + 8 * stage;
             if (rank == 0) mbar_expect_tx(full0 + 8 * stage, tx_bytes);
-            if (up.a_mn) tma_load_3d_cg2(sa, mapA, fb, 0, k0, m0 >> 5);
+            if (skip_a) {}
+            else if (up.a_mn) tma_load_3d_cg2(sa, mapA, fb, 0, k0, m0 >> 5);
             else tma_load_2d_cg2(sa, mapA, fb, k0, m0);
             if (up.b_mn) tma_load_3d_cg2(sb, mapB, fb, 0, k0, n0 >> 5);
             else tma_load_2d_cg2(sb, mapB, fb, k0, n0);
           } else {
             const uint32_t fb = full0 + 8 * stage;
             mbar_expect_tx(fb, tx_bytes);
-            if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
+            if (skip_a) {}
+            else if (up.a_mn) tma_load_3d(sa, mapA, fb, 0, k0, m0 >> 5);
             else tma_load_2d(sa, mapA, fb, k0, m0);
             if (up.b_mn) tma_load_3d(sb, mapB, fb, 0, k0, n0 >> 5);
             else tma_load_2d(sb, mapB, fb, k0, n0);

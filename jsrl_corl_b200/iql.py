@@ -278,7 +278,7 @@ class ReplayBuffer:
         self._slot_i = 0
         self._last_indices = None  # host int64 array of the last sample() call (numpy sampler)
         self._lay_ref = C.byref(self._lay)
-        self._rows_ptr = self._rows.data_ptr()
+        self._dev_index = self._device.index
 
     @property
     def rows(self) -> torch.Tensor:
@@ -293,7 +293,7 @@ class ReplayBuffer:
 
     def _stream(self) -> int:
         # raw handle of torch's current stream on the buffer's device (torch.cuda.current_stream() costs ~7 us of Python)
-        return torch._C._cuda_getCurrentRawStream(self._device.index)
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
     def load_d4rl_dataset(self, data: Dict[str, np.ndarray]):
         if self._size != 0:
@@ -378,7 +378,7 @@ class ReplayBuffer:
         B = int(batch_size)
         dev = self._device
         high = self._high()
-        switch = torch.cuda.current_device() != dev.index
+        switch = torch._C._cuda_getDevice() != self._dev_index
         if switch:
             ctx = torch.cuda.device(dev)
             ctx.__enter__()
@@ -390,7 +390,7 @@ class ReplayBuffer:
                 else:
                     sl = self._out_slot(B)
                 # the indices ride in the kernel parameters: no staging buffer, no host->device copy
-                rc = self._L.iql_replay_sample_host(self._rows_ptr, self._lay_ref, high, B, idx_host.__array_interface__["data"][0],
+                rc = self._L.iql_replay_sample_host(self._rows.data_ptr(), self._lay_ref, high, B, idx_host.__array_interface__["data"][0],
                                                     *sl.ptrs, self._stream())
                 if rc:
                     _lib.check(rc, None, "iql_replay_sample_host")
@@ -401,7 +401,7 @@ class ReplayBuffer:
                     raise ValueError("low >= high")
                 sl = _SampleSlot(self, B) if self._fresh_outputs else self._out_slot(B)
                 sl.idx_host = None
-                rc = self._L.iql_replay_sample(self._rows_ptr, self._lay_ref, high, B, None, self._seed, self._sample_calls,
+                rc = self._L.iql_replay_sample(self._rows.data_ptr(), self._lay_ref, high, B, None, self._seed, self._sample_calls,
                                                *sl.ptrs, None, self._stream())
                 if rc:
                     _lib.check(rc, None, "iql_replay_sample")
@@ -797,11 +797,12 @@ class ImplicitQLearning:
             if self._bound_rows is not rb._rows:
                 eng.bind_replay(0, rb._rows, max(rb._size, 1))
                 self._bound_rows = rb._rows
-            v_loss, q_loss, a_loss = eng.host_step(host_indices=slot.idx_host.__array_interface__["data"][0])
+            eng.host_step(host_indices=slot.idx_host.__array_interface__["data"][0], wait=False)
             self._path_counts[0] += 1
         else:
-            v_loss, q_loss, a_loss = eng.host_step(batch=(observations, actions, rewards, next_observations, dones))
+            eng.host_step(batch=(observations, actions, rewards, next_observations, dones), wait=False)
             self._path_counts[1] += 1
+        # (the step is running: the host-side mirrors of the counters / schedule are updated meanwhile)
         self._total_it += 1
         st = self._steps
         st["v"] += 1
@@ -815,6 +816,7 @@ class ImplicitQLearning:
         else:
             self._publish_optimizer_state()
         self._advance_schedule(1)
+        v_loss, q_loss, a_loss = eng.host_step_wait()
         return {"value_loss": v_loss, "q_loss": q_loss, "actor_loss": a_loss}
 
     # ---- checkpoints (iql.py:565-606) --------------------------------------
