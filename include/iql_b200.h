@@ -231,6 +231,12 @@ int iql_host_step_wait(iql_engine* e, float* host_losses, void* stream);
  * policy on its own block of rows (vectorised envs): states [S][n][state_dim] -> out [S][n][action_dim]. */
 int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float max_action,
             float* out_actions, void* stream);
+/* The same for ONE observation of a HOST caller -- `actor.act(state, device)` as the rollout loops call it once per
+ * env step (eval_actor iql.py:218-238, jsrl_w_iql.py:445-515): host_state[state_dim] and host_action[action_dim] are
+ * host arrays.  The observation travels in the kernel parameters and the action returns through pinned host memory
+ * (no copies, no stream synchronisation); ordered after all work queued on `stream` and `caller_stream`. */
+int iql_act_host(iql_engine* e, int32_t member, const float* host_state, float max_action, float* host_action,
+                 void* stream, void* caller_stream);
 /* Self-test hook for the tcgen05 TF32 GEMM building block (no reference
  * counterpart): C[M,N] = op(A) op(B), mode 0 NT (A[M,K], B[N,K]), 1 NN (A[M,K],
  * B[K,N]), 2 TN (A[K,M], B[K,N]); M multiple of 256, N <= 256 or a multiple of

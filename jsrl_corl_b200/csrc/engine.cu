@@ -141,7 +141,9 @@ struct iql_engine {
   bool use_graphs = true;
   // host-step path (iql_train_host_step): pinned, device-mapped host block = [S][B] int64 indices | [S][4] floats
   // (losses + flag word, written by the loss kernel); events ordering the engine stream against the caller's stream
+  float* h_act = nullptr;        // iql_act_host: pinned, device-mapped [action_dim floats | flag word]
   char* h_mail = nullptr;
+  bool mail_pending = false;     // a host step has been launched and its losses not collected yet
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
@@ -330,6 +332,7 @@ extern "C" void iql_destroy(iql_engine* e) {
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   if (e->h_mail) cudaFreeHost(e->h_mail);
+  if (e->h_act) cudaFreeHost(e->h_act);
   delete e;
 }
 
@@ -1331,6 +1334,35 @@ extern "C" int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mo
 // next step (index draw, Python) overlaps them.  Everything the caller enqueues afterwards is stream-ordered behind
 // the step (ev_out), exactly as after iql_train_steps.
 // ---------------------------------------------------------------------------
+static bool host_events(iql_engine* e) {  // events that order the engine stream against the caller's stream
+  if (e->ev_in && e->ev_out) return true;
+  return cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess;
+}
+
+// Spin until the device has raised `flag` (pinned host memory); bounded, and a failed launch is noticed through the stream.
+static int spin_flag(iql_engine* e, volatile uint32_t* flag, cudaStream_t st, const char* who) {
+  const auto t0 = std::chrono::steady_clock::now();
+  uint32_t spins = 0;
+  while (*flag == 0u) {
+    if ((++spins & 0x3FFFu) == 0u) {
+      const cudaError_t q = cudaStreamQuery(st);
+      if (q == cudaSuccess) {
+        if (*flag == 0u) return fail(e, IQL_ERR_CUDA, std::string(who) + ": the launch finished without reporting its result");
+        break;
+      }
+      if (q != cudaErrorNotReady) return fail(e, IQL_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(q));
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20))
+        return fail(e, IQL_ERR_CUDA, std::string(who) + ": timed out waiting for the device");
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return IQL_OK;
+}
+
 extern "C" int iql_host_step_wait(iql_engine* e, float* host_losses, void* stream);
 extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, float* host_losses, void* stream,
                                    void* caller_stream) {
@@ -1346,16 +1378,23 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
   }
   const size_t idx_bytes = sizeof(int64_t) * (size_t)S * B;
   if (!e->h_mail) {
-    if (cudaHostAlloc((void**)&e->h_mail, idx_bytes + sizeof(float) * 4 * S, cudaHostAllocMapped) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+    if (!host_events(e) || cudaHostAlloc((void**)&e->h_mail, idx_bytes + sizeof(float) * 4 * S, cudaHostAllocMapped) != cudaSuccess) {
       cudaGetLastError();
+      e->h_mail = nullptr;
       return fail(e, IQL_ERR_CUDA, "iql_train_host_step: pinned mailbox / event allocation failed");
     }
     memset(e->h_mail, 0, idx_bytes + sizeof(float) * 4 * S);
   }
   int64_t* mail_idx = (int64_t*)e->h_mail;
   float* mail = (float*)(e->h_mail + idx_bytes);
+  if (e->mail_pending) {  // one step in flight at a time: its gather may not have read the index block yet
+    float drop[3 * 64];
+    std::vector<float> big;
+    float* sink = drop;
+    if (S > 64) { big.resize(3 * (size_t)S); sink = big.data(); }
+    int rcw = iql_host_step_wait(e, sink, stream);
+    if (rcw != IQL_OK) return rcw;
+  }
   if (gather)
     for (int m = 0; m < S; ++m) {
       const int64_t cap = e->h_replay[m].capacity;
@@ -1420,36 +1459,22 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
     if (e->h_hparams[m].cosine_t_max > 0) c.sched_epoch += 1;
     e->preloaded[m] = 0;
   }
+  e->mail_pending = true;
   if (!host_losses) return IQL_OK;  // the caller collects the losses with iql_host_step_wait
   return iql_host_step_wait(e, host_losses, stream);
 }
 
 extern "C" int iql_host_step_wait(iql_engine* e, float* host_losses, void* stream) {
   if (!e || !host_losses) return IQL_ERR_INVALID;
-  if (!e->h_mail) return fail(e, IQL_ERR_STATE, "iql_host_step_wait: no host step in flight");
+  if (!e->h_mail || !e->mail_pending) return fail(e, IQL_ERR_STATE, "iql_host_step_wait: no host step in flight");
+  e->mail_pending = false;
   cudaStream_t st = (cudaStream_t)stream;
   const int S = e->cfg.n_members, B = e->cfg.batch_size;
   float* mail = (float*)(e->h_mail + sizeof(int64_t) * (size_t)S * B);
   // wait for the flag words (bounded: a failed launch never raises them)
-  const auto t0 = std::chrono::steady_clock::now();
   for (int m = 0; m < S; ++m) {
-    volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(mail) + m * 4 + 3;
-    uint32_t spins = 0;
-    while (*flag == 0u) {
-      if ((++spins & 0x3FFFu) == 0u) {
-        const cudaError_t q = cudaStreamQuery(st);
-        if (q == cudaSuccess) {
-          if (*flag == 0u) return fail(e, IQL_ERR_CUDA, "iql_train_host_step: the step finished without reporting its losses");
-          break;
-        }
-        if (q != cudaErrorNotReady) return fail(e, IQL_ERR_CUDA, std::string("iql_train_host_step: ") + cudaGetErrorString(q));
-        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20))
-          return fail(e, IQL_ERR_CUDA, "iql_train_host_step: timed out waiting for the losses");
-      }
-#if defined(__x86_64__) || defined(__i386__)
-      __builtin_ia32_pause();
-#endif
-    }
+    int rc = spin_flag(e, reinterpret_cast<volatile uint32_t*>(mail) + m * 4 + 3, st, "iql_host_step_wait");
+    if (rc != IQL_OK) return rc;
   }
   std::atomic_thread_fence(std::memory_order_acquire);
   for (int m = 0; m < S; ++m)
@@ -1474,6 +1499,44 @@ extern "C" int iql_act(iql_engine* e, int32_t member, const float* states, int64
   launch_act(ctx, e->params + (int64_t)first * e->layout.param_floats, count, e->d_act_off, e->d_act_off + (L + 1), states,
              n, max_action, out_actions, (cudaStream_t)stream);
   CUDA_TRY(e, cudaGetLastError());
+  return IQL_OK;
+}
+
+// One env step of policy.act for a HOST caller (iql.py:371-379, 403-413; the rollout loops eval_actor iql.py:218-238 and
+// jsrl_w_iql.py:445-515 call it once per env step): the observation rides in the kernel parameters, the action comes
+// back through device-mapped pinned memory with a flag word the host spins on -- one launch, no copies, no stream
+// synchronisation.  Ordered after everything queued on `stream` (the last update) and on `caller_stream`.
+extern "C" int iql_act_host(iql_engine* e, int32_t member, const float* host_state, float max_action, float* host_action,
+                            void* stream, void* caller_stream) {
+  if (!e || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_act_host: bad member");
+  if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_act_host: state not bound");
+  if (!host_state || !host_action) return fail(e, IQL_ERR_INVALID, "iql_act_host: null state or action");
+  if (e->cfg.state_dim > act_host_state_max()) return fail(e, IQL_ERR_INVALID, "iql_act_host: state_dim too large for the by-value path (use iql_act)");
+  cudaStream_t st = (cudaStream_t)stream, cur = (cudaStream_t)caller_stream;
+  const int A = e->cfg.action_dim, L = e->cfg.n_hidden;
+  if (!e->h_act) {
+    if (!host_events(e) || cudaHostAlloc((void**)&e->h_act, sizeof(float) * (A + 1), cudaHostAllocMapped) != cudaSuccess) {
+      cudaGetLastError();
+      e->h_act = nullptr;
+      return fail(e, IQL_ERR_CUDA, "iql_act_host: pinned mailbox / event allocation failed");
+    }
+  }
+  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(e->h_act + A);
+  *flag = 0u;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  if (cur != st) {
+    CUDA_TRY(e, cudaEventRecord(e->ev_in, cur));
+    CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_in, 0));
+  }
+  int rc = flush_tables(e, st);
+  if (rc != IQL_OK) return rc;
+  StepCtx ctx = make_ctx(e);
+  launch_act_host(ctx, e->params + (int64_t)member * e->layout.param_floats, e->d_act_off, e->d_act_off + (L + 1), host_state,
+                  max_action, e->h_act, st);
+  CUDA_TRY(e, cudaGetLastError());
+  rc = spin_flag(e, flag, st, "iql_act_host");
+  if (rc != IQL_OK) return rc;
+  for (int i = 0; i < A; ++i) host_action[i] = reinterpret_cast<volatile float*>(e->h_act)[i];
   return IQL_OK;
 }
 

@@ -180,4 +180,9 @@ void launch_first_wgrad(const GemmProb* probs, int nprob, int B, int H, int kmax
 void launch_act(const StepCtx& ctx, const float* actor_block, int n_members, const int64_t* w_off,
                 const int64_t* b_off, const float* states, int64_t n, float max_action, float* out, cudaStream_t st);
 
+// one observation passed by value (state_dim <= act_host_state_max()), action + flag word into pinned host memory
+int act_host_state_max();
+void launch_act_host(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
+                     const float* host_state, float max_action, float* mail, cudaStream_t st);
+
 }  // namespace iql

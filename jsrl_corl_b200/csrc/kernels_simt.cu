@@ -529,21 +529,22 @@ void launch_advance(const StepCtx& ctx, int K, cudaStream_t st) {
 
 // ===========================================================================
 // actor inference (eval mode): out = clamp(max_action * tanh(MLP(s)))
-// one CTA per state row, one warp per output neuron, activations in smem
+// One CTA of 32 warps per state row, activations in shared memory.  A single observation per env step is pure
+// latency (three dependent layers, 256 KB of weights each through one SM), so every warp keeps four output neurons
+// = 8 independent 16-byte weight loads per lane in flight, and a layer costs about one L2 round trip plus the
+// streaming of its weights.  `state_val` != null: the observation rides in the kernel parameters (host callers,
+// iql_act_host); `mail` != null: the action goes to device-mapped pinned host memory, fenced, followed by a flag word.
 // ===========================================================================
-__global__ void __launch_bounds__(256) act_kernel(int S, int A, int H, int L, const float* __restrict__ block0,
-                                                  int64_t member_stride, const int64_t* __restrict__ w_off,
-                                                  const int64_t* __restrict__ b_off,
-                                                  const float* __restrict__ states, float max_action,
-                                                  float* __restrict__ out) {
-  extern __shared__ float sm[];  // 2 * max(H, S)
-  const int width = H > S ? H : S;
+constexpr int ACT_THREADS = 1024, ACT_NEURONS = 4, ACT_STATE_MAX = 512;
+struct ActState { float v[ACT_STATE_MAX]; };
+
+__device__ __forceinline__ void act_body(int S, int A, int H, int L, const float* __restrict__ block,
+                                         const int64_t* __restrict__ w_off, const int64_t* __restrict__ b_off,
+                                         const float* __restrict__ state, float max_action, float* __restrict__ out, float* sm) {
+  const int width = ((H > S ? H : S) + 3) & ~3;
   float* cur = sm;
   float* nxt = sm + width;
-  // blockIdx.y = ensemble member (vectorised-env mode: every member's policy on its own rows), blockIdx.x = row
-  const float* block = block0 + blockIdx.y * member_stride;
-  const int64_t row = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
-  for (int i = threadIdx.x; i < S; i += blockDim.x) cur[i] = states[row * S + i];
+  for (int i = threadIdx.x; i < width; i += blockDim.x) cur[i] = i < S ? state[i] : 0.f;  // zero tail: rows are padded to 4 floats
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   int in_dim = S;
@@ -551,30 +552,91 @@ __global__ void __launch_bounds__(256) act_kernel(int S, int A, int H, int L, co
     const int out_dim = (l == L) ? A : H;
     const float* W = block + w_off[l];
     const float* bias = block + b_off[l];
-    for (int j = warp; j < out_dim; j += nwarp) {
-      float acc = 0.f;
-      const int ldw = (in_dim + 3) & ~3;  // weight rows are padded to a multiple of 4 floats
-      for (int k = lane; k < in_dim; k += 32) acc = fmaf(W[(int64_t)j * ldw + k], cur[k], acc);
+    const int ldw = (in_dim + 3) & ~3;  // weight rows are padded to a multiple of 4 floats (the padding is zero)
+    const int nq = ldw >> 2;
+    for (int j0 = warp * ACT_NEURONS; j0 < out_dim; j0 += nwarp * ACT_NEURONS) {
+      float acc[ACT_NEURONS];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) {
-        acc += bias[j];
-        if (l < L) nxt[j] = fmaxf(acc, 0.f);
-        else out[row * A + j] = fminf(fmaxf(max_action * tanhf(acc), -max_action), max_action);
+      for (int u = 0; u < ACT_NEURONS; ++u) acc[u] = 0.f;
+      for (int q = lane; q < nq; q += 32) {
+        const float4 x = *reinterpret_cast<const float4*>(cur + 4 * q);
+        float4 w[ACT_NEURONS];
+#pragma unroll
+        for (int u = 0; u < ACT_NEURONS; ++u)
+          w[u] = (j0 + u < out_dim) ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)(j0 + u) * ldw) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < ACT_NEURONS; ++u)
+          acc[u] = fmaf(w[u].x, x.x, fmaf(w[u].y, x.y, fmaf(w[u].z, x.z, fmaf(w[u].w, x.w, acc[u]))));
+      }
+#pragma unroll
+      for (int u = 0; u < ACT_NEURONS; ++u) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      }
+      if (lane < ACT_NEURONS && j0 + lane < out_dim) {
+        float a = acc[0];
+#pragma unroll
+        for (int u = 1; u < ACT_NEURONS; ++u) a = (lane == u) ? acc[u] : a;
+        a += bias[j0 + lane];
+        if (l < L) nxt[j0 + lane] = fmaxf(a, 0.f);
+        else out[j0 + lane] = fminf(fmaxf(max_action * tanhf(a), -max_action), max_action);
       }
     }
+    if (l < L)
+      for (int i = out_dim + threadIdx.x; i < width; i += blockDim.x) nxt[i] = 0.f;
     __syncthreads();
     float* t = cur; cur = nxt; nxt = t;
     in_dim = out_dim;
   }
 }
 
+__global__ void __launch_bounds__(ACT_THREADS) act_kernel(int S, int A, int H, int L, const float* __restrict__ block0,
+                                                          int64_t member_stride, const int64_t* __restrict__ w_off,
+                                                          const int64_t* __restrict__ b_off,
+                                                          const float* __restrict__ states, float max_action,
+                                                          float* __restrict__ out) {
+  extern __shared__ float sm[];  // 2 * round_up(max(H, S), 4)
+  // blockIdx.y = ensemble member (vectorised-env mode: every member's policy on its own rows), blockIdx.x = row
+  const int64_t row = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  act_body(S, A, H, L, block0 + blockIdx.y * member_stride, w_off, b_off, states + row * S, max_action, out + row * A, sm);
+}
+
+// one observation from the kernel parameters, the action into pinned host memory + flag word (iql_act_host)
+__global__ void __launch_bounds__(ACT_THREADS) act_host_kernel(int S, int A, int H, int L, const float* __restrict__ block,
+                                                               const int64_t* __restrict__ w_off,
+                                                               const int64_t* __restrict__ b_off,
+                                                               const __grid_constant__ ActState state, float max_action,
+                                                               float* __restrict__ mail) {
+  extern __shared__ float sm[];
+  const int width = ((H > S ? H : S) + 3) & ~3;
+  float* res = sm + 2 * width;  // [A]
+  act_body(S, A, H, L, block, w_off, b_off, state.v, max_action, res, sm);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    for (int i = threadIdx.x; i < A; i += 32) reinterpret_cast<volatile float*>(mail)[i] = res[i];
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(mail + A) = 1u;
+  }
+}
+
 void launch_act(const StepCtx& ctx, const float* actor_block, int n_members, const int64_t* w_off,
                 const int64_t* b_off, const float* states, int64_t n, float max_action, float* out, cudaStream_t st) {
-  const int width = ctx.H > ctx.S_dim ? ctx.H : ctx.S_dim;
+  const int width = ((ctx.H > ctx.S_dim ? ctx.H : ctx.S_dim) + 3) & ~3;
   dim3 grid((unsigned)n, (unsigned)n_members);
-  act_kernel<<<grid, 256, 2 * width * sizeof(float), st>>>(ctx.S_dim, ctx.A_dim, ctx.H, ctx.L, actor_block, ctx.P, w_off,
-                                                           b_off, states, max_action, out);
+  act_kernel<<<grid, ACT_THREADS, 2 * width * sizeof(float), st>>>(ctx.S_dim, ctx.A_dim, ctx.H, ctx.L, actor_block, ctx.P, w_off,
+                                                                   b_off, states, max_action, out);
+}
+
+int act_host_state_max() { return ACT_STATE_MAX; }
+
+void launch_act_host(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
+                     const float* host_state, float max_action, float* mail, cudaStream_t st) {
+  const int width = ((ctx.H > ctx.S_dim ? ctx.H : ctx.S_dim) + 3) & ~3;
+  ActState s;
+  for (int i = 0; i < ACT_STATE_MAX; ++i) s.v[i] = i < ctx.S_dim ? host_state[i] : 0.f;
+  act_host_kernel<<<1, ACT_THREADS, (2 * width + ctx.A_dim) * sizeof(float), st>>>(ctx.S_dim, ctx.A_dim, ctx.H, ctx.L, actor_block,
+                                                                                   w_off, b_off, s, max_action, mail);
 }
 
 }  // namespace iql

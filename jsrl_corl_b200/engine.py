@@ -428,23 +428,26 @@ class EnsembleEngine:
 
     def act_host(self, member: int, state: np.ndarray, max_action: float = 1.0) -> np.ndarray:
         """One env step of ``policy.act`` (iql.py:371-379, 403-413) through the engine's act kernel: the observation
-        goes host -> device from a pinned staging row, the kernel reads the policy weights straight from the
-        parameter arena, the action comes back through a pinned row; everything is queued on the engine stream and
-        one stream synchronize ends the call.  Returns the flat numpy action (scaled and clamped by max_action)."""
+        rides in the kernel parameters, the kernel reads the policy weights straight from the parameter arena, the
+        action comes back through pinned host memory the host spins on (`iql_act_host`: one launch, no copies, no
+        stream synchronisation).  Returns the flat numpy action (scaled and clamped by max_action)."""
         if self._act_in is None:
-            self._act_in = torch.empty(self.state_dim, dtype=torch.float32).pin_memory()
-            self._act_out = torch.empty(self.action_dim, dtype=torch.float32).pin_memory()
-            self._act_in_dev = torch.empty(self.state_dim, dtype=torch.float32, device=self.device)
-            self._act_out_dev = torch.empty(self.action_dim, dtype=torch.float32, device=self.device)
-        self._act_in.numpy()[:] = np.asarray(state, dtype=np.float32).reshape(-1)
-        with torch.cuda.device(self.device):
-            cur = torch.cuda.current_stream(self.device)
-            self.stream.wait_stream(cur)  # parameter writes queued by the caller (checkpoint loads) come first
-            with torch.cuda.stream(self.stream):
-                self._act_in_dev.copy_(self._act_in, non_blocking=True)
-                _lib.check(self._L.iql_act(self._h, member, self._act_in_dev.data_ptr(), 1, float(max_action),
-                                           self._act_out_dev.data_ptr(), self.stream.cuda_stream), self._h, "iql_act")
-                self._act_out.copy_(self._act_out_dev, non_blocking=True)
-            self.stream.synchronize()
+            self._act_in = np.zeros(self.state_dim, dtype=np.float32)
+            self._act_out = np.zeros(self.action_dim, dtype=np.float32)
+            self._act_ptrs = (self._act_in.ctypes.data, self._act_out.ctypes.data)
+            self._stream_raw = self.stream.cuda_stream
+        self._act_in[:] = np.asarray(state, dtype=np.float32).reshape(-1)
+        switch = torch._C._cuda_getDevice() != self._dev_index
+        if switch:
+            guard = torch.cuda.device(self.device)
+            guard.__enter__()
+        try:
+            rc = self._L.iql_act_host(self._h, member, self._act_ptrs[0], float(max_action), self._act_ptrs[1], self._stream_raw,
+                                      torch._C._cuda_getCurrentRawStream(self._dev_index))
+            if rc:
+                _lib.check(rc, self._h, "iql_act_host")
+        finally:
+            if switch:
+                guard.__exit__(None, None, None)
         self.act_calls += 1
-        return self._act_out.numpy().copy()
+        return self._act_out.copy()
