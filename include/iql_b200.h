@@ -176,6 +176,12 @@ int iql_replay_ingest(float* rows, const iql_row_layout* lay, int64_t first_row,
  * `staged_row` is a device row in packed layout) */
 int iql_replay_insert(float* rows, const iql_row_layout* lay, int64_t pointer,
                       const float* staged_row, void* stream);
+/* add_transition for a HOST caller (one env step of the online loop, jsrl_w_iql.py:470-478): state / action /
+ * next_state are host arrays; the packed row travels in the kernel parameters (row_floats <= 960, else
+ * IQL_ERR_SHAPE: stage the row and use iql_replay_insert).  One launch, no staging buffer. */
+int iql_replay_insert_host(float* rows, const iql_row_layout* lay, int64_t pointer, const float* host_state,
+                           const float* host_action, float reward, const float* host_next_state, float done,
+                           void* stream);
 /* replaces: ReplayBuffer.sample iql.py:171-178.  indices == NULL: draw them
  * in-kernel from Philox4x32-10 keyed by (seed, step); else gather the given
  * int64 indices (reference-compatible mode: numpy's MT19937 stream on host).

@@ -98,6 +98,7 @@ SYMBOLS = {
     "iql_replay_ingest": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_int32, C.c_float,
                                     _P, _P, C.c_float, C.c_float, C.c_float, _P]),
     "iql_replay_insert": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, _P, _P]),
+    "iql_replay_insert_host": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, _P, _P, C.c_float, _P, C.c_float, _P]),
     "iql_replay_sample": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, C.c_int64, _P, C.c_uint64, C.c_uint64,
                                     _P, _P, _P, _P, _P, _P, _P]),
     "iql_replay_sample_host": (C.c_int, [_P, C.POINTER(RowLayout), C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),

@@ -125,6 +125,14 @@ __global__ void replay_insert_kernel(float* __restrict__ rows, int RF, int64_t p
   for (int c = threadIdx.x; c < RF; c += blockDim.x) rows[pointer * RF + c] = staged[c];  // any row width
 }
 
+// add_transition for a host caller: the packed row rides in the kernel parameters (rows of up to 960 floats), so an
+// insert is one launch with no staging row, no host->device copy and nothing to guard against reuse
+constexpr int ROW_BYVAL_MAX = 960;
+struct RowPack { float v[ROW_BYVAL_MAX]; };
+__global__ void replay_insert_byval_kernel(float* __restrict__ rows, int RF, int64_t pointer, const __grid_constant__ RowPack row) {
+  for (int c = threadIdx.x; c < RF; c += blockDim.x) rows[pointer * RF + c] = row.v[c];
+}
+
 // ---- sample: Philox (or given) indices + vectorised row gather ------------
 // One thread per float4 of a row; the RF/4 lanes of a row are adjacent, so the
 // row read is a single coalesced burst.  The row is then scattered to the five
@@ -271,5 +279,22 @@ extern "C" int iql_replay_sample_host(const float* rows, const iql_row_layout* l
     replay_sample_byval_kernel<<<(nb * Q + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, *lay, (int)b0, nb, pack, states, actions,
                                                                                         rewards, next_states, dones);
   }
+  return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
+}
+
+extern "C" int iql_replay_insert_host(float* rows, const iql_row_layout* lay, int64_t pointer, const float* host_state,
+                                      const float* host_action, float reward, const float* host_next_state, float done,
+                                      void* stream) {
+  if (!layout_ok(lay) || !rows || pointer < 0 || !host_state || !host_action || !host_next_state) return IQL_ERR_INVALID;
+  if (lay->row_floats > ROW_BYVAL_MAX) return IQL_ERR_SHAPE;  // wider rows: stage the row and use iql_replay_insert
+  RowPack p;
+  const int S = lay->state_dim, A = lay->action_dim, RF = lay->row_floats;
+  for (int c = 0; c < RF; ++c) p.v[c] = 0.f;
+  for (int i = 0; i < S; ++i) p.v[lay->off_state + i] = host_state[i];
+  for (int i = 0; i < A; ++i) p.v[lay->off_action + i] = host_action[i];
+  for (int i = 0; i < S; ++i) p.v[lay->off_next_state + i] = host_next_state[i];
+  p.v[lay->off_reward] = reward;
+  p.v[lay->off_done] = done;
+  replay_insert_byval_kernel<<<1, RF < 256 ? ((RF + 31) / 32) * 32 : 256, 0, (cudaStream_t)stream>>>(rows, RF, pointer, p);
   return cudaGetLastError() == cudaSuccess ? IQL_OK : IQL_ERR_CUDA;
 }
