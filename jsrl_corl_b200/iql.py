@@ -202,7 +202,7 @@ def is_goal_reached(reward: float, info: Dict) -> bool:
 # ---------------------------------------------------------------------------
 # replay buffer (iql.py:122-196) on packed device rows
 # ---------------------------------------------------------------------------
-_N_SLOTS = 4
+_N_SLOTS = 8
 # id(observations tensor) -> slot, for the cached output tensors of every live buffer: `ImplicitQLearning.train(batch)`
 # recognises a batch that came straight out of `ReplayBuffer.sample` (same tensor objects, untouched since) and lets the
 # engine gather the rows itself from the host-drawn indices instead of re-packing the five dense tensors

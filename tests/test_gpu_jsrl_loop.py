@@ -166,6 +166,21 @@ def test_engine_on_a_non_current_device():
     for a, b in zip(logs, logs0):
         for k in a:
             assert a[k] == b[k]  # same kernels, same inputs: bit-identical across devices
+    # the host-caller paths (by-value sample / insert, host step from sample()'s indices, act through pinned memory)
+    from jsrl_corl_b200 import ReplayBuffer
+    outs = []
+    for dev, tr in (("cuda:1", trainer), ("cuda:0", ref)):
+        rb = ReplayBuffer(5, 3, 64, dev)
+        rng = np.random.RandomState(0)
+        for i in range(40):
+            rb.add_transition(rng.randn(5), rng.uniform(-1, 1, 3), float(i), rng.randn(5), i % 5 == 0)
+        np.random.seed(4)
+        log = [tr.train(rb.sample(32)) for _ in range(3)]
+        tr.actor.eval()
+        act = tr.actor.act(np.array([0.1, -0.2, 0.3, 0.4, -0.5], np.float32), dev)
+        assert tr._path_counts[0] == 3 and torch.cuda.current_device() == 0
+        outs.append((log, act))
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
 
 
 def test_wide_row_insert_and_unsynchronised_inserts():
