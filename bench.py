@@ -75,7 +75,27 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
 
+    def _run_nvml(self):
+        # in-process NVML: a sample every 25 ms (an nvidia-smi process per sample gave 3-7 samples in a 2 s region)
+        import pynvml as N
+
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+        while not self._stop.is_set():
+            r = int(get_reasons(h))
+            self.rows.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), "0"] +
+                             ["Active" if r & b else "Not Active" for b, _ in bits])
+            self._stop.wait(0.025)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],

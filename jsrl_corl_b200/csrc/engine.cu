@@ -1181,8 +1181,25 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
   }
   if (forks > 0 || loss_on_side || lb_on_side) cudaStreamWaitEvent(st_main, e->ev_side, 0);  // join before the optimizer
   // Adam: read g, p, m, v + target; write p, m, v + target (+ the TF32 shadow copies in tcgen05 mode)
-  if (tm) tm->mark("adam_polyak", 0, S_d * 4.0 * ((7.0 + (ctx.tf32 ? 1 : 0)) * e->layout.param_floats +
-                                                  (2.0 + (ctx.tf32 ? 1 : 0)) * e->layout.q_floats));
+  if (tm) {
+    // TF32 operand copies the optimizer maintains: everything except the hidden-layer weights when those carry the
+    // rounding bias in place (no shadow), plus the lo parts of the first-layer (and wide policy-head) ranges
+    double shadow_p = 0, shadow_t = 0;
+    if (ctx.tf32) {
+      double hid_p = 0, hid_q = 0, lo_p = 0, lo_q = 0;
+      for (int i = 0; i < ctx.n_hid; ++i) {
+        hid_p += (double)(ctx.hid_end[i] - ctx.hid_begin[i]);
+        if (ctx.hid_begin[i] < ctx.PQ) hid_q += (double)(ctx.hid_end[i] - ctx.hid_begin[i]);
+      }
+      for (int r = 0; r < 5; ++r) {
+        lo_p += (double)(ctx.first_w_end[r] - ctx.first_w_begin[r]);
+        if (ctx.first_w_begin[r] < ctx.PQ) lo_q += (double)(ctx.first_w_end[r] - ctx.first_w_begin[r]);
+      }
+      shadow_p = (double)e->layout.param_floats - hid_p + lo_p;
+      shadow_t = (double)e->layout.q_floats - hid_q + lo_q;
+    }
+    tm->mark("adam_polyak", 0, S_d * 4.0 * (7.0 * e->layout.param_floats + 2.0 * e->layout.q_floats + shadow_p + shadow_t));
+  }
   // (chained backward: its input-layer weight-gradient phase still reads the gathered rows, so the next step's gather
   // cannot run beside it; the caller then gathers at the top of every step)
   const bool fork_gather = gather_next && !tm && e->side != nullptr && !chain;
