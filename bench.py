@@ -612,9 +612,30 @@ def dropin_loop_rate(w, device, rb, steps=3000, warmup=300):
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t0
     assert all(np.isfinite(x) for x in log.values())
-    return {"value": steps / dt, "unit": "steps/s", "members": 1, "steps": steps,
-            "what": "ReplayBuffer.sample() + ImplicitQLearning.train(batch) per step through the drop-in classes "
-                    "(numpy index stream, host-visible log dict every step), wall clock"}
+    out = {"value": steps / dt, "unit": "steps/s", "members": 1, "steps": steps,
+           "what": "ReplayBuffer.sample() + ImplicitQLearning.train(batch) per step through the drop-in classes "
+                   "(numpy index stream, host-visible log dict every step), wall clock"}
+    # the ONLINE loop body as the host sees it (jsrl_w_iql.py:445-548 without the env): act -> add_transition -> sample -> train
+    if not actor.net.has_dropout_modules or w["dropout"] in (None, 0.0):
+        actor.eval()
+        n_on = max(100, steps // 3)
+        obs = np.random.RandomState(1).randn(n_on + 1, w["S"]).astype(np.float32)
+        size0, ptr0 = rb._size, rb._pointer
+        row_keep = rb._rows[0:1].clone()  # the shared bench buffer is full: every insert rewrites row 0, restored below
+        t0 = time.perf_counter()
+        for i in range(n_on):
+            a = actor.act(obs[i], str(device))
+            rb._pointer = 0
+            rb.add_transition(obs[i], a, 1.0, obs[i + 1], False)
+            rb._size = size0
+            log = trainer.train(rb.sample(w["B"]))
+        torch.cuda.synchronize(device)
+        dt_on = time.perf_counter() - t0
+        rb._rows[0:1].copy_(row_keep)
+        rb._size, rb._pointer = size0, ptr0
+        out["online_loop"] = {"value": n_on / dt_on, "unit": "iterations/s", "us_per_iteration": dt_on / n_on * 1e6, "iterations": n_on,
+                              "what": "actor.act(obs) + add_transition + sample(B) + train(batch) per iteration (no env), wall clock"}
+    return out
 
 
 def main():

@@ -420,6 +420,10 @@ class ReplayBuffer:
         ns = np.ascontiguousarray(next_state, dtype=np.float32).reshape(-1)
         if st.size != self._state_dim or ns.size != self._state_dim or ac.size != self._action_dim:
             raise ValueError("transition dims do not match the buffer")
+        if not 0 <= self._pointer < self._buffer_size:
+            # a buffer loaded to the brim leaves _pointer == buffer_size (iql.py:168); the reference's
+            # `self._states[self._pointer] = ...` raises IndexError there too
+            raise IndexError(f"index {self._pointer} is out of bounds for dimension 0 with size {self._buffer_size}")
         switch = torch._C._cuda_getDevice() != self._dev_index
         if switch:
             ctx = torch.cuda.device(self._device)

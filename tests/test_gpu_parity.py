@@ -124,6 +124,15 @@ def test_replay_errors_and_ring_insert():
     got = rb._states.cpu().numpy()[:, 0]
     assert np.array_equal(got, np.array([4, 5, 2, 3], np.float32))
     assert np.array_equal(rb._dones.cpu().numpy()[:, 0], np.array([1, 0, 1, 0], np.float32))
+    # a buffer loaded to the brim has _pointer == buffer_size: the reference's indexed store raises IndexError (iql.py:188)
+    rb3 = ReplayBuffer(3, 2, 4, "cuda")
+    rb3.load_d4rl_dataset({"observations": np.zeros((4, 3), np.float32), "actions": np.zeros((4, 2), np.float32),
+                           "rewards": np.zeros(4, np.float32), "next_observations": np.zeros((4, 3), np.float32),
+                           "terminals": np.zeros(4, bool)})
+    with pytest.raises(IndexError):
+        rb3.add_transition(np.zeros(3), np.zeros(2), 0.0, np.zeros(3), False)
+    with pytest.raises(ValueError):
+        rb.add_transition(np.zeros(4), np.zeros(2), 0.0, np.zeros(3), False)
     rb2 = ReplayBuffer(3, 2, 4, "cuda")
     rb2.add_transition(np.zeros(3), np.zeros(2), 0.0, np.zeros(3), False)
     with pytest.raises(ValueError):
@@ -808,6 +817,13 @@ def test_full_size_properties_64_members_1m_rows():
     s, a, r, s2, d = [t.cpu().numpy() for t in rb_p.sample(B)]
     assert np.array_equal(s, data["observations"][idx[17, 0]]) and np.array_equal(a, data["actions"][idx[17, 0]])
     assert np.array_equal(r[:, 0], data["rewards"][idx[17, 0]]) and np.array_equal(s2, data["next_observations"][idx[17, 0]])
+    # (1b) the host-index path at full size: numpy's stream -> by-value gather == dataset rows, and the host step consumes
+    # exactly those rows (its losses equal a staged copy of the same batch)
+    np.random.seed(11)
+    hb = rb.sample(B)
+    hi = np.asarray(rb._last_indices)
+    assert hi.max() > 900_000 and np.array_equal(hb[0].cpu().numpy(), data["observations"][hi])
+    assert np.array_equal(hb[3].cpu().numpy(), data["next_observations"][hi]) and np.array_equal(hb[2].cpu().numpy()[:, 0], data["rewards"][hi])
     # (2) reproducible
     again = make(seeds)
     l2 = again.train_steps(K).cpu().numpy()
