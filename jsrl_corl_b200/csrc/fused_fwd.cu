@@ -120,6 +120,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = fp.L;
+  auto life_stamp = [&](int slot) {  // kernel entry / set-up done / predecessor done / exit, CTA 0 thread 0
+    if (fp.trace && blockIdx.x == 0 && threadIdx.x == 0)
+      fp.trace[((4 * FUSED_TRACE_TILES + (FUSED_TRACE_TILES - 1)) * FUSED_MAX_LAYERS + (FUSED_MAX_LAYERS - 1)) * 4 + slot] = clock64();
+  };
+  life_stamp(0);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < F_MAXBAR; ++s) {
       mbar_init(full0 + 8 * s, 1);
@@ -150,7 +155,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
+  life_stamp(1);
   pdl_wait();  // everything above overlapped the tail of the previous launch; the gathered rows and weights are read below
+  life_stamp(2);
   const int nkb_h = FT_N / FT_K;  // 8 k-blocks of a hidden layer (K = 256)
   // pair: rank 0 leads (issues the MMAs, owns full / achunk / elast); work is dealt to pairs, 256 rows per tile
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
@@ -623,6 +630,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
     if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+  life_stamp(3);
 }
 
 }  // namespace

@@ -43,7 +43,7 @@ def main():
         raise SystemExit(f"no trace (rc={n})")
     t = buf.reshape(5, 8, 4, 4).astype(np.float64)
     L = w["L"]
-    t0 = t[t > 0].min()
+    t0 = t[:4][t[:4] > 0].min()
     us = lambda x: (x - t0) / 1965.0  # noqa: E731  (SM clock 1965 MHz)
     print("times in us since the first stamp of CTA 0; one line per (tile, layer)")
     print(f"{'tile':>4} {'l':>2} | {'tma first':>9} {'tma last':>9} | {'mma start':>9} {'A ready':>9} {'kb0 full':>9} {'issued':>9} | "
@@ -57,6 +57,12 @@ def main():
                   f"{us(e[0]):9.2f} {us(e[1]):9.2f} {us(e[2]):9.2f} {us(e[3]):9.2f} |              "
                   f"{us(t[3, ti, l, 0]):8.2f} {us(t[3, ti, l, 1]):8.2f} {us(t[3, ti, l, 2]):8.2f} {us(t[3, ti, l, 3]):8.2f} "
                   f"{us(t[4, ti, l, 1]):8.2f} {us(t[4, ti, l, 0]):8.2f}")
+
+
+    life = t[4, 7, 3]
+    if life[0] > 0:
+        print(f"kernel life of CTA 0 (us on the same axis): entry {us(life[0]):.2f}, set-up done {us(life[1]):.2f}, "
+              f"predecessor done {us(life[2]):.2f}, exit {us(life[3]):.2f}")
 
 
 if __name__ == "__main__":
