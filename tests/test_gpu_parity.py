@@ -141,6 +141,54 @@ def test_replay_errors_and_ring_insert():
                                "terminals": np.zeros(1, bool)})
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_replay_buffer_random_op_sequences_against_a_numpy_model(seed):
+    """Random interleavings of load / add_transition / sample (by-value insert and gather, ring wrap, both `high`
+    semantics, batch sizes that need several launches) against a plain numpy model of the reference buffer
+    (iql.py:122-196): every sampled tensor bit-exact."""
+    from jsrl_corl_b200 import ReplayBuffer
+
+    rng = np.random.RandomState(100 + seed)
+    S, A = int(rng.randint(1, 40)), int(rng.randint(1, 12))
+    cap = int(rng.randint(5, 400))
+    offline = bool(seed % 2)
+    rb = ReplayBuffer(S, A, cap, "cuda", offline_semantics=offline)
+    m = {k: np.zeros((cap, d), np.float32) for k, d in (("s", S), ("a", A), ("r", 1), ("s2", S), ("d", 1))}
+    size = ptr = 0
+    n0 = int(rng.randint(0, cap))  # strictly below capacity: the pointer stays a valid row
+    if n0:
+        data = {"observations": rng.randn(n0, S).astype(np.float32), "actions": rng.randn(n0, A).astype(np.float32),
+                "rewards": rng.randn(n0).astype(np.float32), "next_observations": rng.randn(n0, S).astype(np.float32),
+                "terminals": rng.rand(n0) < 0.1}
+        rb.load_d4rl_dataset(data)
+        m["s"][:n0], m["a"][:n0], m["r"][:n0, 0] = data["observations"], data["actions"], data["rewards"]
+        m["s2"][:n0], m["d"][:n0, 0] = data["next_observations"], data["terminals"].astype(np.float32)
+        size, ptr = n0, n0
+    for step in range(300):
+        if rng.rand() < 0.6:
+            s, a, s2 = rng.randn(S).astype(np.float32), rng.randn(A).astype(np.float64), rng.randn(S).astype(np.float32)
+            r, d = float(rng.randn()), bool(rng.rand() < 0.2)
+            rb.add_transition(s, a, r, s2, d)
+            m["s"][ptr], m["a"][ptr], m["r"][ptr, 0], m["s2"][ptr], m["d"][ptr, 0] = s, a.astype(np.float32), np.float32(r), s2, float(d)
+            ptr = (ptr + 1) % cap
+            size = min(size + 1, cap)
+        else:
+            high = min(size, ptr) if offline else size
+            B = int(rng.choice([1, 7, 256, 300, 515]))
+            if high <= 0:
+                with pytest.raises(ValueError):
+                    rb.sample(B)
+                continue
+            st = np.random.get_state()
+            out = rb.sample(B)
+            np.random.set_state(st)
+            idx = np.random.randint(0, high, size=B)
+            assert np.array_equal(np.asarray(rb._last_indices), idx)
+            for t, k in zip(out, ("s", "a", "r", "s2", "d")):
+                assert np.array_equal(t.cpu().numpy(), m[k][idx]), (step, k)
+    assert rb._size == size and rb._pointer == ptr
+
+
 def test_engine_philox_indices_bit_exact():
     from oracle.philox import philox_indices
 
