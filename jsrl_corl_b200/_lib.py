@@ -12,6 +12,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libiql_b200.so")
+if os.environ.get("IQL_B200_DEBUG") and os.environ.get("IQL_B200_LIB"):  # A/B builds of the library (debug only)
+    LIB_PATH = os.environ["IQL_B200_LIB"]
 
 IQL_OK, IQL_ERR_INVALID, IQL_ERR_CUDA, IQL_ERR_STATE, IQL_ERR_SHAPE = 0, 1, 2, 3, 4
 MATH_FP32_SIMT, MATH_TF32_TCGEN05 = 0, 1
