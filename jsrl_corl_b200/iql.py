@@ -814,10 +814,10 @@ class ImplicitQLearning:
         eng = self._ensure_engine(int(observations.shape[0]))
         self._push_hparams()
         slot = _SAMPLED.get(id(observations))
-        if slot is not None and slot.idx_host is not None and slot.untouched(batch):
+        rb = slot.rb() if slot is not None else None
+        if rb is not None and slot.idx_host is not None and rb._device == eng.device and slot.untouched(batch):
             # the batch is what ReplayBuffer.sample just returned: the engine gathers the same rows itself from the
             # host-drawn indices (identical values, no re-pack of the five dense tensors)
-            rb = slot.rb()
             if self._bound_rows is not rb._rows:
                 eng.bind_replay(0, rb._rows, max(rb._size, 1))
                 self._bound_rows = rb._rows
