@@ -264,6 +264,9 @@ int64_t iql_last_launch_count(const iql_engine* e);
  * stamps of the last launch, [3 roles][8 tiles][4 layers][4 stamps] int64, to the host.  Returns the number of
  * words written, < 0 when tracing is off or `max_words` is too small. */
 int iql_debug_fused_trace(long long* out, int32_t max_words);
+/* IQL_STEP_TRACE=1 (with IQL_B200_DEBUG=1): per-launch start / end globaltimer stamps of the step's kernels
+ * (tools/step_trace.py); reset != 0 arms the slots, otherwise copies [12][2] stamps (ns) to `out`. */
+int iql_debug_step_trace(iql_engine* e, int32_t reset, unsigned long long* out, int32_t max_words, void* stream);
 /* IQL_CHAIN_TRACE=1: globaltimer stamps of CTA pair 0 of the last bwd_chain launch (tools/chain_trace.py) */
 int iql_debug_chain_trace(long long* out, int32_t max_words);
 

@@ -115,6 +115,7 @@ SYMBOLS = {
     "iql_last_launch_count": (C.c_int64, [_P]),
     "iql_debug_fused_trace": (C.c_int, [_P, C.c_int32]),
     "iql_debug_chain_trace": (C.c_int, [_P, C.c_int32]),
+    "iql_debug_step_trace": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P]),
     "iql_profile_step": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P, _P]),
     "iql_selftest_umma_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32,
                                           _P, C.c_int32, _P, C.c_size_t, _P]),

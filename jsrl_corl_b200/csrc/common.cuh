@@ -111,6 +111,22 @@ static inline const char* dbg_getenv(const char* name) {
 // then sit on SMs the stragglers' co-runners could use: -7 % in umma_gemm, -1.4 % in fused_fwd), so only last_bwd
 // calls it.  IQL_B200_NO_PDL switches the launch attribute off.
 // ---------------------------------------------------------------------------
+// step timeline (IQL_STEP_TRACE): thread 0 of every CTA folds its start / end into the launch's slot
+__device__ __forceinline__ void stamp_begin(unsigned long long* stamps, int slot) {
+  if (stamps && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(stamps + 2 * slot, t);
+  }
+}
+__device__ __forceinline__ void stamp_end(unsigned long long* stamps, int slot) {
+  if (stamps && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(stamps + 2 * slot + 1, t);
+  }
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

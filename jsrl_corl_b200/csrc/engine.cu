@@ -141,6 +141,7 @@ struct iql_engine {
   bool use_graphs = true;
   // host-step path (iql_train_host_step): pinned, device-mapped host block = [S][B] int64 indices | [S][4] floats
   // (losses + flag word, written by the loss kernel); events ordering the engine stream against the caller's stream
+  unsigned long long* d_stamps = nullptr;  // IQL_STEP_TRACE: [ST_COUNT][2] globaltimer stamps (debug)
   float* h_act = nullptr;        // iql_act_host: pinned, device-mapped [action_dim floats | flag word]
   char* h_mail = nullptr;
   bool mail_pending = false;     // a host step has been launched and its losses not collected yet
@@ -333,6 +334,7 @@ extern "C" void iql_destroy(iql_engine* e) {
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   if (e->h_mail) cudaFreeHost(e->h_mail);
   if (e->h_act) cudaFreeHost(e->h_act);
+  if (e->d_stamps) cudaFree(e->d_stamps);
   delete e;
 }
 
@@ -823,6 +825,10 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
       e->side = nullptr;
     }
   }
+  if (dbg_getenv("IQL_STEP_TRACE") && !e->d_stamps && cudaMalloc((void**)&e->d_stamps, sizeof(unsigned long long) * 2 * ST_COUNT) != cudaSuccess) {
+    cudaGetLastError();
+    e->d_stamps = nullptr;
+  }
   e->bound = true;
   e->tables_dirty = e->scalars_dirty = e->counters_dirty = e->replay_dirty = true;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.first);
@@ -906,6 +912,7 @@ static StepCtx make_ctx(const iql_engine* e) {
   const int Lh = e->cfg.n_hidden;
   c.first_w_begin[4] = e->pol_umma ? e->w_off[IQL_NET_ACTOR][Lh] : 0;
   c.first_w_end[4] = e->pol_umma ? e->w_off[IQL_NET_ACTOR][Lh] + (int64_t)e->cfg.action_dim * e->w_ld[IQL_NET_ACTOR][Lh] : 0;
+  c.stamps = e->d_stamps;
   c.xrow_off_ = e->wl.xrow;
   c.xhi_off = (c.tf32 && e->split_first) ? e->wl.xhi : 0;
   c.xlo_off = (c.tf32 && e->split_first) ? e->wl.xlo : 0;
@@ -1440,16 +1447,11 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
     cudaGraph_t graph = nullptr;
     int64_t launches = 0;
     CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    // the TF32 operand refresh and the gather are independent: side by side, joined in front of the forward
-    const bool fork_refresh = ctx.tf32 && gather && e->side != nullptr;
+    // the TF32 operand refresh and the gather are independent: one launch, which releases the forward at once
+    const bool fork_refresh = ctx.tf32 && gather;
     if (fork_refresh) {
-      cudaEventRecord(e->ev_fork_g, st);
-      cudaStreamWaitEvent(e->side, e->ev_fork_g, 0);
-      launch_refresh_shadow(ctx, e->params, e->target, e->side);
-      cudaEventRecord(e->ev_gather, e->side);
-      launch_gather(ctx, e->d_ws_f, e->wl.member_floats, e->wl.xrow, st);
-      cudaStreamWaitEvent(st, e->ev_gather, 0);
-      launches += 2;
+      launch_gather_refresh(ctx, e->d_ws_f, e->wl.member_floats, e->wl.xrow, e->params, e->target, st);
+      ++launches;
     } else if (ctx.tf32) {
       launch_refresh_shadow(ctx, e->params, e->target, st);
       ++launches;
@@ -1497,6 +1499,24 @@ extern "C" int iql_host_step_wait(iql_engine* e, float* host_losses, void* strea
   for (int m = 0; m < S; ++m)
     for (int j = 0; j < 3; ++j) host_losses[m * 3 + j] = reinterpret_cast<volatile float*>(mail)[m * 4 + j];
   return IQL_OK;
+}
+
+// IQL_STEP_TRACE=1 (debug): reset / read the step timeline.  reset != 0 arms the slots (min = ~0, max = 0) on `stream`;
+// otherwise synchronises the device and copies [ST_COUNT][2] globaltimer stamps (ns) to `out`.
+extern "C" int iql_debug_step_trace(iql_engine* e, int32_t reset, unsigned long long* out, int32_t max_words, void* stream) {
+  if (!e || !e->d_stamps) return -1;
+  if (reset) {
+    std::vector<unsigned long long> init(2 * ST_COUNT);
+    for (int i = 0; i < ST_COUNT; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+    if (cudaMemcpyAsync(e->d_stamps, init.data(), sizeof(unsigned long long) * init.size(), cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+      return -2;
+    return 0;
+  }
+  if (!out || max_words < 2 * ST_COUNT) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpy(out, e->d_stamps, sizeof(unsigned long long) * 2 * ST_COUNT, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  return 2 * ST_COUNT;
 }
 
 extern "C" int64_t iql_last_launch_count(const iql_engine* e) { return e ? e->last_launches : 0; }

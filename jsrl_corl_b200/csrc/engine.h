@@ -98,6 +98,8 @@ struct StepCtx {
   // loss kernel) precedes that launch, and nothing after it in the call reads them.  enqueue_step sets it to -1 once
   // consumed so that the caller knows not to launch advance_kernel.
   int advance_k;
+  // IQL_STEP_TRACE (debug): globaltimer stamps of every launch of a step, [slot][2] = earliest CTA start / latest CTA end
+  unsigned long long* stamps;
   AdamScalars* adam_sc;          // [S][3] device
   int k_max;
   int tf32;                      // 1: tcgen05 path; producers round GEMM operands to nearest TF32
@@ -145,6 +147,10 @@ struct WorkspaceLayout {
   int Ald;
 };
 
+// launch slots of the step timeline (tools/step_trace.py)
+enum StampSlot : int { ST_REFRESH = 0, ST_GATHER, ST_FWD, ST_POLHEAD, ST_LOSS, ST_LASTBWD, ST_LBREDUCE, ST_WGRAD, ST_DGRAD, ST_FWGRAD, ST_ADAM,
+                       ST_ADVANCE, ST_COUNT };
+
 // forward pass ids
 enum Pass : int { PASS_V_NEXT = 0, PASS_V = 1, PASS_TQ1 = 2, PASS_TQ2 = 3, PASS_Q1 = 4, PASS_Q2 = 5, PASS_PI = 6, N_PASS = 7 };
 
@@ -158,6 +164,8 @@ void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_a
                  const float* grads, cudaStream_t st);
 void launch_advance(const StepCtx& ctx, int K, cudaStream_t st);
 void launch_refresh_shadow(const StepCtx& ctx, float* params, float* target, cudaStream_t st);
+void launch_gather_refresh(const StepCtx& ctx, float* ws, int64_t ws_member_floats, int64_t xrow_off, float* params, float* target,
+                           cudaStream_t st);
 void launch_load_batch(const StepCtx& ctx, int member, float* xrow, const float* s, const float* a, const float* r,
                        const float* s2, const float* d, cudaStream_t st);
 // skinny-layer kernels (kernels_skinny.cu)

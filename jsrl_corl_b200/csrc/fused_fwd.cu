@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
       fp.trace[((4 * FUSED_TRACE_TILES + (FUSED_TRACE_TILES - 1)) * FUSED_MAX_LAYERS + (FUSED_MAX_LAYERS - 1)) * 4 + slot] = clock64();
   };
   life_stamp(0);
+  stamp_begin(ctx.stamps, ST_FWD);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < F_MAXBAR; ++s) {
       mbar_init(full0 + 8 * s, 1);
@@ -631,6 +632,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
   life_stamp(3);
+  stamp_end(ctx.stamps, ST_FWD);
 }
 
 }  // namespace

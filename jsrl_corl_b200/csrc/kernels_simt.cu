@@ -175,11 +175,12 @@ void launch_simt_gemm(int mode, const GemmProb* probs, int nprob, int maxM, int 
 // ===========================================================================
 // replay gather into the step workspace: xrow[m][b][:] = rows_m[idx][:]
 // ===========================================================================
-__global__ void __launch_bounds__(256) gather_kernel(StepCtx ctx, float* __restrict__ ws, int64_t ws_member_floats,
-                                                     int64_t xrow_off) {
+__device__ __forceinline__ void gather_body(const StepCtx& ctx, float* __restrict__ ws, int64_t ws_member_floats, int64_t xrow_off,
+                                            int bx) {
   const int m = blockIdx.y;
   const int RF = ctx.row.row_floats, Q = RF >> 2;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = bx * blockDim.x + threadIdx.x;
+  stamp_begin(ctx.stamps, ST_GATHER);
   if (t >= ctx.B * Q) return;
   const int b = t / Q, q = t - b * Q;
   const ReplayBinding rb = ctx.replay[m];
@@ -200,6 +201,12 @@ __global__ void __launch_bounds__(256) gather_kernel(StepCtx ctx, float* __restr
     reinterpret_cast<float4*>(wm + ctx.xlo_off + (int64_t)b * RF)[q] =
         make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
   }
+  stamp_end(ctx.stamps, ST_GATHER);
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(StepCtx ctx, float* __restrict__ ws, int64_t ws_member_floats,
+                                                     int64_t xrow_off) {
+  gather_body(ctx, ws, ws_member_floats, xrow_off, (int)blockIdx.x);
 }
 
 void launch_gather(const StepCtx& ctx, float* ws, int64_t ws_member_floats, int64_t xrow_off, cudaStream_t st) {
@@ -259,6 +266,7 @@ __global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restric
   // per-warp partial sums: [0..3] = value / q1 / q2 / actor loss terms, [4 + a] = d loss / d log_std[a].
   // One shuffle tree per quantity and ONE block barrier; summation order is fixed (rows by lane, warps 0..7).
   __shared__ float red[8][4 + LOSS_MAX_A];
+  stamp_begin(ctx.stamps, ST_LOSS);
   if (blockIdx.x >= ctx.n_members) {
     // Extra CTAs (idle SMs, next to the loss CTAs): the Adam scalars of this step for the optimizer kernel --
     // torch computes the bias corrections and the step size in Python floats, CosineAnnealingLR in closed form.
@@ -291,6 +299,7 @@ __global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restric
       as.bc2_sqrt = (float)sqrt(1.0 - other);
       ctx.adam_sc[idx * 3 + o] = as;
     }
+    stamp_end(ctx.stamps, ST_LOSS);
     return;
   }
   const int m = blockIdx.x;
@@ -401,6 +410,7 @@ __global__ void __launch_bounds__(256) loss_kernel(StepCtx ctx, float* __restric
     const float lsr = log_std[j];
     grads[m * ctx.P + ctx.log_std_off + j] = (lsr >= -20.0f && lsr <= 2.0f) ? red[0][4 + j] : 0.f;
   }
+  stamp_end(ctx.stamps, ST_LOSS);
 }
 
 void launch_loss(const StepCtx& ctx, float* ws, int64_t ws_member_floats, const WorkspaceLayout& wl,
@@ -425,6 +435,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
                                                           const float* __restrict__ grads) {
   const int m = blockIdx.y;
   const MemberScalars* sc = ctx.scalars + m;
+  stamp_begin(ctx.stamps, ST_ADAM);
   pdl_wait();  // gradients, Adam scalars of the step: written by the launches before this one
   if (ctx.advance_k > 0 && blockIdx.x == 0 && threadIdx.x == 0) {  // advance_kernel's work, folded into the call's last launch
     iql_counters c = ctx.counters[m];
@@ -461,13 +472,15 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(StepCtx ctx, float* __
       adam_quad(ctx, m, i, g4[u], p4[u], m4[u], v4[u], t4[u], as[u], adam_w1, adam_beta2, adam_one_minus_b2, adam_eps, tau,
                 one_minus_tau, params, exp_avg, exp_avg_sq, target);
   }
+  stamp_end(ctx.stamps, ST_ADAM);
 }
 
 // TF32-rounded operand copies of params / target, rebuilt at the start of every engine call so that weights
 // written from outside (checkpoint loads, parameter surgery through the torch views) are always picked up.
-__global__ void __launch_bounds__(256) refresh_shadow_kernel(StepCtx ctx, float* __restrict__ params, float* __restrict__ target) {
+__device__ __forceinline__ void refresh_body(const StepCtx& ctx, float* __restrict__ params, float* __restrict__ target, int bx) {
   const int m = blockIdx.y;
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t i = ((int64_t)bx * blockDim.x + threadIdx.x) * 4;
+  stamp_begin(ctx.stamps, ST_REFRESH);
   bool first_layer = false;
 #pragma unroll
   for (int r = 0; r < 5; ++r) first_layer |= (i >= ctx.first_w_begin[r] && i < ctx.first_w_end[r]);
@@ -496,11 +509,35 @@ __global__ void __launch_bounds__(256) refresh_shadow_kernel(StepCtx ctx, float*
             make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
     }
   }
+  stamp_end(ctx.stamps, ST_REFRESH);
+}
+
+__global__ void __launch_bounds__(256) refresh_shadow_kernel(StepCtx ctx, float* __restrict__ params, float* __restrict__ target) {
+  refresh_body(ctx, params, target, (int)blockIdx.x);
 }
 
 void launch_refresh_shadow(const StepCtx& ctx, float* params, float* target, cudaStream_t st) {
   dim3 grid((unsigned)((ctx.P / 4 + 255) / 256), ctx.n_members);
   refresh_shadow_kernel<<<grid, 256, 0, st>>>(ctx, params, target);
+}
+
+// Operand refresh and gather of a host step in ONE launch (they are independent; the first n_gather blocks of a member
+// gather, the rest refresh): the fused forward then has a single predecessor, which releases it at once
+// (griddepcontrol.launch_dependents) so that its set-up -- barrier init, TMEM allocation, tensor-map prefetch -- runs
+// beside this kernel instead of after it.
+__global__ void __launch_bounds__(256) gather_refresh_kernel(StepCtx ctx, float* __restrict__ ws, int64_t ws_member_floats,
+                                                             int64_t xrow_off, float* __restrict__ params,
+                                                             float* __restrict__ target, int n_gather) {
+  pdl_trigger();
+  if ((int)blockIdx.x < n_gather) gather_body(ctx, ws, ws_member_floats, xrow_off, (int)blockIdx.x);
+  else refresh_body(ctx, params, target, (int)blockIdx.x - n_gather);
+}
+
+void launch_gather_refresh(const StepCtx& ctx, float* ws, int64_t ws_member_floats, int64_t xrow_off, float* params, float* target,
+                           cudaStream_t st) {
+  const int n_gather = (ctx.B * (ctx.row.row_floats >> 2) + 255) / 256;
+  dim3 grid((unsigned)(n_gather + (ctx.P / 4 + 255) / 256), ctx.n_members);
+  gather_refresh_kernel<<<grid, 256, 0, st>>>(ctx, ws, ws_member_floats, xrow_off, params, target, n_gather);
 }
 
 void launch_adam(const StepCtx& ctx, float* params, float* exp_avg, float* exp_avg_sq, float* target,

@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
                                                           WorkspaceLayout wl, const float* __restrict__ params, int sel_n,
                                                           int sel_off) {
   extern __shared__ float sm[];  // G tile [B][AMAX], then reduction scratch [4 row groups][256 columns][AMAX + 1]
+  stamp_begin(ctx.stamps, ST_LASTBWD);
   pdl_trigger();
   const int pi = sel_n > 0 ? (int)(blockIdx.x / sel_n) * 4 + sel_off + (int)(blockIdx.x % sel_n) : (int)blockIdx.x;
   const GemmProb pn = probs_dgrad[pi];
@@ -525,6 +526,7 @@ __global__ void __launch_bounds__(256) last_bwd_v4_kernel(const GemmProb* __rest
     for (int b = 0; b < B; ++b) s += gs[b * AMAX + threadIdx.x];
     pw.dbias[threadIdx.x] = s;
   }
+  stamp_end(ctx.stamps, ST_LASTBWD);
 }
 
 // The vectorised kernel covers 256 columns x ALL batch rows per CTA: with few problems and a large batch (stress

@@ -79,6 +79,7 @@ struct UmmaParams {
   // 1 no global stores, 2 operands of 4 problems only (L2 hits), 4 no epilogue, 8 no MMAs, 16 no TMA loads,
   // 32 no tensor-map prefetch, 64 no loads of the A operand
   int dbg;
+  int stamp_slot;  // step-timeline slot of this launch (ST_WGRAD / ST_DGRAD / ST_FWGRAD / ST_POLHEAD)
 };
 
 __device__ __forceinline__ void decode_tile(const UmmaParams& up, int unit, int j, int& prob, int& m0, int& n0) {
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
 umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restrict__ maps,
                  const GemmProb* __restrict__ probs_out, const CUtensorMap* __restrict__ cmaps, UmmaParams up, StepCtx ctx) {
   extern __shared__ uint8_t smem_raw[];
+  stamp_begin(ctx.stamps, up.stamp_slot);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
@@ -542,6 +544,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
     if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+  stamp_end(ctx.stamps, up.stamp_slot);
 }
 
 // bias gradient of the wgrad phases: dbias[m] = sum_k A[k][m]  (A = G, [K = batch rows][M] row-major).
@@ -784,6 +787,7 @@ void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const G
   // fused bias gradient needs all rows of a problem in one CTA (or CTA pair): only worth it while that leaves
   // enough independent units to fill the GPU (batch <= 256); larger batches use tile-major order + colsum_kernel
   up.k_max = maxK;
+  up.stamp_slot = mode == 1 ? ST_DGRAD : (mode == 0 ? ST_POLHEAD : (maxN >= TILE_N ? ST_WGRAD : ST_FWGRAD));
   up.dbg = (int)env_u32("IQL_UMMA_DBG", 0);
   up.prob_major = (epi == EPI_DRELU && umma_dgrad_writes_dbias(maxM)) ? 1 : 0;
   up.tiles_per_unit = up.prob_major ? up.tiles_m : 1;
