@@ -89,11 +89,12 @@ struct FusedParams {
   int dbg;  // IQL_FUSED_DBG timing probes (results are wrong when set): 1 no sign bits, 2 no activation stores, 4 no staging wait, 8 no head / policy math, 16 reversed tile order
   int ks_last0;  // UMMA_K steps that carry data in the last k-block of layer 0 (observation widths <= 24: 3 of 4)
   uint32_t idesc;
+  unsigned trace_cta;  // IQL_FUSED_TRACE_CTA: which CTA records (default 0)
   long long* trace;  // IQL_FUSED_TRACE: clock64 stamps of CTA 0, [3 roles][FUSED_TRACE_TILES][FUSED_MAX_LAYERS][4]
 };
 
 __device__ __forceinline__ void trace_put(const FusedParams& fp, int role, uint32_t tile_it, int l, int slot) {
-  if (fp.trace && blockIdx.x == 0 && tile_it < (uint32_t)FUSED_TRACE_TILES)
+  if (fp.trace && blockIdx.x == fp.trace_cta && tile_it < (uint32_t)FUSED_TRACE_TILES)
     fp.trace[((role * FUSED_TRACE_TILES + tile_it) * FUSED_MAX_LAYERS + l) * 4 + slot] = clock64();
 }
 
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = fp.L;
   auto life_stamp = [&](int slot) {  // kernel entry / set-up done / predecessor done / exit, CTA 0 thread 0
-    if (fp.trace && blockIdx.x == 0 && threadIdx.x == 0)
+    if (fp.trace && blockIdx.x == fp.trace_cta && threadIdx.x == 0)
       fp.trace[((4 * FUSED_TRACE_TILES + (FUSED_TRACE_TILES - 1)) * FUSED_MAX_LAYERS + (FUSED_MAX_LAYERS - 1)) * 4 + slot] = clock64();
   };
   life_stamp(0);
@@ -527,23 +528,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               yacc = fmaf(__uint_as_float(r[4 * j + 3]), w4.w, yacc);
             }
           }
-          if (pol_a > 0 && !(fp.dbg & 8)) {
-            // act_dim dot products per row.  Lane i fetches column 32 c + i of every weight row (one coalesced 128-byte
-            // load per action) and the warp passes the values round with shuffles: every lane needs every weight, and
-            // there is no shared memory left to broadcast them from (uniform global loads serialised on the
-            // register budget: 15 us per actor tile)
-            float wreg[FUSED_POL_MAX];
-            const float* wp = tr->pol_w + c * 32 + lane;
-            const int ldw = tr->pol_ldw;
-#pragma unroll
-            for (int a = 0; a < FUSED_POL_MAX; ++a) wreg[a] = (a < pol_a) ? __ldg(wp + (int64_t)a * ldw) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {  // branch-free: the rows past act_dim carry zero weights
-              const float h = __uint_as_float(r[j]);
-#pragma unroll
-              for (int a = 0; a < FUSED_POL_MAX; ++a) pacc[a] = fmaf(h, __shfl_sync(0xffffffffu, wreg[a], j), pacc[a]);
-            }
-          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(__uint_as_float(r[j])));
           if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 1);
@@ -575,6 +559,34 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               tma_store_2d(fp.smaps[l] + prob, smem_u32(stg), c * 32, m0 + q * 32);
               bulk_commit();
             }
+            if (pol_a > 0 && !(fp.dbg & 8)) {
+              // Policy head z += H_L[:, 32c..32c+31] Wp[:, 32c..]^T on the parked (TF32-exact) chunk with warp-level
+              // tensor-core MMAs: m16n8k8, A fragments straight from the swizzled staging tile (conflict-free), B = the
+              // act_dim <= 8 weight rows split hi + lo on the fly (two accumulating passes: FP32-accurate weights).
+              // 16 MMAs + 32 LDS per chunk instead of 256 shuffles + 256 FMAs (1.4-1.8 us -> ~0.3 us per chunk).
+              const int g = lane >> 2, t = lane & 3;
+              const float* wrow = tr->pol_w + (int64_t)g * tr->pol_ldw + c * 32 + t;
+              const bool wvalid = g < pol_a;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const float w0 = wvalid ? __ldg(wrow + 8 * ks) : 0.f, w1 = wvalid ? __ldg(wrow + 8 * ks + 4) : 0.f;
+                const float w0h = round_tf32(w0), w1h = round_tf32(w1);
+                const uint32_t bh0 = __float_as_uint(w0h), bh1 = __float_as_uint(w1h);
+                const uint32_t bl0 = __float_as_uint(round_tf32(w0 - w0h)), bl1 = __float_as_uint(round_tf32(w1 - w1h));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                  const int r0 = 16 * mt + g, r1 = r0 + 8;  // r0 & 7 == r1 & 7 == g
+                  const int u0 = 4 * ((2 * ks) ^ g) + t, u1 = 4 * ((2 * ks + 1) ^ g) + t;
+                  const uint32_t a0 = __float_as_uint(stg[r0 * 32 + u0]), a1 = __float_as_uint(stg[r1 * 32 + u0]);
+                  const uint32_t a2 = __float_as_uint(stg[r0 * 32 + u1]), a3 = __float_as_uint(stg[r1 * 32 + u1]);
+                  float* d = pacc + 4 * mt;
+                  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bh0), "r"(bh1));
+                  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bl0), "r"(bl1));
+                }
+              }
+            }
           }
           if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 3);
           uint32_t* const bits = tr->bits[l];
@@ -598,8 +610,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           // add them up in a fixed order and write z
           if (lane == 0) bulk_wait_read0();
           __syncwarp();
+          // accumulator fragment of m-tile mt: rows 16 mt + (lane >> 2) (+ 8), actions 2 (lane & 3) (+ 1)
 #pragma unroll
-          for (int a = 0; a < FUSED_POL_MAX; ++a) stg[lane * FUSED_POL_MAX + a] = pacc[a];
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              stg[(16 * mt + (lane >> 2) + 8 * (i >> 1)) * FUSED_POL_MAX + 2 * (lane & 3) + (i & 1)] = pacc[4 * mt + i];
           asm volatile("bar.sync %0, %1;" ::"r"(1 + eg), "r"(F_GROUP_WARPS * 32) : "memory");
           if (ch == 0) {
             float* zrow = tr->pol_out + (int64_t)row * tr->pol_ldc;
@@ -701,6 +717,10 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
     if (n_sm <= 0) n_sm = 148;
   }
   fp.trace = fused_trace_buffer();
+  {
+    static const unsigned tc = dbg_getenv("IQL_FUSED_TRACE_CTA") ? (unsigned)atoi(dbg_getenv("IQL_FUSED_TRACE_CTA")) : 0u;
+    fp.trace_cta = tc;
+  }
   if (!pair) {
     const int grid = fp.units < n_sm ? fp.units : n_sm;
     launch_pdl(fused_fwd_kernel<false>, dim3(grid), dim3(F_THREADS), F_SMEM, st, 1, fp, ctx);
