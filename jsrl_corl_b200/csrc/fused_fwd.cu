@@ -89,6 +89,7 @@ struct FusedParams {
   int dbg;  // IQL_FUSED_DBG timing probes (results are wrong when set): 1 no sign bits, 2 no activation stores, 4 no staging wait, 8 no head / policy math, 16 reversed tile order
   int ks_last0;  // UMMA_K steps that carry data in the last k-block of layer 0 (observation widths <= 24: 3 of 4)
   uint32_t idesc;
+  int wide;  // every CTA (pair) has at most ONE tile: both epilogue groups work on it, 2 chunks per warp and layer instead of 4
   unsigned trace_cta;  // IQL_FUSED_TRACE_CTA: which CTA records (default 0)
   long long* trace;  // IQL_FUSED_TRACE: clock64 stamps of CTA 0, [3 roles][FUSED_TRACE_TILES][FUSED_MAX_LAYERS][4]
 };
@@ -430,14 +431,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int eg = (warp - 2) / F_GROUP_WARPS;         // epilogue group: tiles with tile_it % 2 == eg
     const int ch = ((warp - 2) % F_GROUP_WARPS) >> 2;  // column group within the group: chunks ch, ch + 2, ch + 4, ch + 6
-    const int tr_id = threadIdx.x - 64 - eg * (F_GROUP_WARPS * 32);  // 0..255 within the group
-    const bool tracer = ((warp - 2) % F_GROUP_WARPS) == 0 && lane == 0;
+    // wide: a launch with one tile per CTA (single learners, few members) would leave the other group idle; instead all
+    // 16 warps take the tile, as four column groups of two chunks each (the head partials then add up in four terms)
+    const bool wide = fp.wide != 0;
+    const int cg = wide ? eg * F_CGROUPS + ch : ch;        // column group of this warp
+    const int n_cg = wide ? F_EGROUPS * F_CGROUPS : F_CGROUPS;
+    const int tr_id = wide ? (int)threadIdx.x - 64 : (int)threadIdx.x - 64 - eg * (F_GROUP_WARPS * 32);  // thread index within the tile's warps
+    const int bar_id = wide ? 3 : 1 + eg, bar_n = wide ? F_EPI_WARPS * 32 : F_GROUP_WARPS * 32;
+    const bool tracer = ((warp - 2) % F_GROUP_WARPS) == 0 && lane == 0 && (!wide || eg == 0);
     float* stg = stg_all + (warp - 2) * F_STG_FLOATS;
     uint32_t ev = 0, tile_it = 0;
     const uint32_t elast_lead = CTA2 ? mapa_u32(elast, 0) : elast;
     const uint32_t achunk_lead = CTA2 ? mapa_u32(achunk0, 0) : achunk0;
     for (int u = worker; u < fp.units; u += n_workers, ++tile_it) {
-      if ((int)(tile_it & 1) != eg) continue;  // the other group's tile
+      if (!wide && (int)(tile_it & 1) != eg) continue;  // the other group's tile
       const int prob = unit_prob(fp, u);
       const int m0 = (u % fp.tiles_m) * tile_rows + m_off;
       const uint32_t b = tile_it & 1;
@@ -456,9 +463,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
         const float drop_scale = tr->drop_scale;
         const float* bs = rec + l * FT_N;
         const float* ws = rec + FUSED_MAX_LAYERS * FT_N;
-        float* ypart = ypart_s + (eg * 2 + ((tile_it >> 1) & 1)) * (F_CGROUPS * FT_M);
+        float* ypart = wide ? ypart_s : ypart_s + (eg * 2 + ((tile_it >> 1) & 1)) * (F_CGROUPS * FT_M);
         if (tracer) trace_put(fp, 2, tile_it, l, 0);
-        mbar_wait(tfull0 + 8 * (eg * 2 + (ev & 1)), (ev >> 1) & 1);
+        mbar_wait(tfull0 + 8 * ((wide ? 0 : eg * 2) + (ev & 1)), (ev >> 1) & 1);  // wide: tile 0 belongs to group 0's barriers
         tc_fence_after();
         if (tracer) trace_put(fp, 2, tile_it, l, 1);
         const uint32_t region = tmem_base + (uint32_t)(l & 1) * 256u + ((uint32_t)(q * 32) << 16);
@@ -468,13 +475,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
 #pragma unroll
         for (int a = 0; a < FUSED_POL_MAX; ++a) pacc[a] = 0.f;
 #pragma unroll 1
-        for (int c = ch; c < F_CHUNKS; c += F_CGROUPS) {
+        for (int c = cg; c < F_CHUNKS; c += n_cg) {
           uint32_t r[32];
           tmem_ld32(region + (uint32_t)(c * 32), r);
           tmem_ld_wait();
-          if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 0);
-          if (tracer && c == ch + F_CGROUPS) trace_put(fp, 4, tile_it, l, 0);
-          if (last && c + F_CGROUPS >= F_CHUNKS) {  // this warp's last read of the tile: the region may be overwritten
+          if (tracer && c == cg) trace_put(fp, 3, tile_it, l, 0);
+          if (tracer && c == cg + n_cg) trace_put(fp, 4, tile_it, l, 0);
+          if (last && !wide && c + F_CGROUPS >= F_CHUNKS) {  // this warp's last read of the tile: the region may be overwritten (wide: no next tile)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -530,7 +537,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_tf32(__uint_as_float(r[j])));
-          if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 1);
+          if (tracer && c == cg) trace_put(fp, 3, tile_it, l, 1);
           if (!last) {  // columns [32 c, +32) of the next layer's operand A, in place; the MMAs of k-block c may go
             tmem_st32(region + (uint32_t)(c * 32), r);
             tmem_st_wait();
@@ -541,7 +548,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               else mbar_arrive(achunk0 + 8 * c);
             }
           }
-          if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 2);
+          if (tracer && c == cg) trace_put(fp, 3, tile_it, l, 2);
           if (store && !(fp.dbg & 2)) {
             // every lane holds one full 128-byte row of the chunk: park it (16-byte units XOR-swizzled by the row,
             // the layout a SWIZZLE_128B tensor map expects) and let one TMA store write the 32 x 32 box -- no
@@ -588,7 +595,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
               }
             }
           }
-          if (tracer && c == ch) trace_put(fp, 3, tile_it, l, 3);
+          if (tracer && c == cg) trace_put(fp, 3, tile_it, l, 3);
           uint32_t* const bits = tr->bits[l];
           if (store && bits != nullptr && !(fp.dbg & 1)) {  // 1 bit per element for the dgrad mask (of the ROUNDED value, like the store)
             uint32_t word = 0;
@@ -596,14 +603,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
             for (int j = 0; j < 32; ++j) word |= (__uint_as_float(r[j]) > 0.f ? 1u : 0u) << j;
             bits[(int64_t)row * F_CHUNKS + c] = word;
           }
-          if (tracer && c == ch) trace_put(fp, 4, tile_it, l, 1);
+          if (tracer && c == cg) trace_put(fp, 4, tile_it, l, 1);
         }
         if (tracer) trace_put(fp, 2, tile_it, l, 2);
         if (fuse) {
-          ypart[ch * FT_M + q * 32 + lane] = yacc;
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + eg), "r"(F_GROUP_WARPS * 32) : "memory");
-          if (tr_id < FT_M)
-            tr->head_out[(int64_t)(m0 + tr_id) * tr->head_ldc] = (ypart[tr_id] + ypart[FT_M + tr_id]) + tr->head_b;
+          ypart[cg * FT_M + q * 32 + lane] = yacc;
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
+          if (tr_id < FT_M) {
+            float y = ypart[tr_id] + ypart[FT_M + tr_id];
+            if (wide) y += ypart[2 * FT_M + tr_id] + ypart[3 * FT_M + tr_id];
+            tr->head_out[(int64_t)(m0 + tr_id) * tr->head_ldc] = y + tr->head_b;
+          }
         }
         if (pol_a > 0) {
           // the four column groups park their partial sums in their (idle) staging tiles; the warps of group 0
@@ -616,8 +626,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               stg[(16 * mt + (lane >> 2) + 8 * (i >> 1)) * FUSED_POL_MAX + 2 * (lane & 3) + (i & 1)] = pacc[4 * mt + i];
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + eg), "r"(F_GROUP_WARPS * 32) : "memory");
-          if (ch == 0) {
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
+          if (cg == 0) {
             float* zrow = tr->pol_out + (int64_t)row * tr->pol_ldc;
 #pragma unroll
             for (int a = 0; a < FUSED_POL_MAX; ++a) {
@@ -625,17 +635,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) fused_fwd_kernel(FusedParams fp,
                 const float* p0 = stg + lane * FUSED_POL_MAX + a;  // this warp is group 0 of its quarter; group g4 is 4 g4 tiles further
                 float z = 0.f;
 #pragma unroll
-                for (int g4 = 0; g4 < F_CGROUPS; ++g4) z += p0[g4 * 4 * F_STG_FLOATS];
+                for (int g4 = 0; g4 < F_EGROUPS * F_CGROUPS; ++g4)
+                  if (g4 < n_cg) z += p0[g4 * 4 * F_STG_FLOATS];
                 zrow[a] = z + tr->pol_b[a];
               }
             }
           }
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + eg), "r"(F_GROUP_WARPS * 32) : "memory");  // the staging tiles go back to the activation stores
+          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");  // the staging tiles go back to the activation stores
         }
         if (tracer) trace_put(fp, 2, tile_it, l, 3);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(recempty0 + 8 * b);  // this warp no longer reads the tile's record
+      if (lane == 0 && !wide) mbar_arrive(recempty0 + 8 * b);  // this warp no longer reads the tile's record (wide: never reused)
     }
     bulk_wait0();  // all activation stores of this thread have completed
   }
@@ -721,12 +732,15 @@ void launch_fused_fwd(const FusedFwdArgs& a, const StepCtx& ctx, cudaStream_t st
     static const unsigned tc = dbg_getenv("IQL_FUSED_TRACE_CTA") ? (unsigned)atoi(dbg_getenv("IQL_FUSED_TRACE_CTA")) : 0u;
     fp.trace_cta = tc;
   }
+  static const bool no_wide = dbg_getenv("IQL_B200_NO_WIDE_EPILOGUE") != nullptr;
   if (!pair) {
     const int grid = fp.units < n_sm ? fp.units : n_sm;
+    fp.wide = (fp.units <= n_sm && !no_wide) ? 1 : 0;
     launch_pdl(fused_fwd_kernel<false>, dim3(grid), dim3(F_THREADS), F_SMEM, st, 1, fp, ctx);
     return;
   }
   const int workers = fp.units < n_sm / 2 ? fp.units : n_sm / 2;
+  fp.wide = (fp.units <= n_sm / 2 && !no_wide) ? 1 : 0;
   launch_pdl(fused_fwd_kernel<true>, dim3(2 * workers), dim3(F_THREADS), F_SMEM, st, 2, fp, ctx);
 }
 
