@@ -60,6 +60,7 @@ struct Phase {
   bool umma_ok;  // eligible for the tcgen05 kernel
   int epi;       // common epilogue of the phase
   int kind;      // PH_*: dedicated skinny-layer kernel, or generic grouped GEMM
+  int tile_n = 0;  // N tile of the tcgen05 kernel (0: umma_tile_n(maxN)); 128 for CTA-pair dgrad launches with few problems
 };
 enum { PH_GENERIC = 0, PH_FIRST_FWD = 1, PH_OUT_FWD = 2, PH_LAST_WGRAD = 3, PH_LAST_DGRAD = 4, PH_FIRST_WGRAD = 5 };
 
@@ -663,6 +664,12 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
       // phases run by the fused forward: the weight boxes are full tiles, or half tiles when it runs on CTA pairs
       const bool in_fused = e->fused_fwd && ph.mode == 0 && ph.kind != PH_OUT_FWD;
       ph.cta2 = in_fused ? e->fused_pair : (ph.umma_ok && umma_cta2(ph.mode, ph.count, ph.maxM, ph.maxN, ph.maxK));
+      // few dgrad problems (single learners, small ensembles): two N = 128 units per problem on twice the CTA pairs --
+      // half the MMAs and one epilogue chunk per warp instead of two on the step's critical path
+      ph.tile_n = 0;
+      if (!in_fused && ph.cta2 && ph.mode == 1 && ph.kind == PH_GENERIC && ph.maxN % 256 == 0 && 2 * ph.count * (ph.maxN / 256) <= 74 &&
+          dbg_getenv("IQL_B200_NO_NARROW_DGRAD") == nullptr)
+        ph.tile_n = 128;
       // backward hidden-layer phases: row-layout epilogue (TMA stores; dgrad masks with the sign bits the fused
       // forward wrote -- without the fused forward the bits do not exist and dgrad keeps the FP32 mask)
       // (the same epilogue on the weight-gradient phase measured 46.4 vs 44.2 us: it stays on the transposing one)
@@ -683,7 +690,7 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
   if (e->cfg.math_mode == IQL_MATH_TF32_TCGEN05) {
     auto encode = [&](const Phase& ph) {
       if (!ph.umma_ok || !umma_phase_supported(ph.mode, e->cfg.batch_size, e->cfg.hidden_dim)) return 0;
-      return umma_encode_maps(ph.mode, e->h_probs.data() + ph.first, ph.count, umma_tile_n(ph.maxN),
+      return umma_encode_maps(ph.mode, e->h_probs.data() + ph.first, ph.count, ph.tile_n ? ph.tile_n : umma_tile_n(ph.maxN),
                               e->h_maps.data() + (size_t)256 * ph.first, ph.cta2);
     };
     for (const Phase& ph : e->fwd_phases) if (encode(ph)) return fail(e, IQL_ERR_CUDA, "cuTensorMapEncodeTiled failed (forward phase)");
@@ -1034,7 +1041,7 @@ static int enqueue_step(iql_engine* e, StepCtx& ctx, bool gather, cudaStream_t s
       const int n_scalar = (N_PASS - 1) * e->cfg.n_members;  // problems with a scalar head (V, Q passes)
       launch_umma_gemm(ph.mode, pp, split ? e->d_maps_first : e->d_maps + (size_t)256 * ph.first,
                        fuse ? e->d_probs + next->first : nullptr, ph.epi, ph.count, ph.maxM, ph.maxN, ctx, st, split,
-                       n_scalar, ph.cta2, ph.maxK, ph.rowepi ? e->d_maps_c + (size_t)128 * ph.first : nullptr);
+                       n_scalar, ph.cta2, ph.maxK, ph.rowepi ? e->d_maps_c + (size_t)128 * ph.first : nullptr, ph.tile_n);
       if (fuse) {  // the policy head (N = act_dim) stays with the FP32 output-layer kernel
         const GemmProb* pa = e->d_probs + next->first + n_scalar;
         if (out_ok) launch_out_fwd(pa, ph.count - n_scalar, B, H, A, st);
@@ -1583,6 +1590,7 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
                                       const float* B, int32_t ldb, float* C, int32_t ldc, void* scratch,
                                       size_t scratch_bytes, void* stream) {
   const bool allow_pair = !(mode & 0x100);  // test hook: mode | 0x100 keeps the single-CTA kernel
+  const int tile_n_arg = (mode & 0x200) ? 128 : 0;  // test hook: mode | 0x200 runs N = 128 tiles (CTA pairs: 64 columns of B per CTA)
   mode &= 0xFF;
   if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0 || (M % 256) || (N > 256 && (N % 256)))
     return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: M multiple of 256 and N <= 256 or a multiple of 256 required");
@@ -1595,7 +1603,7 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
   p.epi = EPI_NONE; p.drop_layer = -1;
   alignas(64) char maps[256];
   const bool cta2 = allow_pair && umma_cta2_ok(M, N);
-  if (umma_encode_maps(mode, &p, 1, umma_tile_n(N), maps, cta2)) return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: cuTensorMapEncodeTiled failed");
+  if (umma_encode_maps(mode, &p, 1, tile_n_arg ? tile_n_arg : umma_tile_n(N), maps, cta2)) return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: cuTensorMapEncodeTiled failed");
   cudaStream_t st = (cudaStream_t)stream;
   char* d = (char*)scratch;
   if (cudaMemcpyAsync(d, maps, 256, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -1604,7 +1612,7 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
     return fail(nullptr, IQL_ERR_CUDA, "iql_selftest_umma_gemm: upload failed");
   StepCtx ctx;
   memset(&ctx, 0, sizeof(ctx));
-  launch_umma_gemm(mode, (const GemmProb*)(d + 256), d, nullptr, EPI_NONE, 1, M, N, ctx, st, false, 0, cta2, K);
+  launch_umma_gemm(mode, (const GemmProb*)(d + 256), d, nullptr, EPI_NONE, 1, M, N, ctx, st, false, 0, cta2, K, nullptr, tile_n_arg);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(nullptr, IQL_ERR_CUDA, std::string("iql_selftest_umma_gemm: ") + cudaGetErrorString(err));
   return IQL_OK;

@@ -761,8 +761,8 @@ static void launch_variant(bool cta2, int workers, const GemmProb* probs, const 
 
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
                       int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, int split3, int fuse_count, bool cta2,
-                      int maxK, const void* cmaps) {
-  const int tile_n = umma_tile_n(maxN);
+                      int maxK, const void* cmaps, int tile_n_arg) {
+  const int tile_n = tile_n_arg > 0 ? tile_n_arg : umma_tile_n(maxN);
   UmmaParams up = make_params(mode, tile_n, cta2);
   up.tiles_m = (maxM + up.tile_m - 1) / up.tile_m;
   up.tiles_n = (maxN + tile_n - 1) / tile_n;

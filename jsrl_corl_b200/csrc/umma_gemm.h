@@ -28,7 +28,7 @@ bool umma_dgrad_writes_dbias(int batch);
 // output heads on the tensor cores.
 void launch_umma_gemm(int mode, const GemmProb* probs, const void* maps, const GemmProb* probs_out, int epi, int nprob,
                       int maxM, int maxN, const StepCtx& ctx, cudaStream_t st, int split3 = 0, int fuse_count = 0,
-                      bool cta2 = false, int maxK = 0, const void* cmaps = nullptr);
+                      bool cta2 = false, int maxK = 0, const void* cmaps = nullptr, int tile_n = 0 /* 0: umma_tile_n(maxN) */);
 int umma_encode_maps_split(const GemmProb* h_hi, const GemmProb* h_lo, int nprob, int tile_n, void* h_maps_out, bool cta2);
 // Fused forward (fused_fwd.cu): all hidden layers + scalar heads of every (member, pass) in one launch, hidden
 // activations chained through tensor memory.  Hidden width 256, 1..FUSED_MAX_LAYERS hidden layers.

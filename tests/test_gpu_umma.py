@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(mode, M, N, K, seed=0, single_cta=False):
+def _run(mode, M, N, K, seed=0, single_cta=False, narrow=False):
     from jsrl_corl_b200 import _lib
 
     L = _lib.lib()
@@ -33,7 +33,7 @@ def _run(mode, M, N, K, seed=0, single_cta=False):
     st = torch.cuda.Stream()
     st.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(st):
-        rc = L.iql_selftest_umma_gemm(mode | (0x100 if single_cta else 0), M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+        rc = L.iql_selftest_umma_gemm(mode | (0x100 if single_cta else 0) | (0x200 if narrow else 0), M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
                                       Cout.data_ptr(), Cout.stride(0), scratch.data_ptr(), scratch.numel(), st.cuda_stream)
     _lib.check(rc, None, "iql_selftest_umma_gemm")
     st.synchronize()
@@ -70,6 +70,17 @@ def test_umma_cta_pair_equals_single_cta(mode):
     _, pair, _ = _run(mode, 512, 512, 160, seed=3)
     _, single, _ = _run(mode, 512, 512, 160, seed=3, single_cta=True)
     assert torch.equal(pair, single)
+
+
+@pytest.mark.parametrize("single_cta", [False, True], ids=["cta_pair", "single_cta"])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_umma_narrow_tiles_equal_full_tiles(mode, single_cta):
+    """N = 128 tiles (mode | 0x200; on CTA pairs each CTA stages 64 columns of B): the hidden-layer dgrad of launches with
+    few problems runs this way.  Same products, same accumulation order per output element: bit-identical to N = 256 tiles."""
+    _, narrow, ref = _run(mode, 512, 512, 256, seed=5, single_cta=single_cta, narrow=True)
+    _, full, _ = _run(mode, 512, 512, 256, seed=5, single_cta=single_cta)
+    assert torch.equal(narrow, full)
+    assert float((narrow - ref).norm() / ref.norm()) < 1.5e-3
 
 
 def test_umma_gemm_rejects_bad_shapes():
