@@ -142,7 +142,7 @@ umma_gemm_kernel(const GemmProb* __restrict__ probs, const CUtensorMap* __restri
       mbar_init(tfull0 + 8 * b, 1);
       mbar_init(tempty0 + 8 * b, CTA2 ? 2 * N_EPI_WARPS : N_EPI_WARPS);  // pair: the epilogue warps of both CTAs
     }
-    for (int b = 0; b < PEER_CSUM_SLOTS; ++b) mbar_init(csfull0 + 8 * b, TILE_N);
+    for (int b = 0; b < PEER_CSUM_SLOTS; ++b) mbar_init(csfull0 + 8 * b, up.tile_n);  // one arrival per column of the N tile
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
