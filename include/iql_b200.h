@@ -222,10 +222,11 @@ int iql_train_steps(iql_engine* e, int32_t k_steps, int32_t sample_mode, const i
  * `batch = replay_buffer.sample(B); log_dict = trainer.train(batch)` (offline/iql.py:631-635, finetune/iql.py:542-563),
  * whose log_dict holds the three losses as host floats every step.
  * host_indices: [S][B] int64 in HOST memory (e.g. numpy's np.random.randint stream, iql.py:172), or NULL to consume the
- * batch staged by iql_load_batch.  host_losses: [S][3] floats in HOST memory.  One CUDA-graph launch on `stream`
- * (a non-default stream); the loss kernel writes its scalars into pinned host memory and the call returns as soon as
- * they have landed, while the step's backward / optimizer launches are still in flight -- work the caller enqueues on
- * `caller_stream` (may equal `stream`) afterwards is ordered behind the whole step. */
+ * batch staged by iql_load_batch.  host_losses: [S][3] floats in HOST memory.  One CUDA-graph launch: the graph is
+ * captured once on `stream` (a non-default stream) and launched on `caller_stream` (the stream the caller's own work
+ * is on; may be the default stream), so the step is ordered against the caller's inserts / staged batch / later reads
+ * by plain stream order.  The loss kernel writes its scalars into pinned host memory and the call returns as soon as
+ * they have landed, while the step's backward / optimizer launches are still in flight. */
 int iql_train_host_step(iql_engine* e, const int64_t* host_indices, float* host_losses, void* stream,
                         void* caller_stream);
 /* host_losses == NULL above returns right after the launch; this collects the losses of that step (spins on the

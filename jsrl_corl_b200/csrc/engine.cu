@@ -146,6 +146,8 @@ struct iql_engine {
   float* h_act = nullptr;        // iql_act_host: pinned, device-mapped [action_dim floats | flag word]
   char* h_mail = nullptr;
   bool mail_pending = false;     // a host step has been launched and its losses not collected yet
+  cudaStream_t host_step_stream = nullptr;  // the caller's stream the last host step was launched on
+  bool host_step_stream_set = false;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
@@ -1423,7 +1425,7 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
     std::vector<float> big;
     float* sink = drop;
     if (S > 64) { big.resize(3 * (size_t)S); sink = big.data(); }
-    int rcw = iql_host_step_wait(e, sink, stream);
+    int rcw = iql_host_step_wait(e, sink, e->host_step_stream);
     if (rcw != IQL_OK) return rcw;
   }
   if (gather)
@@ -1437,11 +1439,19 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
     }
   for (int m = 0; m < S; ++m) reinterpret_cast<volatile uint32_t*>(mail)[m * 4 + 3] = 0u;
   std::atomic_thread_fence(std::memory_order_seq_cst);
-  if (cur != st) {  // the step reads what the caller's stream wrote (inserted rows, loaded weights, a staged batch)
-    CUDA_TRY(e, cudaEventRecord(e->ev_in, cur));
-    CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_in, 0));
+  // The graph is captured on `stream` (capture needs a non-default stream) but LAUNCHED on the caller's stream: the
+  // step is then ordered against everything the caller enqueues (inserted rows, a staged batch, later reads of the
+  // weights) by plain stream order -- no event record / wait pairs around every step.  Other engine calls order their
+  // stream against the caller's (iql_act_host, the Python guard around iql_train_steps).  A caller that hops between
+  // streams gets the two ordered by an event.
+  cudaStream_t run = cur;
+  if (e->host_step_stream_set && e->host_step_stream != run) {
+    CUDA_TRY(e, cudaEventRecord(e->ev_in, e->host_step_stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(run, e->ev_in, 0));
   }
-  int rc = flush_tables(e, st);
+  e->host_step_stream = run;
+  e->host_step_stream_set = true;
+  int rc = flush_tables(e, run);
   if (rc != IQL_OK) return rc;
   const auto graph_key = std::make_tuple(gather ? 101 : 102, 1, (uintptr_t)0);
   auto it = e->graphs.find(graph_key);
@@ -1473,12 +1483,8 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
     cudaGraphDestroy(graph);
     it = e->graphs.emplace(graph_key, std::make_pair(exec, launches)).first;
   }
-  CUDA_TRY(e, cudaGraphLaunch(it->second.first, st));
+  CUDA_TRY(e, cudaGraphLaunch(it->second.first, run));
   e->last_launches = it->second.second;
-  if (cur != st) {
-    CUDA_TRY(e, cudaEventRecord(e->ev_out, st));
-    CUDA_TRY(e, cudaStreamWaitEvent(cur, e->ev_out, 0));
-  }
   for (int m = 0; m < S; ++m) {
     iql_counters& c = e->h_counters[m];
     c.v_step += 1; c.q_step += 1; c.actor_step += 1; c.total_it += 1; c.sample_step += 1;
@@ -1487,14 +1493,15 @@ extern "C" int iql_train_host_step(iql_engine* e, const int64_t* host_indices, f
   }
   e->mail_pending = true;
   if (!host_losses) return IQL_OK;  // the caller collects the losses with iql_host_step_wait
-  return iql_host_step_wait(e, host_losses, stream);
+  return iql_host_step_wait(e, host_losses, run);
 }
 
 extern "C" int iql_host_step_wait(iql_engine* e, float* host_losses, void* stream) {
   if (!e || !host_losses) return IQL_ERR_INVALID;
   if (!e->h_mail || !e->mail_pending) return fail(e, IQL_ERR_STATE, "iql_host_step_wait: no host step in flight");
   e->mail_pending = false;
-  cudaStream_t st = (cudaStream_t)stream;
+  (void)stream;
+  cudaStream_t st = e->host_step_stream;  // the stream the step was launched on (a failed launch is noticed through it)
   const int S = e->cfg.n_members, B = e->cfg.batch_size;
   float* mail = (float*)(e->h_mail + sizeof(int64_t) * (size_t)S * B);
   // wait for the flag words (bounded: a failed launch never raises them)
