@@ -241,7 +241,8 @@ int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float
 /* The same for ONE observation of a HOST caller -- `actor.act(state, device)` as the rollout loops call it once per
  * env step (eval_actor iql.py:218-238, jsrl_w_iql.py:445-515): host_state[state_dim] and host_action[action_dim] are
  * host arrays.  The observation travels in the kernel parameters and the action returns through pinned host memory
- * (no copies, no stream synchronisation); ordered after all work queued on `stream` and `caller_stream`. */
+ * (no copies, no stream synchronisation); launched on `caller_stream`, i.e. ordered behind the host steps and
+ * everything else the caller has enqueued there (`stream` is unused and kept for symmetry). */
 int iql_act_host(iql_engine* e, int32_t member, const float* host_state, float max_action, float* host_action,
                  void* stream, void* caller_stream);
 /* Self-test hook for the tcgen05 TF32 GEMM building block (no reference

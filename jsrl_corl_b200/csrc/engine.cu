@@ -1575,17 +1575,20 @@ extern "C" int iql_act_host(iql_engine* e, int32_t member, const float* host_sta
   volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(e->h_act + A);
   *flag = 0u;
   std::atomic_thread_fence(std::memory_order_seq_cst);
-  if (cur != st) {
-    CUDA_TRY(e, cudaEventRecord(e->ev_in, cur));
-    CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_in, 0));
+  // launched on the caller's stream, like the host step: ordered behind the last update by stream order (a K-step call
+  // on the engine's stream is ordered against the caller's stream by the Python guard around iql_train_steps)
+  (void)st;
+  if (e->host_step_stream_set && e->host_step_stream != cur) {
+    CUDA_TRY(e, cudaEventRecord(e->ev_in, e->host_step_stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(cur, e->ev_in, 0));
   }
-  int rc = flush_tables(e, st);
+  int rc = flush_tables(e, cur);
   if (rc != IQL_OK) return rc;
   StepCtx ctx = make_ctx(e);
   launch_act_host(ctx, e->params + (int64_t)member * e->layout.param_floats, e->d_act_off, e->d_act_off + (L + 1), host_state,
-                  max_action, e->h_act, st);
+                  max_action, e->h_act, cur);
   CUDA_TRY(e, cudaGetLastError());
-  rc = spin_flag(e, flag, st, "iql_act_host");
+  rc = spin_flag(e, flag, cur, "iql_act_host");
   if (rc != IQL_OK) return rc;
   for (int i = 0; i < A; ++i) host_action[i] = reinterpret_cast<volatile float*>(e->h_act)[i];
   return IQL_OK;
