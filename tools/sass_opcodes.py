@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Per-kernel histogram of the Blackwell-specific SASS opcodes in libiql_b200.so (tcgen05 MMA / TMEM / TMA / cluster
-barriers), from `cuobjdump -sass`.  Evidence that the tensor-core kernels are tcgen05 + TMA code, not mma.sync:
+barriers), from `cuobjdump -sass`.  Evidence that the GEMMs are tcgen05 + TMA code (UTCHMMA / UTMALDG / LDTM ...); the one
+user of warp-level HMMA is the act_dim <= 8 policy head inside the fused forward's epilogue (16 m16n8k8 MMAs per chunk on an
+operand the warp has just parked in shared memory -- a 32 x 8 output is below the smallest tcgen05 tile):
 
     python tools/sass_opcodes.py > profiles/r02_sass_opcodes.txt
 """
