@@ -233,3 +233,25 @@ def test_host_step_and_host_sample_reject_bad_arguments():
     assert L.iql_replay_sample_host(1, C.byref(lay), 10, 4, None, 1, 1, 1, 1, 1, None) == _lib.IQL_ERR_INVALID
     assert L.iql_replay_sample_host(1, C.byref(lay), 3, 4, idx, 1, 1, 1, 1, 1, None) == _lib.IQL_ERR_INVALID  # index 3 >= size 3
     assert L.iql_replay_sample_host(1, C.byref(lay), 10, 0, None, None, None, None, None, None, None) == _lib.IQL_OK
+
+
+def test_debug_hooks_are_inert_without_their_switches():
+    """The trace hooks (fused forward, chained backward, step timeline) report 'off' unless their debug switches are set."""
+    L = _lib.lib()
+    buf = (C.c_ulonglong * 64)()
+    assert L.iql_debug_step_trace(None, 0, buf, 64, None) < 0
+    cfg = _lib.Config(1, 11, 3, 256, 2, 256, 1, _lib.MATH_FP32_SIMT, 4)
+    h = C.c_void_p()
+    assert L.iql_create(C.byref(cfg), C.byref(h)) == _lib.IQL_OK
+    try:
+        assert L.iql_debug_step_trace(h, 1, None, 0, None) < 0  # no stamp buffer: IQL_STEP_TRACE is not set
+        assert L.iql_host_step_wait(h, (C.c_float * 3)(), None) == _lib.IQL_ERR_STATE  # nothing in flight
+        assert L.iql_act_host(h, 0, (C.c_float * 11)(), 1.0, (C.c_float * 3)(), None, None) == _lib.IQL_ERR_STATE  # not bound
+        assert L.iql_act_host(h, 5, (C.c_float * 11)(), 1.0, (C.c_float * 3)(), None, None) == _lib.IQL_ERR_INVALID
+    finally:
+        L.iql_destroy(h)
+    lay = _lib.RowLayout()
+    assert L.iql_replay_row_layout(600, 8, C.byref(lay)) == _lib.IQL_OK and lay.row_floats > 960
+    z = (C.c_float * 600)()
+    assert L.iql_replay_insert_host(1, C.byref(lay), 0, z, z, 0.0, z, 0.0, None) == _lib.IQL_ERR_SHAPE  # too wide for the by-value row
+    assert L.iql_replay_insert_host(None, C.byref(lay), 0, z, z, 0.0, z, 0.0, None) == _lib.IQL_ERR_INVALID
