@@ -245,6 +245,12 @@ int iql_act(iql_engine* e, int32_t member, const float* states, int64_t n, float
  * everything else the caller has enqueued there (`stream` is unused and kept for symmetry). */
 int iql_act_host(iql_engine* e, int32_t member, const float* host_state, float max_action, float* host_action,
                  void* stream, void* caller_stream);
+/* Training-mode GaussianPolicy.act (iql.py:371-379, `dist.sample()`; the learner's env steps of the online loop,
+ * jsrl_w_iql.py:445-515): the parameters of the action distribution for one host observation -- host_mean[action_dim] =
+ * tanh(MLP(state)) (unscaled) and host_std[action_dim] = exp(clamp(log_std, -20, 2)); the caller draws
+ * mean + std * N(0, 1) on the host and clamps max_action * sample.  Same launch / mailbox as iql_act_host. */
+int iql_act_host_gaussian(iql_engine* e, int32_t member, const float* host_state, float* host_mean, float* host_std,
+                          void* stream, void* caller_stream);
 /* Self-test hook for the tcgen05 TF32 GEMM building block (no reference
  * counterpart): C[M,N] = op(A) op(B), mode 0 NT (A[M,K], B[N,K]), 1 NN (A[M,K],
  * B[K,N]), 2 TN (A[K,M], B[K,N]); M multiple of 256, N <= 256 or a multiple of

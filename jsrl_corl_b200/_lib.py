@@ -112,6 +112,7 @@ SYMBOLS = {
     "iql_host_step_wait": (C.c_int, [_P, _P, _P]),
     "iql_act": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.c_float, _P, _P]),
     "iql_act_host": (C.c_int, [_P, C.c_int32, _P, C.c_float, _P, _P, _P]),
+    "iql_act_host_gaussian": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
     "iql_last_launch_count": (C.c_int64, [_P]),
     "iql_debug_fused_trace": (C.c_int, [_P, C.c_int32]),
     "iql_debug_chain_trace": (C.c_int, [_P, C.c_int32]),

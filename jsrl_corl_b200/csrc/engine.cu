@@ -1557,8 +1557,25 @@ extern "C" int iql_act(iql_engine* e, int32_t member, const float* states, int64
 // jsrl_w_iql.py:445-515 call it once per env step): the observation rides in the kernel parameters, the action comes
 // back through device-mapped pinned memory with a flag word the host spins on -- one launch, no copies, no stream
 // synchronisation.  Ordered after everything queued on `stream` (the last update) and on `caller_stream`.
+static int act_host_impl(iql_engine* e, int32_t member, const float* host_state, float max_action, float* host_action,
+                         float* host_std, void* stream, void* caller_stream);
+
 extern "C" int iql_act_host(iql_engine* e, int32_t member, const float* host_state, float max_action, float* host_action,
                             void* stream, void* caller_stream) {
+  return act_host_impl(e, member, host_state, max_action, host_action, nullptr, stream, caller_stream);
+}
+
+// Training-mode GaussianPolicy.act (iql.py:371-379: `dist.sample()`): the kernel returns the distribution's parameters --
+// mean = tanh(MLP(s)) (unscaled) and std = exp(clamp(log_std, -20, 2)) -- and the caller draws the sample on the host.
+extern "C" int iql_act_host_gaussian(iql_engine* e, int32_t member, const float* host_state, float* host_mean, float* host_std,
+                                     void* stream, void* caller_stream) {
+  if (e && e->cfg.deterministic) return fail(e, IQL_ERR_INVALID, "iql_act_host_gaussian: the policy is deterministic");
+  if (!host_std) return fail(e, IQL_ERR_INVALID, "iql_act_host_gaussian: null std");
+  return act_host_impl(e, member, host_state, 1.0f, host_mean, host_std, stream, caller_stream);
+}
+
+static int act_host_impl(iql_engine* e, int32_t member, const float* host_state, float max_action, float* host_action,
+                         float* host_std, void* stream, void* caller_stream) {
   if (!e || member < 0 || member >= e->cfg.n_members) return fail(e, IQL_ERR_INVALID, "iql_act_host: bad member");
   if (!e->bound) return fail(e, IQL_ERR_STATE, "iql_act_host: state not bound");
   if (!host_state || !host_action) return fail(e, IQL_ERR_INVALID, "iql_act_host: null state or action");
@@ -1566,13 +1583,13 @@ extern "C" int iql_act_host(iql_engine* e, int32_t member, const float* host_sta
   cudaStream_t st = (cudaStream_t)stream, cur = (cudaStream_t)caller_stream;
   const int A = e->cfg.action_dim, L = e->cfg.n_hidden;
   if (!e->h_act) {
-    if (!host_events(e) || cudaHostAlloc((void**)&e->h_act, sizeof(float) * (A + 1), cudaHostAllocMapped) != cudaSuccess) {
+    if (!host_events(e) || cudaHostAlloc((void**)&e->h_act, sizeof(float) * (2 * A + 1), cudaHostAllocMapped) != cudaSuccess) {
       cudaGetLastError();
       e->h_act = nullptr;
       return fail(e, IQL_ERR_CUDA, "iql_act_host: pinned mailbox / event allocation failed");
     }
   }
-  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(e->h_act + A);
+  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(e->h_act + 2 * A);
   *flag = 0u;
   std::atomic_thread_fence(std::memory_order_seq_cst);
   // launched on the caller's stream, like the host step: ordered behind the last update by stream order (a K-step call
@@ -1585,12 +1602,15 @@ extern "C" int iql_act_host(iql_engine* e, int32_t member, const float* host_sta
   int rc = flush_tables(e, cur);
   if (rc != IQL_OK) return rc;
   StepCtx ctx = make_ctx(e);
-  launch_act_host(ctx, e->params + (int64_t)member * e->layout.param_floats, e->d_act_off, e->d_act_off + (L + 1), host_state,
-                  max_action, e->h_act, cur);
+  const float* block = e->params + (int64_t)member * e->layout.param_floats;
+  launch_act_host(ctx, block, e->d_act_off, e->d_act_off + (L + 1), host_state, max_action,
+                  (host_std && !e->cfg.deterministic) ? block + e->log_std_off : nullptr, e->h_act, cur);
   CUDA_TRY(e, cudaGetLastError());
   rc = spin_flag(e, flag, cur, "iql_act_host");
   if (rc != IQL_OK) return rc;
   for (int i = 0; i < A; ++i) host_action[i] = reinterpret_cast<volatile float*>(e->h_act)[i];
+  if (host_std)
+    for (int i = 0; i < A; ++i) host_std[i] = reinterpret_cast<volatile float*>(e->h_act)[A + i];
   return IQL_OK;
 }
 

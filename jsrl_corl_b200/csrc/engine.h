@@ -191,6 +191,7 @@ void launch_act(const StepCtx& ctx, const float* actor_block, int n_members, con
 // one observation passed by value (state_dim <= act_host_state_max()), action + flag word into pinned host memory
 int act_host_state_max();
 void launch_act_host(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
-                     const float* host_state, float max_action, float* mail, cudaStream_t st);
+                     const float* host_state, float max_action, const float* log_std /* null: deterministic policy */, float* mail,
+                     cudaStream_t st);
 
 }  // namespace iql

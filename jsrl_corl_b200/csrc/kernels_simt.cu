@@ -643,17 +643,20 @@ __global__ void __launch_bounds__(ACT_THREADS) act_host_kernel(int S, int A, int
                                                                const int64_t* __restrict__ w_off,
                                                                const int64_t* __restrict__ b_off,
                                                                const __grid_constant__ ActState state, float max_action,
-                                                               float* __restrict__ mail) {
+                                                               const float* __restrict__ log_std, float* __restrict__ mail) {
   extern __shared__ float sm[];
   const int width = ((H > S ? H : S) + 3) & ~3;
   float* res = sm + 2 * width;  // [A]
   act_body(S, A, H, L, block, w_off, b_off, state.v, max_action, res, sm);
   __syncthreads();
-  if (threadIdx.x < 32) {
-    for (int i = threadIdx.x; i < A; i += 32) reinterpret_cast<volatile float*>(mail)[i] = res[i];
+  if (threadIdx.x < 32) {  // mailbox: [A] actions | [A] std = exp(clamp(log_std, -20, 2)) (Gaussian policies) | flag word
+    for (int i = threadIdx.x; i < A; i += 32) {
+      reinterpret_cast<volatile float*>(mail)[i] = res[i];
+      reinterpret_cast<volatile float*>(mail)[A + i] = log_std ? expf(fminf(fmaxf(log_std[i], -20.0f), 2.0f)) : 0.f;
+    }
     __threadfence_system();
     __syncwarp();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(mail + A) = 1u;
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(mail + 2 * A) = 1u;
   }
 }
 
@@ -668,12 +671,12 @@ void launch_act(const StepCtx& ctx, const float* actor_block, int n_members, con
 int act_host_state_max() { return ACT_STATE_MAX; }
 
 void launch_act_host(const StepCtx& ctx, const float* actor_block, const int64_t* w_off, const int64_t* b_off,
-                     const float* host_state, float max_action, float* mail, cudaStream_t st) {
+                     const float* host_state, float max_action, const float* log_std, float* mail, cudaStream_t st) {
   const int width = ((ctx.H > ctx.S_dim ? ctx.H : ctx.S_dim) + 3) & ~3;
   ActState s;
   for (int i = 0; i < ACT_STATE_MAX; ++i) s.v[i] = i < ctx.S_dim ? host_state[i] : 0.f;
   act_host_kernel<<<1, ACT_THREADS, (2 * width + ctx.A_dim) * sizeof(float), st>>>(ctx.S_dim, ctx.A_dim, ctx.H, ctx.L, actor_block,
-                                                                                   w_off, b_off, s, max_action, mail);
+                                                                                   w_off, b_off, s, max_action, log_std, mail);
 }
 
 }  // namespace iql

@@ -105,7 +105,7 @@ class EnsembleEngine:
             raise ValueError(f"math_mode='tf32' with strict_tf32: batch {batch_size} / hidden {hidden_dim} is outside the tcgen05 "
                              "kernels (batch % 128 == 0 and hidden % 256 == 0 required); the FP32 kernels would run")
         self.act_calls = 0
-        self._act_in = self._act_out = self._act_in_dev = None
+        self._act_in = self._act_out = self._act_in_dev = self._act_std = None
         self._hparams = [self._default_hparams(m) for m in range(n_members)]
         self._replay_refs: Dict[int, torch.Tensor] = {}
         self._idx_stage: Dict[int, torch.Tensor] = {}
@@ -451,3 +451,30 @@ class EnsembleEngine:
                 guard.__exit__(None, None, None)
         self.act_calls += 1
         return self._act_out.copy()
+
+    def act_host_gaussian(self, member: int, state: np.ndarray):
+        """(mean, std) of the Gaussian policy's action distribution for one host observation (`iql_act_host_gaussian`):
+        mean = tanh(MLP(state)) unscaled, std = exp(clamp(log_std)); the caller samples on the host."""
+        if self._act_in is None:
+            self._act_in = np.zeros(self.state_dim, dtype=np.float32)
+            self._act_out = np.zeros(self.action_dim, dtype=np.float32)
+            self._act_ptrs = (self._act_in.ctypes.data, self._act_out.ctypes.data)
+            self._stream_raw = self.stream.cuda_stream
+        if self._act_std is None:
+            self._act_std = np.zeros(self.action_dim, dtype=np.float32)
+            self._act_std_ptr = self._act_std.ctypes.data
+        self._act_in[:] = np.asarray(state, dtype=np.float32).reshape(-1)
+        switch = torch._C._cuda_getDevice() != self._dev_index
+        if switch:
+            guard = torch.cuda.device(self.device)
+            guard.__enter__()
+        try:
+            rc = self._L.iql_act_host_gaussian(self._h, member, self._act_ptrs[0], self._act_ptrs[1], self._act_std_ptr, self._stream_raw,
+                                               torch._C._cuda_getCurrentRawStream(self._dev_index))
+            if rc:
+                _lib.check(rc, self._h, "iql_act_host_gaussian")
+        finally:
+            if switch:
+                guard.__exit__(None, None, None)
+        self.act_calls += 1
+        return self._act_out.copy(), self._act_std.copy()

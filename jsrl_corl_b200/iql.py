@@ -561,9 +561,31 @@ class GaussianPolicy(_PolicyBase):
             a = self._engine_act(state)
             if a is not None:
                 return a
+        elif not (self.net.has_dropout_modules and self.net.dropout_p > 0.0):
+            # training mode, no active dropout (the learner's env steps of the online loop): the engine kernel returns the
+            # distribution's mean and std, the sample `mean + std * N(0, 1)` is drawn on the host from torch's CPU generator
+            # (the reference draws it from the generator of the policy's device: same distribution, seeded by the same
+            # torch.manual_seed, not the same stream -- sampled actions are not part of the parity contract)
+            ms = self._engine_gaussian(state)
+            if ms is not None:
+                mean, std = ms
+                sample = mean + std * torch.randn(mean.shape[0]).numpy()
+                return np.clip(self.max_action * sample, -self.max_action, self.max_action).astype(np.float32)
         obs = torch.tensor(state.reshape(1, -1), device=device, dtype=torch.float32)
         dist = self(obs)
         return self._clip(dist.sample() if self.training else dist.mean)
+
+    def _engine_gaussian(self, state: np.ndarray):
+        ref = self._engine_ref
+        if ref is None:
+            return None
+        eng, member = ref
+        p = self.net.net[0].weight
+        if p.device != eng.device or p.data_ptr() < eng.params.data_ptr() or \
+                p.data_ptr() >= eng.params.data_ptr() + eng.params.numel() * 4 or \
+                self.log_std.data_ptr() < eng.params.data_ptr() or self.log_std.data_ptr() >= eng.params.data_ptr() + eng.params.numel() * 4:
+            return None  # parameters were re-pointed (module moved / re-initialised): stock torch path
+        return eng.act_host_gaussian(member, state)
 
 
 class DeterministicPolicy(_PolicyBase):

@@ -110,10 +110,34 @@ def test_policy_act_runs_on_the_engine_kernel(det):
         want = torch.clamp(0.8 * mean, -0.8, 0.8).cpu().numpy().flatten()
     np.testing.assert_allclose(a, want, rtol=0, atol=2e-6)
     actor.train()
-    if not det:  # training mode keeps dist.sample(): stock torch path
+    if not det:
+        # training mode (`dist.sample()`, iql.py:377): mean and std come from the engine kernel, the sample is drawn on the
+        # host from torch's CPU generator -- reproducible under torch.manual_seed, distributed as Normal(mean, std)
         calls1 = eng.act_calls
-        actor.act(state, "cuda")
-        assert eng.act_calls == calls1
+        torch.manual_seed(7)
+        s1 = actor.act(state, "cuda")
+        assert eng.act_calls == calls1 + 1 and s1.shape == (3,) and s1.dtype == np.float32
+        torch.manual_seed(7)
+        assert np.array_equal(actor.act(state, "cuda"), s1)
+        m_eng, std_eng = eng.act_host_gaussian(0, state)
+        with torch.no_grad():
+            dist = actor(torch.tensor(state.reshape(1, -1), device="cuda"))
+        np.testing.assert_allclose(m_eng, dist.mean.cpu().numpy().flatten(), rtol=0, atol=2e-6)
+        np.testing.assert_allclose(std_eng, dist.stddev.cpu().numpy().flatten(), rtol=1e-6)
+        torch.manual_seed(7)
+        eps = torch.randn(3).numpy()
+        np.testing.assert_allclose(s1, np.clip(0.8 * (m_eng + std_eng * eps), -0.8, 0.8), rtol=1e-6, atol=1e-7)
+        draws = np.stack([actor.act(state, "cuda") for _ in range(400)])
+        inside = np.abs(0.8 * (m_eng + 3 * std_eng)) < 0.8  # components whose +-3 sigma range is not clipped
+        if inside.any():
+            assert np.all(np.abs(draws.mean(0)[inside] - 0.8 * m_eng[inside]) < 0.25 * 0.8 * std_eng[inside])
+        # with active dropout the stock torch path keeps the masks
+        drop = _make_trainer(False, dropout=0.1)
+        drop.train(_batch())
+        drop.actor.train()
+        c0 = drop._engine.act_calls
+        drop.actor.act(state, "cuda")
+        assert drop._engine.act_calls == c0
     import copy
     clone = copy.deepcopy(actor).eval()  # a copy owns its parameters: no engine behind it
     assert clone._engine_ref is None
