@@ -205,9 +205,10 @@ def _agent_action(agent, env, state, device):
         return agent(torch.tensor(state.reshape(1, -1), device=device, dtype=torch.float32))
 
 
-def learner_or_guide_action(state, step, env, learner, guide, config, device, eval=False):
+def learner_or_guide_action(state, step, env, learner, guide, config, device, eval=False, as_numpy=False):
     """Pick the acting agent for this env step (jsrl_utils.py:547-622): with no guide the learner always
-    acts (the horizon is still evaluated for logging)."""
+    acts (the horizon is still evaluated for logging).  ``as_numpy`` (not in the reference): hand a numpy action back
+    as it is instead of wrapping it in a CPU tensor the caller converts back (16 us per env step)."""
     use_learner, horizon = HORIZON_FNS[horizon_str]["horizon_fn"](step, state, env, config)
     if guide is None:
         use_learner = True
@@ -215,6 +216,9 @@ def learner_or_guide_action(state, step, env, learner, guide, config, device, ev
         action = _agent_action(learner, env, state, device)
     else:
         action = _agent_action(guide, env, state, device)
+    if as_numpy and not eval and isinstance(action, np.ndarray):
+        return action.reshape(-1), use_learner, horizon
+    if not use_learner:
         if not eval and not isinstance(action, torch.Tensor):
             action = torch.tensor(action)
     if eval and isinstance(action, torch.Tensor):

@@ -138,12 +138,21 @@ def train_loop(config, env, eval_env, replay_buffer: Optional[ReplayBuffer], sta
                 config.ep_agent_type = 0
             else:
                 config.ep_agent_type = np.mean(ep_types)
-            action, use_learner, _ = jsrl.learner_or_guide_action(state, ep_step, env, actor, guide, config, config.device)
+            action, use_learner, _ = jsrl.learner_or_guide_action(state, ep_step, env, actor, guide, config, config.device,
+                                                                  as_numpy=True)
             ep_types.append(1 if use_learner else 0)
-            if use_learner and config.iql_deterministic:
-                noise = (torch.randn_like(action) * config.expl_noise).clamp(-config.noise_clip, config.noise_clip)
-                action = action + noise
-            action = torch.clamp(max_action * action, -max_action, max_action).cpu().numpy().flatten()
+            if isinstance(action, np.ndarray):
+                # engine-backed policies hand back numpy: the exploration noise still comes from torch's CPU generator
+                # (what `torch.randn_like` of the reference's CPU action tensor draws from), everything else stays numpy
+                if use_learner and config.iql_deterministic:
+                    noise = (torch.randn(action.shape[0]) * config.expl_noise).clamp(-config.noise_clip, config.noise_clip)
+                    action = action + noise.numpy()
+                action = np.clip(max_action * action, -max_action, max_action).astype(np.float32).flatten()
+            else:
+                if use_learner and config.iql_deterministic:
+                    noise = (torch.randn_like(action) * config.expl_noise).clamp(-config.noise_clip, config.noise_clip)
+                    action = action + noise
+                action = torch.clamp(max_action * action, -max_action, max_action).cpu().numpy().flatten()
             next_state, reward, done, info = _step(env, action)
             ep_step += 1
             goal = goal or is_goal_reached(reward, info)
