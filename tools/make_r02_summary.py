@@ -79,7 +79,7 @@ CUDA graph launch), {b['steps']} timed calls = {b['ms_per_step'] * b['steps'] / 
   H2D {b['e2e']['h2d_bytes_per_step']} B from pinned memory + losses D2H {b['e2e']['d2h_bytes_per_step']} B, one sync per call).
 * one drop-in learner, `rb.sample(256); trainer.train(batch)` with a host-visible log dict every step: **{b['e2e_dropin']['value']:.0f} steps/s**
   (host-step path: one graph launch per iteration, losses written by the loss kernel into pinned host memory, the host returns while
-  the backward still runs; tools/dropin_profile.py: sample ~16 us + train ~47 us of wall clock; before this path: 6.2 k steps/s).
+  the backward still runs; tools/dropin_profile.py: sample ~15 us + train ~36 us of wall clock, GPU-bound on the ~43 us K = 1 step; before this path: 6.2 k steps/s).
   The online-loop body act + add_transition + sample + train: profiles/r02_online_loop.json.
 * the UNMODIFIED reference on the same box (`kind: reference`): torch eager on this B200 **{b['torch_eager_b200']['value']:.0f} steps/s**; host CPU
   {b['cpu_baseline']['value']:.0f} steps/s on {b['cpu_baseline']['cores']} threads, {b['cpu_baseline']['one_thread']:.0f} on one ({b['cpu_baseline']['cpu_model']}, nproc {b['cpu_baseline']['nproc']};
