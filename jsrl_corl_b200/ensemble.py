@@ -91,6 +91,20 @@ class IQLEnsemble:
         """K fused sample+update steps for every member; losses [S, K, 3] on device."""
         return self.engine.train_steps(k_steps, **kw)
 
+    def train_step_logged(self, indices: Optional[np.ndarray] = None) -> np.ndarray:
+        """ONE update step of every member with the losses on the host when it returns ([S, 3] float32:
+        value_loss, q_loss, actor_loss) -- the ensemble form of the reference's `log_dict = trainer.train(batch)`
+        (offline/iql.py:631-635), for loops that log or branch on the losses every step.  ``indices``: [S, B] int64 rows of
+        the bound buffers (drawn here with numpy, like `ReplayBuffer.sample`, when omitted).  Runs through
+        `iql_train_host_step`: one graph launch, the call returns while the backward of the step is still running."""
+        e = self.engine
+        if indices is None:
+            indices = np.stack([np.random.randint(0, rb._high(), size=e.batch_size) for rb in self._buffers])
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        if idx.shape != (e.n_members, e.batch_size):
+            raise ValueError(f"indices must be [{e.n_members}, {e.batch_size}]")
+        return np.asarray(e.host_step(host_indices=idx.ctypes.data), dtype=np.float32).reshape(e.n_members, 3)
+
     # ---- checkpoints in the reference layout --------------------------------
     def member_state_dict(self, m: int) -> Dict[str, Any]:
         """Checkpoint of member ``m`` with the keys and tensor layout of

@@ -786,6 +786,31 @@ def test_replay_offline_semantics_and_ensemble_shared_vs_private_buffers():
     assert np.array_equal(l2[0], l2[1]) and np.array_equal(l2[0], losses[0])
 
 
+def test_ensemble_logged_step_equals_k_step_call():
+    """`IQLEnsemble.train_step_logged` (host step for S members: losses on the host every step) == `train_steps(1,
+    mode="indices")` on the same indices, bit for bit, members on their own rows."""
+    from jsrl_corl_b200 import IQLEnsemble, ReplayBuffer
+    from oracle.iql_numpy import synthetic_dataset
+
+    rb = ReplayBuffer(17, 6, 4000, "cuda")
+    rb.load_d4rl_dataset(synthetic_dataset(4000, 17, 6, 1))
+    a = IQLEnsemble(3, 17, 6, 256, 2, 256, math_mode="tf32", seeds=[5, 6, 7], max_steps_per_call=4)
+    b = IQLEnsemble(3, 17, 6, 256, 2, 256, math_mode="tf32", seeds=[5, 6, 7], max_steps_per_call=4)
+    a.bind_replay(rb)
+    b.bind_replay(rb)
+    rng = np.random.RandomState(3)
+    for _ in range(4):
+        idx = rng.randint(0, 4000, size=(3, 256))
+        la = a.train_step_logged(idx)
+        lb = b.train_steps(1, mode="indices", indices=torch.from_numpy(idx).cuda().view(3, 1, 256)).cpu().numpy()[:, 0]
+        assert la.shape == (3, 3) and np.array_equal(la, lb)
+    assert torch.equal(a.engine.params, b.engine.params) and torch.equal(a.engine.exp_avg_sq, b.engine.exp_avg_sq)
+    np.random.seed(0)
+    assert np.isfinite(a.train_step_logged()).all()  # indices drawn here (numpy stream), one row set per member
+    with pytest.raises(ValueError):
+        a.train_step_logged(np.zeros((2, 256), np.int64))
+
+
 def test_resume_from_reference_written_checkpoint():
     """Load a checkpoint_19.pt written by the REFERENCE trainer (torch.save(trainer.state_dict())), continue for 20
     steps on the same index stream, compare with what a fresh reference trainer did after loading the same file."""
