@@ -529,8 +529,8 @@ def test_tcgen05_path_general_shapes_match_oracle(B, H, L, A):
         assert worst < TF32_W30_TOL, (worst, where)
 
 
-@pytest.mark.parametrize("S_dim,A,dropout", [(45, 24, 0.0), (17, 6, 0.0), (29, 8, 0.0), (45, 24, 0.1)])
-def test_fused_forward_several_tiles_per_cta_pair_match_oracle(S_dim, A, dropout):
+@pytest.mark.parametrize("S_dim,A,dropout,L", [(45, 24, 0.0, 2), (17, 6, 0.0, 2), (29, 8, 0.0, 2), (45, 24, 0.1, 2), (29, 8, 0.0, 3)])
+def test_fused_forward_several_tiles_per_cta_pair_match_oracle(S_dim, A, dropout, L):
     """32 members x 7 passes = 224 tiles on the 74 CTA pairs of a B200: every pair walks 3-4 tiles, which is what
     exercises the cross-tile machinery of the fused forward (operands of the next tile requested ahead, the two
     epilogue groups on alternate tiles, the accumulator hand-over between tiles).  pen shape: three layer-0 k-blocks
@@ -540,7 +540,7 @@ def test_fused_forward_several_tiles_per_cta_pair_match_oracle(S_dim, A, dropout
     from oracle.iql_numpy import NumpyIQL, OracleConfig, synthetic_dataset
     from oracle.philox import philox_indices
 
-    members, B, H, L, n_rows, steps = 32, 256, 256, 2, 5000, 2
+    members, B, H, n_rows, steps = 32, 256, 256, 5000, 2
     data = synthetic_dataset(n_rows, S_dim, A, 2)
     rb = ReplayBuffer(S_dim, A, n_rows, "cuda")
     rb.load_d4rl_dataset(data)
@@ -561,8 +561,11 @@ def test_fused_forward_several_tiles_per_cta_pair_match_oracle(S_dim, A, dropout
         if mode == "tf32":
             trees = {m: _cpu_tree(ens.engine.param_views(m, dropout > 0)) for m in (0, 17, 31)}
     assert np.isfinite(out["tf32"]).all()
+    # three hidden layers carry one more TF32 GEMM per pass: the depth scaling of the general-shape test (the value loss is
+    # ~5e-4 here, a difference of two O(1) network outputs -- measured 1.7e-3 relative on one member of 32 at step 2)
+    TF32_TOL_L = TF32_TOL * (L - 1)
     for m in range(members):
-        assert _loss_errors(out["tf32"][m], out["fp32"][m]).max() < TF32_TOL, (m, out["tf32"][m], out["fp32"][m])
+        assert _loss_errors(out["tf32"][m], out["fp32"][m]).max() < TF32_TOL_L, (m, out["tf32"][m], out["fp32"][m])
     for m in (0, 17, 31):
         orc = NumpyIQL(OracleConfig(S_dim, A, H, L, False, dropout, max_steps=50), init[m], np.float32)
         ref = []
@@ -570,7 +573,7 @@ def test_fused_forward_several_tiles_per_cta_pair_match_oracle(S_dim, A, dropout
             mk = masks[m, k].numpy().astype(bool) if masks is not None else None
             lo = orc.train(batch_from(data, philox_indices(seeds[m], k, n_rows, B)), dropout_masks=mk)
             ref.append([lo["value_loss"], lo["q_loss"], lo["actor_loss"]])
-        assert _loss_errors(out["tf32"][m], np.array(ref)).max() < TF32_TOL, (m, out["tf32"][m], ref)
+        assert _loss_errors(out["tf32"][m], np.array(ref)).max() < TF32_TOL_L, (m, out["tf32"][m], ref)
         worst, where = tree_max_rel(trees[m], orc.state())
         assert worst < TF32_W30_TOL, (m, worst, where)
 
