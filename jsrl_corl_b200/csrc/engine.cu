@@ -666,12 +666,12 @@ extern "C" int iql_bind_state(iql_engine* e, float* params, float* exp_avg, floa
       // phases run by the fused forward: the weight boxes are full tiles, or half tiles when it runs on CTA pairs
       const bool in_fused = e->fused_fwd && ph.mode == 0 && ph.kind != PH_OUT_FWD;
       ph.cta2 = in_fused ? e->fused_pair : (ph.umma_ok && umma_cta2(ph.mode, ph.count, ph.maxM, ph.maxN, ph.maxK));
-      // few dgrad problems (single learners, small ensembles): two N = 128 units per problem on twice the CTA pairs --
-      // half the MMAs and one epilogue chunk per warp instead of two on the step's critical path
+      // few dgrad problems (single learners, small ensembles): two N = 128 (or four N = 64) units per problem on more CTA
+      // pairs -- fewer MMAs and one epilogue chunk per warp instead of two on the step's critical path
       ph.tile_n = 0;
       if (!in_fused && ph.cta2 && ph.mode == 1 && ph.kind == PH_GENERIC && ph.maxN % 256 == 0 && 2 * ph.count * (ph.maxN / 256) <= 74 &&
           dbg_getenv("IQL_B200_NO_NARROW_DGRAD") == nullptr)
-        ph.tile_n = 128;
+        ph.tile_n = (4 * ph.count * (ph.maxN / 256) <= 74 && dbg_getenv("IQL_B200_NO_DGRAD_N64") == nullptr) ? 64 : 128;  // single learners: four units
       // backward hidden-layer phases: row-layout epilogue (TMA stores; dgrad masks with the sign bits the fused
       // forward wrote -- without the fused forward the bits do not exist and dgrad keeps the FP32 mask)
       // (the same epilogue on the weight-gradient phase measured 46.4 vs 44.2 us: it stays on the transposing one)
@@ -1620,7 +1620,7 @@ extern "C" int iql_selftest_umma_gemm(int32_t mode, int32_t M, int32_t N, int32_
                                       const float* B, int32_t ldb, float* C, int32_t ldc, void* scratch,
                                       size_t scratch_bytes, void* stream) {
   const bool allow_pair = !(mode & 0x100);  // test hook: mode | 0x100 keeps the single-CTA kernel
-  const int tile_n_arg = (mode & 0x200) ? 128 : 0;  // test hook: mode | 0x200 runs N = 128 tiles (CTA pairs: 64 columns of B per CTA)
+  const int tile_n_arg = (mode & 0x400) ? 64 : ((mode & 0x200) ? 128 : 0);  // test hooks: mode | 0x200 / 0x400 run N = 128 / 64 tiles
   mode &= 0xFF;
   if (mode < 0 || mode > 2 || M <= 0 || N <= 0 || K <= 0 || (M % 256) || (N > 256 && (N % 256)))
     return fail(nullptr, IQL_ERR_INVALID, "iql_selftest_umma_gemm: M multiple of 256 and N <= 256 or a multiple of 256 required");

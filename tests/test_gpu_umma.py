@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(mode, M, N, K, seed=0, single_cta=False, narrow=False):
+def _run(mode, M, N, K, seed=0, single_cta=False, narrow=False, narrow64=False):
     from jsrl_corl_b200 import _lib
 
     L = _lib.lib()
@@ -33,7 +33,7 @@ def _run(mode, M, N, K, seed=0, single_cta=False, narrow=False):
     st = torch.cuda.Stream()
     st.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(st):
-        rc = L.iql_selftest_umma_gemm(mode | (0x100 if single_cta else 0) | (0x200 if narrow else 0), M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+        rc = L.iql_selftest_umma_gemm(mode | (0x100 if single_cta else 0) | (0x200 if narrow else 0) | (0x400 if narrow64 else 0), M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
                                       Cout.data_ptr(), Cout.stride(0), scratch.data_ptr(), scratch.numel(), st.cuda_stream)
     _lib.check(rc, None, "iql_selftest_umma_gemm")
     st.synchronize()
@@ -81,6 +81,8 @@ def test_umma_narrow_tiles_equal_full_tiles(mode, single_cta):
     _, full, _ = _run(mode, 512, 512, 256, seed=5, single_cta=single_cta)
     assert torch.equal(narrow, full)
     assert float((narrow - ref).norm() / ref.norm()) < 1.5e-3
+    _, n64, _ = _run(mode, 512, 512, 256, seed=5, single_cta=single_cta, narrow64=True)
+    assert torch.equal(n64, full)
 
 
 def test_umma_gemm_rejects_bad_shapes():
